@@ -1,0 +1,145 @@
+/*
+ * justpic_c.h -- C ABI of libjustpic_sm100a.so
+ *
+ * The drop-in boundary for JustPIC.jl's particle-in-cell hot path on NVIDIA
+ * B200 (sm_100a).  JustPIC.jl has no FFI of its own: its seam is Julia dispatch
+ * on the backend type, ending in `launch!(ka_backend(x), kernel!, ndrange, ...)`
+ * (reference src/launch.jl:65-69) with allocation/conversion supplied by
+ * ext/JustPICCUDAExt.jl:22-45.  Each entry point below replaces one L4 launcher
+ * of the reference (file:line cited per function); julia/JustPICSM100aExt.jl
+ * shows the `ccall` stubs a maintainer would add, INTEGRATION.md explains them.
+ *
+ * Conventions
+ *  - Every array pointer is a DEVICE pointer owned by the caller (CuArray /
+ *    torch tensor); the library never retains it past the call.  Only
+ *    jp_grid_desc carries HOST pointers (the grid vectors are a few KB and are
+ *    copied into the context once).
+ *  - CellArray layout = the reference's CUDA layout (blocklength 0,
+ *    ext/JustPICCUDAExt.jl:26-30): element (cell c, slot s) at c + s*C,
+ *    c = i + nx*(j + ny*k) 0-based, C = nx*ny*nz.  `index` is 1 byte per slot.
+ *  - Grid-node arrays are column-major (x fastest) like Julia Arrays.
+ *  - All calls are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *    the reference's "launch then synchronize" semantics (src/launch.jl:60-69)
+ *    are kept by the caller synchronising the stream.
+ *  - Return 0 on success, negative jp_status on error; jp_last_error() returns
+ *    a thread-local message.  Nothing throws across the boundary.
+ *  - There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef JUSTPIC_C_H
+#define JUSTPIC_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JP_MAX_ARGS 16   /* particle fields carried by move/inject/clean/halo in one call */
+#define JP_MAX_SLOTS 64  /* max_xcell supported by the occupancy-word kernels */
+#define JP_MAX_PHASES 32
+
+typedef enum {
+    JP_OK = 0,
+    JP_ERR_INVALID = -1,     /* bad argument (dims, null pointer, alpha out of (0,1), ...) */
+    JP_ERR_CUDA = -2,        /* CUDA runtime error (message holds cudaGetErrorString) */
+    JP_ERR_UNSUPPORTED = -3  /* e.g. S > JP_MAX_SLOTS, nargs > JP_MAX_ARGS */
+} jp_status;
+
+typedef enum { JP_EULER = 0, JP_RK2 = 1, JP_RK4 = 2 } jp_scheme;
+
+/* Grid description (HOST pointers).  Mirrors the grid part of the reference's
+ * `Particles` struct (src/particles.jl:17-46): xvi, xci, xi_vel, and whether
+ * `di` holds scalar spacings (range grids, particles_utils.jl:137-140) or
+ * diff() vectors (array grids, particles_utils.jl:76-79). */
+typedef struct {
+    int32_t ndim;              /* 2 or 3 */
+    int32_t n[3];              /* cells per dimension (n[2] ignored in 2D) */
+    int32_t S;                 /* slots per cell = max_xcell */
+    int32_t uniform;           /* 1: spacing = x[1]-x[0] everywhere; 0: x[i+1]-x[i] */
+    const double *xv[3];       /* vertex coordinates, n[d]+1 */
+    const double *xc[3];       /* centre coordinates, n[d] */
+    const double *xvel[3][3];  /* xvel[comp][dim]: staggered velocity grid vectors */
+    int32_t nvel[3][3];        /* their lengths (n, n+1 or n+2) */
+} jp_grid_desc;
+
+/* Particle storage (DEVICE pointers): coords[d] and index are [C*S]. */
+typedef struct {
+    double *coords[3];
+    uint8_t *index;
+} jp_particles;
+
+/* Opaque context: device copy of the grid + derived tables + workspace. */
+typedef struct jp_ctx jp_ctx;
+
+/* Create/destroy a context on CUDA device `device`.  One per Particles object
+ * (the Julia shim creates it in init_particles and caches it). */
+int  jp_ctx_create(const jp_grid_desc *grid, int device, jp_ctx **out);
+void jp_ctx_destroy(jp_ctx *ctx);
+const char *jp_last_error(void);
+int  jp_version(void);
+
+/* init_particles(backend, nxcell, max_xcell, min_xcell, xi_vel...)
+ * (src/Particles/particles_utils.jl:108-166, kernel fill_coords_index! :168-194).
+ * Fills coords with NaN / index with 0, then seeds ceil(nxcell/2^N) particles per
+ * quadrant with Philox4x32-10 keyed (seed, cell, slot). */
+int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxcell, uint64_t seed, void *stream);
+
+/* advection!(particles, method, V, dt)
+ * (src/Particles/Advection/advection.jl:21-91; Euler.jl, RK2.jl, RK4.jl).
+ * V[comp] are the staggered velocity arrays with extents nvel[comp][0..ndim). */
+int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha,
+              const double *const *V, double dt, void *stream);
+
+/* move_particles!(particles, args) (src/Particles/move_safe.jl:21-125).
+ * Bit-exact with the reference's 3^N colour sweeps for displacements <= 1 cell. */
+int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream);
+/* Counters of the last jp_move on this context: {moved, dropped (destination
+ * full), deleted (left the domain)}.  Synchronises `stream`. */
+int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream);
+
+/* inject_particles!(particles, args) (src/Particles/injection.jl:19-131).
+ * RNG: Philox4x32-10 keyed (seed, step, cell, slot). */
+int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs,
+              int32_t min_xcell, uint64_t seed, uint32_t step, void *stream);
+/* Number of particles injected by the last jp_inject.  Synchronises `stream`. */
+int jp_inject_stats(jp_ctx *ctx, int64_t *out, void *stream);
+
+/* clean_particles!(particles, grid, args) (src/Particles/move_safe.jl:289-320). */
+int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream);
+
+/* grid2particle!(Fp, F, particles) (src/Interpolations/grid_to_particle.jl:26-82).
+ * F: vertex field (n+1 per dim).  Fp: [C*S]. */
+int jp_grid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *F, void *stream);
+
+/* centroid2particle!(Fp, F, particles) (src/Interpolations/centroid_to_particle.jl:13-46).
+ * Fc: centre field (n per dim). */
+int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *Fc, void *stream);
+
+/* particle2grid!(F, Fp, particles) (src/Interpolations/particle_to_grid.jl:23-151). */
+int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, const double *Fp, void *stream);
+
+/* particle2centroid!(F, Fp, particles) (src/Interpolations/particle_to_grid_centroid.jl:10-99). */
+int jp_particle2centroid(jp_ctx *ctx, const jp_particles *p, double *Fc, const double *Fp, void *stream);
+
+/* phase_ratios_center!(phase_ratios, particles, phases) (src/PhaseRatios/centers.jl:3-30).
+ * ratios: CellArray [C*K], element (cell c, phase k) at c + k*C.  phases: [C*S] fp64 ids 1..K. */
+int jp_phase_ratios_center(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases,
+                           int32_t K, void *stream);
+
+/* update_cell_halo! building blocks (src/CellArrays/ImplicitGlobalGrid.jl:36-41):
+ * gather / scatter one cell-plane (all S slots) of every listed CellArray into /
+ * from one contiguous device buffer; the transport between ranks (NCCL
+ * send/recv) is done by the host layer.  Buffer layout: for each fp64 array in
+ * order, then the index bytes; within an array slot-major, then the plane's
+ * cells in memory order.  jp_halo_plane_bytes returns the buffer size. */
+int64_t jp_halo_plane_bytes(const jp_ctx *ctx, int32_t dim, int32_t narrays);
+int jp_halo_pack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays, int32_t narrays,
+                 const uint8_t *index, void *buf, void *stream);
+int jp_halo_unpack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays, int32_t narrays,
+                   uint8_t *index, const void *buf, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JUSTPIC_C_H */

@@ -1,0 +1,99 @@
+"""ctypes binding of libjustpic_sm100a.so (include/justpic_c.h).
+
+The library is the product: if it is missing or fails to load this module
+raises -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "libjustpic_sm100a.so"
+
+JP_MAX_ARGS = 16
+JP_MAX_SLOTS = 64
+JP_MAX_PHASES = 32
+
+c_double_p = C.POINTER(C.c_double)
+
+
+class GridDesc(C.Structure):
+    """jp_grid_desc (HOST pointers)."""
+    _fields_ = [
+        ("ndim", C.c_int32),
+        ("n", C.c_int32 * 3),
+        ("S", C.c_int32),
+        ("uniform", C.c_int32),
+        ("xv", c_double_p * 3),
+        ("xc", c_double_p * 3),
+        ("xvel", (c_double_p * 3) * 3),
+        ("nvel", (C.c_int32 * 3) * 3),
+    ]
+
+
+class ParticlesC(C.Structure):
+    """jp_particles (DEVICE pointers)."""
+    _fields_ = [("coords", C.c_void_p * 3), ("index", C.c_void_p)]
+
+
+# every symbol include/justpic_c.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "jp_ctx_create": (C.c_int, [C.POINTER(GridDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "jp_ctx_destroy": (None, [C.c_void_p]),
+    "jp_last_error": (C.c_char_p, []),
+    "jp_version": (C.c_int, []),
+    "jp_init_particles": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_uint64, C.c_void_p]),
+    "jp_advect": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
+                            C.POINTER(C.c_void_p), C.c_double, C.c_void_p]),
+    "jp_move": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "jp_move_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "jp_inject": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
+                            C.c_uint64, C.c_uint32, C.c_void_p]),
+    "jp_inject_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "jp_clean": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "jp_grid2particle": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jp_centroid2particle": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jp_particle2grid": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jp_particle2centroid": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jp_phase_ratios_center": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p]),
+    "jp_halo_plane_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32]),
+    "jp_halo_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                               C.c_void_p, C.c_void_p]),
+    "jp_halo_unpack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class JustPICError(RuntimeError):
+    """Non-zero status from libjustpic_sm100a.so (message from jp_last_error)."""
+
+
+def load():
+    """Load the shared library and declare every prototype.  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m justpic.jl_b200._build` "
+            "(nvcc, sm_100a).  There is no CPU fallback for the JustPIC hot path."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, who: str = "") -> None:
+    if rc != 0:
+        msg = load().jp_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{who}: {msg}")   # the reference throws ArgumentError host-side
+        raise JustPICError(f"{who} failed (status {rc}): {msg}")

@@ -1,0 +1,437 @@
+"""Host-side mirror of JustPIC.jl's public API for the particle-in-cell hot path.
+
+Same names (minus Julia's ``!``), argument order and error behaviour as the
+reference, so a test written against the reference reads the same here:
+
+    particles = init_particles(CUDABackend, 24, 48, 12, grid_vx, grid_vy, grid_vz)
+    pT, = init_cell_arrays(particles, 1)
+    grid2particle(pT, T, particles)
+    advection(particles, RungeKutta2(), V, dt)
+    move_particles(particles, (pT,))
+    inject_particles(particles, (pT,))
+    particle2grid(T, pT, particles)
+
+Every call goes through the C ABI of libjustpic_sm100a.so (include/justpic_c.h);
+torch is only the allocator / stream provider.  There is no CPU path.
+
+Memory layout.  A CellArray with S slots over cells (nx, ny[, nz]) is a
+contiguous torch tensor of shape (S, [nz,] ny, nx): element (slot s, cell
+i,j,k) sits at i + nx*(j + ny*k) + s*C, i.e. exactly the reference's CUDA
+CellArray layout (ext/JustPICCUDAExt.jl:26-30).  Grid fields are torch tensors
+of shape ([nz,] ny, nx) (+1 for vertex fields) = Julia's column-major
+(nx, ny[, nz]) arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+__all__ = [
+    "CUDABackend", "LinRange", "expand_range", "add_ghost_nodes",
+    "Euler", "RungeKutta2", "RungeKutta4",
+    "Particles", "PhaseRatios",
+    "init_particles", "init_cell_arrays", "cell_array",
+    "advection", "move_particles", "inject_particles", "clean_particles",
+    "grid2particle", "centroid2particle", "particle2grid", "particle2centroid",
+    "phase_ratios_center", "set_synchronous",
+]
+
+
+class CUDABackend:
+    """Backend tag (reference: CUDA.CUDABackend).  The only backend there is."""
+
+
+_SYNC = False
+
+
+def set_synchronous(flag: bool) -> None:
+    """``True`` reproduces the reference's launch-then-synchronize semantics
+    (src/launch.jl:60-69); default is stream-ordered asynchronous execution."""
+    global _SYNC
+    _SYNC = bool(flag)
+
+
+# --------------------------------------------------------------------------- grids
+class LinRange:
+    """Julia ``LinRange(start, stop, len)``: element i (0-based) is
+    ``(1-t)*start + t*stop`` with ``t = i/(len-1)`` (Base.lerpi).  Passing
+    LinRange grids selects the reference's *range* code path (scalar spacings
+    ``x[2]-x[1]``, src/Particles/particles_utils.jl:108-166); passing arrays
+    selects the vector path (``diff(x)``, :48-106)."""
+
+    def __init__(self, start: float, stop: float, length: int):
+        self.start, self.stop, self.len = float(start), float(stop), int(length)
+
+    def __len__(self) -> int:
+        return self.len
+
+    def __array__(self, dtype=None, copy=None):
+        j = np.arange(self.len, dtype=np.float64)
+        t = j / float(self.len - 1) if self.len > 1 else j
+        a = (1.0 - t) * self.start + t * self.stop
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, i):
+        return np.asarray(self)[i]
+
+
+def expand_range(x: LinRange) -> LinRange:
+    """``expand_range`` of the reference scripts/tests (e.g.
+    scripts/temperature_advection3D.jl:12-19): one ghost node on either side."""
+    a = np.asarray(x)
+    dx = a[1] - a[0]
+    return LinRange(a.min() - dx, a.max() + dx, len(a) + 2)
+
+
+def add_ghost_nodes(x, dx, origin=None) -> np.ndarray:
+    """``add_ghost_nodes`` (src/Utils.jl:10-16) for array grids."""
+    a = np.asarray(x, dtype=np.float64)
+    return np.concatenate(([a.min() - dx], a, [a.max() + dx]))
+
+
+# --------------------------------------------------------------------------- integrators
+class Euler:
+    """``Euler()`` (src/Advection/types.jl:17-19); accepts and ignores any arguments."""
+    scheme = 0
+    alpha = 0.0
+
+    def __init__(self, *_):
+        pass
+
+
+class RungeKutta2:
+    """``RungeKutta2(α=0.5)`` (src/Advection/types.jl:27-40): requires 0 < α < 1."""
+    scheme = 1
+
+    def __init__(self, alpha: float = 0.5):
+        if not (0 < alpha < 1):
+            raise ValueError("Only 0 < α < 1 is supported")
+        self.alpha = float(alpha)
+
+
+class RungeKutta4:
+    """``RungeKutta4()`` (src/Advection/types.jl:47-49)."""
+    scheme = 2
+    alpha = 0.0
+
+    def __init__(self, *_):
+        pass
+
+
+# --------------------------------------------------------------------------- containers
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _done() -> None:
+    if _SYNC:
+        torch.cuda.current_stream().synchronize()
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (C.c_void_p * max(len(tensors), 1))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+@dataclass
+class Particles:
+    """Mirror of the reference ``Particles`` struct (src/particles.jl:17-46)."""
+    coords: Tuple[torch.Tensor, ...]
+    index: torch.Tensor
+    nxcell: int
+    max_xcell: int
+    min_xcell: int
+    np: int
+    di: SimpleNamespace
+    xci: Tuple[np.ndarray, ...]
+    xvi: Tuple[np.ndarray, ...]
+    xi_vel: Tuple[Tuple[np.ndarray, ...], ...]
+    uniform: bool
+    seed: int = 42
+    _ctx: Optional[int] = field(default=None, repr=False)
+    _keep: list = field(default_factory=list, repr=False)
+    _inject_step: int = 0
+
+    @property
+    def ndim(self) -> int:
+        return len(self.coords)
+
+    @property
+    def ncells(self) -> Tuple[int, ...]:
+        """(nx, ny[, nz])"""
+        return tuple(len(x) for x in self.xci)
+
+    @property
+    def device(self) -> torch.device:
+        return self.index.device
+
+    def _c(self) -> _cabi.ParticlesC:
+        pc = _cabi.ParticlesC()
+        for d in range(3):
+            pc.coords[d] = self.coords[d].data_ptr() if d < self.ndim else None
+        pc.index = self.index.data_ptr()
+        return pc
+
+    def __del__(self):
+        try:
+            if self._ctx:
+                _cabi.load().jp_ctx_destroy(C.c_void_p(self._ctx))
+                self._ctx = None
+        except Exception:
+            pass
+
+
+def _make_ctx(ndim, n, S, uniform, xvi, xci, xi_vel, device_index) -> Tuple[int, list]:
+    lib = _cabi.load()
+    keep = []
+    gd = _cabi.GridDesc()
+    gd.ndim, gd.S, gd.uniform = ndim, S, 1 if uniform else 0
+
+    def ptr(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        keep.append(a)
+        return a.ctypes.data_as(_cabi.c_double_p)
+
+    for d in range(3):
+        gd.n[d] = n[d] if d < ndim else 1
+    for d in range(ndim):
+        gd.xv[d] = ptr(xvi[d])
+        gd.xc[d] = ptr(xci[d])
+        for c in range(ndim):
+            gd.xvel[c][d] = ptr(xi_vel[c][d])
+            gd.nvel[c][d] = len(xi_vel[c][d])
+    out = C.c_void_p()
+    _cabi.check(lib.jp_ctx_create(C.byref(gd), device_index, C.byref(out)), "jp_ctx_create")
+    return out.value, keep
+
+
+def cell_array(x, ncells: Sequence[int], ni: Sequence[int], device=None, dtype=None) -> torch.Tensor:
+    """``cell_array(backend, x, ncells, ni)`` (src/launch.jl:101-108): a CellArray with
+    ``prod(ncells)`` entries per cell over the grid ``ni`` = (nx, ny[, nz]), filled with ``x``."""
+    if dtype is None:
+        dtype = torch.uint8 if isinstance(x, (bool, np.bool_)) else torch.float64
+    shape = (int(np.prod(ncells)), *reversed([int(v) for v in ni]))
+    return torch.full(shape, x, dtype=dtype, device=device or "cuda")
+
+
+def init_particles(backend, nxcell: int, max_xcell: int, min_xcell: int, *xi_vel, seed: int = 42,
+                   device=None) -> Particles:
+    """``init_particles(backend, nxcell, max_xcell, min_xcell, grid_vx, grid_vy[, grid_vz])``
+    (src/Particles/particles_utils.jl:30-35, :48-166): random-in-quadrant seeding.
+    ``xi_vel[i]`` is the tuple of 1-D coordinate vectors of velocity component i
+    (LinRange -> range path, arrays -> vector path)."""
+    if len(xi_vel) == 1 and isinstance(xi_vel[0], (tuple, list)) and len(xi_vel[0]) and isinstance(xi_vel[0][0], (tuple, list)):
+        xi_vel = tuple(xi_vel[0])
+    if len(xi_vel) == 0:
+        raise ValueError("The velocity grid cannot be empty")
+    N = len(xi_vel)
+    if N not in (2, 3) or any(len(g) != N for g in xi_vel):
+        raise ValueError("expected N velocity grids of N coordinate vectors each, N = 2 or 3")
+    if not isinstance(nxcell, (int, np.integer)):
+        raise NotImplementedError("regular (NTuple nxcell) particle layouts are dead code in the reference and not supported")
+    uniform = all(isinstance(x, LinRange) for g in xi_vel for x in g)
+    xv_np = tuple(tuple(np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in g) for g in xi_vel)
+    # centre / vertex grids exactly as the reference derives them (:56-74 / :117-135)
+    if N == 3:
+        xci = (xv_np[1][0][1:-1].copy(), xv_np[0][1][1:-1].copy(), xv_np[0][2][1:-1].copy())
+    else:
+        xci = (xv_np[1][0][1:-1].copy(), xv_np[0][1][1:-1].copy())
+    xvi = tuple(xv_np[i][i] for i in range(N))
+    if uniform:
+        di = SimpleNamespace(center=tuple(x[1] - x[0] for x in xci), vertex=tuple(x[1] - x[0] for x in xvi),
+                             velocity=tuple(tuple(x[1] - x[0] for x in g) for g in xv_np))
+    else:
+        di = SimpleNamespace(center=tuple(np.diff(x) for x in xci), vertex=tuple(np.diff(x) for x in xvi),
+                             velocity=tuple(tuple(np.diff(x) for x in g) for g in xv_np))
+    ni = tuple(len(x) for x in xci)
+    NQ = 4 if N == 2 else 8
+    np_quadrant = math.ceil(nxcell / NQ)
+    nxcell = np_quadrant * NQ
+    max_xcell = max(nxcell, int(max_xcell))
+    npart = max_xcell * int(np.prod(ni))
+    dev = torch.device(device or "cuda")
+    if dev.type != "cuda":
+        raise RuntimeError("justpic.jl_b200 has no CPU path: particles must live on a CUDA device")
+    dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+    dev = torch.device("cuda", dev_index)
+    ctx, keep = _make_ctx(N, ni, max_xcell, uniform, xvi, xci, xv_np, dev_index)
+    with torch.cuda.device(dev):
+        coords = tuple(torch.empty((max_xcell, *reversed(ni)), dtype=torch.float64, device=dev) for _ in range(N))
+        index = torch.empty((max_xcell, *reversed(ni)), dtype=torch.uint8, device=dev)
+        p = Particles(coords, index, nxcell, max_xcell, int(min_xcell), npart, di, xci, xvi, xv_np, uniform,
+                      seed=int(seed), _ctx=ctx, _keep=keep)
+        pc = p._c()
+        _cabi.check(_cabi.load().jp_init_particles(C.c_void_p(ctx), C.byref(pc), nxcell, C.c_uint64(int(seed)), _stream()),
+                    "init_particles")
+        _done()
+    return p
+
+
+def init_cell_arrays(particles: Particles, n: int) -> Tuple[torch.Tensor, ...]:
+    """``init_cell_arrays(particles, Val(N))`` (src/Particles/particles_utils.jl:294-301)."""
+    return tuple(torch.zeros_like(particles.coords[0]) for _ in range(int(n)))
+
+
+def _field(t: torch.Tensor, p: Particles, numel: int, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or t.dtype != torch.float64 or t.device != p.device or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous float64 tensor on {p.device}")
+    if t.numel() != numel:
+        raise ValueError(f"{name}: expected {numel} elements, got {t.numel()}")
+    return t
+
+
+def _pfield(t, p, name):
+    return _field(t, p, p.index.numel(), name)
+
+
+def _nodes(p: Particles, plus: int) -> int:
+    return int(np.prod([n + plus for n in p.ncells]))
+
+
+def _args(args, p: Particles):
+    if isinstance(args, torch.Tensor):
+        args = (args,)
+    args = tuple(args)
+    if len(args) > _cabi.JP_MAX_ARGS:
+        raise ValueError(f"at most {_cabi.JP_MAX_ARGS} particle fields per call")
+    for i, a in enumerate(args):
+        _pfield(a, p, f"args[{i}]")
+    return args
+
+
+# --------------------------------------------------------------------------- hot path
+def advection(particles: Particles, method, V, dt: float) -> None:
+    """``advection!(particles, method, V, dt)`` (src/Particles/Advection/advection.jl:21-62)."""
+    p = particles
+    V = tuple(V)
+    if len(V) != p.ndim:
+        raise ValueError("V must hold one staggered array per dimension")
+    for c, v in enumerate(V):
+        _field(v, p, int(np.prod([len(x) for x in p.xi_vel[c]])), f"V[{c}]")
+    lib = _cabi.load()
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(lib.jp_advect(C.c_void_p(p._ctx), C.byref(pc), method.scheme, float(method.alpha),
+                                  _ptr_array(V), float(dt), _stream()), "advection")
+        _done()
+
+
+def move_particles(particles: Particles, args=()) -> None:
+    """``move_particles!(particles, args)`` (src/Particles/move_safe.jl:21-49)."""
+    p = particles
+    args = _args(args, p)
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_move(C.c_void_p(p._ctx), C.byref(pc), _ptr_array(args), len(args), _stream()),
+                    "move_particles")
+        _done()
+
+
+def move_stats(particles: Particles) -> Tuple[int, int, int]:
+    """(moved, dropped, deleted) of the last ``move_particles`` (synchronises)."""
+    out = (C.c_int64 * 3)()
+    with torch.cuda.device(particles.device):
+        _cabi.check(_cabi.load().jp_move_stats(C.c_void_p(particles._ctx), out, _stream()), "move_stats")
+    return int(out[0]), int(out[1]), int(out[2])
+
+
+def inject_particles(particles: Particles, args=(), step: Optional[int] = None) -> None:
+    """``inject_particles!(particles, args)`` (src/Particles/injection.jl:19-53).  The reference
+    draws from the backend's global RNG; here the stream is Philox keyed
+    (particles.seed, step, cell, slot) with ``step`` auto-incremented per call."""
+    p = particles
+    args = _args(args, p)
+    if step is None:
+        step = p._inject_step
+        p._inject_step += 1
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_inject(C.c_void_p(p._ctx), C.byref(pc), _ptr_array(args), len(args), p.min_xcell,
+                                           C.c_uint64(p.seed), C.c_uint32(int(step)), _stream()), "inject_particles")
+        _done()
+
+
+def inject_stats(particles: Particles) -> int:
+    out = C.c_int64()
+    with torch.cuda.device(particles.device):
+        _cabi.check(_cabi.load().jp_inject_stats(C.c_void_p(particles._ctx), C.byref(out), _stream()), "inject_stats")
+    return int(out.value)
+
+
+def clean_particles(particles: Particles, grid=None, args=()) -> None:
+    """``clean_particles!(particles, grid, args)`` (src/Particles/move_safe.jl:289-320);
+    ``grid`` must be the particles' own vertex grid (or None)."""
+    p = particles
+    args = _args(args, p)
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_clean(C.c_void_p(p._ctx), C.byref(pc), _ptr_array(args), len(args), _stream()),
+                    "clean_particles")
+        _done()
+
+
+def _call5(fn_name, p, a, b, who):
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        fn = getattr(_cabi.load(), fn_name)
+        _cabi.check(fn(C.c_void_p(p._ctx), C.byref(pc), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), _stream()), who)
+        _done()
+
+
+def grid2particle(Fp, F, particles: Particles) -> None:
+    """``grid2particle!(Fp, F, particles)`` (src/Interpolations/grid_to_particle.jl:26-35)."""
+    _call5("jp_grid2particle", particles, _pfield(Fp, particles, "Fp"), _field(F, particles, _nodes(particles, 1), "F"),
+           "grid2particle")
+
+
+def centroid2particle(Fp, F, particles: Particles) -> None:
+    """``centroid2particle!(Fp, F, particles)`` (src/Interpolations/centroid_to_particle.jl:13-20)."""
+    _call5("jp_centroid2particle", particles, _pfield(Fp, particles, "Fp"), _field(F, particles, _nodes(particles, 0), "F"),
+           "centroid2particle")
+
+
+def particle2grid(F, Fp, particles: Particles) -> None:
+    """``particle2grid!(F, Fp, particles)`` (src/Interpolations/particle_to_grid.jl:23-28)."""
+    _call5("jp_particle2grid", particles, _field(F, particles, _nodes(particles, 1), "F"), _pfield(Fp, particles, "Fp"),
+           "particle2grid")
+
+
+def particle2centroid(F, Fp, particles: Particles) -> None:
+    """``particle2centroid!(F, Fp, particles)`` (src/Interpolations/particle_to_grid_centroid.jl:10-16)."""
+    _call5("jp_particle2centroid", particles, _field(F, particles, _nodes(particles, 0), "F"), _pfield(Fp, particles, "Fp"),
+           "particle2centroid")
+
+
+@dataclass
+class PhaseRatios:
+    """``PhaseRatios(backend, nphases, ni)`` (src/PhaseRatios/constructors.jl:18-47).  Only the
+    ``center`` field is on the hot path; vertex/face/midpoint ratios are listed as "next"."""
+    center: torch.Tensor
+    nphases: int
+
+    def __init__(self, backend, nphases: int, ni: Sequence[int], device=None):
+        self.nphases = int(nphases)
+        self.center = cell_array(0.0, (nphases,), ni, device=device)
+
+
+def phase_ratios_center(phase_ratios: PhaseRatios, particles: Particles, phases: torch.Tensor) -> None:
+    """``phase_ratios_center!(phase_ratios, particles, phases)`` (src/PhaseRatios/centers.jl:3-30)."""
+    p = particles
+    K = phase_ratios.nphases
+    r = _field(phase_ratios.center, p, K * int(np.prod(p.ncells)), "phase_ratios.center")
+    ph = _pfield(phases, p, "phases")
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_phase_ratios_center(C.c_void_p(p._ctx), C.byref(pc), C.c_void_p(r.data_ptr()),
+                                                        C.c_void_p(ph.data_ptr()), K, _stream()), "phase_ratios_center")
+        _done()

@@ -1,0 +1,632 @@
+// justpic_sm100a.cu -- CUDA kernels (sm_100a) + C ABI of libjustpic_sm100a.so.
+// See include/justpic_c.h for the boundary and DESIGN.md for the kernel notes.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        (no implicit FMA contraction: fma() is explicit where the reference fuses).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../../include/justpic_c.h"
+#include "jp_core.h"
+#include "jp_host_grid.h"
+
+// ---------------------------------------------------------------------------
+// error plumbing
+static thread_local char g_err[512] = "";
+static int jp_fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define JP_CUDA(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) return jp_fail(JP_ERR_CUDA, #call ": %s", cudaGetErrorString(e__)); \
+    } while (0)
+#define JP_CHECK_LAUNCH()                                                              \
+    do {                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) return jp_fail(JP_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" const char *jp_last_error(void) { return g_err; }
+extern "C" int jp_version(void) { return 100; }
+
+struct jp_ctx {
+    int device;
+    JpGrid g;             // device pointers
+    void *gridmem;        // one allocation holding all grid vectors
+    uint64_t *occ, *leave;  // [C] occupancy / leave words (move, inject)
+    uint8_t *flag;        // [C] inject candidate flags
+    long long *stats;     // device counters: [0..2] move, [3] inject
+};
+
+struct Ptr3 { double *p[3]; };
+struct CPtr3 { const double *p[3]; };
+
+// ---------------------------------------------------------------------------
+// thread <-> cell mapping shared by all cell kernels: 32 x 8 tiles, z = blockIdx.z
+#define JP_BX 32
+#define JP_BY 8
+template <int N>
+__device__ __forceinline__ bool tile_cell(const JpGrid &g, int *ci, int64_t &c) {
+    ci[0] = blockIdx.x * JP_BX + threadIdx.x;
+    ci[1] = blockIdx.y * JP_BY + threadIdx.y;
+    ci[2] = N == 3 ? blockIdx.z : 0;
+    const bool ok = ci[0] < g.n[0] && ci[1] < g.n[1];
+    c = ok ? jp_cell_lin<N>(g, ci) : 0;
+    return ok;
+}
+static dim3 tile_grid(int nx, int ny, int nz) { return dim3((nx + JP_BX - 1) / JP_BX, (ny + JP_BY - 1) / JP_BY, nz); }
+
+// live mask of a cell: bit s = index[c + s*C] != 0   (S independent byte loads in flight)
+__device__ __forceinline__ uint64_t load_mask(const uint8_t *__restrict__ index, int64_t c, int64_t C, int S, bool ok) {
+    uint64_t m = 0;
+    if (ok) {
+#pragma unroll 8
+        for (int s = 0; s < S; s++) m |= (uint64_t)(index[c + (int64_t)s * C] != 0) << s;
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256) k_init(JpGrid g, Ptr3 co, uint8_t *index, int npq, uint64_t seed) {
+    int ci[3]; int64_t c;
+    if (!tile_cell<N>(g, ci, c)) return;
+    jp_init_cell<N>(g, co.p, index, npq, seed, c);
+}
+
+// advection!: thread = cell, slot planes in lock-step across the warp (coalesced
+// 256 B per coordinate load), planes that are dead for the whole warp skipped by ballot.
+template <int N, int SCHEME, bool FAST, bool UNIFORM>
+__global__ void __launch_bounds__(256) k_advect(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V, double alpha, double dt) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    const int cell1[3] = {ci[0] + 1, ci[1] + 1, ci[2] + 1};
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        if (live) {
+            const int64_t e = c + (int64_t)s * g.C;
+            double p0[3], p1[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) p0[d] = co.p[d][e];
+            jp_advect_particle<N, SCHEME, FAST, UNIFORM>(g, alpha, V.p, dt, cell1, p0, p1);
+#pragma unroll
+            for (int d = 0; d < N; d++) co.p[d][e] = p1[d];
+        }
+    }
+}
+
+// move_particles! pass A: occupancy + leave words (order-free, coalesced)
+template <int N>
+__global__ void __launch_bounds__(256) k_move_classify(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, uint64_t *occ, uint64_t *leave) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    uint64_t lv = 0;
+    double corner[3], dx[3];
+    if (ok)
+        for (int d = 0; d < N; d++) { corner[d] = g.xv[d][ci[d]]; dx[d] = jp_d_of(g.xv[d], g.uniform, ci[d]); }
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        if (live) {
+            const int64_t e = c + (int64_t)s * g.C;
+            double p[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+            if (!jp_isincell<N>(p, corner, dx)) lv |= 1ull << s;
+        }
+    }
+    if (ok) { occ[c] = m; leave[c] = lv; }
+}
+
+// move_particles! pass B: one colour of the 3^N sweeps (thread = source cell)
+template <int N>
+__global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ, uint64_t *leave,
+                                                    int ox, int oy, int oz, long long *stats) {
+    int ci[3];
+    ci[0] = 3 * (blockIdx.x * JP_BX + threadIdx.x) + ox;
+    ci[1] = 3 * (blockIdx.y * JP_BY + threadIdx.y) + oy;
+    ci[2] = N == 3 ? 3 * blockIdx.z + oz : 0;
+    if (ci[0] >= g.n[0] || ci[1] >= g.n[1] || (N == 3 && ci[2] >= g.n[2])) return;
+    const int64_t c = jp_cell_lin<N>(g, ci);
+    int st[3] = {0, 0, 0};
+    jp_move_cell<N>(g, co.p, index, args, occ, leave, c, ci, st);
+    if (st[0]) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)st[0]);
+    if (st[1]) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)st[1]);
+    if (st[2]) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)st[2]);
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) k_clean(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        if (live) {
+            const int64_t e = c + (int64_t)s * g.C;
+            double p[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+            if (jp_clean_removes<N>(g, ci, p)) {
+                index[e] = 0;
+#pragma unroll
+                for (int d = 0; d < N; d++) co.p[d][e] = NAN;
+                for (int a = 0; a < args.n; a++) args.a[a][e] = NAN;
+            }
+        }
+    }
+}
+
+// inject_particles! pass A: flag the cells the reference would inject into
+template <int N>
+__global__ void __launch_bounds__(256) k_inject_classify(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, int min_xq, uint8_t *flag) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    double vq[3], dq[3];
+    if (ok)
+        for (int d = 0; d < N; d++) { vq[d] = g.xv[d][ci[d]]; dq[d] = jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; }
+    int nq0 = 0;
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        if (live) {
+            const int64_t e = c + (int64_t)s * g.C;
+            double p[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+            nq0 += jp_isincell<N>(p, vq, dq) ? 1 : 0;
+        }
+    }
+    if (ok) flag[c] = jp_inject_candidate(nq0, __popcll(m), g.S, min_xq) ? 1 : 0;
+}
+
+// inject_particles! pass B: one colour of the 2^N sweeps, flagged cells only
+template <int N>
+__global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, const uint8_t *__restrict__ flag,
+                                                      int min_xcell, uint64_t seed, uint32_t step, int ox, int oy, int oz, long long *stats) {
+    int ci[3];
+    ci[0] = 2 * (blockIdx.x * JP_BX + threadIdx.x) + ox;
+    ci[1] = 2 * (blockIdx.y * JP_BY + threadIdx.y) + oy;
+    ci[2] = N == 3 ? 2 * blockIdx.z + oz : 0;
+    if (ci[0] >= g.n[0] || ci[1] >= g.n[1] || (N == 3 && ci[2] >= g.n[2])) return;
+    const int64_t c = jp_cell_lin<N>(g, ci);
+    if (!flag[c]) return;
+    const int inj = jp_inject_cell<N>(g, co.p, index, args, min_xcell, seed, step, c, ci);
+    if (inj) atomicAdd((unsigned long long *)&stats[3], (unsigned long long)inj);
+}
+
+// grid2particle!
+template <int N>
+__global__ void __launch_bounds__(256) k_g2p(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, double *__restrict__ Fp, const double *__restrict__ F) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    double v[8], xcorner[3], idx[3];
+    if (ok) {
+        const int64_t s1 = g.n[0] + 1, s2 = (int64_t)(g.n[0] + 1) * (g.n[1] + 1);
+        jp_corners<N>(F, ci[0] + s1 * ci[1] + (N == 3 ? s2 * ci[2] : 0), s1, s2, v);
+        for (int d = 0; d < N; d++) { xcorner[d] = g.xv[d][ci[d]]; idx[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
+    }
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        if (live) {
+            const int64_t e = c + (int64_t)s * g.C;
+            double p[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+            Fp[e] = jp_g2p<N>(v, xcorner, idx, p);
+        }
+    }
+}
+
+// centroid2particle!: liveness = !any(isnan, coords)  (the reference does not read the mask here)
+template <int N>
+__global__ void __launch_bounds__(256) k_c2p(JpGrid g, CPtr3 co, double *__restrict__ Fp, const double *__restrict__ Fc) {
+    int ci[3]; int64_t c;
+    if (!tile_cell<N>(g, ci, c)) return;
+    for (int s = 0; s < g.S; s++) {
+        const int64_t e = c + (int64_t)s * g.C;
+        double p[3];
+        bool nan = false;
+#pragma unroll
+        for (int d = 0; d < N; d++) { p[d] = co.p[d][e]; nan |= isnan(p[d]); }
+        if (nan) continue;
+        Fp[e] = jp_c2p<N>(g, Fc, ci, p);
+    }
+}
+
+// particle2grid!: thread = node; fixed summation order (k, j, i, slot)
+template <int N>
+__global__ void __launch_bounds__(256) k_p2g(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, double *__restrict__ F, const double *__restrict__ Fp) {
+    const int in = blockIdx.x * JP_BX + threadIdx.x, jn = blockIdx.y * JP_BY + threadIdx.y, kn = N == 3 ? blockIdx.z : 0;
+    const int nx = g.n[0], ny = g.n[1], nz = N == 3 ? g.n[2] : 1;
+    if (in > nx || jn > ny) return;
+    const double xn[3] = {g.xv[0][in], g.xv[1][jn], N == 3 ? g.xv[2][kn] : 0.0};
+    double w = 0.0, wF = 0.0;
+    for (int ko = (N == 3 ? -1 : 0); ko <= 0; ko++) {
+        const int kc = kn + ko;
+        if (N == 3 && (kc < 0 || kc >= nz)) continue;
+        for (int jo = -1; jo <= 0; jo++) {
+            const int jc = jn + jo;
+            if (jc < 0 || jc >= ny) continue;
+            for (int io = -1; io <= 0; io++) {
+                const int ic = in + io;
+                if (ic < 0 || ic >= nx) continue;
+                const int64_t c = ic + (int64_t)nx * (jc + (int64_t)ny * kc);
+                for (int s = 0; s < g.S; s++) {
+                    const int64_t e = c + (int64_t)s * g.C;
+                    if (!index[e]) continue;
+                    double p[3];
+#pragma unroll
+                    for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+                    const double wi = jp_p2g_weight<N>(xn, p);
+                    w += wi;
+                    wF = fma(wi, Fp[e], wF);
+                }
+            }
+        }
+    }
+    const int64_t nd = in + (int64_t)(nx + 1) * (jn + (N == 3 ? (int64_t)(ny + 1) * kn : 0));
+    F[nd] = N == 2 ? wF / w : wF * (1.0 / w);
+}
+
+// particle2centroid!
+template <int N>
+__global__ void __launch_bounds__(256) k_p2c(JpGrid g, CPtr3 co, double *__restrict__ Fc, const double *__restrict__ Fp) {
+    int ci[3]; int64_t c;
+    if (!tile_cell<N>(g, ci, c)) return;
+    double xcn[3], idi[3];
+    for (int d = 0; d < N; d++) { xcn[d] = g.xc[d][ci[d]]; idi[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
+    double w = 0.0, wF = 0.0;
+    for (int s = 0; s < g.S; s++) {
+        const int64_t e = c + (int64_t)s * g.C;
+        double p[3];
+#pragma unroll
+        for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+        if (N == 2 ? (isnan(p[0]) || isnan(p[1])) : isnan(p[0])) continue;
+        const double wi = jp_bilinear_weight<N>(xcn, p, idi);
+        w += wi;
+        wF = fma(wi, Fp[e], wF);
+    }
+    Fc[c] = N == 2 ? wF / w : wF * (1.0 / w);
+}
+
+// phase_ratios_center!
+template <int N, int KMAX>
+__global__ void __launch_bounds__(256) k_phase(JpGrid g, CPtr3 co, double *__restrict__ ratios, const double *__restrict__ phases, int K) {
+    int ci[3]; int64_t c;
+    if (!tile_cell<N>(g, ci, c)) return;
+    double xcn[3], idi[3], w[KMAX];
+    for (int d = 0; d < N; d++) { xcn[d] = g.xc[d][ci[d]]; idi[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) w[k] = 0.0;
+    for (int s = 0; s < g.S; s++) {
+        const int64_t e = c + (int64_t)s * g.C;
+        double p[3];
+#pragma unroll
+        for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+        if (isnan(p[0])) continue;
+        const double x = jp_bilinear_weight<N>(xcn, p, idi);
+        const double ph = phases[e];
+#pragma unroll
+        for (int k = 0; k < KMAX; k++)
+            if (k < K) w[k] = w[k] + (ph == (double)(k + 1) ? x : copysign(0.0, x));
+    }
+    double sum = w[0];
+#pragma unroll
+    for (int k = 1; k < KMAX; k++) if (k < K) sum = sum + w[k];
+    const double inv = 1.0 / sum;
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) if (k < K) ratios[c + (int64_t)k * g.C] = w[k] * inv;
+}
+
+// update_cell_halo! pack / unpack of one cell-plane
+struct HaloArrs { double *a[JP_MAX_ARGS + 3]; int n; };
+template <bool PACK>
+__global__ void __launch_bounds__(256) k_halo(JpGrid g, int dim, int plane, HaloArrs arrs, uint8_t *index, unsigned char *buf, int64_t M) {
+    const int64_t total = (int64_t)(arrs.n + 1) * g.S * M;
+    const int nx = g.n[0], ny = g.n[1];
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = t % M;
+        const int s = (int)((t / M) % g.S);
+        const int a = (int)(t / (M * g.S));
+        int i, j, k;
+        if (dim == 0) { i = plane; j = (int)(m % ny); k = (int)(m / ny); }
+        else if (dim == 1) { i = (int)(m % nx); j = plane; k = (int)(m / nx); }
+        else { i = (int)(m % nx); j = (int)(m / nx); k = plane; }
+        const int64_t e = i + (int64_t)nx * (j + (int64_t)ny * k) + (int64_t)s * g.C;
+        if (a < arrs.n) {
+            double *b = (double *)buf + ((int64_t)a * g.S + s) * M + m;
+            if (PACK) *b = arrs.a[a][e]; else arrs.a[a][e] = *b;
+        } else {
+            unsigned char *b = buf + (int64_t)arrs.n * g.S * M * 8 + (int64_t)s * M + m;
+            if (PACK) *b = index[e]; else index[e] = *b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+extern "C" int jp_ctx_create(const jp_grid_desc *d, int device, jp_ctx **out) {
+    if (!d || !out) return jp_fail(JP_ERR_INVALID, "jp_ctx_create: null argument");
+    JpGrid g;
+    JpGridOffsets off;
+    std::vector<double> h;
+    const char *msg = jp_grid_build(d, g, h, off);
+    if (msg) return jp_fail(strstr(msg, "max_xcell") ? JP_ERR_UNSUPPORTED : JP_ERR_INVALID, "jp_ctx_create: %s", msg);
+    JP_CUDA(cudaSetDevice(device));
+    jp_ctx *ctx = (jp_ctx *)calloc(1, sizeof(jp_ctx));
+    ctx->device = device;
+    double *dm = nullptr;
+    cudaError_t e = cudaMalloc(&dm, h.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(dm, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->occ, g.C * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->leave, g.C * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->flag, g.C);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->stats, 8 * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemset(ctx->stats, 0, 8 * sizeof(long long));
+    if (e != cudaSuccess) {
+        cudaFree(dm); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->flag); cudaFree(ctx->stats);
+        free(ctx);
+        return jp_fail(JP_ERR_CUDA, "jp_ctx_create: %s", cudaGetErrorString(e));
+    }
+    ctx->gridmem = dm;
+    jp_grid_rebase(g, off, dm);
+    ctx->g = g;
+    *out = ctx;
+    return JP_OK;
+}
+
+extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->flag); cudaFree(ctx->stats);
+    free(ctx);
+}
+
+static int check_particles(const jp_ctx *ctx, const jp_particles *p, const char *who) {
+    if (!ctx || !p) return jp_fail(JP_ERR_INVALID, "%s: null context/particles", who);
+    for (int d = 0; d < ctx->g.ndim; d++)
+        if (!p->coords[d]) return jp_fail(JP_ERR_INVALID, "%s: null coordinate array", who);
+    if (!p->index) return jp_fail(JP_ERR_INVALID, "%s: null index array", who);
+    return JP_OK;
+}
+static int pack_args(double *const *args, int nargs, JpArgs &out, const char *who) {
+    if (nargs < 0 || nargs > JP_MAX_ARGS) return jp_fail(JP_ERR_UNSUPPORTED, "%s: 0 <= nargs <= 16 required", who);
+    out.n = nargs;
+    for (int a = 0; a < nargs; a++) {
+        if (!args || !args[a]) return jp_fail(JP_ERR_INVALID, "%s: null particle field", who);
+        out.a[a] = args[a];
+    }
+    for (int a = nargs; a < JP_MAX_ARGS; a++) out.a[a] = nullptr;
+    return JP_OK;
+}
+#define PREP(who)                                                    \
+    int rc__ = check_particles(ctx, p, who);                         \
+    if (rc__) return rc__;                                           \
+    JP_CUDA(cudaSetDevice(ctx->device));                             \
+    const JpGrid &g = ctx->g;                                        \
+    cudaStream_t st = (cudaStream_t)stream;                          \
+    Ptr3 co = {{p->coords[0], p->coords[1], p->coords[2]}};          \
+    CPtr3 cco = {{p->coords[0], p->coords[1], p->coords[2]}};        \
+    const dim3 blk(JP_BX, JP_BY, 1);                                 \
+    const dim3 grd = tile_grid(g.n[0], g.n[1], g.n[2]);              \
+    (void)co; (void)cco; (void)blk; (void)grd; (void)st;
+
+extern "C" int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxcell, uint64_t seed, void *stream) {
+    PREP("jp_init_particles");
+    const int NQ = g.ndim == 2 ? 4 : 8;
+    if (nxcell < 1) return jp_fail(JP_ERR_INVALID, "jp_init_particles: nxcell < 1");
+    const int npq = (nxcell + NQ - 1) / NQ;
+    if (npq * NQ > g.S) return jp_fail(JP_ERR_INVALID, "jp_init_particles: nxcell (rounded up to a multiple of 2^N) exceeds max_xcell");
+    if (g.ndim == 2) k_init<2><<<grd, blk, 0, st>>>(g, co, p->index, npq, seed);
+    else             k_init<3><<<grd, blk, 0, st>>>(g, co, p->index, npq, seed);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+template <int N, int SCHEME>
+static void launch_advect(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
+    if (g.fast) {
+        if (g.uniform) k_advect<N, SCHEME, true, true><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
+        else           k_advect<N, SCHEME, true, false><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
+    } else             k_advect<N, SCHEME, false, false><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
+}
+
+extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt, void *stream) {
+    PREP("jp_advect");
+    if (!V) return jp_fail(JP_ERR_INVALID, "jp_advect: null velocity tuple");
+    CPtr3 v = {{nullptr, nullptr, nullptr}};
+    for (int d = 0; d < g.ndim; d++) {
+        if (!V[d]) return jp_fail(JP_ERR_INVALID, "jp_advect: null velocity component");
+        v.p[d] = V[d];
+    }
+    if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect: Only 0 < alpha < 1 is supported");
+    if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect: unknown integrator");
+    if (g.ndim == 2) {
+        if (scheme == 0) launch_advect<2, 0>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        else if (scheme == 1) launch_advect<2, 1>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        else launch_advect<2, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
+    } else {
+        if (scheme == 0) launch_advect<3, 0>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        else if (scheme == 1) launch_advect<3, 1>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        else launch_advect<3, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
+    }
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream) {
+    PREP("jp_move");
+    JpArgs a;
+    int rc = pack_args(args, nargs, a, "jp_move");
+    if (rc) return rc;
+    JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
+    if (g.ndim == 2) k_move_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
+    else             k_move_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
+    JP_CHECK_LAUNCH();
+    const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = g.ndim == 3 ? (g.n[2] + 2) / 3 : 1;
+    const dim3 sg = tile_grid(ncx, ncy, ncz);
+    for (int ox = 0; ox < 3; ox++)
+        for (int oy = 0; oy < 3; oy++)
+            for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {
+                if (g.ndim == 2) k_move_sweep<2><<<sg, blk, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ctx->stats);
+                else             k_move_sweep<3><<<sg, blk, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ctx->stats);
+            }
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream) {
+    if (!ctx || !out) return jp_fail(JP_ERR_INVALID, "jp_move_stats: null argument");
+    JP_CUDA(cudaSetDevice(ctx->device));
+    long long h[3];
+    JP_CUDA(cudaMemcpyAsync(h, ctx->stats, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    JP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    return JP_OK;
+}
+
+extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream) {
+    PREP("jp_inject");
+    JpArgs a;
+    int rc = pack_args(args, nargs, a, "jp_inject");
+    if (rc) return rc;
+    if (step >= (1u << 31)) return jp_fail(JP_ERR_INVALID, "jp_inject: step must be < 2^31");
+    const int NQ = g.ndim == 2 ? 4 : 8;
+    const int min_xq = (min_xcell + NQ - 1) / NQ;
+    JP_CUDA(cudaMemsetAsync(ctx->stats + 3, 0, sizeof(long long), st));
+    if (g.ndim == 2) k_inject_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->flag);
+    else             k_inject_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->flag);
+    JP_CHECK_LAUNCH();
+    const int ncx = (g.n[0] + 1) / 2, ncy = (g.n[1] + 1) / 2, ncz = g.ndim == 3 ? (g.n[2] + 1) / 2 : 1;
+    const dim3 sg = tile_grid(ncx, ncy, ncz);
+    for (int ox = 0; ox < 2; ox++)
+        for (int oy = 0; oy < 2; oy++)
+            for (int oz = 0; oz < (g.ndim == 3 ? 2 : 1); oz++) {
+                if (g.ndim == 2) k_inject_sweep<2><<<sg, blk, 0, st>>>(g, co, p->index, a, ctx->flag, min_xcell, seed, step, ox, oy, oz, ctx->stats);
+                else             k_inject_sweep<3><<<sg, blk, 0, st>>>(g, co, p->index, a, ctx->flag, min_xcell, seed, step, ox, oy, oz, ctx->stats);
+            }
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_inject_stats(jp_ctx *ctx, int64_t *out, void *stream) {
+    if (!ctx || !out) return jp_fail(JP_ERR_INVALID, "jp_inject_stats: null argument");
+    JP_CUDA(cudaSetDevice(ctx->device));
+    long long h;
+    JP_CUDA(cudaMemcpyAsync(&h, ctx->stats + 3, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    JP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *out = h;
+    return JP_OK;
+}
+
+extern "C" int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream) {
+    PREP("jp_clean");
+    JpArgs a;
+    int rc = pack_args(args, nargs, a, "jp_clean");
+    if (rc) return rc;
+    if (g.ndim == 2) k_clean<2><<<grd, blk, 0, st>>>(g, co, p->index, a);
+    else             k_clean<3><<<grd, blk, 0, st>>>(g, co, p->index, a);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_grid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *F, void *stream) {
+    PREP("jp_grid2particle");
+    if (!Fp || !F) return jp_fail(JP_ERR_INVALID, "jp_grid2particle: null field");
+    if (g.ndim == 2) k_g2p<2><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F);
+    else             k_g2p<3><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *Fc, void *stream) {
+    PREP("jp_centroid2particle");
+    if (!Fp || !Fc) return jp_fail(JP_ERR_INVALID, "jp_centroid2particle: null field");
+    if (g.ndim == 2) k_c2p<2><<<grd, blk, 0, st>>>(g, cco, Fp, Fc);
+    else             k_c2p<3><<<grd, blk, 0, st>>>(g, cco, Fp, Fc);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, const double *Fp, void *stream) {
+    PREP("jp_particle2grid");
+    if (!Fp || !F) return jp_fail(JP_ERR_INVALID, "jp_particle2grid: null field");
+    const dim3 ng = tile_grid(g.n[0] + 1, g.n[1] + 1, g.ndim == 3 ? g.n[2] + 1 : 1);
+    if (g.ndim == 2) k_p2g<2><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
+    else             k_p2g<3><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_particle2centroid(jp_ctx *ctx, const jp_particles *p, double *Fc, const double *Fp, void *stream) {
+    PREP("jp_particle2centroid");
+    if (!Fp || !Fc) return jp_fail(JP_ERR_INVALID, "jp_particle2centroid: null field");
+    if (g.ndim == 2) k_p2c<2><<<grd, blk, 0, st>>>(g, cco, Fc, Fp);
+    else             k_p2c<3><<<grd, blk, 0, st>>>(g, cco, Fc, Fp);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+template <int N>
+static void launch_phase(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, CPtr3 cco, double *ratios, const double *phases, int K) {
+    if (K <= 2) k_phase<N, 2><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
+    else if (K <= 4) k_phase<N, 4><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
+    else if (K <= 8) k_phase<N, 8><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
+    else if (K <= 16) k_phase<N, 16><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
+    else k_phase<N, 32><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
+}
+
+extern "C" int jp_phase_ratios_center(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases, int32_t K, void *stream) {
+    PREP("jp_phase_ratios_center");
+    if (!ratios || !phases) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_center: null field");
+    if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_center: 1 <= nphases <= 32 required");
+    if (g.ndim == 2) launch_phase<2>(g, grd, blk, st, cco, ratios, phases, K);
+    else             launch_phase<3>(g, grd, blk, st, cco, ratios, phases, K);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+static int64_t plane_cells(const JpGrid &g, int dim) {
+    return dim == 0 ? (int64_t)g.n[1] * g.n[2] : dim == 1 ? (int64_t)g.n[0] * g.n[2] : (int64_t)g.n[0] * g.n[1];
+}
+extern "C" int64_t jp_halo_plane_bytes(const jp_ctx *ctx, int32_t dim, int32_t narrays) {
+    if (!ctx || dim < 0 || dim >= ctx->g.ndim || narrays < 0) return -1;
+    return plane_cells(ctx->g, dim) * ctx->g.S * (8 * (int64_t)narrays + 1);
+}
+static int halo_common(jp_ctx *ctx, int dim, int plane, double *const *arrays, int narrays, uint8_t *index, void *buf, void *stream, bool pack) {
+    if (!ctx || !buf || !index) return jp_fail(JP_ERR_INVALID, "jp_halo: null argument");
+    const JpGrid &g = ctx->g;
+    if (dim < 0 || dim >= g.ndim || plane < 0 || plane >= g.n[dim]) return jp_fail(JP_ERR_INVALID, "jp_halo: bad dim/plane");
+    if (narrays < 0 || narrays > JP_MAX_ARGS + 3) return jp_fail(JP_ERR_UNSUPPORTED, "jp_halo: too many arrays");
+    HaloArrs h; h.n = narrays;
+    for (int a = 0; a < narrays; a++) {
+        if (!arrays || !arrays[a]) return jp_fail(JP_ERR_INVALID, "jp_halo: null array");
+        h.a[a] = arrays[a];
+    }
+    JP_CUDA(cudaSetDevice(ctx->device));
+    const int64_t M = plane_cells(g, dim);
+    const int64_t total = (int64_t)(narrays + 1) * g.S * M;
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    if (pack) k_halo<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
+    else      k_halo<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+extern "C" int jp_halo_pack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays, int32_t narrays, const uint8_t *index, void *buf, void *stream) {
+    return halo_common(ctx, dim, plane, arrays, narrays, (uint8_t *)index, buf, stream, true);
+}
+extern "C" int jp_halo_unpack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays, int32_t narrays, uint8_t *index, const void *buf, void *stream) {
+    return halo_common(ctx, dim, plane, arrays, narrays, index, (void *)buf, stream, false);
+}

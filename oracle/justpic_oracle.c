@@ -1,0 +1,646 @@
+/*
+ * justpic_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE ONLY).
+ *
+ * A plain-C restatement of the JustPIC.jl particle-in-cell hot path, written
+ * from the reference's Julia sources (file:line cited at every function; paths
+ * are relative to /root/reference).  It exists to check the CUDA library
+ * (libjustpic_sm100a.so) bit-for-bit.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it; the product
+ * path never does.
+ *
+ * PARITY PIN STATUS.  Julia is absent from this image, so the reference itself
+ * cannot be run.  Pinned by the reference's own known-answer tests (see
+ * tests/test_oracle_kat.py): integrator stage formulas
+ * (test/test_integrators.jl:11-78) and N-linear lerp
+ * (test/test_interpolation_kernels.jl:47-60), plus the reference's property
+ * tests (linear-field grid2particle == coordinate, phase ratios sum to 1, cell
+ * bracket).  move_particles!/inject_particles!/particle2grid! slot-level
+ * results are NOT pinned by any reference test ("parity unpinned"): this
+ * literal restatement is the only pin.  RNG streams are unpinned in the
+ * reference (backend rand()); both this oracle and the CUDA library use
+ * Philox4x32-10 keyed (seed, step, cell, slot).
+ *
+ * Floating-point contract: compile with -O2 -ffp-contract=off; fma() is
+ * called exactly where the reference has muladd/fma/@muladd; everything else
+ * is unfused, evaluated in the reference's order.
+ *
+ * Layout: CUDA CellArray layout, element (cell c, slot
+ * s) at c + s*C with c = i + nx*(j + ny*k) (0-based), index = 1 byte/slot.
+ * Grids: xv[d] (n_d+1 vertices), xc[d] (n_d centres), xvel[comp][dim]
+ * staggered velocity grid vectors with ghost nodes.  Velocity component
+ * arrays are column-major with extents nvel[comp][0..2].
+ *
+ * Multi-threading: OpenMP over cells (cell-local kernels) or over same-colour
+ * cells (move/inject), exactly the reference's parallel decomposition.  With
+ * jpo_set_threads(1) execution is serial and deterministic for any input.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef struct {
+    int32_t ndim;            /* 2 or 3 */
+    int32_t n[3];            /* cells per dim (n[2] = 1 in 2D) */
+    int32_t S;               /* slots per cell (max_xcell) */
+    int32_t uniform;         /* 1: scalar spacings x[1]-x[0] (range grids), 0: diff(x)[i] */
+    const double *xv[3];     /* n+1 */
+    const double *xc[3];     /* n */
+    const double *xvel[3][3];/* xvel[comp][dim] */
+    int32_t nvel[3][3];      /* lengths of xvel[comp][dim] */
+} jpo_grid;
+
+static int g_threads = 1;
+void jpo_set_threads(int n) {
+    g_threads = n < 1 ? 1 : n;
+#ifdef _OPENMP
+    omp_set_num_threads(g_threads);
+#endif
+}
+int jpo_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
+
+#define NCELLS(g) ((int64_t)(g)->n[0] * (g)->n[1] * ((g)->ndim == 3 ? (g)->n[2] : 1))
+
+/* ---- spacing accessors: particles.di.{vertex,center,velocity} -------------
+ * range grids: scalar x[2]-x[1]   (src/Particles/particles_utils.jl:137-140)
+ * array grids: diff(x)[i]         (src/Particles/particles_utils.jl:76-79)
+ * @dxi / getindex_dxi             (src/Utils.jl:66-88)                      */
+static inline double d_of(const double *x, int uniform, int i0) {
+    return uniform ? x[1] - x[0] : x[i0 + 1] - x[i0];
+}
+
+/* ---- find_parent_cell_bisection (src/Utils.jl:117-130) -------------------
+ * 1-based arithmetic kept literally (div(hi + seed, 2)).  len = length(x).   */
+static inline int bisect1(double px, const double *x, int len, int seed1) {
+    int lo = 1, hi = len, seed = seed1;
+    for (;;) {
+        if (x[seed - 1] <= px && px <= x[seed]) return seed;
+        if (x[seed - 1] < px) { lo = seed; seed = (hi + seed) / 2; }
+        else                  { hi = seed; seed = (lo + seed) / 2; }
+    }
+}
+
+/* ---- lerp (src/Interpolations/ndlerp.jl:11-15) ---------------------------- */
+static inline double lerp1(double t, double v0, double v1) {
+    return fma(t, v1, fma(-t, v0, v0));
+}
+static inline double lerp2(const double *v, const double *t) {
+    return lerp1(t[1], lerp1(t[0], v[0], v[1]), lerp1(t[0], v[2], v[3]));
+}
+static inline double lerp3(const double *v, const double *t) {
+    double a = lerp1(t[1], lerp1(t[0], v[0], v[1]), lerp1(t[0], v[2], v[3]));
+    double b = lerp1(t[1], lerp1(t[0], v[4], v[5]), lerp1(t[0], v[6], v[7]));
+    return lerp1(t[2], a, b);
+}
+double jpo_lerp(int ndim, const double *v, const double *t) {
+    return ndim == 1 ? lerp1(t[0], v[0], v[1]) : ndim == 2 ? lerp2(v, t) : lerp3(v, t);
+}
+
+/* ---- integrator stages (src/Advection/Euler.jl:1-6, RK2.jl:1-38) ----------
+ * @muladd a + s*c*dt*v  ->  muladd((s*c)*dt, v, a)   (MuladdMacro 0.2.4)     */
+void jpo_first_stage(int scheme, double alpha, double dt, int n, const double *v, const double *p, double *out) {
+    double c = scheme == 0 ? 1.0 * dt : (1.0 * alpha) * dt;
+    for (int i = 0; i < n; i++) out[i] = fma(c, v[i], p[i]);
+}
+void jpo_second_stage(double alpha, double dt, int n, const double *v0, const double *v1, const double *p, double *out) {
+    if (alpha == 0.5) {
+        for (int i = 0; i < n; i++) out[i] = fma(1.0 * dt, v1[i], p[i]);
+    } else {
+        double b = 0.5 * (1.0 / alpha);      /* half * inv(alpha) */
+        double a = 1.0 - b;                  /* one - half*inv(alpha) (exact either way: 0.5*x is exact) */
+        for (int i = 0; i < n; i++) {
+            double inner = fma(b, v1[i], a * v0[i]);
+            out[i] = fma(1.0 * dt, inner, p[i]);
+        }
+    }
+}
+
+/* ---- interp_velocity2particle (src/Particles/Advection/advection.jl:93-148,
+ *      src/Advection/advection.jl:3-47, src/Interpolations/utils.jl:54-58) -- */
+static inline void interp_velocity(const jpo_grid *g, const double *const *V, const double *p,
+                                   const int *cell1 /* 1-based storage cell */, double *vout) {
+    const int N = g->ndim;
+    for (int c = 0; c < N; c++) {
+        /* check_local_limits: inclusive, all dims, this component's grid */
+        int ok = 1;
+        for (int d = 0; d < N; d++) {
+            const double *x = g->xvel[c][d];
+            if (!(x[0] <= p[d] && p[d] <= x[g->nvel[c][d] - 1])) { ok = 0; break; }
+        }
+        if (!ok) { vout[c] = INFINITY; continue; }
+        int idx[3] = {1, 1, 1};
+        double t[3];
+        for (int d = 0; d < N; d++) {
+            const double *x = g->xvel[c][d];
+            idx[d] = bisect1(p[d], x, g->nvel[c][d], cell1[d]);
+            double dx = d_of(x, g->uniform, idx[d] - 1);
+            t[d] = (p[d] - x[idx[d] - 1]) * (1.0 / dx);
+        }
+        const double *F = V[c];
+        const int64_t s1 = g->nvel[c][0], s2 = (int64_t)g->nvel[c][0] * g->nvel[c][1];
+        const int64_t b = (idx[0] - 1) + s1 * (idx[1] - 1) + (N == 3 ? s2 * (idx[2] - 1) : 0);
+        if (N == 2) {
+            double v[4] = {F[b], F[b + 1], F[b + s1], F[b + s1 + 1]};
+            vout[c] = lerp2(v, t);
+        } else {
+            double v[8] = {F[b], F[b + 1], F[b + s1], F[b + s1 + 1],
+                           F[b + s2], F[b + s2 + 1], F[b + s2 + s1], F[b + s2 + s1 + 1]};
+            vout[c] = lerp3(v, t);
+        }
+    }
+}
+
+/* ---- advect_particle (src/Particles/Advection/Euler.jl:1-20, RK2.jl:1-26,
+ *      RK4.jl:1-19) -------------------------------------------------------- */
+static inline void advect_particle(const jpo_grid *g, int scheme, double alpha, const double *const *V,
+                                   double dt, const int *cell1, const double *p0, double *pout) {
+    const int N = g->ndim;
+    double k1[3], k2[3], k3[3], k4[3], q[3];
+    interp_velocity(g, V, p0, cell1, k1);
+    if (scheme == 0) { jpo_first_stage(0, alpha, dt, N, k1, p0, pout); return; }
+    if (scheme == 1) {
+        jpo_first_stage(1, alpha, dt, N, k1, p0, q);
+        interp_velocity(g, V, q, cell1, k2);
+        jpo_second_stage(alpha, dt, N, k1, k2, p0, pout);
+        return;
+    }
+    /* RK4: unfused, left to right */
+    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k1[d] / 2;
+    interp_velocity(g, V, q, cell1, k2);
+    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k2[d] / 2;
+    interp_velocity(g, V, q, cell1, k3);
+    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k3[d];
+    interp_velocity(g, V, q, cell1, k4);
+    for (int d = 0; d < N; d++)
+        pout[d] = p0[d] + dt * (((k1[d] + 2 * k2[d]) + 2 * k3[d]) + k4[d]) / 6;
+}
+
+/* advection! (src/Particles/Advection/advection.jl:35-91) */
+int jpo_advect(const jpo_grid *g, double *const *coords, const uint8_t *index, int scheme, double alpha,
+               const double *const *V, double dt) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    if (scheme == 1 && !(0 < alpha && alpha < 1)) return -1;
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c = 0; c < C; c++) {
+        int cell1[3] = {(int)(c % nx) + 1, (int)((c / nx) % ny) + 1, (int)(c / ((int64_t)nx * ny)) + 1};
+        for (int s = 0; s < g->S; s++) {
+            const int64_t e = c + (int64_t)s * C;
+            if (!index[e]) continue;
+            double p0[3], p1[3];
+            for (int d = 0; d < N; d++) p0[d] = coords[d][e];
+            advect_particle(g, scheme, alpha, V, dt, cell1, p0, p1);
+            for (int d = 0; d < N; d++) coords[d][e] = p1[d];
+        }
+    }
+    return 0;
+}
+
+/* ---- Philox4x32-10 (Salmon et al. 2011), counter-based RNG ---------------- */
+static inline void philox4x32_10(uint32_t ctr[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * ctr[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * ctr[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ ctr[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ ctr[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+static inline double u01(uint32_t hi, uint32_t lo) {   /* 53-bit uniform in [0,1) */
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return (double)(x >> 11) * 0x1.0p-53;
+}
+/* three uniforms for (seed, purpose, step, cell, slot): ctr = {cell, slot, purpose, step<<1|sub} */
+void jpo_rand3(uint64_t seed, uint32_t purpose, uint32_t step, uint32_t cell, uint32_t slot, double *r) {
+    uint32_t a[4] = {cell, slot, purpose, (step << 1) | 0u};
+    uint32_t b[4] = {cell, slot, purpose, (step << 1) | 1u};
+    philox4x32_10(a, (uint32_t)seed, (uint32_t)(seed >> 32));
+    philox4x32_10(b, (uint32_t)seed, (uint32_t)(seed >> 32));
+    r[0] = u01(a[0], a[1]); r[1] = u01(a[2], a[3]); r[2] = u01(b[0], b[1]);
+}
+
+/* ---- init_particles / fill_coords_index! (src/Particles/particles_utils.jl:
+ *      108-194, quadrant_masks :224-240) ----------------------------------- */
+int jpo_init_particles(const jpo_grid *g, double *const *coords, uint8_t *index, int nxcell, uint64_t seed) {
+    const int N = g->ndim, NQ = N == 2 ? 4 : 8;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    const int npq = (nxcell + NQ - 1) / NQ;
+    if (npq * NQ > g->S) return -1;
+    for (int d = 0; d < N; d++)
+        for (int64_t e = 0; e < C * g->S; e++) coords[d][e] = NAN;
+    memset(index, 0, (size_t)(C * g->S));
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c = 0; c < C; c++) {
+        int ci[3] = {(int)(c % nx), (int)((c / nx) % ny), (int)(c / ((int64_t)nx * ny))};
+        double x0[3], dx[3];
+        for (int d = 0; d < N; d++) { x0[d] = g->xv[d][ci[d]]; dx[d] = d_of(g->xv[d], g->uniform, ci[d]); }
+        int l = 0;
+        for (int iq = 0; iq < NQ; iq++) {
+            double xq[3];
+            for (int d = 0; d < N; d++) xq[d] = x0[d] + dx[d] * (double)((iq >> d) & 1) / 2;
+            for (int k = 0; k < npq; k++, l++) {
+                double r[3];
+                jpo_rand3(seed, 0u, 0u, (uint32_t)c, (uint32_t)l, r);
+                const int64_t e = c + (int64_t)l * C;
+                for (int d = 0; d < N; d++) coords[d][e] = xq[d] + dx[d] / 2 * r[d];
+                index[e] = 1;
+            }
+        }
+    }
+    return 0;
+}
+
+/* ---- move_particles! (src/Particles/move_safe.jl:21-125; isincell
+ *      src/Particles/utils.jl:7-15; indomain :199-206; find_free_memory
+ *      :192-197) ------------------------------------------------------------ */
+static void move_cell(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs,
+                      const int *ci /*0-based*/, int64_t *n_moved, int64_t *n_dropped, int64_t *n_deleted) {
+    const int N = g->ndim, S = g->S;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    const int64_t c = ci[0] + (int64_t)nx * (ci[1] + (int64_t)ny * (N == 3 ? ci[2] : 0));
+    double corner[3], dx[3], lo[3], hi[3];
+    for (int d = 0; d < N; d++) {
+        corner[d] = g->xv[d][ci[d]];
+        dx[d] = d_of(g->xv[d], g->uniform, ci[d]);
+        lo[d] = g->xv[d][0]; hi[d] = g->xv[d][g->n[d]];
+    }
+    int starting_point = 0;                         /* 0-based cursor */
+    double cache[64];
+    for (int ip = 0; ip < S; ip++) {
+        const int64_t e = c + (int64_t)ip * C;
+        if (!index[e]) continue;
+        double p[3];
+        int incell = 1, indom = 1;
+        for (int d = 0; d < N; d++) {
+            p[d] = coords[d][e];
+            incell &= (corner[d] < p[d]) & (p[d] < corner[d] + dx[d]);
+        }
+        if (incell) continue;
+        for (int d = 0; d < N; d++) if (!(lo[d] < p[d] && p[d] < hi[d])) { indom = 0; break; }
+        if (!indom) {
+            index[e] = 0;
+            for (int d = 0; d < N; d++) coords[d][e] = NAN;
+            for (int a = 0; a < nargs; a++) args[a][e] = NAN;
+            (*n_deleted)++;
+            continue;
+        }
+        int nc[3] = {0, 0, 0};
+        for (int d = 0; d < N; d++) nc[d] = bisect1(p[d], g->xv[d], g->n[d] + 1, ci[d] + 1) - 1;
+        for (int a = 0; a < nargs; a++) cache[a] = args[a][e];
+        index[e] = 0;
+        for (int d = 0; d < N; d++) coords[d][e] = NAN;
+        for (int a = 0; a < nargs; a++) args[a][e] = NAN;
+        const int64_t c2 = nc[0] + (int64_t)nx * (nc[1] + (int64_t)ny * (N == 3 ? nc[2] : 0));
+        int free_idx = -1;
+        for (int i = starting_point; i < S; i++)
+            if (!index[c2 + (int64_t)i * C]) { free_idx = i; break; }
+        if (free_idx < 0) { (*n_dropped)++; continue; }
+        starting_point = free_idx;
+        const int64_t e2 = c2 + (int64_t)free_idx * C;
+        index[e2] = 1;
+        for (int d = 0; d < N; d++) coords[d][e2] = p[d];
+        for (int a = 0; a < nargs; a++) args[a][e2] = cache[a];
+        (*n_moved)++;
+    }
+}
+
+int jpo_move(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs,
+             int64_t *stats /* moved, dropped, deleted */) {
+    const int N = g->ndim;
+    if (nargs > 64) return -1;
+    int ncol[3] = {(g->n[0] + 2) / 3, (g->n[1] + 2) / 3, N == 3 ? (g->n[2] + 2) / 3 : 1};
+    int64_t moved = 0, dropped = 0, deleted = 0;
+    const int oz_max = N == 3 ? 3 : 1;
+    for (int ox = 0; ox < 3; ox++)
+        for (int oy = 0; oy < 3; oy++)
+            for (int oz = 0; oz < oz_max; oz++) {
+                const int64_t nt = (int64_t)ncol[0] * ncol[1] * ncol[2];
+#pragma omp parallel for schedule(static) reduction(+ : moved, dropped, deleted) if (g_threads > 1)
+                for (int64_t t = 0; t < nt; t++) {
+                    int I = (int)(t % ncol[0]), J = (int)((t / ncol[0]) % ncol[1]), K = (int)(t / ((int64_t)ncol[0] * ncol[1]));
+                    int ci[3] = {3 * I + ox, 3 * J + oy, N == 3 ? 3 * K + oz : 0};
+                    if (ci[0] >= g->n[0] || ci[1] >= g->n[1] || (N == 3 && ci[2] >= g->n[2])) continue;
+                    move_cell(g, coords, index, args, nargs, ci, &moved, &dropped, &deleted);
+                }
+            }
+    if (stats) { stats[0] = moved; stats[1] = dropped; stats[2] = deleted; }
+    return 0;
+}
+
+/* ---- clean_particles! (src/Particles/move_safe.jl:289-320) ---------------- */
+int jpo_clean(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c = 0; c < C; c++) {
+        int ci[3] = {(int)(c % nx), (int)((c / nx) % ny), (int)(c / ((int64_t)nx * ny))};
+        for (int s = 0; s < g->S; s++) {
+            const int64_t e = c + (int64_t)s * C;
+            if (!index[e]) continue;
+            int incell = 1;
+            for (int d = 0; d < N; d++) {
+                double xvd = g->xv[d][ci[d]], dx = d_of(g->xv[d], g->uniform, ci[d]), p = coords[d][e];
+                incell &= (xvd < p) & (p < xvd + dx);
+            }
+            if (incell) continue;
+            index[e] = 0;
+            for (int d = 0; d < N; d++) coords[d][e] = NAN;
+            for (int a = 0; a < nargs; a++) args[a][e] = NAN;
+        }
+    }
+    return 0;
+}
+
+/* ---- inject_particles! (src/Particles/injection.jl:19-131; index_min_distance
+ *      :330-393; new_particle :411-417; quadrant_corners :442-461; distance
+ *      src/Interpolations/utils.jl:9-19) ------------------------------------ */
+static void inject_cell(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs,
+                        int min_xcell, uint64_t seed, uint32_t step, const int *ci, int64_t *n_injected) {
+    const int N = g->ndim, S = g->S, NQ = N == 2 ? 4 : 8;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1], nz = N == 3 ? g->n[2] : 1;
+    const int64_t c = ci[0] + (int64_t)nx * (ci[1] + (int64_t)ny * (N == 3 ? ci[2] : 0));
+    double xvc[3], dq[3];
+    for (int d = 0; d < N; d++) { xvc[d] = g->xv[d][ci[d]]; dq[d] = d_of(g->xv[d], g->uniform, ci[d]) / 2; }
+    const int min_xq = (min_xcell + NQ - 1) / NQ;      /* cld(min_xcell, NQ) */
+    for (int iq = 0; iq < NQ; iq++) {
+        double vq[3];
+        for (int d = 0; d < N; d++) vq[d] = xvc[d] + dq[d] * (double)((iq >> d) & 1);
+        int num = 0;
+        for (int i = 0; i < S; i++) {
+            const int64_t e = c + (int64_t)i * C;
+            if (!index[e]) continue;
+            int in = 1;
+            for (int d = 0; d < N; d++) { double p = coords[d][e]; in &= (vq[d] < p) & (p < vq[d] + dq[d]); }
+            num += in;
+        }
+        if (num >= min_xq) break;                      /* leaves the quadrant loop (injection.jl:100) */
+        for (int i = 0; i < S; i++) {
+            const int64_t e = c + (int64_t)i * C;
+            if (index[e]) continue;
+            num++;
+            double r[3], pn[3];
+            jpo_rand3(seed, 1u, step, (uint32_t)c, (uint32_t)i, r);
+            for (int d = 0; d < N; d++) pn[d] = vq[d] + dq[d] * fma(0.95, r[d], 0.05);
+            for (int d = 0; d < N; d++) coords[d][e] = pn[d];
+            index[e] = 1;
+            (*n_injected)++;
+            /* nearest live particle in the 3^N neighbourhood, k,j,i outer, slot inner, strict < */
+            double dmin = INFINITY; int64_t emin = -1;
+            for (int kk = (N == 3 ? ci[2] - 1 : 0); kk <= (N == 3 ? ci[2] + 1 : 0); kk++)
+                for (int jj = ci[1] - 1; jj <= ci[1] + 1; jj++)
+                    for (int ii = ci[0] - 1; ii <= ci[0] + 1; ii++) {
+                        if (ii < 0 || jj < 0 || kk < 0 || ii >= nx || jj >= ny || kk >= nz) continue;
+                        const int64_t c2 = ii + (int64_t)nx * (jj + (int64_t)ny * kk);
+                        for (int ip = 0; ip < S; ip++) {
+                            if (c2 == c && ip == i) continue;
+                            const int64_t e2 = c2 + (int64_t)ip * C;
+                            if (!index[e2]) continue;
+                            double s = 0;
+                            for (int d = 0; d < N; d++) {
+                                double del = coords[d][e2] - pn[d];
+                                s = d == 0 ? del * del : s + del * del;
+                            }
+                            double dist = sqrt(s);
+                            if (dist < dmin) { dmin = dist; emin = e2; }
+                        }
+                    }
+            if (emin >= 0)
+                for (int a = 0; a < nargs; a++) args[a][e] = args[a][emin];
+            /* no live donor anywhere: reference reads out of bounds (UB); args left untouched here */
+            if (num >= min_xq) break;
+        }
+    }
+}
+
+int jpo_inject(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs,
+               int min_xcell, uint64_t seed, uint32_t step, int64_t *n_injected_out) {
+    const int N = g->ndim;
+    int ncol[3] = {(g->n[0] + 1) / 2, (g->n[1] + 1) / 2, N == 3 ? (g->n[2] + 1) / 2 : 1};
+    int64_t injected = 0;
+    const int oz_max = N == 3 ? 2 : 1;
+    for (int ox = 0; ox < 2; ox++)
+        for (int oy = 0; oy < 2; oy++)
+            for (int oz = 0; oz < oz_max; oz++) {
+                const int64_t nt = (int64_t)ncol[0] * ncol[1] * ncol[2];
+#pragma omp parallel for schedule(static) reduction(+ : injected) if (g_threads > 1)
+                for (int64_t t = 0; t < nt; t++) {
+                    int I = (int)(t % ncol[0]), J = (int)((t / ncol[0]) % ncol[1]), K = (int)(t / ((int64_t)ncol[0] * ncol[1]));
+                    int ci[3] = {2 * I + ox, 2 * J + oy, N == 3 ? 2 * K + oz : 0};
+                    if (ci[0] >= g->n[0] || ci[1] >= g->n[1] || (N == 3 && ci[2] >= g->n[2])) continue;
+                    inject_cell(g, coords, index, args, nargs, min_xcell, seed, step, ci, &injected);
+                }
+            }
+    if (n_injected_out) *n_injected_out = injected;
+    return 0;
+}
+
+/* ---- grid2particle! (src/Interpolations/grid_to_particle.jl:26-82, :265-273;
+ *      field_corners src/Interpolations/utils.jl:98-118) -------------------- */
+int jpo_grid2particle(const jpo_grid *g, const double *const *coords, const uint8_t *index, double *Fp, const double *F) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    const int64_t s1 = nx + 1, s2 = (int64_t)(nx + 1) * (ny + 1);
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c = 0; c < C; c++) {
+        int ci[3] = {(int)(c % nx), (int)((c / nx) % ny), (int)(c / ((int64_t)nx * ny))};
+        const int64_t b = ci[0] + s1 * ci[1] + (N == 3 ? s2 * ci[2] : 0);
+        double v[8], xcn[3], idx[3];
+        v[0] = F[b]; v[1] = F[b + 1]; v[2] = F[b + s1]; v[3] = F[b + s1 + 1];
+        if (N == 3) { v[4] = F[b + s2]; v[5] = F[b + s2 + 1]; v[6] = F[b + s2 + s1]; v[7] = F[b + s2 + s1 + 1]; }
+        for (int d = 0; d < N; d++) { xcn[d] = g->xv[d][ci[d]]; idx[d] = 1.0 / d_of(g->xv[d], g->uniform, ci[d]); }
+        for (int s = 0; s < g->S; s++) {
+            const int64_t e = c + (int64_t)s * C;
+            if (!index[e]) continue;
+            double t[3];
+            for (int d = 0; d < N; d++) t[d] = (coords[d][e] - xcn[d]) * idx[d];
+            Fp[e] = N == 2 ? lerp2(v, t) : lerp3(v, t);
+        }
+    }
+    return 0;
+}
+
+/* ---- centroid2particle! (src/Interpolations/centroid_to_particle.jl:13-76) - */
+int jpo_centroid2particle(const jpo_grid *g, const double *const *coords, double *Fp, const double *Fc) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    const int64_t s1 = nx, s2 = (int64_t)nx * ny;
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c = 0; c < C; c++) {
+        int ci[3] = {(int)(c % nx), (int)((c / nx) % ny), (int)(c / ((int64_t)nx * ny))};
+        for (int s = 0; s < g->S; s++) {
+            const int64_t e = c + (int64_t)s * C;
+            double p[3], t[3];
+            int anynan = 0, cc[3] = {0, 0, 0};
+            for (int d = 0; d < N; d++) { p[d] = coords[d][e]; anynan |= isnan(p[d]); }
+            if (anynan) continue;
+            for (int d = 0; d < N; d++) {
+                int i1 = ci[d] + 1;                           /* 1-based */
+                if (p[d] < g->xc[d][ci[d]]) i1 -= 1;           /* shifted_index */
+                int hi1 = g->n[d] - 1;                        /* clamp(., 1, size(F)-1) */
+                if (i1 > hi1) i1 = hi1;                       /* Base.clamp: x > hi ? hi : (x < lo ? lo : x) */
+                else if (i1 < 1) i1 = 1;
+                cc[d] = i1 - 1;
+                double dx = d_of(g->xc[d], g->uniform, cc[d]);
+                t[d] = (p[d] - g->xc[d][cc[d]]) * (1.0 / dx);
+            }
+            const int64_t b = cc[0] + s1 * cc[1] + (N == 3 ? s2 * cc[2] : 0);
+            double v[8];
+            v[0] = Fc[b]; v[1] = Fc[b + 1]; v[2] = Fc[b + s1]; v[3] = Fc[b + s1 + 1];
+            if (N == 3) { v[4] = Fc[b + s2]; v[5] = Fc[b + s2 + 1]; v[6] = Fc[b + s2 + s1]; v[7] = Fc[b + s2 + s1 + 1]; }
+            Fp[e] = N == 2 ? lerp2(v, t) : lerp3(v, t);
+        }
+    }
+    return 0;
+}
+
+/* ---- particle2grid! (src/Interpolations/particle_to_grid.jl:23-68 (2D),
+ *      :113-151 (3D), distance_weight :203-205) ----------------------------- */
+int jpo_particle2grid(const jpo_grid *g, const double *const *coords, const uint8_t *index, double *F, const double *Fp) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1], nz = N == 3 ? g->n[2] : 0;
+    const int64_t NN = (int64_t)(nx + 1) * (ny + 1) * (N == 3 ? nz + 1 : 1);
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t nd = 0; nd < NN; nd++) {
+        int in = (int)(nd % (nx + 1)), jn = (int)((nd / (nx + 1)) % (ny + 1)), kn = (int)(nd / ((int64_t)(nx + 1) * (ny + 1)));
+        double xn[3] = {g->xv[0][in], g->xv[1][jn], N == 3 ? g->xv[2][kn] : 0.0};
+        double w = 0.0, wF = 0.0;
+        for (int ko = (N == 3 ? -1 : 0); ko <= 0; ko++) {
+            int kc = kn + ko;
+            if (N == 3 && (kc < 0 || kc >= nz)) continue;
+            for (int jo = -1; jo <= 0; jo++) {
+                int jc = jn + jo;
+                if (jc < 0 || jc >= ny) continue;
+                for (int io = -1; io <= 0; io++) {
+                    int ic = in + io;
+                    if (ic < 0 || ic >= nx) continue;
+                    const int64_t c = ic + (int64_t)nx * (jc + (int64_t)ny * (N == 3 ? kc : 0));
+                    for (int s = 0; s < g->S; s++) {
+                        const int64_t e = c + (int64_t)s * C;
+                        if (!index[e]) continue;
+                        double ss = 0;
+                        for (int d = 0; d < N; d++) {
+                            double del = xn[d] - coords[d][e];
+                            ss = d == 0 ? del * del : ss + del * del;
+                        }
+                        double dist = sqrt(ss);
+                        double wi = 1.0 / (dist * dist);
+                        w += wi;
+                        wF = fma(wi, Fp[e], wF);
+                    }
+                }
+            }
+        }
+        F[nd] = N == 2 ? wF / w : wF * (1.0 / w);
+    }
+    return 0;
+}
+
+/* bilinear_weight (src/Interpolations/particle_to_grid.jl:211-223,
+ * src/PhaseRatios/utils.jl:64-74): prod_d muladd(-|a-b|, inv(d), 1) */
+static inline double bilinear_weight(int N, const double *a, const double *b, const double *di) {
+    double val = 1.0;
+    for (int d = 0; d < N; d++) val *= fma(-fabs(a[d] - b[d]), 1.0 / di[d], 1.0);
+    return val;
+}
+
+/* ---- particle2centroid! (src/Interpolations/particle_to_grid_centroid.jl:
+ *      10-45 (2D: any(isnan), w/F), :78-99 (3D: isnan(px), wF*inv(w))) ------ */
+int jpo_particle2centroid(const jpo_grid *g, const double *const *coords, double *Fc, const double *Fp) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c = 0; c < C; c++) {
+        int ci[3] = {(int)(c % nx), (int)((c / nx) % ny), (int)(c / ((int64_t)nx * ny))};
+        double xcn[3], di[3];
+        for (int d = 0; d < N; d++) { xcn[d] = g->xc[d][ci[d]]; di[d] = d_of(g->xv[d], g->uniform, ci[d]); }
+        double w = 0.0, wF = 0.0;
+        for (int s = 0; s < g->S; s++) {
+            const int64_t e = c + (int64_t)s * C;
+            double p[3];
+            for (int d = 0; d < N; d++) p[d] = coords[d][e];
+            if (N == 2 ? (isnan(p[0]) || isnan(p[1])) : isnan(p[0])) continue;
+            double wi = bilinear_weight(N, xcn, p, di);
+            w += wi;
+            wF = fma(wi, Fp[e], wF);
+        }
+        Fc[c] = N == 2 ? wF / w : wF * (1.0 / w);
+    }
+    return 0;
+}
+
+/* ---- phase_ratios_center! (src/PhaseRatios/centers.jl:3-30;
+ *      phase_ratio_weights src/PhaseRatios/utils.jl:45-62) ------------------
+ * ratios layout: CellArray data[C, K] -> element (cell c, phase k) at c + k*C */
+int jpo_phase_ratios_center(const jpo_grid *g, const double *const *coords, double *ratios, const double *phases, int K) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    if (K > 64) return -1;
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c = 0; c < C; c++) {
+        int ci[3] = {(int)(c % nx), (int)((c / nx) % ny), (int)(c / ((int64_t)nx * ny))};
+        double xcn[3], di[3], w[64];
+        for (int d = 0; d < N; d++) { xcn[d] = g->xc[d][ci[d]]; di[d] = d_of(g->xv[d], g->uniform, ci[d]); }
+        for (int k = 0; k < K; k++) w[k] = 0.0;
+        for (int s = 0; s < g->S; s++) {
+            const int64_t e = c + (int64_t)s * C;
+            double p[3];
+            for (int d = 0; d < N; d++) p[d] = coords[d][e];
+            if (isnan(p[0])) continue;
+            double x = bilinear_weight(N, xcn, p, di);
+            double ph = phases[e];
+            /* w .+ x .* (ph == j): x*false is a strong zero (copysign(0,x)) */
+            for (int k = 0; k < K; k++) w[k] = w[k] + (ph == (double)(k + 1) ? x : copysign(0.0, x));
+        }
+        double sum = w[0];
+        for (int k = 1; k < K; k++) sum = sum + w[k];
+        double inv = 1.0 / sum;
+        for (int k = 0; k < K; k++) ratios[c + (int64_t)k * C] = w[k] * inv;
+    }
+    return 0;
+}
+
+/* ---- update_cell_halo! semantics for ONE array on ONE axis (test helper) ---
+ * ImplicitGlobalGrid.update_halo! with overlap 2 / halowidth 1
+ * (src/CellArrays/ImplicitGlobalGrid.jl:36-41): my plane 2 -> left nbr's plane
+ * n; my plane n-1 -> right nbr's plane 1 (1-based).  Pack/unpack a cell-plane
+ * (all slots) of a [C*S] array of `esz`-byte elements.                       */
+int jpo_plane_copy(const jpo_grid *g, void *array, void *buf, int esz, int dim, int plane0, int pack) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1], nz = N == 3 ? g->n[2] : 1;
+    int ext[3] = {nx, ny, nz};
+    int64_t m = 0;
+    for (int s = 0; s < g->S; s++)
+        for (int k = 0; k < (dim == 2 ? 1 : ext[2]); k++)
+            for (int j = 0; j < (dim == 1 ? 1 : ext[1]); j++)
+                for (int i = 0; i < (dim == 0 ? 1 : ext[0]); i++) {
+                    int ci[3] = {dim == 0 ? plane0 : i, dim == 1 ? plane0 : j, dim == 2 ? plane0 : k};
+                    const int64_t e = ci[0] + (int64_t)nx * (ci[1] + (int64_t)ny * ci[2]) + (int64_t)s * C;
+                    if (pack) memcpy((char *)buf + m * esz, (char *)array + e * esz, (size_t)esz);
+                    else      memcpy((char *)array + e * esz, (char *)buf + m * esz, (size_t)esz);
+                    m++;
+                }
+    return 0;
+}

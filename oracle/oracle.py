@@ -1,0 +1,168 @@
+"""ctypes front-end of the CPU oracle (oracle/justpic_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never by the product.
+Arrays are numpy, CellArrays have shape (S, [nz,] ny, nx) (same memory layout
+as the product's torch tensors).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "libjustpic_oracle.so"
+c_double_p = C.POINTER(C.c_double)
+
+
+class OGrid(C.Structure):
+    _fields_ = [("ndim", C.c_int32), ("n", C.c_int32 * 3), ("S", C.c_int32), ("uniform", C.c_int32),
+                ("xv", c_double_p * 3), ("xc", c_double_p * 3), ("xvel", (c_double_p * 3) * 3),
+                ("nvel", (C.c_int32 * 3) * 3)]
+
+
+def build(force: bool = False) -> Path:
+    src = HERE / "justpic_oracle.c"
+    if force or not LIB.exists() or LIB.stat().st_mtime < src.stat().st_mtime:
+        res = subprocess.run(["make", "-C", str(HERE), "-B"], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("oracle build failed:\n" + res.stdout + res.stderr)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(LIB))
+        _lib.jpo_lerp.restype = C.c_double
+        _lib.jpo_lerp.argtypes = [C.c_int, c_double_p, c_double_p]
+        _lib.jpo_max_threads.restype = C.c_int
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _pp(arrs):
+    out = (c_double_p * max(len(arrs), 1))()
+    for i, a in enumerate(arrs):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+        out[i] = _dp(a)
+    return out
+
+
+class Oracle:
+    """Grid + call wrappers.  xvi/xci: tuples of 1-D arrays; xi_vel[comp][dim]."""
+
+    def __init__(self, xvi, xci, xi_vel, S, uniform):
+        self.N = len(xvi)
+        self.n = tuple(len(x) for x in xci)
+        self.S = int(S)
+        self._keep = []
+        g = OGrid()
+        g.ndim, g.S, g.uniform = self.N, self.S, 1 if uniform else 0
+        for d in range(3):
+            g.n[d] = self.n[d] if d < self.N else 1
+
+        def ptr(a):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            self._keep.append(a)
+            return _dp(a)
+
+        for d in range(self.N):
+            g.xv[d] = ptr(xvi[d])
+            g.xc[d] = ptr(xci[d])
+            for c in range(self.N):
+                g.xvel[c][d] = ptr(xi_vel[c][d])
+                g.nvel[c][d] = len(xi_vel[c][d])
+        self.g = g
+        self.C = int(np.prod(self.n))
+
+    @staticmethod
+    def set_threads(n):
+        lib().jpo_set_threads(int(n))
+
+    @staticmethod
+    def max_threads():
+        return int(lib().jpo_max_threads())
+
+    def cell_shape(self, K=None):
+        return ((self.S if K is None else K), *reversed(self.n))
+
+    def init_particles(self, nxcell, seed):
+        coords = [np.empty(self.cell_shape()) for _ in range(self.N)]
+        index = np.empty(self.cell_shape(), dtype=np.uint8)
+        rc = lib().jpo_init_particles(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), int(nxcell),
+                                      C.c_uint64(int(seed)))
+        assert rc == 0
+        return coords, index
+
+    def advect(self, coords, index, scheme, alpha, V, dt):
+        return lib().jpo_advect(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), int(scheme),
+                                C.c_double(alpha), _pp(V), C.c_double(dt))
+
+    def move(self, coords, index, args):
+        st = (C.c_int64 * 3)()
+        rc = lib().jpo_move(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args), st)
+        assert rc == 0
+        return tuple(int(v) for v in st)
+
+    def clean(self, coords, index, args):
+        return lib().jpo_clean(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args))
+
+    def inject(self, coords, index, args, min_xcell, seed, step):
+        n = C.c_int64()
+        rc = lib().jpo_inject(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args),
+                              int(min_xcell), C.c_uint64(int(seed)), C.c_uint32(int(step)), C.byref(n))
+        assert rc == 0
+        return int(n.value)
+
+    def grid2particle(self, coords, index, Fp, F):
+        return lib().jpo_grid2particle(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _dp(Fp), _dp(F))
+
+    def centroid2particle(self, coords, Fp, Fc):
+        return lib().jpo_centroid2particle(C.byref(self.g), _pp(coords), _dp(Fp), _dp(Fc))
+
+    def particle2grid(self, coords, index, F, Fp):
+        return lib().jpo_particle2grid(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _dp(F), _dp(Fp))
+
+    def particle2centroid(self, coords, Fc, Fp):
+        return lib().jpo_particle2centroid(C.byref(self.g), _pp(coords), _dp(Fc), _dp(Fp))
+
+    def phase_ratios_center(self, coords, ratios, phases, K):
+        return lib().jpo_phase_ratios_center(C.byref(self.g), _pp(coords), _dp(ratios), _dp(phases), int(K))
+
+
+def lerp(v, t):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    return float(lib().jpo_lerp(len(t), _dp(v), _dp(t)))
+
+
+def first_stage(scheme, alpha, dt, v, p):
+    v = np.ascontiguousarray(v, dtype=np.float64); p = np.ascontiguousarray(p, dtype=np.float64)
+    out = np.empty_like(p)
+    lib().jpo_first_stage(int(scheme), C.c_double(alpha), C.c_double(dt), len(p), _dp(v), _dp(p), _dp(out))
+    return out
+
+
+def second_stage(alpha, dt, v0, v1, p):
+    v0 = np.ascontiguousarray(v0, dtype=np.float64); v1 = np.ascontiguousarray(v1, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    out = np.empty_like(p)
+    lib().jpo_second_stage(C.c_double(alpha), C.c_double(dt), len(p), _dp(v0), _dp(v1), _dp(p), _dp(out))
+    return out
+
+
+def rand3(seed, purpose, step, cell, slot):
+    r = np.empty(3)
+    lib().jpo_rand3(C.c_uint64(int(seed)), C.c_uint32(purpose), C.c_uint32(step), C.c_uint32(cell), C.c_uint32(slot), _dp(r))
+    return r

@@ -1,0 +1,155 @@
+// jp_emul.cpp -- CPU emulation of the CUDA kernels' decomposition (TEST ONLY).
+// Compiles justpic/jl_b200/csrc/jp_core.h (the exact source the kernels use)
+// for the host and mimics each kernel's thread decomposition with plain loops:
+// classify pass + ordered colour sweeps for move/inject, fast/literal velocity
+// interpolation for advect.  Lets the no-GPU test-suite check the kernel logic
+// against the oracle.  Never loaded by the product.
+// Build: g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -mfma
+#include <stdlib.h>
+#include <vector>
+#include "../../justpic/jl_b200/csrc/jp_host_grid.h"
+
+struct Emul {
+    JpGrid g;
+    std::vector<double> h;
+    std::vector<uint64_t> occ, leave;
+    std::vector<uint8_t> flag;
+};
+
+extern "C" Emul *jpe_create(const jp_grid_desc *d) {
+    Emul *e = new Emul;
+    JpGridOffsets off;
+    if (jp_grid_build(d, e->g, e->h, off)) { delete e; return nullptr; }
+    jp_grid_rebase(e->g, off, e->h.data());
+    e->occ.assign(e->g.C, 0); e->leave.assign(e->g.C, 0); e->flag.assign(e->g.C, 0);
+    return e;
+}
+extern "C" void jpe_destroy(Emul *e) { delete e; }
+extern "C" int jpe_fast(Emul *e) { return e->g.fast; }
+extern "C" void jpe_vkind(Emul *e, int *out) { for (int c = 0; c < 3; c++) for (int d = 0; d < 3; d++) out[c * 3 + d] = e->g.vkind[c][d]; }
+
+template <int N> static void init_t(Emul *e, double *const *co, uint8_t *index, int npq, uint64_t seed) {
+    for (int64_t c = 0; c < e->g.C; c++) jp_init_cell<N>(e->g, co, index, npq, seed, c);
+}
+extern "C" int jpe_init(Emul *e, double *const *co, uint8_t *index, int nxcell, uint64_t seed) {
+    const int NQ = e->g.ndim == 2 ? 4 : 8, npq = (nxcell + NQ - 1) / NQ;
+    if (npq * NQ > e->g.S) return -1;
+    if (e->g.ndim == 2) init_t<2>(e, co, index, npq, seed); else init_t<3>(e, co, index, npq, seed);
+    return 0;
+}
+
+template <int N, int SCHEME, bool FAST, bool UNIFORM>
+static void advect_t(Emul *e, double *const *co, const uint8_t *index, const double *const *V, double alpha, double dt) {
+    const JpGrid &g = e->g;
+    for (int64_t c = 0; c < g.C; c++) {
+        int ci[3];
+        jp_cell_ijk<N>(g, c, ci);
+        const int cell1[3] = {ci[0] + 1, ci[1] + 1, ci[2] + 1};
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            if (!index[el]) continue;
+            double p0[3], p1[3];
+            for (int d = 0; d < N; d++) p0[d] = co[d][el];
+            jp_advect_particle<N, SCHEME, FAST, UNIFORM>(g, alpha, V, dt, cell1, p0, p1);
+            for (int d = 0; d < N; d++) co[d][el] = p1[d];
+        }
+    }
+}
+template <int N, int SCHEME>
+static void advect_s(Emul *e, double *const *co, const uint8_t *index, const double *const *V, double alpha, double dt, int force_literal) {
+    if (e->g.fast && !force_literal) {
+        if (e->g.uniform) advect_t<N, SCHEME, true, true>(e, co, index, V, alpha, dt);
+        else advect_t<N, SCHEME, true, false>(e, co, index, V, alpha, dt);
+    } else advect_t<N, SCHEME, false, false>(e, co, index, V, alpha, dt);
+}
+extern "C" int jpe_advect(Emul *e, double *const *co, const uint8_t *index, int scheme, double alpha, const double *const *V, double dt, int force_literal) {
+    if (e->g.ndim == 2) {
+        if (scheme == 0) advect_s<2, 0>(e, co, index, V, alpha, dt, force_literal);
+        else if (scheme == 1) advect_s<2, 1>(e, co, index, V, alpha, dt, force_literal);
+        else advect_s<2, 2>(e, co, index, V, alpha, dt, force_literal);
+    } else {
+        if (scheme == 0) advect_s<3, 0>(e, co, index, V, alpha, dt, force_literal);
+        else if (scheme == 1) advect_s<3, 1>(e, co, index, V, alpha, dt, force_literal);
+        else advect_s<3, 2>(e, co, index, V, alpha, dt, force_literal);
+    }
+    return 0;
+}
+
+template <int N>
+static void move_t(Emul *e, double *const *co, uint8_t *index, const JpArgs &args, int64_t *stats) {
+    const JpGrid &g = e->g;
+    // pass A: classify (k_move_classify)
+    for (int64_t c = 0; c < g.C; c++) {
+        int ci[3];
+        jp_cell_ijk<N>(g, c, ci);
+        uint64_t m = 0, lv = 0;
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            if (!index[el]) continue;
+            m |= 1ull << s;
+            double p[3];
+            for (int d = 0; d < N; d++) p[d] = co[d][el];
+            if (jp_move_leaves<N>(g, ci, p)) lv |= 1ull << s;
+        }
+        e->occ[c] = m; e->leave[c] = lv;
+    }
+    // pass B: 3^N ordered colour sweeps (k_move_sweep)
+    int st[3] = {0, 0, 0};
+    for (int ox = 0; ox < 3; ox++)
+        for (int oy = 0; oy < 3; oy++)
+            for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
+                for (int k = oz; k < g.n[2]; k += 3)
+                    for (int j = oy; j < g.n[1]; j += 3)
+                        for (int i = ox; i < g.n[0]; i += 3) {
+                            int ci[3] = {i, j, k};
+                            jp_move_cell<N>(g, co, index, args, e->occ.data(), e->leave.data(), jp_cell_lin<N>(g, ci), ci, st);
+                        }
+    stats[0] = st[0]; stats[1] = st[1]; stats[2] = st[2];
+}
+extern "C" int jpe_move(Emul *e, double *const *co, uint8_t *index, double *const *args, int nargs, int64_t *stats) {
+    JpArgs a; a.n = nargs;
+    for (int i = 0; i < nargs; i++) a.a[i] = args[i];
+    if (e->g.ndim == 2) move_t<2>(e, co, index, a, stats); else move_t<3>(e, co, index, a, stats);
+    return 0;
+}
+
+template <int N>
+static int64_t inject_t(Emul *e, double *const *co, uint8_t *index, const JpArgs &args, int min_xcell, uint64_t seed, uint32_t step) {
+    const JpGrid &g = e->g;
+    const int NQ = N == 2 ? 4 : 8, min_xq = (min_xcell + NQ - 1) / NQ;
+    for (int64_t c = 0; c < g.C; c++) {      // k_inject_classify
+        int ci[3];
+        jp_cell_ijk<N>(g, c, ci);
+        double vq[3], dq[3];
+        for (int d = 0; d < N; d++) { vq[d] = g.xv[d][ci[d]]; dq[d] = jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; }
+        int nq0 = 0, nlive = 0;
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            if (!index[el]) continue;
+            nlive++;
+            double p[3];
+            for (int d = 0; d < N; d++) p[d] = co[d][el];
+            nq0 += jp_isincell<N>(p, vq, dq) ? 1 : 0;
+        }
+        e->flag[c] = jp_inject_candidate(nq0, nlive, g.S, min_xq) ? 1 : 0;
+    }
+    int64_t inj = 0;
+    for (int ox = 0; ox < 2; ox++)           // k_inject_sweep
+        for (int oy = 0; oy < 2; oy++)
+            for (int oz = 0; oz < (N == 3 ? 2 : 1); oz++)
+                for (int k = oz; k < g.n[2]; k += 2)
+                    for (int j = oy; j < g.n[1]; j += 2)
+                        for (int i = ox; i < g.n[0]; i += 2) {
+                            int ci[3] = {i, j, k};
+                            const int64_t c = jp_cell_lin<N>(g, ci);
+                            if (!e->flag[c]) continue;
+                            inj += jp_inject_cell<N>(g, co, index, args, min_xcell, seed, step, c, ci);
+                        }
+    return inj;
+}
+extern "C" int64_t jpe_inject(Emul *e, double *const *co, uint8_t *index, double *const *args, int nargs, int min_xcell, uint64_t seed, uint32_t step) {
+    JpArgs a; a.n = nargs;
+    for (int i = 0; i < nargs; i++) a.a[i] = args[i];
+    return e->g.ndim == 2 ? inject_t<2>(e, co, index, a, min_xcell, seed, step) : inject_t<3>(e, co, index, a, min_xcell, seed, step);
+}
+
