@@ -1,0 +1,300 @@
+"""GPU parity: every C-ABI entry point of libjustpic_sm100a.so against the CPU
+oracle on the same seeded inputs.  Bar: bit-exact for masks / slot assignment
+AND for fp64 values (both sides use only +,-,*,fma,/,sqrt in the same order);
+the stated tolerance for floating point is 1e-12 relative (north_star), kept as
+a second, looser assertion so a 1-ulp library difference is reported as such."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle import Oracle
+from tests.problems import (centre_field_linear, cfl_dt, make_grids, rotation_velocity, stream_velocity,
+                            vertex_field_linear)
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def jp():
+    import justpic.jl_b200 as J
+    return J
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_same(gpu, ref, what):
+    g = host(gpu) if isinstance(gpu, torch.Tensor) else gpu
+    if g.dtype == np.uint8:
+        assert np.array_equal(g, ref), f"{what}: masks differ at {int((g != ref).sum())} slots"
+        return
+    assert np.array_equal(np.isnan(g), np.isnan(ref)), f"{what}: NaN pattern differs"
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isinf(g), np.isinf(ref)), f"{what}: Inf pattern differs"
+    np.testing.assert_allclose(g[ok], ref[ok], rtol=RTOL, atol=0, err_msg=f"{what}: beyond the stated 1e-12 tolerance")
+    nbad = int((g[ok] != ref[ok]).sum())
+    assert nbad == 0, f"{what}: within 1e-12 but not bit-exact at {nbad} entries"
+
+
+class Twin:
+    """The same problem on the GPU (public API) and in the oracle."""
+
+    def __init__(self, ndim, n, uniform=True, stretch=0.3, nxcell=12, max_xcell=24, min_xcell=8, seed=7):
+        J = jp()
+        self.gr = gr = make_grids(n, ndim, uniform=uniform, stretch=stretch)
+        grids = gr.grid_vel if uniform else gr.xi_vel
+        self.p = J.init_particles(J.CUDABackend, nxcell, max_xcell, min_xcell, *grids, seed=seed)
+        self.o = Oracle(gr.xvi, gr.xci, gr.xi_vel, self.p.max_xcell, uniform)
+        self.co, self.idx = self.o.init_particles(nxcell, seed)
+        self.min_xcell = min_xcell
+        self.seed = seed
+
+    def check_state(self, what, gargs=(), oargs=()):
+        for d in range(self.gr.ndim):
+            assert_same(self.p.coords[d], self.co[d], f"{what}: coords[{d}]")
+        assert_same(self.p.index, self.idx, f"{what}: index")
+        for i, (a, b) in enumerate(zip(gargs, oargs)):
+            assert_same(a, b, f"{what}: args[{i}]")
+
+
+GRIDS = [
+    (2, 24, True), (2, (19, 33), False), (3, 10, True), (3, (9, 7, 12), False),
+]
+ids = lambda g: f"{g[0]}D-{g[1]}-{'range' if g[2] else 'vector'}"
+
+
+@pytest.mark.parametrize("g", GRIDS, ids=ids)
+def test_init_particles(g):
+    t = Twin(*g)
+    t.check_state("init_particles")
+    assert t.p.np == t.p.max_xcell * int(np.prod(t.gr.n))
+
+
+@pytest.mark.parametrize("g", GRIDS, ids=ids)
+@pytest.mark.parametrize("method", ["euler", "rk2", "rk2_23", "rk4"])
+def test_advection(g, method):
+    J = jp()
+    t = Twin(*g)
+    V = stream_velocity(t.gr)
+    Vd = [dev(v) for v in V]
+    m = {"euler": (J.Euler(), 0, 0.0), "rk2": (J.RungeKutta2(), 1, 0.5), "rk2_23": (J.RungeKutta2(2 / 3), 1, 2 / 3),
+         "rk4": (J.RungeKutta4(), 2, 0.0)}[method]
+    for cfl in (0.5, 1.6):
+        dt = cfl_dt(t.gr, V, cfl)
+        J.advection(t.p, m[0], Vd, dt)
+        t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
+        t.check_state(f"advection {method} cfl {cfl}")
+
+
+@pytest.mark.parametrize("g", GRIDS, ids=ids)
+def test_interpolations(g):
+    J = jp()
+    t = Twin(*g)
+    gr = t.gr
+    T = vertex_field_linear(gr) + 0.25 * np.sin(7 * vertex_field_linear(gr, 0))
+    Tc = centre_field_linear(gr) ** 2 + centre_field_linear(gr, 0)
+    Td, Tcd = dev(T), dev(Tc)
+    pT, = J.init_cell_arrays(t.p, 1)
+    opT = np.zeros_like(t.co[0])
+    J.grid2particle(pT, Td, t.p); t.o.grid2particle(t.co, t.idx, opT, T)
+    assert_same(pT, opT, "grid2particle")
+    # reference property: linear field -> pT ≈ coordinate
+    lin = vertex_field_linear(gr)
+    pL, = J.init_cell_arrays(t.p, 1)
+    J.grid2particle(pL, dev(lin), t.p)
+    live = t.idx > 0
+    np.testing.assert_allclose(host(pL)[live], t.co[-1][live], rtol=math.sqrt(np.finfo(float).eps))
+    T2 = torch.empty_like(Td); oT2 = np.empty_like(T)
+    J.particle2grid(T2, pT, t.p); t.o.particle2grid(t.co, t.idx, oT2, opT)
+    assert_same(T2, oT2, "particle2grid")
+    J.centroid2particle(pT, Tcd, t.p); t.o.centroid2particle(t.co, opT, Tc)
+    assert_same(pT, opT, "centroid2particle")
+    Tc2 = torch.empty_like(Tcd); oTc2 = np.empty_like(Tc)
+    J.particle2centroid(Tc2, pT, t.p); t.o.particle2centroid(t.co, oTc2, opT)
+    assert_same(Tc2, oTc2, "particle2centroid")
+
+
+@pytest.mark.parametrize("g", GRIDS, ids=ids)
+@pytest.mark.parametrize("K", [2, 5])
+def test_phase_ratios_center(g, K):
+    J = jp()
+    t = Twin(*g)
+    rng = np.random.default_rng(K)
+    ph = rng.integers(1, K + 1, size=t.idx.shape).astype(np.float64)
+    pr = J.PhaseRatios(J.CUDABackend, K, t.gr.n)
+    J.phase_ratios_center(pr, t.p, dev(ph))
+    ratios = np.zeros(t.o.cell_shape(K))
+    t.o.phase_ratios_center(t.co, ratios, ph, K)
+    assert_same(pr.center, ratios, "phase_ratios_center")
+    np.testing.assert_allclose(host(pr.center).sum(axis=0), 1.0, rtol=1e-14)
+
+
+@pytest.mark.parametrize("g", GRIDS + [(2, 17, True), (3, (7, 5, 6), True)], ids=ids)
+def test_trajectory_advect_move_inject(g):
+    """L2 protocol: coupled steps; any divergence shows up at the first differing call."""
+    J = jp()
+    tight = g in [(2, 17, True)]
+    t = Twin(*g, nxcell=12, max_xcell=12 if tight else 24, min_xcell=6 if tight else 8)
+    gr = t.gr
+    V = stream_velocity(gr)
+    Vd = [dev(v) for v in V]
+    dt = cfl_dt(gr, V, 0.9)
+    T = vertex_field_linear(gr)
+    pT, ph = J.init_cell_arrays(t.p, 2)
+    J.grid2particle(pT, dev(T), t.p)
+    opT = np.zeros_like(t.co[0]); t.o.grid2particle(t.co, t.idx, opT, T)
+    oph = np.where(t.idx > 0, 1.0 + (t.co[0] < t.co[-1]), 0.0)
+    ph.copy_(dev(oph))
+    methods = [(J.RungeKutta2(), 1, 0.5), (J.RungeKutta4(), 2, 0.0), (J.RungeKutta2(2 / 3), 1, 2 / 3), (J.Euler(), 0, 0.0)]
+    for it in range(8):
+        m = methods[it % 4]
+        J.advection(t.p, m[0], Vd, dt); t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
+        t.check_state(f"step {it} advection")
+        J.move_particles(t.p, (pT, ph)); st = t.o.move(t.co, t.idx, [opT, oph])
+        t.check_state(f"step {it} move_particles", (pT, ph), (opT, oph))
+        assert J.move_stats(t.p) == st
+        J.inject_particles(t.p, (pT, ph), step=it); inj = t.o.inject(t.co, t.idx, [opT, oph], t.min_xcell, t.seed, it)
+        t.check_state(f"step {it} inject_particles", (pT, ph), (opT, oph))
+        assert J.inject_stats(t.p) == inj
+    Tg = torch.empty_like(dev(T)); oT = np.empty_like(T)
+    J.particle2grid(Tg, pT, t.p); t.o.particle2grid(t.co, t.idx, oT, opT)
+    assert_same(Tg, oT, "final particle2grid")
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_ties_nan_inf_and_clean(ndim):
+    J = jp()
+    t = Twin(ndim, 6, True, nxcell=8, max_xcell=12, min_xcell=8, seed=5)
+    gr = t.gr
+    rng = np.random.default_rng(1)
+    live = np.argwhere(t.idx > 0)
+    for tt in live[rng.choice(len(live), size=len(live) // 3, replace=False)]:
+        for d in range(ndim):
+            if rng.random() < 0.6:
+                cell = tt[ndim - d]
+                cand = [gr.xvi[d][cell], gr.xvi[d][cell + 1], gr.xci[d][cell], np.nan, np.inf, -1e-3, 1.001,
+                        np.nextafter(gr.xvi[d][cell + 1], 2.0)]
+                t.co[d][tuple(tt)] = cand[rng.integers(len(cand))]
+    for d in range(ndim):
+        t.p.coords[d].copy_(dev(t.co[d]))
+    pT, = J.init_cell_arrays(t.p, 1)
+    opT = np.where(t.idx > 0, rng.random(t.idx.shape), 0.0)
+    pT.copy_(dev(opT))
+    # clean on a copy
+    c2 = [a.copy() for a in t.co]; i2 = t.idx.copy(); a2 = opT.copy()
+    t.o.clean(c2, i2, [a2])
+    import copy
+    pc = [c.clone() for c in t.p.coords]; pi = t.p.index.clone(); pa = pT.clone()
+    J.clean_particles(t.p, None, (pT,))
+    for d in range(ndim):
+        assert_same(t.p.coords[d], c2[d], "clean coords")
+    assert_same(t.p.index, i2, "clean index"); assert_same(pT, a2, "clean args")
+    for d in range(ndim):
+        t.p.coords[d].copy_(pc[d])
+    t.p.index.copy_(pi); pT.copy_(pa)
+    V = stream_velocity(gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(gr, V, 0.5)
+    for it, m in enumerate([(J.RungeKutta2(), 1, 0.5), (J.RungeKutta4(), 2, 0.0), (J.Euler(), 0, 0.0)]):
+        J.advection(t.p, m[0], Vd, dt); t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
+        t.check_state(f"ties advection {it}")
+        J.move_particles(t.p, (pT,)); st = t.o.move(t.co, t.idx, [opT])
+        t.check_state(f"ties move {it}", (pT,), (opT,))
+        assert J.move_stats(t.p) == st
+        J.inject_particles(t.p, (pT,), step=it); t.o.inject(t.co, t.idx, [opT], 8, 5, it)
+        t.check_state(f"ties inject {it}", (pT,), (opT,))
+
+
+def test_rotating_circle_rk4_inject_cell_assignment():
+    """BASELINE config 2 in miniature (scripts/rotating_circle.jl): solid rotation, RK4,
+    inject_particles! reseeding; cell assignment (masks) must be bit-exact."""
+    J = jp()
+    t = Twin(2, 48, True, nxcell=24, max_xcell=48, min_xcell=12, seed=42)
+    V = rotation_velocity(t.gr); Vd = [dev(v) for v in V]
+    dt = 200.0 * 25
+    ph, = J.init_cell_arrays(t.p, 1)
+    r2 = (t.co[0] - 0.5) ** 2 + (t.co[1] - 0.75) ** 2
+    oph = np.where(t.idx > 0, 1.0 + (r2 < 0.15 ** 2), 0.0)
+    ph.copy_(dev(oph))
+    for it in range(6):
+        J.advection(t.p, J.RungeKutta4(), Vd, dt); t.o.advect(t.co, t.idx, 2, 0.0, V, dt)
+        J.move_particles(t.p, (ph,)); t.o.move(t.co, t.idx, [oph])
+        J.inject_particles(t.p, (ph,), step=it); t.o.inject(t.co, t.idx, [oph], 12, 42, it)
+        t.check_state(f"rotating circle step {it}", (ph,), (oph,))
+
+
+def test_api_errors():
+    J = jp()
+    t = Twin(2, 8, True)
+    V = [dev(v) for v in stream_velocity(t.gr)]
+    with pytest.raises(ValueError):
+        J.RungeKutta2(1.1)
+    with pytest.raises(ValueError):
+        J.advection(t.p, J.Euler(), V[:1], 0.1)
+    with pytest.raises(ValueError):
+        J.grid2particle(torch.zeros(3, device="cuda", dtype=torch.float64), V[0], t.p)
+    with pytest.raises(ValueError):
+        J.init_particles(J.CUDABackend, 12, 24, 8)
+
+
+# ------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("cfg", ["cfg1_2d_256", "cfg3_3d_128"])
+def test_full_size_invariants(cfg):
+    """BASELINE.json sizes: the oracle is too slow, so size-independent properties:
+    count conservation (live = initial - dropped - deleted + injected), every live
+    particle inside its cell, dead slots NaN, linear field reproduced by g2p, p2g of
+    a constant field is that constant, phase ratios sum to 1, idempotent move."""
+    J = jp()
+    ndim, n = (2, 256) if cfg == "cfg1_2d_256" else (3, 128)
+    gr = make_grids(n, ndim, True)
+    p = J.init_particles(J.CUDABackend, 24, 48, 12, *gr.grid_vel, seed=42)
+    V = stream_velocity(gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(gr, V, 0.75 if ndim == 2 else 0.5)
+    T = dev(vertex_field_linear(gr))
+    pT, pc = J.init_cell_arrays(p, 2)
+    J.grid2particle(pT, T, p)
+    pc.fill_(3.25)
+    n_live = int(p.index.sum().item())
+    assert n_live == 24 * int(np.prod(gr.n))
+    for it in range(3):
+        J.advection(p, J.RungeKutta2(), Vd, dt)
+        J.move_particles(p, (pT, pc))
+        moved, dropped, deleted = J.move_stats(p)
+        J.inject_particles(p, (pT, pc), step=it)
+        inj = J.inject_stats(p)
+        n_new = int(p.index.sum().item())
+        assert n_new == n_live - dropped - deleted + inj
+        assert moved > 0
+        n_live = n_new
+    live = p.index > 0
+    for d in range(ndim):
+        shape = [1] * (ndim + 1); shape[ndim - d] = -1
+        lo = dev(gr.xvi[d][:-1]).reshape(shape); hi = dev(gr.xvi[d][1:]).reshape(shape)
+        c = p.coords[d]
+        assert bool((((c >= lo) & (c <= hi)) | ~live).all())
+        assert bool((torch.isnan(c) == ~live).all())
+    # idempotence: a second move changes nothing
+    before = [c.clone() for c in p.coords]; ib = p.index.clone()
+    J.move_particles(p, (pT, pc))
+    assert J.move_stats(p) == (0, 0, 0)
+    assert all(torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)) for a, b in zip(before, p.coords))
+    assert torch.equal(ib, p.index)
+    # constant field survives p2g exactly up to rounding of the weighted mean
+    F = torch.empty_like(T)
+    J.particle2grid(F, pc, p)
+    assert bool(torch.allclose(F, torch.full_like(F, 3.25), rtol=1e-13, atol=0))
+    pL, = J.init_cell_arrays(p, 1)
+    J.grid2particle(pL, T, p)
+    assert bool(torch.allclose(pL[live], p.coords[-1][live], rtol=1e-8, atol=1e-12))
+    K = 3
+    ph = torch.where(live, 1.0 + torch.floor(p.coords[0].nan_to_num() * K).clamp(0, K - 1), torch.zeros_like(pL))
+    pr = J.PhaseRatios(J.CUDABackend, K, gr.n)
+    J.phase_ratios_center(pr, p, ph)
+    s = pr.center.sum(dim=0)
+    assert bool(torch.allclose(s, torch.ones_like(s), rtol=1e-13))
