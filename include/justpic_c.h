@@ -47,6 +47,8 @@ typedef enum {
 } jp_status;
 
 typedef enum { JP_EULER = 0, JP_RK2 = 1, JP_RK4 = 2 } jp_scheme;
+typedef enum { JP_OPT_P2G_MODE = 1 } jp_option;
+typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1 } jp_p2g_mode;
 
 /* Grid description (HOST pointers).  Mirrors the grid part of the reference's
  * `Particles` struct (src/particles.jl:17-46): xvi, xci, xi_vel, and whether
@@ -78,6 +80,7 @@ int  jp_ctx_create(const jp_grid_desc *grid, int device, jp_ctx **out);
 void jp_ctx_destroy(jp_ctx *ctx);
 const char *jp_last_error(void);
 int  jp_version(void);
+int  jp_set_option(jp_ctx *ctx, int32_t option, int32_t value);
 
 /* init_particles(backend, nxcell, max_xcell, min_xcell, xi_vel...)
  * (src/Particles/particles_utils.jl:108-166, kernel fill_coords_index! :168-194).
@@ -116,7 +119,14 @@ int jp_grid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const doubl
  * Fc: centre field (n per dim). */
 int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *Fc, void *stream);
 
-/* particle2grid!(F, Fp, particles) (src/Interpolations/particle_to_grid.jl:23-151). */
+/* particle2grid!(F, Fp, particles) (src/Interpolations/particle_to_grid.jl:23-151).
+ * Two modes (jp_set_option(ctx, JP_OPT_P2G_MODE, ...)):
+ *  JP_P2G_TWOPASS (default): cell-centric partial sums + node-centric gather, no
+ *    atomics, fixed summation order; every particle is read once.  Same weights and
+ *    terms as the reference, different association: agrees to a few ulp (stated
+ *    tolerance 1e-12 relative), deterministic run to run.
+ *  JP_P2G_EXACT: one thread per node, the reference's single running sum in its
+ *    (k, j, i, slot) order: bit-exact with the reference, reads every particle 2^N times. */
 int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, const double *Fp, void *stream);
 
 /* particle2centroid!(F, Fp, particles) (src/Interpolations/particle_to_grid_centroid.jl:10-99). */

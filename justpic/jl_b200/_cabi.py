@@ -14,6 +14,8 @@ LIB_PATH = HERE / "libjustpic_sm100a.so"
 JP_MAX_ARGS = 16
 JP_MAX_SLOTS = 64
 JP_MAX_PHASES = 32
+JP_OPT_P2G_MODE = 1
+JP_P2G_EXACT, JP_P2G_TWOPASS = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
 
@@ -43,6 +45,7 @@ SYMBOLS = {
     "jp_ctx_destroy": (None, [C.c_void_p]),
     "jp_last_error": (C.c_char_p, []),
     "jp_version": (C.c_int, []),
+    "jp_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "jp_init_particles": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_uint64, C.c_void_p]),
     "jp_advect": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
                             C.POINTER(C.c_void_p), C.c_double, C.c_void_p]),

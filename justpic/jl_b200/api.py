@@ -50,6 +50,7 @@ class CUDABackend:
 
 
 _SYNC = False
+P2G_MODE = "twopass"   # module default for particle2grid (see its docstring)
 
 
 def set_synchronous(flag: bool) -> None:
@@ -400,8 +401,15 @@ def centroid2particle(Fp, F, particles: Particles) -> None:
            "centroid2particle")
 
 
-def particle2grid(F, Fp, particles: Particles) -> None:
-    """``particle2grid!(F, Fp, particles)`` (src/Interpolations/particle_to_grid.jl:23-28)."""
+def particle2grid(F, Fp, particles: Particles, mode: Optional[str] = None) -> None:
+    """``particle2grid!(F, Fp, particles)`` (src/Interpolations/particle_to_grid.jl:23-28).
+    ``mode``: "twopass" (default: deterministic cell-partials + node gather, within 1e-12 of
+    the reference) or "exact" (the reference's running sum, bit-exact, 2^N x the traffic)."""
+    m = (mode or P2G_MODE).lower()
+    if m not in ("exact", "twopass"):
+        raise ValueError("particle2grid mode must be 'exact' or 'twopass'")
+    _cabi.check(_cabi.load().jp_set_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_P2G_MODE,
+                                           _cabi.JP_P2G_EXACT if m == "exact" else _cabi.JP_P2G_TWOPASS), "jp_set_option")
     _call5("jp_particle2grid", particles, _field(F, particles, _nodes(particles, 1), "F"), _pfield(Fp, particles, "Fp"),
            "particle2grid")
 

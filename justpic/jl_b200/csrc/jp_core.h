@@ -318,14 +318,13 @@ JP_HD bool jp_move_leaves(const JpGrid &g, const int *ci, const double *p) {
 // stats: [0] moved, [1] dropped, [2] deleted (accumulated by the caller).
 template <int N>
 JP_HD void jp_move_cell(const JpGrid &g, double *const *coords, uint8_t *index, const JpArgs &args,
-                        uint64_t *occ, uint64_t *leave, int64_t c, const int *ci, int *stats) {
+                        uint64_t *occ, uint64_t *leave, int64_t c, const int *ci, int *stats, int cursor = 0) {
     uint64_t lv = leave[c];
     if (lv == 0) return;
     const int S = g.S;
     const uint64_t smask = S == 64 ? ~0ull : ((1ull << S) - 1);
     double lo[3], hi[3];
     for (int d = 0; d < N; d++) { lo[d] = g.xv[d][0]; hi[d] = g.xv[d][g.n[d]]; }
-    int cursor = 0;
     uint64_t occ_c = occ[c];
     while (lv) {
 #if defined(__CUDA_ARCH__)

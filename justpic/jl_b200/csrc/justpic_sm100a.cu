@@ -40,6 +40,8 @@ struct jp_ctx {
     uint64_t *occ, *leave;  // [C] occupancy / leave words (move, inject)
     uint8_t *flag;        // [C] inject candidate flags
     long long *stats;     // device counters: [0..2] move, [3] inject
+    double *p2g_ws;       // [2 * 2^N * C] per-cell partial sums of the two-pass particle2grid (lazy)
+    int p2g_mode;         // JP_P2G_EXACT / JP_P2G_TWOPASS
 };
 
 struct Ptr3 { double *p[3]; };
@@ -125,21 +127,135 @@ __global__ void __launch_bounds__(256) k_move_classify(JpGrid g, CPtr3 co, const
     if (ok) { occ[c] = m; leave[c] = lv; }
 }
 
-// move_particles! pass B: one colour of the 3^N sweeps (thread = source cell)
+// move_particles! pass B: one colour of the 3^N sweeps.  One WARP per source
+// cell: lanes = the cell's leaving particles (chunks of 32).  Coordinates, the
+// destination cell (seeded bisection) and the destination occupancy words are
+// fetched by all lanes in parallel; the order-dependent part of the reference
+// loop (src/Particles/move_safe.jl:72-125: first free slot >= cursor, in slot
+// order, cursor shared across destinations) runs as a warp-uniform loop over
+// shuffled values and touches registers only; payloads then move in parallel.
+// A cell holding a particle that fails isincell but bisects back into its own
+// cell (exactly on a face / ulp gap) takes the serial literal routine.
+__device__ __forceinline__ int nth_set_bit64(uint64_t m, int i) {
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    const int nlo = __popc(lo);
+    return i < nlo ? (int)__fns(lo, 0, i + 1) : 32 + (int)__fns(hi, 0, i - nlo + 1);
+}
+
 template <int N>
 __global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ, uint64_t *leave,
-                                                    int ox, int oy, int oz, long long *stats) {
+                                                    int ox, int oy, int oz, int ncx, int ncy, int64_t ncol, long long *stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= ncol) return;                                   // warp-uniform
     int ci[3];
-    ci[0] = 3 * (blockIdx.x * JP_BX + threadIdx.x) + ox;
-    ci[1] = 3 * (blockIdx.y * JP_BY + threadIdx.y) + oy;
-    ci[2] = N == 3 ? 3 * blockIdx.z + oz : 0;
+    ci[0] = 3 * (int)(t % ncx) + ox;
+    ci[1] = 3 * (int)((t / ncx) % ncy) + oy;
+    ci[2] = N == 3 ? 3 * (int)(t / ((int64_t)ncx * ncy)) + oz : 0;
     if (ci[0] >= g.n[0] || ci[1] >= g.n[1] || (N == 3 && ci[2] >= g.n[2])) return;
     const int64_t c = jp_cell_lin<N>(g, ci);
-    int st[3] = {0, 0, 0};
-    jp_move_cell<N>(g, co.p, index, args, occ, leave, c, ci, st);
-    if (st[0]) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)st[0]);
-    if (st[1]) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)st[1]);
-    if (st[2]) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)st[2]);
+    uint64_t lv = leave[c];
+    if (lv == 0) return;
+    const int S = g.S;
+    const uint64_t smask = S == 64 ? ~0ull : ((1ull << S) - 1);
+    uint64_t occ_c = occ[c];
+    int cursor = 0, n_moved = 0, n_dropped = 0, n_deleted = 0;
+    double lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < N; d++) { lo[d] = g.xv[d][0]; hi[d] = g.xv[d][g.n[d]]; }
+    while (lv) {
+        const int n = min(__popcll(lv), 32);
+        // ---- parallel: classify my particle
+        const bool act = lane < n;
+        int ip = 0;
+        int64_t e = 0, c2 = -1;
+        double p[3] = {0, 0, 0};
+        bool indom = false, tie = false, fails_dest = false;
+        uint64_t my_occ = 0;
+        if (act) {
+            ip = nth_set_bit64(lv, lane);
+            e = c + (int64_t)ip * g.C;
+            indom = true;
+#pragma unroll
+            for (int d = 0; d < N; d++) { p[d] = co.p[d][e]; indom = indom && (lo[d] < p[d] && p[d] < hi[d]); }
+            if (indom) {
+                int nc[3] = {0, 0, 0};
+                double corner[3], dx[3];
+#pragma unroll
+                for (int d = 0; d < N; d++) {
+                    nc[d] = jp_bisect1(p[d], g.xv[d], g.n[d] + 1, ci[d] + 1) - 1;
+                    corner[d] = g.xv[d][nc[d]];
+                    dx[d] = jp_d_of(g.xv[d], g.uniform, nc[d]);
+                }
+                c2 = jp_cell_lin<N>(g, nc);
+                tie = c2 == c;
+                fails_dest = !jp_isincell<N>(p, corner, dx);
+                if (!tie) my_occ = occ[c2];
+            }
+        }
+        if (__any_sync(0xffffffffu, tie)) {
+            // rare: serial literal routine for the whole cell (nothing has been modified yet in this chunk)
+            if (lane == 0) {
+                leave[c] = lv; occ[c] = occ_c;
+                int st[3] = {0, 0, 0};
+                // the cursor of the chunks already done carries over: emulate by a cursor-aware call
+                jp_move_cell<N>(g, co.p, index, args, occ, leave, c, ci, st, cursor);
+                n_moved += st[0]; n_dropped += st[1]; n_deleted += st[2];
+            }
+            lv = 0;
+            occ_c = 0;   // already stored by jp_move_cell
+            __syncwarp();
+            if (lane == 0) {
+                if (n_moved) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)n_moved);
+                if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
+                if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);
+            }
+            return;
+        }
+        // ---- serial (warp-uniform): slot assignment in slot order
+        int my_fs = -1;
+        for (int k = 0; k < n; k++) {
+            const int ipk = __shfl_sync(0xffffffffu, ip, k);
+            const long long c2k = __shfl_sync(0xffffffffu, (long long)c2, k);
+            const unsigned long long o2 = __shfl_sync(0xffffffffu, (unsigned long long)my_occ, k);
+            occ_c &= ~(1ull << ipk);
+            if (c2k < 0) { n_deleted++; continue; }
+            const uint64_t freebits = ~o2 & smask & (~0ull << cursor);
+            if (freebits == 0) { n_dropped++; continue; }
+            const int fs = __ffsll((long long)freebits) - 1;
+            cursor = fs;
+            if (c2 == c2k) my_occ = o2 | (1ull << fs);
+            if (lane == k) my_fs = fs;
+            n_moved++;
+        }
+        // ---- parallel: move payloads
+        if (act) {
+            index[e] = 0;
+#pragma unroll
+            for (int d = 0; d < N; d++) co.p[d][e] = NAN;
+            if (my_fs >= 0) {
+                const int64_t e2 = c2 + (int64_t)my_fs * g.C;
+                index[e2] = 1;
+#pragma unroll
+                for (int d = 0; d < N; d++) co.p[d][e2] = p[d];
+                for (int a = 0; a < args.n; a++) { args.a[a][e2] = args.a[a][e]; args.a[a][e] = NAN; }
+                occ[c2] = my_occ;                       // same final value from every lane targeting c2
+                if (fails_dest) atomicOr((unsigned long long *)&leave[c2], 1ull << my_fs);
+            } else {
+                for (int a = 0; a < args.n; a++) args.a[a][e] = NAN;
+            }
+        }
+        // consume the processed bits
+        for (int k = 0; k < n; k++) lv &= lv - 1;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        occ[c] = occ_c;
+        leave[c] = 0;
+        if (n_moved) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)n_moved);
+        if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
+        if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);
+    }
 }
 
 template <int N>
@@ -280,6 +396,84 @@ __global__ void __launch_bounds__(256) k_p2g(JpGrid g, CPtr3 co, const uint8_t *
     F[nd] = N == 2 ? wF / w : wF * (1.0 / w);
 }
 
+// particle2grid!, two-pass deterministic variant (JP_P2G_TWOPASS).
+// Pass 1 (cell-centric, streams every particle exactly once): for each cell the
+// partial sums  sum_w[q], sum_wF[q]  of its particles w.r.t. each of its 2^N corner
+// nodes q, accumulated in slot order with the reference's per-particle weight
+// (sqrt -> square -> inv) and the reference's muladd.  Pass 2 (node-centric gather,
+// no atomics): each node adds the partials of its <= 2^N adjacent cells in the
+// reference's (k, j, i) order.  Same terms as the reference, fixed order, but the
+// association is (cell sums) + ... instead of one running chain: results agree with
+// the reference to a few ulp (stated tolerance 1e-12), not bit-for-bit.
+template <int N>
+__global__ void __launch_bounds__(256) k_p2g_cell(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, const double *__restrict__ Fp,
+                                                  double *__restrict__ PW, double *__restrict__ PWF) {
+    constexpr int NQ = N == 2 ? 4 : 8;
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    double xn[3][2];
+    if (ok)
+        for (int d = 0; d < N; d++) { xn[d][0] = g.xv[d][ci[d]]; xn[d][1] = g.xv[d][ci[d] + 1]; }
+    double aw[NQ], awf[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) { aw[q] = 0.0; awf[q] = 0.0; }
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        if (live) {
+            const int64_t e = c + (int64_t)s * g.C;
+            double d2[3][2];
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                const double pd = co.p[d][e];
+                const double a0 = xn[d][0] - pd, a1 = xn[d][1] - pd;
+                d2[d][0] = a0 * a0; d2[d][1] = a1 * a1;
+            }
+            const double f = Fp[e];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                double ss = d2[0][q & 1] + d2[1][(q >> 1) & 1];
+                if (N == 3) ss = ss + d2[2][(q >> 2) & 1];
+                const double dist = sqrt(ss);
+                const double wi = 1.0 / (dist * dist);
+                aw[q] += wi;
+                awf[q] = fma(wi, f, awf[q]);
+            }
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) { PW[(int64_t)q * g.C + c] = aw[q]; PWF[(int64_t)q * g.C + c] = awf[q]; }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) k_p2g_node(JpGrid g, const double *__restrict__ PW, const double *__restrict__ PWF, double *__restrict__ F) {
+    const int in = blockIdx.x * JP_BX + threadIdx.x, jn = blockIdx.y * JP_BY + threadIdx.y, kn = N == 3 ? blockIdx.z : 0;
+    const int nx = g.n[0], ny = g.n[1], nz = N == 3 ? g.n[2] : 1;
+    if (in > nx || jn > ny) return;
+    double w = 0.0, wF = 0.0;
+    for (int ko = (N == 3 ? -1 : 0); ko <= 0; ko++) {
+        const int kc = kn + ko;
+        if (N == 3 && (kc < 0 || kc >= nz)) continue;
+        for (int jo = -1; jo <= 0; jo++) {
+            const int jc = jn + jo;
+            if (jc < 0 || jc >= ny) continue;
+            for (int io = -1; io <= 0; io++) {
+                const int ic = in + io;
+                if (ic < 0 || ic >= nx) continue;
+                const int64_t c = ic + (int64_t)nx * (jc + (int64_t)ny * kc);
+                const int q = (io < 0 ? 1 : 0) | (jo < 0 ? 2 : 0) | ((N == 3 && ko < 0) ? 4 : 0);
+                w = w + PW[(int64_t)q * g.C + c];
+                wF = wF + PWF[(int64_t)q * g.C + c];
+            }
+        }
+    }
+    const int64_t nd = in + (int64_t)(nx + 1) * (jn + (N == 3 ? (int64_t)(ny + 1) * kn : 0));
+    F[nd] = N == 2 ? wF / w : wF * (1.0 / w);
+}
+
 // particle2centroid!
 template <int N>
 __global__ void __launch_bounds__(256) k_p2c(JpGrid g, CPtr3 co, double *__restrict__ Fc, const double *__restrict__ Fp) {
@@ -383,6 +577,7 @@ extern "C" int jp_ctx_create(const jp_grid_desc *d, int device, jp_ctx **out) {
     ctx->gridmem = dm;
     jp_grid_rebase(g, off, dm);
     ctx->g = g;
+    ctx->p2g_mode = JP_P2G_TWOPASS;
     *out = ctx;
     return JP_OK;
 }
@@ -391,6 +586,7 @@ extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->flag); cudaFree(ctx->stats);
+    cudaFree(ctx->p2g_ws);
     free(ctx);
 }
 
@@ -476,12 +672,13 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     else             k_move_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
     JP_CHECK_LAUNCH();
     const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = g.ndim == 3 ? (g.n[2] + 2) / 3 : 1;
-    const dim3 sg = tile_grid(ncx, ncy, ncz);
+    const int64_t ncol = (int64_t)ncx * ncy * ncz;          // source cells per colour (upper bound)
+    const unsigned nblk = (unsigned)((ncol + 7) / 8);        // one warp per source cell, 8 warps per block
     for (int ox = 0; ox < 3; ox++)
         for (int oy = 0; oy < 3; oy++)
             for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {
-                if (g.ndim == 2) k_move_sweep<2><<<sg, blk, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ctx->stats);
-                else             k_move_sweep<3><<<sg, blk, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ctx->stats);
+                if (g.ndim == 2) k_move_sweep<2><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats);
+                else             k_move_sweep<3><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats);
             }
     JP_CHECK_LAUNCH();
     return JP_OK;
@@ -560,12 +757,31 @@ extern "C" int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *
     return JP_OK;
 }
 
+extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
+    if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_set_option: null context");
+    if (option == JP_OPT_P2G_MODE && (value == JP_P2G_EXACT || value == JP_P2G_TWOPASS)) { ctx->p2g_mode = value; return JP_OK; }
+    return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
+}
+
 extern "C" int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, const double *Fp, void *stream) {
     PREP("jp_particle2grid");
     if (!Fp || !F) return jp_fail(JP_ERR_INVALID, "jp_particle2grid: null field");
     const dim3 ng = tile_grid(g.n[0] + 1, g.n[1] + 1, g.ndim == 3 ? g.n[2] + 1 : 1);
-    if (g.ndim == 2) k_p2g<2><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
-    else             k_p2g<3><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
+    if (ctx->p2g_mode == JP_P2G_EXACT) {
+        if (g.ndim == 2) k_p2g<2><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
+        else             k_p2g<3><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
+    } else {
+        const int NQ = g.ndim == 2 ? 4 : 8;
+        if (!ctx->p2g_ws) JP_CUDA(cudaMalloc(&ctx->p2g_ws, sizeof(double) * 2 * NQ * g.C));
+        double *PW = ctx->p2g_ws, *PWF = ctx->p2g_ws + (int64_t)NQ * g.C;
+        if (g.ndim == 2) {
+            k_p2g_cell<2><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
+            k_p2g_node<2><<<ng, blk, 0, st>>>(g, PW, PWF, F);
+        } else {
+            k_p2g_cell<3><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
+            k_p2g_node<3><<<ng, blk, 0, st>>>(g, PW, PWF, F);
+        }
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }

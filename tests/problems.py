@@ -33,9 +33,12 @@ def make_grids(n, ndim, uniform=True, L=1.0, stretch=0.0):
     for comp in range(ndim):
         grid_vel.append(tuple(xv[d] if d == comp else xg[d] for d in range(ndim)))
     asnp = lambda t: tuple(np.ascontiguousarray(np.asarray(x, dtype=np.float64)) for x in t)
+    xi_vel = tuple(asnp(g) for g in grid_vel)
+    # centres are DERIVED from the velocity grids, as init_particles does
+    # (src/Particles/particles_utils.jl:56-70): xci = interior of the ghosted vectors
+    xci = (xi_vel[1][0][1:-1].copy(), xi_vel[0][1][1:-1].copy()) + ((xi_vel[0][2][1:-1].copy(),) if ndim == 3 else ())
     return SimpleNamespace(ndim=ndim, n=ns, uniform=uniform, grid_vel=tuple(grid_vel),
-                           xvi=asnp(xv), xci=asnp(xc),
-                           xi_vel=tuple(asnp(g) for g in grid_vel))
+                           xvi=asnp(xv), xci=xci, xi_vel=xi_vel)
 
 
 def stream_velocity(gr, amp=250.0):
