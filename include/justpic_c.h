@@ -48,7 +48,7 @@ typedef enum {
 
 typedef enum { JP_EULER = 0, JP_RK2 = 1, JP_RK4 = 2 } jp_scheme;
 typedef enum { JP_OPT_P2G_MODE = 1 } jp_option;
-typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1 } jp_p2g_mode;
+typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;
 
 /* Grid description (HOST pointers).  Mirrors the grid part of the reference's
  * `Particles` struct (src/particles.jl:17-46): xvi, xci, xi_vel, and whether
@@ -125,6 +125,8 @@ int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const d
  *    atomics, fixed summation order; every particle is read once.  Same weights and
  *    terms as the reference, different association: agrees to a few ulp (stated
  *    tolerance 1e-12 relative), deterministic run to run.
+ *  JP_P2G_TWOPASS_FASTW: as TWOPASS with the weight evaluated as 1/sum(d^2) instead of the
+ *    reference's inv(sqrt(sum(d^2))^2) (differs by <= 2 ulp per weight; same 1e-12 tolerance).
  *  JP_P2G_EXACT: one thread per node, the reference's single running sum in its
  *    (k, j, i, slot) order: bit-exact with the reference, reads every particle 2^N times. */
 int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, const double *Fp, void *stream);

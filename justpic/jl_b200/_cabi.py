@@ -15,7 +15,7 @@ JP_MAX_ARGS = 16
 JP_MAX_SLOTS = 64
 JP_MAX_PHASES = 32
 JP_OPT_P2G_MODE = 1
-JP_P2G_EXACT, JP_P2G_TWOPASS = 0, 1
+JP_P2G_EXACT, JP_P2G_TWOPASS, JP_P2G_TWOPASS_FASTW = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 

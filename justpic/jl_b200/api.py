@@ -404,12 +404,13 @@ def centroid2particle(Fp, F, particles: Particles) -> None:
 def particle2grid(F, Fp, particles: Particles, mode: Optional[str] = None) -> None:
     """``particle2grid!(F, Fp, particles)`` (src/Interpolations/particle_to_grid.jl:23-28).
     ``mode``: "twopass" (default: deterministic cell-partials + node gather, within 1e-12 of
-    the reference) or "exact" (the reference's running sum, bit-exact, 2^N x the traffic)."""
+    the reference), "twopass_fastw" (same with the weight as 1/sum(d^2)), or "exact" (the
+    reference's running sum, bit-exact, 2^N x the traffic)."""
     m = (mode or P2G_MODE).lower()
-    if m not in ("exact", "twopass"):
-        raise ValueError("particle2grid mode must be 'exact' or 'twopass'")
-    _cabi.check(_cabi.load().jp_set_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_P2G_MODE,
-                                           _cabi.JP_P2G_EXACT if m == "exact" else _cabi.JP_P2G_TWOPASS), "jp_set_option")
+    modes = {"exact": _cabi.JP_P2G_EXACT, "twopass": _cabi.JP_P2G_TWOPASS, "twopass_fastw": _cabi.JP_P2G_TWOPASS_FASTW}
+    if m not in modes:
+        raise ValueError("particle2grid mode must be one of " + ", ".join(modes))
+    _cabi.check(_cabi.load().jp_set_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_P2G_MODE, modes[m]), "jp_set_option")
     _call5("jp_particle2grid", particles, _field(F, particles, _nodes(particles, 1), "F"), _pfield(Fp, particles, "Fp"),
            "particle2grid")
 

@@ -1,0 +1,225 @@
+// jp_advect_tile.cuh -- advection! for the standard staggered layout
+// (xvel[c][d] = vertex vector if c == d, ghosted-centre vector otherwise).
+//
+// One CTA owns a brick of TX x TY x TZ cells (one warp per x-run of 32 cells):
+//  1. the brick's velocity stencils -- origin one node below the brick, extent
+//     T+4 nodes per dimension, which covers every stage position of a particle
+//     displaced by at most one cell -- are staged in shared memory together with
+//     the grid-vector segments, so the 2^N-corner gathers of every RK stage are
+//     LDS with compile-time strides instead of 64-bit-addressed global loads;
+//  2. each warp ballots its cells' occupancy masks slot by slot and writes a
+//     compacted (slot, cell) work list to shared memory; the list is consumed 32
+//     entries at a time, so every lane carries a live particle even when the slot
+//     planes are half empty (the reference's first-free-slot policy leaves them at
+//     ~50-60 % occupancy), while loads stay coalesced because the list is
+//     slot-major;
+//  3. a particle whose stage position leaves the staged stencil, sits exactly on
+//     a grid node, or is NaN/outside the domain takes the literal global-memory
+//     routine (jp_interp_velocity_literal), so results are bitwise those of the
+//     literal code in every case.
+#pragma once
+#include "jp_core.h"
+
+template <int N> struct AdvTile {
+    static constexpr int TX = 32;
+    static constexpr int TY = N == 3 ? 4 : 8;
+    static constexpr int TZ = N == 3 ? 2 : 1;
+    static constexpr int EX = TX + 4, EY = TY + 4, EZ = N == 3 ? TZ + 4 : 1;   // staged nodes per dim
+    static constexpr int VOL = EX * EY * EZ;
+    static constexpr int NW = TY * TZ;                                          // warps per CTA
+};
+
+// shared-memory layout (doubles first, then the uint16 work lists)
+template <int N> struct AdvSmem {
+    using T = AdvTile<N>;
+    static constexpr int V_OFF = 0;                       // N tiles of VOL doubles
+    static constexpr int XV_OFF = N * T::VOL;             // per dim: EX/EY/EZ entries (xv), padded to 40
+    static constexpr int VEC = 40;
+    static constexpr int XG_OFF = XV_OFF + 3 * VEC;
+    static constexpr int IXV_OFF = XG_OFF + 3 * VEC;
+    static constexpr int IXG_OFF = IXV_OFF + 3 * VEC;
+    static constexpr int NDOUBLES = IXG_OFF + 3 * VEC;
+    static size_t bytes(int S) { return sizeof(double) * NDOUBLES + sizeof(uint16_t) * T::NW * 32 * S; }
+};
+
+// velocity at p from the staged stencils; r0[d] = tile-relative index of the seed
+// (storage) cell, c0[d] = global index of the tile's first staged node.
+template <int N, bool UNIFORM>
+__device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *__restrict__ sm, const int *c0, const int *r0,
+                                                const double *p, double *vout) {
+    using T = AdvTile<N>;
+    using L = AdvSmem<N>;
+    int iv[3], ig[3];
+    double tv[3], tg[3];
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+        const double *xv = sm + L::XV_OFF + d * L::VEC;
+        const double *xg = sm + L::XG_OFF + d * L::VEC;
+        const double pd = p[d];
+        int r = r0[d];
+        double a = xv[r], b = xv[r + 1];
+        if (!(a < pd && pd < b)) {
+            if (pd > b) r += 1; else if (pd < a) r -= 1; else return false;
+            const int gi = c0[d] + r;
+            if (gi < 0 || gi >= g.n[d]) return false;
+            a = xv[r]; b = xv[r + 1];
+            if (!(a < pd && pd < b)) return false;
+        }
+        iv[d] = r;
+        tv[d] = (pd - a) * (UNIFORM ? g.inv_dv[d] : sm[L::IXV_OFF + d * L::VEC + r]);
+        const double m = xg[r + 1];
+        if (pd == m) return false;
+        const bool lower = pd < m;
+        ig[d] = lower ? r : r + 1;
+        tg[d] = (pd - (lower ? xg[r] : m)) * (UNIFORM ? g.inv_dg[d] : sm[L::IXG_OFF + d * L::VEC + ig[d]]);
+    }
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        const int ix = c == 0 ? iv[0] : ig[0];
+        const int iy = c == 1 ? iv[1] : ig[1];
+        const int iz = N == 3 ? (c == 2 ? iv[2] : ig[2]) : 0;
+        const double t[3] = {c == 0 ? tv[0] : tg[0], c == 1 ? tv[1] : tg[1], N == 3 ? (c == 2 ? tv[2] : tg[2]) : 0.0};
+        const double *F = sm + L::V_OFF + c * T::VOL + ix + T::EX * (iy + T::EY * iz);
+        double v[8];
+        v[0] = F[0]; v[1] = F[1]; v[2] = F[T::EX]; v[3] = F[T::EX + 1];
+        if (N == 3) {
+            v[4] = F[T::EX * T::EY]; v[5] = F[T::EX * T::EY + 1];
+            v[6] = F[T::EX * T::EY + T::EX]; v[7] = F[T::EX * T::EY + T::EX + 1];
+        }
+        vout[c] = jp_lerp<N>(v, t);
+    }
+    return true;
+}
+
+template <int N, bool UNIFORM>
+__device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__restrict__ sm, const double *const *V, const int *c0,
+                                           const int *r0, const int *cell1, const double *p, double *vout) {
+    if (adv_interp_tile<N, UNIFORM>(g, sm, c0, r0, p, vout)) return;
+    jp_interp_velocity_literal<N>(g, V, p, cell1, vout);
+}
+
+template <int N, int SCHEME, bool UNIFORM>
+__global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
+                                                                     double alpha, double dt) {
+    using T = AdvTile<N>;
+    using L = AdvSmem<N>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    uint16_t *wl_all = reinterpret_cast<uint16_t *>(smem_raw + sizeof(double) * L::NDOUBLES);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // brick origin (cells) and first staged node (one below)
+    const int b0[3] = {(int)blockIdx.x * T::TX, (int)blockIdx.y * T::TY, N == 3 ? (int)blockIdx.z * T::TZ : 0};
+    const int c0[3] = {b0[0] - 1, b0[1] - 1, N == 3 ? b0[2] - 1 : 0};
+
+    // ---- 1. stage velocity stencils and grid-vector segments
+    for (int c = 0; c < N; c++) {
+        const double *__restrict__ F = V.p[c];
+        const int n0 = g.nvel[c][0], n1 = g.nvel[c][1], n2 = N == 3 ? g.nvel[c][2] : 1;
+        for (int t = tid; t < T::VOL; t += T::NW * 32) {
+            const int ix = t % T::EX, iy = (t / T::EX) % T::EY, iz = t / (T::EX * T::EY);
+            const int gx = c0[0] + ix, gy = c0[1] + iy, gz = N == 3 ? c0[2] + iz : 0;
+            double val = 0.0;
+            if (gx >= 0 && gx < n0 && gy >= 0 && gy < n1 && gz >= 0 && gz < n2)
+                val = F[gx + (int64_t)n0 * (gy + (int64_t)n1 * gz)];
+            sm[L::V_OFF + c * T::VOL + t] = val;
+        }
+    }
+    if (tid < 3 * L::VEC) {
+        const int d = tid / L::VEC, j = tid % L::VEC;
+        if (d < N) {
+            const int gi = c0[d] + j;
+            sm[L::XV_OFF + tid] = (gi >= 0 && gi <= g.n[d]) ? g.xv[d][gi] : NAN;
+            sm[L::XG_OFF + tid] = (gi >= 0 && gi <= g.n[d] + 1) ? g.xg[d][gi] : NAN;
+            if (!UNIFORM) {
+                sm[L::IXV_OFF + tid] = (gi >= 0 && gi < g.n[d]) ? g.ixv[d][gi] : NAN;
+                sm[L::IXG_OFF + tid] = (gi >= 0 && gi <= g.n[d]) ? g.ixg[d][gi] : NAN;
+            }
+        }
+    }
+
+    // ---- 2. this warp's x-run of cells: occupancy masks -> compacted work list
+    const int wy = warp % T::TY, wz = warp / T::TY;
+    const int cy = b0[1] + wy, cz = b0[2] + wz;
+    const int cx = b0[0] + lane;
+    const bool row_ok = cy < g.n[1] && (N == 2 || cz < g.n[2]);
+    const bool ok = row_ok && cx < g.n[0];
+    const int64_t crow = (int64_t)g.n[0] * (cy + (N == 3 ? (int64_t)g.n[1] * cz : 0));   // linear index of cell (0, cy, cz)
+    uint64_t m = 0;
+    if (ok) {
+        const uint8_t *ip = index + crow + cx;
+#pragma unroll 8
+        for (int s = 0; s < g.S; s++) m |= (uint64_t)(ip[(int64_t)s * g.C] != 0) << s;
+    }
+    uint16_t *wl = wl_all + warp * 32 * g.S;
+    int count = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        if (live) wl[count + __popc(bal & lt)] = (uint16_t)((s << 5) | lane);
+        count += __popc(bal);
+    }
+    __syncthreads();                      // stencils staged (all warps) + list visible
+
+    // ---- 3. consume the list 32 particles at a time
+    const double *Vp[3] = {V.p[0], V.p[1], V.p[2]};
+    for (int k0 = 0; k0 < count; k0 += 32) {
+        const int k = k0 + lane;
+        if (k < count) {
+            const int ent = wl[k];
+            const int s = ent >> 5, l = ent & 31;
+            const int64_t e = crow + b0[0] + l + (int64_t)s * g.C;
+            const int r0[3] = {l + 1, wy + 1, wz + 1};
+            const int cell1[3] = {b0[0] + l + 1, cy + 1, cz + 1};
+            double p0[3], k1[3], k2[3], q[3], pn[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) p0[d] = co.p[d][e];
+            adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, p0, k1);
+            if (SCHEME == 0) {
+                const double cdt = 1.0 * dt;
+#pragma unroll
+                for (int d = 0; d < N; d++) pn[d] = fma(cdt, k1[d], p0[d]);
+            } else if (SCHEME == 1) {
+                const double cdt = (1.0 * alpha) * dt;
+#pragma unroll
+                for (int d = 0; d < N; d++) q[d] = fma(cdt, k1[d], p0[d]);
+                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k2);
+                if (alpha == 0.5) {
+#pragma unroll
+                    for (int d = 0; d < N; d++) pn[d] = fma(1.0 * dt, k2[d], p0[d]);
+                } else {
+                    const double bb = 0.5 * (1.0 / alpha), aa = 1.0 - bb;
+#pragma unroll
+                    for (int d = 0; d < N; d++) pn[d] = fma(1.0 * dt, fma(bb, k2[d], aa * k1[d]), p0[d]);
+                }
+            } else {
+                double k3[3], k4[3];
+#pragma unroll
+                for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k1[d] / 2;
+                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k2);
+#pragma unroll
+                for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k2[d] / 2;
+                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k3);
+#pragma unroll
+                for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k3[d];
+                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k4);
+#pragma unroll
+                for (int d = 0; d < N; d++) pn[d] = p0[d] + dt * (((k1[d] + 2 * k2[d]) + 2 * k3[d]) + k4[d]) / 6;
+            }
+#pragma unroll
+            for (int d = 0; d < N; d++) co.p[d][e] = pn[d];
+        }
+    }
+}
+
+// true when xvel[c][d] is the vertex vector for c == d and the ghosted-centre vector otherwise
+static inline bool jp_standard_staggering(const JpGrid &g) {
+    if (!g.fast) return false;
+    for (int c = 0; c < g.ndim; c++)
+        for (int d = 0; d < g.ndim; d++) {
+            if (g.vkind[c][d] != (c == d ? 1 : 2)) return false;
+            if (c != d && !g.xg[d]) return false;
+        }
+    return true;
+}

@@ -47,6 +47,8 @@ struct jp_ctx {
 struct Ptr3 { double *p[3]; };
 struct CPtr3 { const double *p[3]; };
 
+#include "jp_advect_tile.cuh"
+
 // ---------------------------------------------------------------------------
 // thread <-> cell mapping shared by all cell kernels: 32 x 8 tiles, z = blockIdx.z
 #define JP_BX 32
@@ -405,10 +407,11 @@ __global__ void __launch_bounds__(256) k_p2g(JpGrid g, CPtr3 co, const uint8_t *
 // reference's (k, j, i) order.  Same terms as the reference, fixed order, but the
 // association is (cell sums) + ... instead of one running chain: results agree with
 // the reference to a few ulp (stated tolerance 1e-12), not bit-for-bit.
-template <int N>
+template <int N, bool FASTW>
 __global__ void __launch_bounds__(256) k_p2g_cell(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, const double *__restrict__ Fp,
                                                   double *__restrict__ PW, double *__restrict__ PWF) {
     constexpr int NQ = N == 2 ? 4 : 8;
+    constexpr int U = 4;                       // slots per batch: loads of a batch are issued together
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
@@ -418,27 +421,37 @@ __global__ void __launch_bounds__(256) k_p2g_cell(JpGrid g, CPtr3 co, const uint
     double aw[NQ], awf[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) { aw[q] = 0.0; awf[q] = 0.0; }
-    for (int s = 0; s < g.S; s++) {
-        const bool live = (m >> s) & 1ull;
-        if (!__any_sync(0xffffffffu, live)) continue;
-        if (live) {
-            const int64_t e = c + (int64_t)s * g.C;
-            double d2[3][2];
+    for (int s0 = 0; s0 < g.S; s0 += U) {
+        const unsigned bits = (unsigned)(m >> s0) & ((1u << U) - 1u);
+        if (!__any_sync(0xffffffffu, bits != 0)) continue;
+        double pp[U][3], ff[U];
 #pragma unroll
-            for (int d = 0; d < N; d++) {
-                const double pd = co.p[d][e];
-                const double a0 = xn[d][0] - pd, a1 = xn[d][1] - pd;
-                d2[d][0] = a0 * a0; d2[d][1] = a1 * a1;
-            }
-            const double f = Fp[e];
+        for (int u = 0; u < U; u++) {
+            const int64_t e = c + (int64_t)(s0 + u) * g.C;
+            const bool live = (bits >> u) & 1u;
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                double ss = d2[0][q & 1] + d2[1][(q >> 1) & 1];
-                if (N == 3) ss = ss + d2[2][(q >> 2) & 1];
-                const double dist = sqrt(ss);
-                const double wi = 1.0 / (dist * dist);
-                aw[q] += wi;
-                awf[q] = fma(wi, f, awf[q]);
+            for (int d = 0; d < N; d++) pp[u][d] = live ? co.p[d][e] : 0.0;
+            ff[u] = live ? Fp[e] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if ((bits >> u) & 1u) {
+                double d2[3][2];
+#pragma unroll
+                for (int d = 0; d < N; d++) {
+                    const double a0 = xn[d][0] - pp[u][d], a1 = xn[d][1] - pp[u][d];
+                    d2[d][0] = a0 * a0; d2[d][1] = a1 * a1;
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    double ss = d2[0][q & 1] + d2[1][(q >> 1) & 1];
+                    if (N == 3) ss = ss + d2[2][(q >> 2) & 1];
+                    double wi;
+                    if (FASTW) wi = 1.0 / ss;
+                    else { const double dist = sqrt(ss); wi = 1.0 / (dist * dist); }
+                    aw[q] += wi;
+                    awf[q] = fma(wi, ff[u], awf[q]);
+                }
             }
         }
     }
@@ -495,26 +508,38 @@ __global__ void __launch_bounds__(256) k_p2c(JpGrid g, CPtr3 co, double *__restr
     Fc[c] = N == 2 ? wF / w : wF * (1.0 / w);
 }
 
-// phase_ratios_center!
+// phase_ratios_center!  Liveness is the reference's isnan(px) test, so px of EVERY slot
+// is read; slots are processed in batches of U with the loads of a batch in flight together.
 template <int N, int KMAX>
 __global__ void __launch_bounds__(256) k_phase(JpGrid g, CPtr3 co, double *__restrict__ ratios, const double *__restrict__ phases, int K) {
+    constexpr int U = 8;
     int ci[3]; int64_t c;
     if (!tile_cell<N>(g, ci, c)) return;
     double xcn[3], idi[3], w[KMAX];
     for (int d = 0; d < N; d++) { xcn[d] = g.xc[d][ci[d]]; idi[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
 #pragma unroll
     for (int k = 0; k < KMAX; k++) w[k] = 0.0;
-    for (int s = 0; s < g.S; s++) {
-        const int64_t e = c + (int64_t)s * g.C;
-        double p[3];
+    for (int s0 = 0; s0 < g.S; s0 += U) {
+        double px[U], py[U], pz[U], ph[U];
 #pragma unroll
-        for (int d = 0; d < N; d++) p[d] = co.p[d][e];
-        if (isnan(p[0])) continue;
-        const double x = jp_bilinear_weight<N>(xcn, p, idi);
-        const double ph = phases[e];
+        for (int u = 0; u < U; u++) px[u] = (s0 + u < g.S) ? co.p[0][c + (int64_t)(s0 + u) * g.C] : NAN;
 #pragma unroll
-        for (int k = 0; k < KMAX; k++)
-            if (k < K) w[k] = w[k] + (ph == (double)(k + 1) ? x : copysign(0.0, x));
+        for (int u = 0; u < U; u++) {
+            const bool live = !isnan(px[u]);
+            const int64_t e = c + (int64_t)(s0 + u) * g.C;
+            py[u] = live ? co.p[1][e] : 0.0;
+            pz[u] = (N == 3 && live) ? co.p[2][e] : 0.0;
+            ph[u] = live ? phases[e] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (isnan(px[u])) continue;
+            const double p[3] = {px[u], py[u], pz[u]};
+            const double x = jp_bilinear_weight<N>(xcn, p, idi);
+#pragma unroll
+            for (int k = 0; k < KMAX; k++)
+                if (k < K) w[k] = w[k] + (ph[u] == (double)(k + 1) ? x : copysign(0.0, x));
+        }
     }
     double sum = w[0];
 #pragma unroll
@@ -631,12 +656,32 @@ extern "C" int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxc
     return JP_OK;
 }
 
+template <int N, int SCHEME, bool UNIFORM>
+static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
+    using T = AdvTile<N>;
+    const size_t smem = AdvSmem<N>::bytes(g.S);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdvSmem<N>::bytes(JP_MAX_SLOTS));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const dim3 grd((g.n[0] + T::TX - 1) / T::TX, (g.n[1] + T::TY - 1) / T::TY, N == 3 ? (g.n[2] + T::TZ - 1) / T::TZ : 1);
+    k_advect_tile<N, SCHEME, UNIFORM><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt);
+    return cudaSuccess;
+}
+
 template <int N, int SCHEME>
-static void launch_advect(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
+static cudaError_t launch_advect(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
+    if (jp_standard_staggering(g)) {
+        return g.uniform ? launch_advect_tile<N, SCHEME, true>(g, st, co, index, V, alpha, dt)
+                         : launch_advect_tile<N, SCHEME, false>(g, st, co, index, V, alpha, dt);
+    }
     if (g.fast) {
         if (g.uniform) k_advect<N, SCHEME, true, true><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
         else           k_advect<N, SCHEME, true, false><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
     } else             k_advect<N, SCHEME, false, false><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
+    return cudaSuccess;
 }
 
 extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt, void *stream) {
@@ -649,15 +694,17 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
     }
     if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect: Only 0 < alpha < 1 is supported");
     if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect: unknown integrator");
+    cudaError_t le;
     if (g.ndim == 2) {
-        if (scheme == 0) launch_advect<2, 0>(g, grd, blk, st, co, p->index, v, alpha, dt);
-        else if (scheme == 1) launch_advect<2, 1>(g, grd, blk, st, co, p->index, v, alpha, dt);
-        else launch_advect<2, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        if (scheme == 0) le = launch_advect<2, 0>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        else if (scheme == 1) le = launch_advect<2, 1>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        else le = launch_advect<2, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
     } else {
-        if (scheme == 0) launch_advect<3, 0>(g, grd, blk, st, co, p->index, v, alpha, dt);
-        else if (scheme == 1) launch_advect<3, 1>(g, grd, blk, st, co, p->index, v, alpha, dt);
-        else launch_advect<3, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        if (scheme == 0) le = launch_advect<3, 0>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        else if (scheme == 1) le = launch_advect<3, 1>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        else le = launch_advect<3, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
     }
+    if (le != cudaSuccess) return jp_fail(JP_ERR_CUDA, "jp_advect: %s", cudaGetErrorString(le));
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -759,7 +806,7 @@ extern "C" int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *
 
 extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_set_option: null context");
-    if (option == JP_OPT_P2G_MODE && (value == JP_P2G_EXACT || value == JP_P2G_TWOPASS)) { ctx->p2g_mode = value; return JP_OK; }
+    if (option == JP_OPT_P2G_MODE && (value == JP_P2G_EXACT || value == JP_P2G_TWOPASS || value == JP_P2G_TWOPASS_FASTW)) { ctx->p2g_mode = value; return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
 }
 
@@ -774,11 +821,14 @@ extern "C" int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, c
         const int NQ = g.ndim == 2 ? 4 : 8;
         if (!ctx->p2g_ws) JP_CUDA(cudaMalloc(&ctx->p2g_ws, sizeof(double) * 2 * NQ * g.C));
         double *PW = ctx->p2g_ws, *PWF = ctx->p2g_ws + (int64_t)NQ * g.C;
+        const bool fw = ctx->p2g_mode == JP_P2G_TWOPASS_FASTW;
         if (g.ndim == 2) {
-            k_p2g_cell<2><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
+            if (fw) k_p2g_cell<2, true><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
+            else    k_p2g_cell<2, false><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
             k_p2g_node<2><<<ng, blk, 0, st>>>(g, PW, PWF, F);
         } else {
-            k_p2g_cell<3><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
+            if (fw) k_p2g_cell<3, true><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
+            else    k_p2g_cell<3, false><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
             k_p2g_node<3><<<ng, blk, 0, st>>>(g, PW, PWF, F);
         }
     }

@@ -127,6 +127,9 @@ def test_interpolations(g):
     T3 = torch.empty_like(Td)
     J.particle2grid(T3, pT, t.p, mode="twopass")
     assert_close(T3, oT2, "particle2grid (two-pass mode)")
+    T5 = torch.empty_like(Td)
+    J.particle2grid(T5, pT, t.p, mode="twopass_fastw")
+    assert_close(T5, oT2, "particle2grid (two-pass, fast weights)")
     T4 = torch.empty_like(Td)
     J.particle2grid(T4, pT, t.p, mode="twopass")
     assert torch.equal(T3, T4), "two-pass particle2grid must be deterministic run to run"
