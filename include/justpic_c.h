@@ -47,7 +47,8 @@ typedef enum {
 } jp_status;
 
 typedef enum { JP_EULER = 0, JP_RK2 = 1, JP_RK4 = 2 } jp_scheme;
-typedef enum { JP_OPT_P2G_MODE = 1 } jp_option;
+typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2 } jp_option;
+typedef enum { JP_MOVE_AUTO = 0, JP_MOVE_DIRECT = 1 } jp_move_mode;
 typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;
 
 /* Grid description (HOST pointers).  Mirrors the grid part of the reference's
@@ -95,11 +96,17 @@ int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha,
               const double *const *V, double dt, void *stream);
 
 /* move_particles!(particles, args) (src/Particles/move_safe.jl:21-125).
- * Bit-exact with the reference's 3^N colour sweeps for displacements <= 1 cell. */
+ * Slot assignment bit-exact with the reference's 3^N colour sweeps (for displacements
+ * <= 1 cell; larger ones are racy in the reference itself).  JP_MOVE_AUTO plans the
+ * sweeps on per-cell occupancy words and moves payloads in two streaming passes, and
+ * falls back to JP_MOVE_DIRECT (literal sweeps on the particle arrays) when a particle
+ * sits exactly on a cell face.  Synchronises `stream` internally (two 4-byte read-backs). */
 int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream);
 /* Counters of the last jp_move on this context: {moved, dropped (destination
  * full), deleted (left the domain)}.  Synchronises `stream`. */
 int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream);
+/* 0 = the last jp_move took the plan/gather/scatter path, 1 = direct sweeps. */
+int jp_last_move_path(const jp_ctx *ctx);
 
 /* inject_particles!(particles, args) (src/Particles/injection.jl:19-131).
  * RNG: Philox4x32-10 keyed (seed, step, cell, slot). */

@@ -15,6 +15,8 @@ JP_MAX_ARGS = 16
 JP_MAX_SLOTS = 64
 JP_MAX_PHASES = 32
 JP_OPT_P2G_MODE = 1
+JP_OPT_MOVE_MODE = 2
+JP_MOVE_AUTO, JP_MOVE_DIRECT = 0, 1
 JP_P2G_EXACT, JP_P2G_TWOPASS, JP_P2G_TWOPASS_FASTW = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
@@ -51,6 +53,7 @@ SYMBOLS = {
                             C.POINTER(C.c_void_p), C.c_double, C.c_void_p]),
     "jp_move": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "jp_move_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "jp_last_move_path": (C.c_int, [C.c_void_p]),
     "jp_inject": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                             C.c_uint64, C.c_uint32, C.c_void_p]),
     "jp_inject_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),

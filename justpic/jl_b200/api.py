@@ -50,6 +50,7 @@ class CUDABackend:
 
 
 _SYNC = False
+MOVE_MODE = "auto"      # module default for move_particles
 P2G_MODE = "twopass"   # module default for particle2grid (see its docstring)
 
 
@@ -327,12 +328,20 @@ def advection(particles: Particles, method, V, dt: float) -> None:
         _done()
 
 
-def move_particles(particles: Particles, args=()) -> None:
-    """``move_particles!(particles, args)`` (src/Particles/move_safe.jl:21-49)."""
+def move_particles(particles: Particles, args=(), mode: Optional[str] = None) -> None:
+    """``move_particles!(particles, args)`` (src/Particles/move_safe.jl:21-49).
+    ``mode``: "auto" (default: sweeps planned on occupancy words + streaming payload passes,
+    direct sweeps when a particle sits exactly on a face) or "direct" (always the literal
+    sweeps on the particle arrays).  Both give the reference's slot assignment bit for bit."""
     p = particles
     args = _args(args, p)
     pc = p._c()
+    m = (mode or MOVE_MODE).lower()
+    if m not in ("auto", "direct"):
+        raise ValueError("move_particles mode must be 'auto' or 'direct'")
     with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_MOVE_MODE,
+                                               _cabi.JP_MOVE_AUTO if m == "auto" else _cabi.JP_MOVE_DIRECT), "jp_set_option")
         _cabi.check(_cabi.load().jp_move(C.c_void_p(p._ctx), C.byref(pc), _ptr_array(args), len(args), _stream()),
                     "move_particles")
         _done()
@@ -344,6 +353,11 @@ def move_stats(particles: Particles) -> Tuple[int, int, int]:
     with torch.cuda.device(particles.device):
         _cabi.check(_cabi.load().jp_move_stats(C.c_void_p(particles._ctx), out, _stream()), "move_stats")
     return int(out[0]), int(out[1]), int(out[2])
+
+
+def last_move_path(particles: Particles) -> str:
+    """"plan" or "direct": which implementation the last ``move_particles`` call took."""
+    return "plan" if _cabi.load().jp_last_move_path(C.c_void_p(particles._ctx)) == 0 else "direct"
 
 
 def inject_particles(particles: Particles, args=(), step: Optional[int] = None) -> None:

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <cub/device/device_scan.cuh>
 
 #include "../../../include/justpic_c.h"
 #include "jp_core.h"
@@ -33,6 +34,17 @@ static int jp_fail(int code, const char *fmt, const char *detail = "") {
 extern "C" const char *jp_last_error(void) { return g_err; }
 extern "C" int jp_version(void) { return 100; }
 
+struct MovePlanWs {
+    uint64_t *occ;        // [C] running occupancy (plan) -> final occupancy
+    uint64_t *leave;      // [C] slots vacated by the move (original leavers)
+    uint64_t *code;       // [2][C] packed 5-bit destination codes, slot order
+    uint64_t *arr;        // [NP][C] arrival lists; plane 0 holds the count in bits 56..62
+    uint64_t *arrmask;    // [C] slots receiving an arrival
+    uint32_t *cnt;        // [C] arrivals per cell
+    uint32_t *off;        // [C] exclusive scan of cnt
+    int np;               // planes in arr
+};
+
 struct jp_ctx {
     int device;
     JpGrid g;             // device pointers
@@ -41,7 +53,14 @@ struct jp_ctx {
     uint8_t *flag;        // [C] inject candidate flags
     long long *stats;     // device counters: [0..2] move, [3] inject
     double *p2g_ws;       // [2 * 2^N * C] per-cell partial sums of the two-pass particle2grid (lazy)
-    int p2g_mode;         // JP_P2G_EXACT / JP_P2G_TWOPASS
+    int p2g_mode;         // JP_P2G_EXACT / JP_P2G_TWOPASS / JP_P2G_TWOPASS_FASTW
+    int move_mode;        // JP_MOVE_AUTO (plan/gather/scatter, direct sweeps on ties) / JP_MOVE_DIRECT
+    int last_move_path;   // 0 = plan, 1 = direct (diagnostics)
+    MovePlanWs mp;        // plan workspace (lazy); occ/leave alias the fields above
+    unsigned int *mp_flag;   // device: "complex" flag
+    void *cub_tmp; size_t cub_tmp_bytes;
+    double *stage; size_t stage_elems;   // staging buffer (grow-only)
+    unsigned int *h_pinned;  // pinned host scratch for flag / totals
 };
 
 struct Ptr3 { double *p[3]; };
@@ -73,6 +92,8 @@ __device__ __forceinline__ uint64_t load_mask(const uint8_t *__restrict__ index,
     }
     return m;
 }
+
+#include "jp_move_plan.cuh"
 
 // ---------------------------------------------------------------------------
 template <int N>
@@ -612,6 +633,9 @@ extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->flag); cudaFree(ctx->stats);
     cudaFree(ctx->p2g_ws);
+    cudaFree(ctx->mp.code); cudaFree(ctx->mp.arr); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
+    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     free(ctx);
 }
 
@@ -709,12 +733,94 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
     return JP_OK;
 }
 
+static int move_plan_alloc(jp_ctx *ctx) {
+    const JpGrid &g = ctx->g;
+    if (ctx->mp.code) return JP_OK;
+    const int np = (g.S + 2) / 3;
+    JP_CUDA(cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * 2 * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.arr, sizeof(uint64_t) * (size_t)np * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.arrmask, sizeof(uint64_t) * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.cnt, sizeof(uint32_t) * (g.C + 1)));
+    JP_CUDA(cudaMalloc(&ctx->mp.off, sizeof(uint32_t) * (g.C + 1)));
+    JP_CUDA(cudaMemset(ctx->mp.cnt, 0, sizeof(uint32_t) * (g.C + 1)));
+    JP_CUDA(cudaMalloc(&ctx->mp_flag, sizeof(unsigned int)));
+    JP_CUDA(cudaMallocHost(&ctx->h_pinned, 4 * sizeof(unsigned int)));
+    ctx->mp.occ = ctx->occ; ctx->mp.leave = ctx->leave; ctx->mp.np = np;
+    size_t tmp = 0;
+    JP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->mp.cnt, ctx->mp.off, (int)(g.C + 1)));
+    JP_CUDA(cudaMalloc(&ctx->cub_tmp, tmp));
+    ctx->cub_tmp_bytes = tmp;
+    return JP_OK;
+}
+
+// plan / gather / scatter path; returns 1 when the call must take the direct sweeps instead
+template <int N>
+static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cudaStream_t st) {
+    const JpGrid &g = ctx->g;
+    int rc = move_plan_alloc(ctx);
+    if (rc) return rc;
+    const dim3 blk(JP_BX, JP_BY, 1);
+    const dim3 grd = tile_grid(g.n[0], g.n[1], g.n[2]);
+    CPtr3 cco = {{p->coords[0], p->coords[1], p->coords[2]}};
+    JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
+    k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
+    JP_CHECK_LAUNCH();
+    JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->mp_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    JP_CUDA(cudaStreamSynchronize(st));
+    if (ctx->h_pinned[0]) return 1;                       // ties / far moves / overfull leave list: direct sweeps
+    const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = N == 3 ? (g.n[2] + 2) / 3 : 1;
+    const int64_t ncol = (int64_t)ncx * ncy * ncz;
+    const unsigned nblk = (unsigned)((ncol + 255) / 256);
+    for (int ox = 0; ox < 3; ox++)
+        for (int oy = 0; oy < 3; oy++)
+            for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
+                k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats);
+    const unsigned cblk = (unsigned)((g.C + 255) / 256);
+    k_move_finalize<N><<<cblk, 256, 0, st>>>(g, ctx->mp);
+    JP_CHECK_LAUNCH();
+    JP_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, ctx->cub_tmp_bytes, ctx->mp.cnt, ctx->mp.off, (int)(g.C + 1), st));
+    k_move_set_moved<<<1, 1, 0, st>>>(ctx->stats, ctx->mp.off + g.C);
+    JP_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->mp.off + g.C, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    JP_CUDA(cudaStreamSynchronize(st));
+    const size_t M = ctx->h_pinned[1];
+    if (M == 0) {                                        // nothing arrives; still vacate deleted / dropped slots
+        MoveArrays arrs; arrs.n = 0;
+        for (int d = 0; d < N; d++) arrs.a[arrs.n++] = p->coords[d];
+        for (int i = 0; i < a.n; i++) arrs.a[arrs.n++] = a.a[i];
+        k_move_scatter<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, p->index, ctx->stage, 0);
+        JP_CHECK_LAUNCH();
+        return JP_OK;
+    }
+    MoveArrays arrs; arrs.n = 0;
+    for (int d = 0; d < N; d++) arrs.a[arrs.n++] = p->coords[d];
+    for (int i = 0; i < a.n; i++) arrs.a[arrs.n++] = a.a[i];
+    const size_t need = M * (size_t)arrs.n;
+    if (need > ctx->stage_elems) {
+        if (ctx->stage) JP_CUDA(cudaFree(ctx->stage));
+        ctx->stage = nullptr; ctx->stage_elems = 0;
+        const size_t want = need + need / 4;
+        JP_CUDA(cudaMalloc(&ctx->stage, want * sizeof(double)));
+        ctx->stage_elems = want;
+    }
+    const int64_t stride = (int64_t)(ctx->stage_elems / arrs.n);
+    k_move_gather<N><<<cblk, 256, 0, st>>>(g, ctx->mp, arrs, ctx->stage, stride);
+    k_move_scatter<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, p->index, ctx->stage, stride);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
 extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream) {
     PREP("jp_move");
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_move");
     if (rc) return rc;
     JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
+    if (ctx->move_mode == JP_MOVE_AUTO) {
+        rc = g.ndim == 2 ? move_planned<2>(ctx, p, a, st) : move_planned<3>(ctx, p, a, st);
+        if (rc <= 0) { ctx->last_move_path = 0; return rc; }
+        JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
+    }
+    ctx->last_move_path = 1;
     if (g.ndim == 2) k_move_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
     else             k_move_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
     JP_CHECK_LAUNCH();
@@ -730,6 +836,8 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
+
+extern "C" int jp_last_move_path(const jp_ctx *ctx) { return ctx ? ctx->last_move_path : -1; }
 
 extern "C" int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream) {
     if (!ctx || !out) return jp_fail(JP_ERR_INVALID, "jp_move_stats: null argument");
@@ -806,6 +914,7 @@ extern "C" int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *
 
 extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_set_option: null context");
+    if (option == JP_OPT_MOVE_MODE && (value == JP_MOVE_AUTO || value == JP_MOVE_DIRECT)) { ctx->move_mode = value; return JP_OK; }
     if (option == JP_OPT_P2G_MODE && (value == JP_P2G_EXACT || value == JP_P2G_TWOPASS || value == JP_P2G_TWOPASS_FASTW)) { ctx->p2g_mode = value; return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
 }

@@ -155,9 +155,12 @@ def test_phase_ratios_center(g, K):
     np.testing.assert_allclose(host(pr.center).sum(axis=0), 1.0, rtol=1e-14)
 
 
-@pytest.mark.parametrize("g", GRIDS + [(2, 17, True), (3, (7, 5, 6), True)], ids=ids)
-def test_trajectory_advect_move_inject(g):
-    """L2 protocol: coupled steps; any divergence shows up at the first differing call."""
+@pytest.mark.parametrize("move_mode", ["auto", "direct"])
+@pytest.mark.parametrize("g", GRIDS + [(2, 17, True), (3, (7, 5, 6), True), (2, (40, 9), True)], ids=ids)
+def test_trajectory_advect_move_inject(g, move_mode):
+    """L2 protocol: coupled steps; any divergence shows up at the first differing call.
+    Both move implementations (planned sweeps + streaming payload passes, and the direct
+    literal sweeps) must reproduce the reference's slot assignment bit for bit."""
     J = jp()
     tight = g in [(2, 17, True)]
     t = Twin(*g, nxcell=12, max_xcell=12 if tight else 24, min_xcell=6 if tight else 8)
@@ -176,9 +179,10 @@ def test_trajectory_advect_move_inject(g):
         m = methods[it % 4]
         J.advection(t.p, m[0], Vd, dt); t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
         t.check_state(f"step {it} advection")
-        J.move_particles(t.p, (pT, ph)); st = t.o.move(t.co, t.idx, [opT, oph])
-        t.check_state(f"step {it} move_particles", (pT, ph), (opT, oph))
+        J.move_particles(t.p, (pT, ph), mode=move_mode); st = t.o.move(t.co, t.idx, [opT, oph])
+        t.check_state(f"step {it} move_particles[{move_mode}]", (pT, ph), (opT, oph))
         assert J.move_stats(t.p) == st
+        assert J.last_move_path(t.p) == ("plan" if move_mode == "auto" else "direct")
         J.inject_particles(t.p, (pT, ph), step=it); inj = t.o.inject(t.co, t.idx, [opT, oph], t.min_xcell, t.seed, it)
         t.check_state(f"step {it} inject_particles", (pT, ph), (opT, oph))
         assert J.inject_stats(t.p) == inj
@@ -228,6 +232,8 @@ def test_ties_nan_inf_and_clean(ndim):
         J.move_particles(t.p, (pT,)); st = t.o.move(t.co, t.idx, [opT])
         t.check_state(f"ties move {it}", (pT,), (opT,))
         assert J.move_stats(t.p) == st
+        if it == 0:
+            assert J.last_move_path(t.p) == "direct"      # particles exactly on faces: literal sweeps
         J.inject_particles(t.p, (pT,), step=it); t.o.inject(t.co, t.idx, [opT], 8, 5, it)
         t.check_state(f"ties inject {it}", (pT,), (opT,))
 
