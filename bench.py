@@ -266,6 +266,7 @@ def run_ours(args):
     live = int(p.index.sum().item())
     step()
     moved, dropped, deleted = J.move_stats(p)
+    move_path = J.last_move_path(p)
     f_mig = (moved + dropped + deleted) / max(live, 1)
     # particles processed per step ~ live count (changes by drops only); use mean of start/end
     updates = 0.5 * (live0 + live) * args.steps
@@ -328,7 +329,7 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, world), "cells_per_gpu": n ** 3, "live_particles_per_gpu": int(nlive_mean),
-                       "migrant_fraction": round(f_mig, 4), "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
+                       "migrant_fraction": round(f_mig, 4), "move_path": move_path, "dropped_per_step": dropped, "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
                        "topology": list(topo.dims)},
             "gpu_launches": args.steps * (1 + 28 + 1 + 1 + (6 * sum(1 for d in topo.dims if d > 1) if world > 1 else 0)),
             "phase_ms": per_phase,

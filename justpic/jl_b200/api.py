@@ -357,7 +357,13 @@ def move_stats(particles: Particles) -> Tuple[int, int, int]:
 
 def last_move_path(particles: Particles) -> str:
     """"plan" or "direct": which implementation the last ``move_particles`` call took."""
-    return "plan" if _cabi.load().jp_last_move_path(C.c_void_p(particles._ctx)) == 0 else "direct"
+    return "plan" if (_cabi.load().jp_last_move_path(C.c_void_p(particles._ctx)) & 0xff) == 0 else "direct"
+
+
+def last_move_reasons(particles: Particles) -> int:
+    """Why the last move fell back to the direct sweeps (bit mask: 1 displacement > 1 cell, 2 particle on a
+    face of its own cell, 4 particle on a face of its destination, 8 more than 24 leavers in one cell)."""
+    return _cabi.load().jp_last_move_path(C.c_void_p(particles._ctx)) >> 8
 
 
 def inject_particles(particles: Particles, args=(), step: Optional[int] = None) -> None:

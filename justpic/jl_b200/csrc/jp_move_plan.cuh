@@ -16,12 +16,12 @@
 //  B. k_move_plan x 3^N (ordered, same colour order as the reference; touches
 //     8-byte words only): literal slot logic -- vacate in slot order, first free
 //     slot >= cursor, cursor shared across destinations, drop when full -- on the
-//     occupancy words; every placement is appended to the destination cell's
-//     arrival list (17-bit entries: dest slot, direction, source slot).
-//  C. k_move_finalize + exclusive scan: arrival mask / count per cell -> offsets
-//     into a compact staging buffer (ordered by destination cell, then slot).
-//  D. k_move_gather: every arrival's payload (coords + fields) is read from its
-//     source slot (neighbouring cell: L1/L2-local) into staging.
+//     occupancy words; the slot given to each leaver is recorded (7 bits each).
+//  C. k_move_finalize + exclusive scan: arrival mask (= final occupancy minus the
+//     original occupants that stayed) / count per cell -> offsets into a compact
+//     staging buffer (ordered by destination cell, then slot).
+//  D. k_move_gather (source-centric, slot-synchronous, streaming): every placed
+//     leaver's payload (coords + fields) -> staging.
 //  E. k_move_scatter: one coalesced slot-synchronous pass writes arrivals from
 //     staging, NaN into vacated slots that stayed empty, and the mask bytes;
 //     x-adjacent lanes hit the same 32-byte sectors in the same instruction.
@@ -45,6 +45,10 @@ __device__ __forceinline__ void jp_code_dir(int code, int *dv) {
 }
 
 // ---- A. classify
+// Destination by comparisons against the four vertices around the storage cell:
+// a particle strictly inside (xv[j], xv[j+1]) for j in {i-1, i, i+1} is exactly where the
+// reference's seeded bisection puts it; anything else (on a vertex, further away) is
+// left to the direct sweeps.
 template <int N>
 __global__ void __launch_bounds__(256) k_move_classify2(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
                                                         unsigned int *complex_flag) {
@@ -53,12 +57,17 @@ __global__ void __launch_bounds__(256) k_move_classify2(JpGrid g, CPtr3 co, cons
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
     uint64_t lv = 0, code0 = 0, code1 = 0;
     int nl = 0;
-    bool cplx = false;
-    double corner[3], dx[3], lo[3], hi[3];
+    unsigned cplx = 0;     // reason bits: 1 far, 2 same cell (tie), 4 fails isincell in destination, 8 > 24 leavers
+    double am[3], a[3], b[3], bp[3], dx[3], lo[3], hi[3];
     if (ok)
         for (int d = 0; d < N; d++) {
-            corner[d] = g.xv[d][ci[d]]; dx[d] = jp_d_of(g.xv[d], g.uniform, ci[d]);
-            lo[d] = g.xv[d][0]; hi[d] = g.xv[d][g.n[d]];
+            const double *xv = g.xv[d];
+            const int i = ci[d];
+            a[d] = xv[i]; b[d] = xv[i + 1];
+            am[d] = i > 0 ? xv[i - 1] : NAN;
+            bp[d] = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
+            dx[d] = jp_d_of(xv, g.uniform, i);
+            lo[d] = xv[0]; hi[d] = xv[g.n[d]];
         }
     for (int s = 0; s < g.S; s++) {
         const bool live = (m >> s) & 1ull;
@@ -68,7 +77,10 @@ __global__ void __launch_bounds__(256) k_move_classify2(JpGrid g, CPtr3 co, cons
             double p[3];
 #pragma unroll
             for (int d = 0; d < N; d++) p[d] = co.p[d][e];
-            if (!jp_isincell<N>(p, corner, dx)) {
+            bool incell = true;
+#pragma unroll
+            for (int d = 0; d < N; d++) incell = incell & (a[d] < p[d]) & (p[d] < a[d] + dx[d]);
+            if (!incell) {
                 lv |= 1ull << s;
                 bool indom = true;
 #pragma unroll
@@ -79,32 +91,36 @@ __global__ void __launch_bounds__(256) k_move_classify2(JpGrid g, CPtr3 co, cons
                     bool far = false, dest_ok = true;
 #pragma unroll
                     for (int d = 0; d < N; d++) {
-                        const int nc = jp_bisect1(p[d], g.xv[d], g.n[d] + 1, ci[d] + 1) - 1;
-                        dv[d] = nc - ci[d];
-                        far = far || dv[d] < -1 || dv[d] > 1;
-                        const double cd = g.xv[d][nc], dd = jp_d_of(g.xv[d], g.uniform, nc);
-                        dest_ok = dest_ok && (cd < p[d]) && (p[d] < cd + dd);
+                        const double pd = p[d];
+                        double lower, dxd;
+                        if (a[d] < pd && pd < b[d]) { dv[d] = 0; lower = a[d]; dxd = g.uniform ? dx[d] : b[d] - a[d]; }
+                        else if (am[d] < pd && pd < a[d]) { dv[d] = -1; lower = am[d]; dxd = g.uniform ? dx[d] : a[d] - am[d]; }
+                        else if (b[d] < pd && pd < bp[d]) { dv[d] = 1; lower = b[d]; dxd = g.uniform ? dx[d] : bp[d] - b[d]; }
+                        else { far = true; lower = a[d]; dxd = dx[d]; }        // on a vertex or more than one cell away
+                        dest_ok = dest_ok && (lower < pd) && (pd < lower + dxd);
                     }
                     const bool same = dv[0] == 0 && dv[1] == 0 && (N == 2 || dv[2] == 0);
-                    if (far || same || !dest_ok) cplx = true;
+                    if (far || same || !dest_ok) cplx |= (far ? 1u : 0u) | ((same && !far) ? 2u : 0u) | ((!dest_ok && !far) ? 4u : 0u);
                     else code = jp_dir_code(dv, N);
                 }
                 if (nl < 12) code0 |= (uint64_t)code << (5 * nl);
                 else if (nl < 24) code1 |= (uint64_t)code << (5 * (nl - 12));
-                else cplx = true;
+                else cplx |= 8u;
                 nl++;
             }
         }
     }
     if (ok) {
-        ws.occ[c] = m; ws.leave[c] = lv;
+        ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
         ws.code[c] = code0; ws.code[g.C + c] = code1;
-        ws.arr[c] = 0;                        // plane 0: count = 0, no entries
     }
-    if (__any_sync(0xffffffffu, cplx) && threadIdx.x == 0) atomicOr(complex_flag, 1u);
+    const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
+    if (wc && threadIdx.x == 0) atomicOr(complex_flag, wc);
 }
 
-// ---- B. one colour of the plan (thread = source cell; words only)
+// ---- B. one colour of the plan (thread = source cell; 8-byte words only).
+// Literal slot logic of move_kernel! (src/Particles/move_safe.jl:72-125) on the occupancy
+// words; the slot given to the k-th leaver goes to res (7 bits: slot | placed << 6).
 template <int N>
 __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
                                                    long long *stats) {
@@ -121,12 +137,13 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
     const uint64_t smask = g.S == 64 ? ~0ull : ((1ull << g.S) - 1);
     uint64_t occ_c = ws.occ[c];
     const uint64_t code0 = ws.code[c], code1 = ws.code[g.C + c];
+    uint64_t res[3] = {0, 0, 0};
     int cursor = 0, k = 0, n_dropped = 0, n_deleted = 0;
     while (lv) {
         const int ip = __ffsll((long long)lv) - 1;
         lv &= lv - 1;
         const int code = (int)((k < 12 ? code0 >> (5 * k) : code1 >> (5 * (k - 12))) & 31);
-        k++;
+        const int kk = k++;
         occ_c &= ~(1ull << ip);
         if (code == JP_CODE_DELETE) { n_deleted++; continue; }
         int dv[3];
@@ -138,67 +155,62 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
         const int fs = __ffsll((long long)freebits) - 1;
         cursor = fs;
         ws.occ[c2] = o2 | (1ull << fs);
-        // append (fs, direction, source slot) to the destination's arrival list
-        const uint64_t entry = (uint64_t)fs | ((uint64_t)code << 6) | ((uint64_t)ip << 11);
-        uint64_t w0 = ws.arr[c2];
-        const int na = (int)((w0 >> 56) & 127);
-        const int pl = na / 3, pos = na % 3;
-        w0 = (w0 & ~(127ull << 56)) | ((uint64_t)(na + 1) << 56);
-        if (pl == 0) ws.arr[c2] = w0 | (entry << (17 * pos));
-        else {
-            ws.arr[c2] = w0;
-            uint64_t *wp = &ws.arr[(int64_t)pl * g.C + c2];
-            *wp = pos == 0 ? entry : (*wp | (entry << (17 * pos)));
-        }
+        res[kk / 9] |= (uint64_t)(fs | 64) << (7 * (kk % 9));
     }
     ws.occ[c] = occ_c;
+    ws.res[c] = res[0];
+    if (k > 9) ws.res[g.C + c] = res[1];
+    if (k > 18) ws.res[2 * g.C + c] = res[2];
     if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
     if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);
 }
 
-__device__ __forceinline__ uint64_t jp_arr_entry(const MovePlanWs &ws, int64_t C, int64_t c, uint64_t w0, int k, uint64_t &wcur, int &plcur) {
-    const int pl = k / 3, pos = k % 3;
-    if (pl != plcur) { wcur = pl == 0 ? w0 : ws.arr[(int64_t)pl * C + c]; plcur = pl; }
-    return (wcur >> (17 * pos)) & 0x1ffffull;
-}
-
-// ---- C. arrival mask + count per cell
+// ---- C. arrival mask + count per cell: every slot occupied at the end that is not a
+// non-leaving original occupant holds an arrival.
 template <int N>
 __global__ void __launch_bounds__(256) k_move_finalize(JpGrid g, MovePlanWs ws) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.C) return;
-    const uint64_t w0 = ws.arr[c];
-    const int na = (int)((w0 >> 56) & 127);
-    uint64_t mask = 0, wcur = w0;
-    int plcur = 0;
-    for (int k = 0; k < na; k++) mask |= 1ull << (jp_arr_entry(ws, g.C, c, w0, k, wcur, plcur) & 63);
-    ws.arrmask[c] = mask;
-    ws.cnt[c] = (uint32_t)na;
+    const uint64_t am = ws.occ[c] & (~ws.occ0[c] | ws.leave[c]);
+    ws.arrmask[c] = am;
+    ws.cnt[c] = (uint32_t)__popcll(am);
 }
 
 struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 
-// ---- D. gather arrivals' payloads into staging (thread = destination cell)
+// ---- D. gather (source-centric, slot-synchronous => every source sector is read once, in
+// streaming order): payload of each placed leaver -> staging[off[dest] + rank of its slot]
 template <int N>
 __global__ void __launch_bounds__(256) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* staging stride */) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= g.C) return;
-    const uint64_t w0 = ws.arr[c];
-    const int na = (int)((w0 >> 56) & 127);
-    if (na == 0) return;
-    const uint64_t amask = ws.arrmask[c];
-    const int64_t base = ws.off[c];
-    uint64_t wcur = w0;
-    int plcur = 0;
-    for (int k = 0; k < na; k++) {
-        const uint64_t en = jp_arr_entry(ws, g.C, c, w0, k, wcur, plcur);
-        const int fs = (int)(en & 63), code = (int)((en >> 6) & 31), ip = (int)((en >> 11) & 63);
-        int dv[3];
-        jp_code_dir(code, dv);
-        const int64_t csrc = c - (dv[0] + (int64_t)g.n[0] * (dv[1] + (N == 3 ? (int64_t)g.n[1] * dv[2] : 0)));
-        const int64_t es = csrc + (int64_t)ip * g.C;
-        const int64_t pos = base + __popcll(amask & ((1ull << fs) - 1));
-        for (int a = 0; a < arrs.n; a++) stage[(int64_t)a * M + pos] = arrs.a[a][es];
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t lv = ok ? ws.leave[c] : 0;
+    if (!__any_sync(0xffffffffu, lv != 0)) return;
+    uint64_t code0 = 0, code1 = 0, res0 = 0, res1 = 0, res2 = 0;
+    const int nl = __popcll(lv);
+    if (lv) {
+        code0 = ws.code[c]; res0 = ws.res[c];
+        if (nl > 9) res1 = ws.res[g.C + c];
+        if (nl > 12) code1 = ws.code[g.C + c];
+        if (nl > 18) res2 = ws.res[2 * g.C + c];
+    }
+    for (int s = 0; s < g.S; s++) {
+        const bool lvs = (lv >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, lvs)) continue;
+        if (lvs) {
+            const int k = __popcll(lv & ((1ull << s) - 1));
+            const int r = (int)(((k < 9 ? res0 >> (7 * k) : k < 18 ? res1 >> (7 * (k - 9)) : res2 >> (7 * (k - 18)))) & 127);
+            if (r & 64) {
+                const int fs = r & 63;
+                const int code = (int)((k < 12 ? code0 >> (5 * k) : code1 >> (5 * (k - 12))) & 31);
+                int dv[3];
+                jp_code_dir(code, dv);
+                const int64_t c2 = c + dv[0] + (int64_t)g.n[0] * (dv[1] + (N == 3 ? (int64_t)g.n[1] * dv[2] : 0));
+                const int64_t pos = (int64_t)ws.off[c2] + __popcll(ws.arrmask[c2] & ((1ull << fs) - 1));
+                const int64_t e = c + (int64_t)s * g.C;
+                for (int a = 0; a < arrs.n; a++) stage[(int64_t)a * M + pos] = arrs.a[a][e];
+            }
+        }
     }
 }
 

@@ -36,13 +36,13 @@ extern "C" int jp_version(void) { return 100; }
 
 struct MovePlanWs {
     uint64_t *occ;        // [C] running occupancy (plan) -> final occupancy
+    uint64_t *occ0;       // [C] occupancy before the move
     uint64_t *leave;      // [C] slots vacated by the move (original leavers)
-    uint64_t *code;       // [2][C] packed 5-bit destination codes, slot order
-    uint64_t *arr;        // [NP][C] arrival lists; plane 0 holds the count in bits 56..62
+    uint64_t *code;       // [2][C] packed 5-bit destination codes of the leavers, slot order
+    uint64_t *res;        // [3][C] packed 7-bit results (dest slot | placed << 6), slot order
     uint64_t *arrmask;    // [C] slots receiving an arrival
-    uint32_t *cnt;        // [C] arrivals per cell
-    uint32_t *off;        // [C] exclusive scan of cnt
-    int np;               // planes in arr
+    uint32_t *cnt;        // [C+1] arrivals per cell
+    uint32_t *off;        // [C+1] exclusive scan of cnt (off[C] = total)
 };
 
 struct jp_ctx {
@@ -56,6 +56,7 @@ struct jp_ctx {
     int p2g_mode;         // JP_P2G_EXACT / JP_P2G_TWOPASS / JP_P2G_TWOPASS_FASTW
     int move_mode;        // JP_MOVE_AUTO (plan/gather/scatter, direct sweeps on ties) / JP_MOVE_DIRECT
     int last_move_path;   // 0 = plan, 1 = direct (diagnostics)
+    int last_complex;     // reason bits of the last classification (diagnostics)
     MovePlanWs mp;        // plan workspace (lazy); occ/leave alias the fields above
     unsigned int *mp_flag;   // device: "complex" flag
     void *cub_tmp; size_t cub_tmp_bytes;
@@ -633,7 +634,7 @@ extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->flag); cudaFree(ctx->stats);
     cudaFree(ctx->p2g_ws);
-    cudaFree(ctx->mp.code); cudaFree(ctx->mp.arr); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
+    cudaFree(ctx->mp.code); cudaFree(ctx->mp.res); cudaFree(ctx->mp.occ0); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
     cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     free(ctx);
@@ -736,16 +737,16 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
 static int move_plan_alloc(jp_ctx *ctx) {
     const JpGrid &g = ctx->g;
     if (ctx->mp.code) return JP_OK;
-    const int np = (g.S + 2) / 3;
     JP_CUDA(cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * 2 * g.C));
-    JP_CUDA(cudaMalloc(&ctx->mp.arr, sizeof(uint64_t) * (size_t)np * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.res, sizeof(uint64_t) * 3 * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.occ0, sizeof(uint64_t) * g.C));
     JP_CUDA(cudaMalloc(&ctx->mp.arrmask, sizeof(uint64_t) * g.C));
     JP_CUDA(cudaMalloc(&ctx->mp.cnt, sizeof(uint32_t) * (g.C + 1)));
     JP_CUDA(cudaMalloc(&ctx->mp.off, sizeof(uint32_t) * (g.C + 1)));
     JP_CUDA(cudaMemset(ctx->mp.cnt, 0, sizeof(uint32_t) * (g.C + 1)));
     JP_CUDA(cudaMalloc(&ctx->mp_flag, sizeof(unsigned int)));
     JP_CUDA(cudaMallocHost(&ctx->h_pinned, 4 * sizeof(unsigned int)));
-    ctx->mp.occ = ctx->occ; ctx->mp.leave = ctx->leave; ctx->mp.np = np;
+    ctx->mp.occ = ctx->occ; ctx->mp.leave = ctx->leave;
     size_t tmp = 0;
     JP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->mp.cnt, ctx->mp.off, (int)(g.C + 1)));
     JP_CUDA(cudaMalloc(&ctx->cub_tmp, tmp));
@@ -767,6 +768,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     JP_CHECK_LAUNCH();
     JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->mp_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     JP_CUDA(cudaStreamSynchronize(st));
+    ctx->last_complex = (int)ctx->h_pinned[0];
     if (ctx->h_pinned[0]) return 1;                       // ties / far moves / overfull leave list: direct sweeps
     const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = N == 3 ? (g.n[2] + 2) / 3 : 1;
     const int64_t ncol = (int64_t)ncx * ncy * ncz;
@@ -803,7 +805,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
         ctx->stage_elems = want;
     }
     const int64_t stride = (int64_t)(ctx->stage_elems / arrs.n);
-    k_move_gather<N><<<cblk, 256, 0, st>>>(g, ctx->mp, arrs, ctx->stage, stride);
+    k_move_gather<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, ctx->stage, stride);
     k_move_scatter<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, p->index, ctx->stage, stride);
     JP_CHECK_LAUNCH();
     return JP_OK;
@@ -837,7 +839,7 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     return JP_OK;
 }
 
-extern "C" int jp_last_move_path(const jp_ctx *ctx) { return ctx ? ctx->last_move_path : -1; }
+extern "C" int jp_last_move_path(const jp_ctx *ctx) { return ctx ? (ctx->last_move_path | (ctx->last_complex << 8)) : -1; }
 
 extern "C" int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream) {
     if (!ctx || !out) return jp_fail(JP_ERR_INVALID, "jp_move_stats: null argument");

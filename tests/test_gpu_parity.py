@@ -224,6 +224,19 @@ def test_ties_nan_inf_and_clean(ndim):
     for d in range(ndim):
         t.p.coords[d].copy_(pc[d])
     t.p.index.copy_(pi); pT.copy_(pa)
+    # move straight from the tie positions (both implementations), on copies
+    for mode in ("auto", "direct"):
+        c3 = [a.copy() for a in t.co]; i3 = t.idx.copy(); a3 = opT.copy()
+        st = t.o.move(c3, i3, [a3])
+        J.move_particles(t.p, (pT,), mode=mode)
+        for d in range(ndim):
+            assert_same(t.p.coords[d], c3[d], f"tie move[{mode}] coords")
+        assert_same(t.p.index, i3, f"tie move[{mode}] index"); assert_same(pT, a3, f"tie move[{mode}] args")
+        assert J.move_stats(t.p) == st and st[2] > 0
+        assert J.last_move_path(t.p) == "direct"          # particles exactly on faces: literal sweeps
+        for d in range(ndim):
+            t.p.coords[d].copy_(pc[d])
+        t.p.index.copy_(pi); pT.copy_(pa)
     V = stream_velocity(gr); Vd = [dev(v) for v in V]
     dt = cfl_dt(gr, V, 0.5)
     for it, m in enumerate([(J.RungeKutta2(), 1, 0.5), (J.RungeKutta4(), 2, 0.0), (J.Euler(), 0, 0.0)]):
@@ -232,8 +245,6 @@ def test_ties_nan_inf_and_clean(ndim):
         J.move_particles(t.p, (pT,)); st = t.o.move(t.co, t.idx, [opT])
         t.check_state(f"ties move {it}", (pT,), (opT,))
         assert J.move_stats(t.p) == st
-        if it == 0:
-            assert J.last_move_path(t.p) == "direct"      # particles exactly on faces: literal sweeps
         J.inject_particles(t.p, (pT,), step=it); t.o.inject(t.co, t.idx, [opT], 8, 5, it)
         t.check_state(f"ties inject {it}", (pT,), (opT,))
 
