@@ -128,11 +128,11 @@ int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const d
 
 /* particle2grid!(F, Fp, particles) (src/Interpolations/particle_to_grid.jl:23-151).
  * Two modes (jp_set_option(ctx, JP_OPT_P2G_MODE, ...)):
- *  JP_P2G_TWOPASS (default): cell-centric partial sums + node-centric gather, no
+ *  JP_P2G_TWOPASS: cell-centric partial sums + node-centric gather, no
  *    atomics, fixed summation order; every particle is read once.  Same weights and
  *    terms as the reference, different association: agrees to a few ulp (stated
  *    tolerance 1e-12 relative), deterministic run to run.
- *  JP_P2G_TWOPASS_FASTW: as TWOPASS with the weight evaluated as 1/sum(d^2) instead of the
+ *  JP_P2G_TWOPASS_FASTW (default): as TWOPASS with the weight evaluated as 1/sum(d^2) instead of the
  *    reference's inv(sqrt(sum(d^2))^2) (differs by <= 2 ulp per weight; same 1e-12 tolerance).
  *  JP_P2G_EXACT: one thread per node, the reference's single running sum in its
  *    (k, j, i, slot) order: bit-exact with the reference, reads every particle 2^N times. */

@@ -51,7 +51,7 @@ class CUDABackend:
 
 _SYNC = False
 MOVE_MODE = "auto"      # module default for move_particles
-P2G_MODE = "twopass"   # module default for particle2grid (see its docstring)
+P2G_MODE = "twopass_fastw"   # module default for particle2grid (see its docstring)
 
 
 def set_synchronous(flag: bool) -> None:
@@ -423,9 +423,10 @@ def centroid2particle(Fp, F, particles: Particles) -> None:
 
 def particle2grid(F, Fp, particles: Particles, mode: Optional[str] = None) -> None:
     """``particle2grid!(F, Fp, particles)`` (src/Interpolations/particle_to_grid.jl:23-28).
-    ``mode``: "twopass" (default: deterministic cell-partials + node gather, within 1e-12 of
-    the reference), "twopass_fastw" (same with the weight as 1/sum(d^2)), or "exact" (the
-    reference's running sum, bit-exact, 2^N x the traffic)."""
+    ``mode``: "twopass_fastw" (default: deterministic cell-partials + node gather with the weight
+    evaluated as 1/sum(d^2); within the stated 1e-12 of the reference), "twopass" (same with the
+    reference's inv(sqrt(.)^2) weight), or "exact" (the reference's single running sum: bit-exact,
+    2^N x the traffic)."""
     m = (mode or P2G_MODE).lower()
     modes = {"exact": _cabi.JP_P2G_EXACT, "twopass": _cabi.JP_P2G_TWOPASS, "twopass_fastw": _cabi.JP_P2G_TWOPASS_FASTW}
     if m not in modes:

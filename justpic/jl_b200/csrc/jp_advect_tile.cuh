@@ -7,9 +7,9 @@
 //     displaced by at most one cell -- are staged in shared memory together with
 //     the grid-vector segments, so the 2^N-corner gathers of every RK stage are
 //     LDS with compile-time strides instead of 64-bit-addressed global loads;
-//  2. each warp ballots its cells' occupancy masks slot by slot and writes a
-//     compacted (slot, cell) work list to shared memory; the list is consumed 32
-//     entries at a time, so every lane carries a live particle even when the slot
+//  2. each warp ballots its cells' occupancy masks slot by slot into a small
+//     shared-memory ring of compacted (slot, cell) entries, consumed 32 entries at
+//     a time, so every lane carries a live particle even when the slot
 //     planes are half empty (the reference's first-free-slot policy leaves them at
 //     ~50-60 % occupancy), while loads stay coalesced because the list is
 //     slot-major;
@@ -39,7 +39,8 @@ template <int N> struct AdvSmem {
     static constexpr int IXV_OFF = XG_OFF + 3 * VEC;
     static constexpr int IXG_OFF = IXV_OFF + 3 * VEC;
     static constexpr int NDOUBLES = IXG_OFF + 3 * VEC;
-    static size_t bytes(int S) { return sizeof(double) * NDOUBLES + sizeof(uint16_t) * T::NW * 32 * S; }
+    static constexpr int RING = 128;                       // per-warp ring of compacted (slot, cell) entries
+    static size_t bytes(int) { return sizeof(double) * NDOUBLES + sizeof(uint16_t) * T::NW * RING; }
 };
 
 // velocity at p from the staged stencils; r0[d] = tile-relative index of the seed
@@ -151,64 +152,70 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, P
 #pragma unroll 8
         for (int s = 0; s < g.S; s++) m |= (uint64_t)(ip[(int64_t)s * g.C] != 0) << s;
     }
-    uint16_t *wl = wl_all + warp * 32 * g.S;
-    int count = 0;
-    const unsigned lt = (1u << lane) - 1u;
-    for (int s = 0; s < g.S; s++) {
-        const bool live = (m >> s) & 1ull;
-        const unsigned bal = __ballot_sync(0xffffffffu, live);
-        if (live) wl[count + __popc(bal & lt)] = (uint16_t)((s << 5) | lane);
-        count += __popc(bal);
-    }
-    __syncthreads();                      // stencils staged (all warps) + list visible
+    __syncthreads();                      // stencils staged by all warps
 
-    // ---- 3. consume the list 32 particles at a time
+    // ---- 3. ballot the occupancy masks slot by slot into a small ring of compacted
+    //         (slot, cell) entries and consume it 32 live particles at a time
+    uint16_t *ring = wl_all + warp * L::RING;
+    const unsigned lt = (1u << lane) - 1u;
     const double *Vp[3] = {V.p[0], V.p[1], V.p[2]};
-    for (int k0 = 0; k0 < count; k0 += 32) {
-        const int k = k0 + lane;
-        if (k < count) {
-            const int ent = wl[k];
-            const int s = ent >> 5, l = ent & 31;
-            const int64_t e = crow + b0[0] + l + (int64_t)s * g.C;
-            const int r0[3] = {l + 1, wy + 1, wz + 1};
-            const int cell1[3] = {b0[0] + l + 1, cy + 1, cz + 1};
-            double p0[3], k1[3], k2[3], q[3], pn[3];
+    int head = 0, tail = 0;
+    for (int s = 0; s <= g.S; s++) {
+        if (s < g.S) {
+            const bool live = (m >> s) & 1ull;
+            const unsigned bal = __ballot_sync(0xffffffffu, live);
+            if (live) ring[(tail + __popc(bal & lt)) & (L::RING - 1)] = (uint16_t)((s << 5) | lane);
+            tail += __popc(bal);
+            __syncwarp();
+        }
+        while (tail - head >= 32 || (s == g.S && tail > head)) {
+            const int k = head + lane;
+            if (k < tail) {
+                const int ent = ring[k & (L::RING - 1)];
+                const int sl = ent >> 5, l = ent & 31;
+                const int64_t e = crow + b0[0] + l + (int64_t)sl * g.C;
+                const int r0[3] = {l + 1, wy + 1, wz + 1};
+                const int cell1[3] = {b0[0] + l + 1, cy + 1, cz + 1};
+                double p0[3], k1[3], k2[3], q[3], pn[3];
 #pragma unroll
-            for (int d = 0; d < N; d++) p0[d] = co.p[d][e];
-            adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, p0, k1);
-            if (SCHEME == 0) {
-                const double cdt = 1.0 * dt;
+                for (int d = 0; d < N; d++) p0[d] = co.p[d][e];
+                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, p0, k1);
+                if (SCHEME == 0) {
+                    const double cdt = 1.0 * dt;
 #pragma unroll
-                for (int d = 0; d < N; d++) pn[d] = fma(cdt, k1[d], p0[d]);
-            } else if (SCHEME == 1) {
-                const double cdt = (1.0 * alpha) * dt;
+                    for (int d = 0; d < N; d++) pn[d] = fma(cdt, k1[d], p0[d]);
+                } else if (SCHEME == 1) {
+                    const double cdt = (1.0 * alpha) * dt;
 #pragma unroll
-                for (int d = 0; d < N; d++) q[d] = fma(cdt, k1[d], p0[d]);
-                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k2);
-                if (alpha == 0.5) {
+                    for (int d = 0; d < N; d++) q[d] = fma(cdt, k1[d], p0[d]);
+                    adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k2);
+                    if (alpha == 0.5) {
 #pragma unroll
-                    for (int d = 0; d < N; d++) pn[d] = fma(1.0 * dt, k2[d], p0[d]);
+                        for (int d = 0; d < N; d++) pn[d] = fma(1.0 * dt, k2[d], p0[d]);
+                    } else {
+                        const double bb = 0.5 * (1.0 / alpha), aa = 1.0 - bb;
+#pragma unroll
+                        for (int d = 0; d < N; d++) pn[d] = fma(1.0 * dt, fma(bb, k2[d], aa * k1[d]), p0[d]);
+                    }
                 } else {
-                    const double bb = 0.5 * (1.0 / alpha), aa = 1.0 - bb;
+                    double k3[3], k4[3];
 #pragma unroll
-                    for (int d = 0; d < N; d++) pn[d] = fma(1.0 * dt, fma(bb, k2[d], aa * k1[d]), p0[d]);
+                    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k1[d] / 2;
+                    adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k2);
+#pragma unroll
+                    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k2[d] / 2;
+                    adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k3);
+#pragma unroll
+                    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k3[d];
+                    adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k4);
+#pragma unroll
+                    for (int d = 0; d < N; d++) pn[d] = p0[d] + dt * (((k1[d] + 2 * k2[d]) + 2 * k3[d]) + k4[d]) / 6;
                 }
-            } else {
-                double k3[3], k4[3];
 #pragma unroll
-                for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k1[d] / 2;
-                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k2);
-#pragma unroll
-                for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k2[d] / 2;
-                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k3);
-#pragma unroll
-                for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k3[d];
-                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k4);
-#pragma unroll
-                for (int d = 0; d < N; d++) pn[d] = p0[d] + dt * (((k1[d] + 2 * k2[d]) + 2 * k3[d]) + k4[d]) / 6;
+                for (int d = 0; d < N; d++) co.p[d][e] = pn[d];
             }
-#pragma unroll
-            for (int d = 0; d < N; d++) co.p[d][e] = pn[d];
+            head += 32;
+            __syncwarp();
         }
     }
 }

@@ -179,7 +179,10 @@ __global__ void __launch_bounds__(256) k_move_finalize(JpGrid g, MovePlanWs ws) 
 struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 
 // ---- D. gather (source-centric, slot-synchronous => every source sector is read once, in
-// streaming order): payload of each placed leaver -> staging[off[dest] + rank of its slot]
+// streaming order): payload of each placed leaver -> staging[off[dest] + rank of its slot].
+// Slots are handled in batches of U with all loads of a batch issued before the stores.
+#define JP_MV_U 4
+#define JP_MV_A 4      // arrays handled per register batch (coords + fields); more arrays loop again
 template <int N>
 __global__ void __launch_bounds__(256) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* staging stride */) {
     int ci[3]; int64_t c;
@@ -194,22 +197,41 @@ __global__ void __launch_bounds__(256) k_move_gather(JpGrid g, MovePlanWs ws, Mo
         if (nl > 12) code1 = ws.code[g.C + c];
         if (nl > 18) res2 = ws.res[2 * g.C + c];
     }
-    for (int s = 0; s < g.S; s++) {
-        const bool lvs = (lv >> s) & 1ull;
-        if (!__any_sync(0xffffffffu, lvs)) continue;
-        if (lvs) {
-            const int k = __popcll(lv & ((1ull << s) - 1));
-            const int r = (int)(((k < 9 ? res0 >> (7 * k) : k < 18 ? res1 >> (7 * (k - 9)) : res2 >> (7 * (k - 18)))) & 127);
-            if (r & 64) {
-                const int fs = r & 63;
-                const int code = (int)((k < 12 ? code0 >> (5 * k) : code1 >> (5 * (k - 12))) & 31);
-                int dv[3];
-                jp_code_dir(code, dv);
-                const int64_t c2 = c + dv[0] + (int64_t)g.n[0] * (dv[1] + (N == 3 ? (int64_t)g.n[1] * dv[2] : 0));
-                const int64_t pos = (int64_t)ws.off[c2] + __popcll(ws.arrmask[c2] & ((1ull << fs) - 1));
-                const int64_t e = c + (int64_t)s * g.C;
-                for (int a = 0; a < arrs.n; a++) stage[(int64_t)a * M + pos] = arrs.a[a][e];
+    for (int s0 = 0; s0 < g.S; s0 += JP_MV_U) {
+        const unsigned bits = (unsigned)(lv >> s0) & ((1u << JP_MV_U) - 1u);
+        if (!__any_sync(0xffffffffu, bits != 0)) continue;
+        int64_t pos[JP_MV_U], e[JP_MV_U];
+        bool act[JP_MV_U];
+#pragma unroll
+        for (int u = 0; u < JP_MV_U; u++) {
+            const int s = s0 + u;
+            act[u] = false; pos[u] = 0; e[u] = c + (int64_t)s * g.C;
+            if ((bits >> u) & 1u) {
+                const int k = __popcll(lv & ((1ull << s) - 1));
+                const int r = (int)(((k < 9 ? res0 >> (7 * k) : k < 18 ? res1 >> (7 * (k - 9)) : res2 >> (7 * (k - 18)))) & 127);
+                if (r & 64) {
+                    const int fs = r & 63;
+                    const int code = (int)((k < 12 ? code0 >> (5 * k) : code1 >> (5 * (k - 12))) & 31);
+                    int dv[3];
+                    jp_code_dir(code, dv);
+                    const int64_t c2 = c + dv[0] + (int64_t)g.n[0] * (dv[1] + (N == 3 ? (int64_t)g.n[1] * dv[2] : 0));
+                    pos[u] = (int64_t)ws.off[c2] + __popcll(ws.arrmask[c2] & ((1ull << fs) - 1));
+                    act[u] = true;
+                }
             }
+        }
+        for (int a0 = 0; a0 < arrs.n; a0 += JP_MV_A) {
+            double v[JP_MV_U][JP_MV_A];
+#pragma unroll
+            for (int u = 0; u < JP_MV_U; u++)
+#pragma unroll
+                for (int a = 0; a < JP_MV_A; a++)
+                    if (act[u] && a0 + a < arrs.n) v[u][a] = arrs.a[a0 + a][e[u]];
+#pragma unroll
+            for (int u = 0; u < JP_MV_U; u++)
+#pragma unroll
+                for (int a = 0; a < JP_MV_A; a++)
+                    if (act[u] && a0 + a < arrs.n) stage[(int64_t)(a0 + a) * M + pos[u]] = v[u][a];
         }
     }
 }
@@ -223,18 +245,32 @@ __global__ void __launch_bounds__(256) k_move_scatter(JpGrid g, MovePlanWs ws, M
     const uint64_t changed = amask | lmask;
     if (!__any_sync(0xffffffffu, changed != 0)) return;
     const int64_t base = ok ? ws.off[c] : 0;
-    for (int s = 0; s < g.S; s++) {
-        const bool ch = (changed >> s) & 1ull;
-        if (!__any_sync(0xffffffffu, ch)) continue;
-        if (ch) {
-            const int64_t e = c + (int64_t)s * g.C;
-            if ((amask >> s) & 1ull) {
-                const int64_t pos = base + __popcll(amask & ((1ull << s) - 1));
-                for (int a = 0; a < arrs.n; a++) arrs.a[a][e] = stage[(int64_t)a * M + pos];
-                if (!((lmask >> s) & 1ull)) index[e] = 1;      // was free (else it was live and stays live)
-            } else {
-                for (int a = 0; a < arrs.n; a++) arrs.a[a][e] = NAN;
-                index[e] = 0;
+    for (int s0 = 0; s0 < g.S; s0 += JP_MV_U) {
+        const unsigned chb = (unsigned)(changed >> s0) & ((1u << JP_MV_U) - 1u);
+        if (!__any_sync(0xffffffffu, chb != 0)) continue;
+        const unsigned arb = (unsigned)(amask >> s0) & ((1u << JP_MV_U) - 1u);
+        int64_t pos[JP_MV_U];
+#pragma unroll
+        for (int u = 0; u < JP_MV_U; u++) pos[u] = base + __popcll(amask & ((1ull << (s0 + u)) - 1));
+        for (int a0 = 0; a0 < arrs.n; a0 += JP_MV_A) {
+            double v[JP_MV_U][JP_MV_A];
+#pragma unroll
+            for (int u = 0; u < JP_MV_U; u++)
+#pragma unroll
+                for (int a = 0; a < JP_MV_A; a++)
+                    if (a0 + a < arrs.n && ((chb >> u) & 1u)) v[u][a] = ((arb >> u) & 1u) ? stage[(int64_t)(a0 + a) * M + pos[u]] : NAN;
+#pragma unroll
+            for (int u = 0; u < JP_MV_U; u++)
+#pragma unroll
+                for (int a = 0; a < JP_MV_A; a++)
+                    if (a0 + a < arrs.n && ((chb >> u) & 1u)) arrs.a[a0 + a][c + (int64_t)(s0 + u) * g.C] = v[u][a];
+        }
+#pragma unroll
+        for (int u = 0; u < JP_MV_U; u++) {
+            if ((chb >> u) & 1u) {
+                const int s = s0 + u;
+                if ((arb >> u) & 1u) { if (!((lmask >> s) & 1ull)) index[c + (int64_t)s * g.C] = 1; }
+                else index[c + (int64_t)s * g.C] = 0;
             }
         }
     }

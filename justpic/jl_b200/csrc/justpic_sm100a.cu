@@ -533,8 +533,8 @@ __global__ void __launch_bounds__(256) k_p2c(JpGrid g, CPtr3 co, double *__restr
 // phase_ratios_center!  Liveness is the reference's isnan(px) test, so px of EVERY slot
 // is read; slots are processed in batches of U with the loads of a batch in flight together.
 template <int N, int KMAX>
-__global__ void __launch_bounds__(256) k_phase(JpGrid g, CPtr3 co, double *__restrict__ ratios, const double *__restrict__ phases, int K) {
-    constexpr int U = 8;
+__global__ void __launch_bounds__(256, KMAX <= 8 ? 3 : 1) k_phase(JpGrid g, CPtr3 co, double *__restrict__ ratios, const double *__restrict__ phases, int K) {
+    constexpr int U = 4;
     int ci[3]; int64_t c;
     if (!tile_cell<N>(g, ci, c)) return;
     double xcn[3], idi[3], w[KMAX];
@@ -624,7 +624,7 @@ extern "C" int jp_ctx_create(const jp_grid_desc *d, int device, jp_ctx **out) {
     ctx->gridmem = dm;
     jp_grid_rebase(g, off, dm);
     ctx->g = g;
-    ctx->p2g_mode = JP_P2G_TWOPASS;
+    ctx->p2g_mode = JP_P2G_TWOPASS_FASTW;
     *out = ctx;
     return JP_OK;
 }
