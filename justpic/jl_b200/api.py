@@ -362,7 +362,7 @@ def last_move_path(particles: Particles) -> str:
 
 def last_move_reasons(particles: Particles) -> int:
     """Why the last move fell back to the direct sweeps (bit mask: 1 displacement > 1 cell, 2 particle on a
-    face of its own cell, 4 particle on a face of its destination, 8 more than 24 leavers in one cell)."""
+    face of its own cell, 4 particle on a face of its destination)."""
     return _cabi.load().jp_last_move_path(C.c_void_p(particles._ctx)) >> 8
 
 

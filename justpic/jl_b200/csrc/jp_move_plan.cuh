@@ -10,9 +10,9 @@
 //     codes (one of the 3^N neighbours, or "left the domain").  Anything the
 //     planner cannot express exactly -- a particle that fails isincell but
 //     bisects back into its own cell or fails isincell in its destination (on a
-//     face / in the fl(x+dx) ulp gap), a displacement of more than one cell,
-//     more than 24 leavers in one cell -- raises a flag and the whole call takes
-//     the direct sweep kernels (k_move_sweep), which handle every case.
+//     face / in the fl(x+dx) ulp gap) or a displacement of more than one cell --
+//     raises a flag and the whole call takes the direct sweep kernels
+//     (k_move_sweep), which handle every case.
 //  B. k_move_plan x 3^N (ordered, same colour order as the reference; touches
 //     8-byte words only): literal slot logic -- vacate in slot order, first free
 //     slot >= cursor, cursor shared across destinations, drop when full -- on the
@@ -33,7 +33,6 @@
 #include "jp_core.h"
 
 #define JP_CODE_DELETE 27
-#define JP_MAX_PLAN_LEAVERS 24      // 2 words x 12 codes of 5 bits
 
 // struct MovePlanWs is defined in justpic_sm100a.cu (it is a member of jp_ctx)
 
@@ -55,9 +54,9 @@ __global__ void __launch_bounds__(256) k_move_classify2(JpGrid g, CPtr3 co, cons
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
-    uint64_t lv = 0, code0 = 0, code1 = 0;
+    uint64_t lv = 0, codew = 0;
     int nl = 0;
-    unsigned cplx = 0;     // reason bits: 1 far, 2 same cell (tie), 4 fails isincell in destination, 8 > 24 leavers
+    unsigned cplx = 0;     // reason bits: 1 far, 2 same cell (tie), 4 fails isincell in destination
     double am[3], a[3], b[3], bp[3], dx[3], lo[3], hi[3];
     if (ok)
         for (int d = 0; d < N; d++) {
@@ -103,16 +102,15 @@ __global__ void __launch_bounds__(256) k_move_classify2(JpGrid g, CPtr3 co, cons
                     if (far || same || !dest_ok) cplx |= (far ? 1u : 0u) | ((same && !far) ? 2u : 0u) | ((!dest_ok && !far) ? 4u : 0u);
                     else code = jp_dir_code(dv, N);
                 }
-                if (nl < 12) code0 |= (uint64_t)code << (5 * nl);
-                else if (nl < 24) code1 |= (uint64_t)code << (5 * (nl - 12));
-                else cplx |= 8u;
+                codew |= (uint64_t)code << (5 * (nl % 12));
                 nl++;
+                if (nl % 12 == 0) { ws.code[(int64_t)(nl / 12 - 1) * g.C + c] = codew; codew = 0; }
             }
         }
     }
     if (ok) {
         ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
-        ws.code[c] = code0; ws.code[g.C + c] = code1;
+        if (nl % 12 != 0) ws.code[(int64_t)(nl / 12) * g.C + c] = codew;
     }
     const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
     if (wc && threadIdx.x == 0) atomicOr(complex_flag, wc);
@@ -136,13 +134,14 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
     if (lv == 0) return;
     const uint64_t smask = g.S == 64 ? ~0ull : ((1ull << g.S) - 1);
     uint64_t occ_c = ws.occ[c];
-    const uint64_t code0 = ws.code[c], code1 = ws.code[g.C + c];
-    uint64_t res[3] = {0, 0, 0};
+    uint64_t codew = 0, resw = 0;
     int cursor = 0, k = 0, n_dropped = 0, n_deleted = 0;
     while (lv) {
         const int ip = __ffsll((long long)lv) - 1;
         lv &= lv - 1;
-        const int code = (int)((k < 12 ? code0 >> (5 * k) : code1 >> (5 * (k - 12))) & 31);
+        if (k % 12 == 0) codew = ws.code[(int64_t)(k / 12) * g.C + c];
+        if (k % 9 == 0 && k > 0) { ws.res[(int64_t)(k / 9 - 1) * g.C + c] = resw; resw = 0; }
+        const int code = (int)((codew >> (5 * (k % 12))) & 31);
         const int kk = k++;
         occ_c &= ~(1ull << ip);
         if (code == JP_CODE_DELETE) { n_deleted++; continue; }
@@ -155,12 +154,10 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
         const int fs = __ffsll((long long)freebits) - 1;
         cursor = fs;
         ws.occ[c2] = o2 | (1ull << fs);
-        res[kk / 9] |= (uint64_t)(fs | 64) << (7 * (kk % 9));
+        resw |= (uint64_t)(fs | 64) << (7 * (kk % 9));
     }
     ws.occ[c] = occ_c;
-    ws.res[c] = res[0];
-    if (k > 9) ws.res[g.C + c] = res[1];
-    if (k > 18) ws.res[2 * g.C + c] = res[2];
+    ws.res[(int64_t)((k - 1) / 9) * g.C + c] = resw;
     if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
     if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);
 }
@@ -189,14 +186,8 @@ __global__ void __launch_bounds__(256) k_move_gather(JpGrid g, MovePlanWs ws, Mo
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t lv = ok ? ws.leave[c] : 0;
     if (!__any_sync(0xffffffffu, lv != 0)) return;
-    uint64_t code0 = 0, code1 = 0, res0 = 0, res1 = 0, res2 = 0;
-    const int nl = __popcll(lv);
-    if (lv) {
-        code0 = ws.code[c]; res0 = ws.res[c];
-        if (nl > 9) res1 = ws.res[g.C + c];
-        if (nl > 12) code1 = ws.code[g.C + c];
-        if (nl > 18) res2 = ws.res[2 * g.C + c];
-    }
+    uint64_t codew = 0, resw = 0;
+    int codepl = -1, respl = -1;
     for (int s0 = 0; s0 < g.S; s0 += JP_MV_U) {
         const unsigned bits = (unsigned)(lv >> s0) & ((1u << JP_MV_U) - 1u);
         if (!__any_sync(0xffffffffu, bits != 0)) continue;
@@ -208,10 +199,12 @@ __global__ void __launch_bounds__(256) k_move_gather(JpGrid g, MovePlanWs ws, Mo
             act[u] = false; pos[u] = 0; e[u] = c + (int64_t)s * g.C;
             if ((bits >> u) & 1u) {
                 const int k = __popcll(lv & ((1ull << s) - 1));
-                const int r = (int)(((k < 9 ? res0 >> (7 * k) : k < 18 ? res1 >> (7 * (k - 9)) : res2 >> (7 * (k - 18)))) & 127);
+                if (k / 9 != respl) { respl = k / 9; resw = ws.res[(int64_t)respl * g.C + c]; }
+                const int r = (int)((resw >> (7 * (k % 9))) & 127);
                 if (r & 64) {
                     const int fs = r & 63;
-                    const int code = (int)((k < 12 ? code0 >> (5 * k) : code1 >> (5 * (k - 12))) & 31);
+                    if (k / 12 != codepl) { codepl = k / 12; codew = ws.code[(int64_t)codepl * g.C + c]; }
+                    const int code = (int)((codew >> (5 * (k % 12))) & 31);
                     int dv[3];
                     jp_code_dir(code, dv);
                     const int64_t c2 = c + dv[0] + (int64_t)g.n[0] * (dv[1] + (N == 3 ? (int64_t)g.n[1] * dv[2] : 0));

@@ -38,8 +38,8 @@ struct MovePlanWs {
     uint64_t *occ;        // [C] running occupancy (plan) -> final occupancy
     uint64_t *occ0;       // [C] occupancy before the move
     uint64_t *leave;      // [C] slots vacated by the move (original leavers)
-    uint64_t *code;       // [2][C] packed 5-bit destination codes of the leavers, slot order
-    uint64_t *res;        // [3][C] packed 7-bit results (dest slot | placed << 6), slot order
+    uint64_t *code;       // [ceil(S/12)][C] packed 5-bit destination codes of the leavers, slot order
+    uint64_t *res;        // [ceil(S/9)][C] packed 7-bit results (dest slot | placed << 6), slot order
     uint64_t *arrmask;    // [C] slots receiving an arrival
     uint32_t *cnt;        // [C+1] arrivals per cell
     uint32_t *off;        // [C+1] exclusive scan of cnt (off[C] = total)
@@ -737,8 +737,8 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
 static int move_plan_alloc(jp_ctx *ctx) {
     const JpGrid &g = ctx->g;
     if (ctx->mp.code) return JP_OK;
-    JP_CUDA(cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * 2 * g.C));
-    JP_CUDA(cudaMalloc(&ctx->mp.res, sizeof(uint64_t) * 3 * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * (size_t)((g.S + 11) / 12) * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.res, sizeof(uint64_t) * (size_t)((g.S + 8) / 9) * g.C));
     JP_CUDA(cudaMalloc(&ctx->mp.occ0, sizeof(uint64_t) * g.C));
     JP_CUDA(cudaMalloc(&ctx->mp.arrmask, sizeof(uint64_t) * g.C));
     JP_CUDA(cudaMalloc(&ctx->mp.cnt, sizeof(uint32_t) * (g.C + 1)));
@@ -763,12 +763,18 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     const dim3 blk(JP_BX, JP_BY, 1);
     const dim3 grd = tile_grid(g.n[0], g.n[1], g.n[2]);
     CPtr3 cco = {{p->coords[0], p->coords[1], p->coords[2]}};
+    static const bool timing = getenv("JP_MOVE_TIMING") != nullptr;
+    cudaEvent_t ev[8];
+    int nev = 0;
+    auto mark = [&]() { if (timing) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); nev++; } };
+    mark();
     JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
     k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
     JP_CHECK_LAUNCH();
     JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->mp_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     JP_CUDA(cudaStreamSynchronize(st));
     ctx->last_complex = (int)ctx->h_pinned[0];
+    mark();
     if (ctx->h_pinned[0]) return 1;                       // ties / far moves / overfull leave list: direct sweeps
     const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = N == 3 ? (g.n[2] + 2) / 3 : 1;
     const int64_t ncol = (int64_t)ncx * ncy * ncz;
@@ -778,6 +784,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
             for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
                 k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats);
     const unsigned cblk = (unsigned)((g.C + 255) / 256);
+    mark();
     k_move_finalize<N><<<cblk, 256, 0, st>>>(g, ctx->mp);
     JP_CHECK_LAUNCH();
     JP_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, ctx->cub_tmp_bytes, ctx->mp.cnt, ctx->mp.off, (int)(g.C + 1), st));
@@ -785,6 +792,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     JP_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->mp.off + g.C, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     JP_CUDA(cudaStreamSynchronize(st));
     const size_t M = ctx->h_pinned[1];
+    mark();
     if (M == 0) {                                        // nothing arrives; still vacate deleted / dropped slots
         MoveArrays arrs; arrs.n = 0;
         for (int d = 0; d < N; d++) arrs.a[arrs.n++] = p->coords[d];
@@ -805,9 +813,20 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
         ctx->stage_elems = want;
     }
     const int64_t stride = (int64_t)(ctx->stage_elems / arrs.n);
+    mark();
     k_move_gather<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, ctx->stage, stride);
+    mark();
     k_move_scatter<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, p->index, ctx->stage, stride);
+    mark();
     JP_CHECK_LAUNCH();
+    if (timing) {
+        cudaStreamSynchronize(st);
+        const char *names[] = {"classify+flag", "plan", "finalize+scan+M", "alloc", "gather", "scatter"};
+        fprintf(stderr, "[jp_move]");
+        for (int i = 0; i + 1 < nev; i++) { float ms; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, " %s %.3f", names[i], ms); }
+        fprintf(stderr, " M=%zu\n", M);
+        for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
+    }
     return JP_OK;
 }
 

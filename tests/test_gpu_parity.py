@@ -194,6 +194,23 @@ def test_trajectory_advect_move_inject(g, move_mode):
 
 
 @pytest.mark.parametrize("ndim", [2, 3])
+def test_move_many_leavers_full_occupancy_word(ndim):
+    """64 slots, ~50 particles per cell, large CFL: cells with more than 24 / 36 leavers
+    (several packed code / result words per cell) and destinations that fill up."""
+    J = jp()
+    t = Twin(ndim, 12 if ndim == 2 else (6, 5, 7), True, nxcell=48, max_xcell=64, min_xcell=16, seed=11)
+    V = stream_velocity(t.gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(t.gr, V, 0.98)
+    pT, = J.init_cell_arrays(t.p, 1)
+    opT = np.where(t.idx > 0, t.co[0] * 3.0, 0.0); pT.copy_(dev(opT))
+    for it in range(5):
+        J.advection(t.p, J.RungeKutta2(), Vd, dt); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+        J.move_particles(t.p, (pT,)); st = t.o.move(t.co, t.idx, [opT])
+        t.check_state(f"many leavers step {it}", (pT,), (opT,))
+        assert J.move_stats(t.p) == st and J.last_move_path(t.p) == "plan"
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
 def test_ties_nan_inf_and_clean(ndim):
     J = jp()
     t = Twin(ndim, 6, True, nxcell=8, max_xcell=12, min_xcell=8, seed=5)
