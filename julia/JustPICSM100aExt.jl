@@ -1,0 +1,176 @@
+# JustPICSM100aExt.jl -- reference-side binding of libjustpic_sm100a.so.
+#
+# What a JustPIC.jl maintainer would add (as a package extension next to
+# ext/JustPICCUDAExt.jl) to route the particle-in-cell hot path of
+# `Particles{CUDABackend}` through the B200-native library instead of the
+# KernelAbstractions kernels.  It defines more specific methods of the L4
+# launchers (the functions that today end in `launch!(ka_backend(x), kernel!, ...)`,
+# src/launch.jl:65-69) and `ccall`s the C ABI of include/justpic_c.h.
+#
+# NOT EXECUTED IN THIS REPOSITORY: the build image has no Julia.  It is kept thin
+# on purpose -- pointer plumbing only, every decision lives behind the C ABI, which
+# the Python mirror (justpic/jl_b200/api.py) exercises call for call.
+#
+# Memory: CuCellArray{T,N,0} (blocklength 0, ext/JustPICCUDAExt.jl:26-30) stores
+# `data[C, S, 1]` column-major, i.e. element (cell c, slot s) at c + s*C -- exactly
+# the layout the library expects, so `pointer(A.data)` is passed as is; nothing is
+# copied or converted, and `Array(particles)`, `copy`, JLD2 checkpointing keep working.
+module JustPICSM100aExt
+
+using CUDA, JustPIC, CellArrays
+using CUDA: CUDABackend
+import JustPIC: Particles, Euler, RungeKutta2, RungeKutta4, AbstractAdvectionIntegrator
+
+const libjustpic = get(ENV, "JUSTPIC_SM100A_LIB", "libjustpic_sm100a.so")
+
+# ---- C structs (include/justpic_c.h) ---------------------------------------
+struct JpGridDesc
+    ndim::Int32
+    n::NTuple{3, Int32}
+    S::Int32
+    uniform::Int32
+    xv::NTuple{3, Ptr{Float64}}
+    xc::NTuple{3, Ptr{Float64}}
+    xvel::NTuple{9, Ptr{Float64}}      # [comp][dim], row-major like the C array
+    nvel::NTuple{9, Int32}
+end
+
+struct JpParticles
+    coords::NTuple{3, CuPtr{Float64}}
+    index::CuPtr{UInt8}
+end
+
+check(rc::Cint, who) = rc == 0 ? nothing :
+    (msg = unsafe_string(ccall((:jp_last_error, libjustpic), Cstring, ()));
+     rc == -1 ? throw(ArgumentError("$who: $msg")) : error("$who failed ($rc): $msg"))
+
+# ---- one context per Particles object (created lazily, cached by objectid) --
+const CONTEXTS = Dict{UInt, Ptr{Cvoid}}()
+const HOST_GRIDS = Dict{UInt, Any}()       # keeps the host copies of the grid vectors alive
+
+pad3(t::NTuple{2}, x) = (t[1], t[2], x)
+pad3(t::NTuple{3}, x) = t
+
+function context(p::Particles{CUDABackend, N}) where {N}
+    get!(CONTEXTS, objectid(p)) do
+        # range grids -> scalar spacings (particles_utils.jl:137-140), arrays -> diff() (:76-79)
+        uniform = p.di.vertex[1] isa Number
+        host(x) = collect(Float64, Array(x))
+        xv = map(host, p.xvi); xc = map(host, p.xci)
+        xvel = ntuple(c -> map(host, p.xi_vel[c]), Val(N))
+        HOST_GRIDS[objectid(p)] = (xv, xc, xvel)
+        nullp = Ptr{Float64}(0)
+        xvel9 = ntuple(i -> (c = (i - 1) ÷ 3 + 1; d = (i - 1) % 3 + 1; (c <= N && d <= N) ? pointer(xvel[c][d]) : nullp), 9)
+        nvel9 = ntuple(i -> (c = (i - 1) ÷ 3 + 1; d = (i - 1) % 3 + 1; (c <= N && d <= N) ? Int32(length(xvel[c][d])) : Int32(0)), 9)
+        desc = Ref(JpGridDesc(Int32(N), pad3(Int32.(size(p.index)), Int32(1)), Int32(p.max_xcell), Int32(uniform),
+                              pad3(map(pointer, xv), nullp), pad3(map(pointer, xc), nullp), xvel9, nvel9))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:jp_ctx_create, libjustpic), Cint, (Ref{JpGridDesc}, Cint, Ref{Ptr{Cvoid}}),
+                    desc, CUDA.deviceid(CUDA.device()), out), "jp_ctx_create")
+        out[]
+    end
+end
+
+cptr(A::CellArray) = pointer(A.data)
+jp(p::Particles{CUDABackend, N}) where {N} =
+    Ref(JpParticles(pad3(map(cptr, p.coords), CuPtr{Float64}(0)), cptr(p.index)))
+stream() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
+argptrs(args) = CuPtr{Float64}[cptr(a) for a in args]
+# the reference's launch! synchronises after every kernel (src/launch.jl:60-69)
+done() = CUDA.synchronize()
+
+scheme(::Euler) = (Int32(0), 0.0)
+scheme(m::RungeKutta2) = (Int32(1), Float64(m.α))
+scheme(::RungeKutta4) = (Int32(2), 0.0)
+
+# ---- L4 launchers ------------------------------------------------------------
+# advection!(particles, method, V, grid_vi, dt, dxi)   src/Particles/Advection/advection.jl:35-62
+function JustPIC.advection!(p::Particles{CUDABackend, N}, method::AbstractAdvectionIntegrator, V, grid_vi::NTuple{N, NTuple{N, T}}, dt, dxi) where {N, T}
+    s, α = scheme(method)
+    Vp = CuPtr{Float64}[pointer(v) for v in V]
+    check(ccall((:jp_advect, libjustpic), Cint,
+                (Ptr{Cvoid}, Ref{JpParticles}, Int32, Float64, Ptr{CuPtr{Float64}}, Float64, Ptr{Cvoid}),
+                context(p), jp(p), s, α, Vp, Float64(dt), stream()), "advection!")
+    done()
+end
+
+# move_particles!(particles, grid, args, dxi)           src/Particles/move_safe.jl:23-49
+function JustPIC.move_particles!(p::Particles{CUDABackend}, grid::NTuple{N}, args, dxi) where {N}
+    a = argptrs(args)
+    check(ccall((:jp_move, libjustpic), Cint, (Ptr{Cvoid}, Ref{JpParticles}, Ptr{CuPtr{Float64}}, Int32, Ptr{Cvoid}),
+                context(p), jp(p), a, Int32(length(a)), stream()), "move_particles!")
+    done()
+end
+
+# inject_particles!(particles, args, grid, di)          src/Particles/injection.jl:21-53
+const INJECT_STEP = Ref{UInt32}(0)
+function JustPIC.inject_particles!(p::Particles{CUDABackend}, args, grid::NTuple{N}, di) where {N}
+    a = argptrs(args)
+    check(ccall((:jp_inject, libjustpic), Cint,
+                (Ptr{Cvoid}, Ref{JpParticles}, Ptr{CuPtr{Float64}}, Int32, Int32, UInt64, UInt32, Ptr{Cvoid}),
+                context(p), jp(p), a, Int32(length(a)), Int32(p.min_xcell), UInt64(42), INJECT_STEP[], stream()), "inject_particles!")
+    INJECT_STEP[] += UInt32(1)
+    done()
+end
+
+# clean_particles!(particles, grid, args)               src/Particles/move_safe.jl:289-295
+function JustPIC.clean_particles!(p::Particles{CUDABackend}, grid, args)
+    a = argptrs(args)
+    check(ccall((:jp_clean, libjustpic), Cint, (Ptr{Cvoid}, Ref{JpParticles}, Ptr{CuPtr{Float64}}, Int32, Ptr{Cvoid}),
+                context(p), jp(p), a, Int32(length(a)), stream()), "clean_particles!")
+    done()
+end
+
+# grid2particle!(Fp, xvi, F, particles, di)             src/Interpolations/grid_to_particle.jl:28-35
+function JustPIC.grid2particle!(Fp::CellArray, xvi, F::CuArray, p::Particles{CUDABackend}, di)
+    check(ccall((:jp_grid2particle, libjustpic), Cint, (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                context(p), jp(p), cptr(Fp), pointer(F), stream()), "grid2particle!")
+    done()
+end
+
+# centroid2particle!(Fp, xci, F, particles, di)         src/Interpolations/centroid_to_particle.jl:15-20
+function JustPIC.centroid2particle!(Fp::CellArray, xci, F::CuArray, p::Particles{CUDABackend}, di)
+    check(ccall((:jp_centroid2particle, libjustpic), Cint, (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                context(p), jp(p), cptr(Fp), pointer(F), stream()), "centroid2particle!")
+    done()
+end
+
+# particle2grid!(F, Fp, particles)                      src/Interpolations/particle_to_grid.jl:23-28
+function JustPIC.particle2grid!(F::CuArray, Fp::CellArray, p::Particles{CUDABackend})
+    check(ccall((:jp_particle2grid, libjustpic), Cint, (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                context(p), jp(p), pointer(F), cptr(Fp), stream()), "particle2grid!")
+    done()
+end
+
+# particle2centroid!(F, Fp, xci, particles, di)         src/Interpolations/particle_to_grid_centroid.jl:12-16
+function JustPIC.particle2centroid!(F::CuArray, Fp::CellArray, xci::NTuple, p::Particles{CUDABackend}, di)
+    check(ccall((:jp_particle2centroid, libjustpic), Cint, (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                context(p), jp(p), pointer(F), cptr(Fp), stream()), "particle2centroid!")
+    done()
+end
+
+# phase_ratios_center!(phase_ratios, particles, phases) src/PhaseRatios/centers.jl:3-11
+function JustPIC.phase_ratios_center!(pr::JustPIC.PhaseRatios{CUDABackend}, p::Particles{CUDABackend}, phases)
+    K = JustPIC.numphases(pr)
+    check(ccall((:jp_phase_ratios_center, libjustpic), Cint,
+                (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, Int32, Ptr{Cvoid}),
+                context(p), jp(p), cptr(pr.center), cptr(phases), Int32(K), stream()), "phase_ratios_center!")
+    done()
+end
+
+# init_particles: allocation stays in Julia (cell_array, src/launch.jl:101-108; the
+# CuCellArrays are owned by Julia), only the fill kernel (fill_coords_index!,
+# particles_utils.jl:168-194) is replaced.  Called from the tail of the reference's
+# init_particles instead of `launch!(..., fill_coords_index!, ...)`.
+function fill_coords_index!(p::Particles{CUDABackend}; seed::UInt64 = UInt64(42))
+    check(ccall((:jp_init_particles, libjustpic), Cint, (Ptr{Cvoid}, Ref{JpParticles}, Int32, UInt64, Ptr{Cvoid}),
+                context(p), jp(p), Int32(p.nxcell), seed, stream()), "init_particles")
+    done()
+end
+
+# update_cell_halo!: jp_halo_pack / jp_halo_unpack replace the per-array
+# ImplicitGlobalGrid.update_halo! calls (src/CellArrays/ImplicitGlobalGrid.jl:36-41);
+# the transport between ranks stays with the host (MPI.Isend/Irecv of ONE packed
+# buffer per face, or NCCL as in justpic/jl_b200/halo.py).
+
+end # module

@@ -1,0 +1,87 @@
+"""jp_halo_pack / jp_halo_unpack kernels (single GPU) and the NCCL exchange (2 GPUs if present)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _particles(ndim, n, seed=3):
+    import justpic.jl_b200 as J
+    from tests.problems import make_grids
+    gr = make_grids(n, ndim, True)
+    return J, gr, J.init_particles(J.CUDABackend, 12, 16, 6, *gr.grid_vel, seed=seed)
+
+
+@pytest.mark.parametrize("ndim,n", [(2, (9, 7)), (3, (6, 5, 7))])
+def test_halo_pack_unpack_kernels(ndim, n):
+    from justpic.jl_b200 import halo
+    J, gr, p = _particles(ndim, n)
+    pT, = J.init_cell_arrays(p, 1)
+    pT.copy_(torch.rand_like(pT))
+    arrays = tuple(p.coords) + (pT,)
+    for dim in range(ndim):
+        nb = halo.plane_bytes(p.ncells, p.max_xcell, dim, len(arrays))
+        buf = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        src_plane, dst_plane = 1, p.ncells[dim] - 1
+        halo._cuda_pack(p, dim, src_plane, arrays, buf)
+        # reference packing with torch slicing: arrays in order (slot-major, plane cells in memory order), then index bytes
+        parts = [a.select(ndim - dim, src_plane).contiguous().view(torch.uint8).reshape(-1) for a in arrays]
+        parts.append(p.index.select(ndim - dim, src_plane).contiguous().reshape(-1))
+        assert torch.equal(buf, torch.cat(parts))
+        before = [a.clone() for a in arrays] + [p.index.clone()]
+        halo._cuda_unpack(p, dim, dst_plane, arrays, buf)
+        for a, b in zip(list(arrays) + [p.index], before):
+            got = a.select(ndim - dim, dst_plane)
+            want = b.select(ndim - dim, src_plane)
+            assert torch.equal(torch.nan_to_num(got.double(), nan=-1.0), torch.nan_to_num(want.double(), nan=-1.0))
+            keep = [i for i in range(p.ncells[dim]) if i != dst_plane]
+            idx = torch.tensor(keep, device="cuda")
+            assert torch.equal(torch.nan_to_num(a.index_select(ndim - dim, idx).double(), nan=-1.0),
+                               torch.nan_to_num(b.index_select(ndim - dim, idx).double(), nan=-1.0))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
+def _nccl_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import justpic.jl_b200 as J
+        from justpic.jl_b200.halo import CartesianTopology, update_cell_halo
+        from tests.problems import make_grids
+        gr = make_grids((6, 5, 7), 3, True)
+        p = J.init_particles(J.CUDABackend, 12, 16, 6, *gr.grid_vel, seed=10 + rank, device=f"cuda:{rank}")
+        pT, = J.init_cell_arrays(p, 1)
+        pT.fill_(float(rank) + 0.5)
+        before = [c.clone().cpu() for c in p.coords] + [pT.clone().cpu(), p.index.clone().cpu()]
+        topo = CartesianTopology((2, 1, 1), rank)
+        sent = update_cell_halo(p, (pT,), topo)
+        torch.cuda.synchronize()
+        after = [c.cpu() for c in p.coords] + [pT.cpu(), p.index.cpu()]
+        torch.save({"before": before, "after": after, "sent": sent}, out + f".{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_update_cell_halo_nccl_two_gpus(tmp_path):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "halo")
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = [torch.load(out + f".{k}") for k in range(2)]
+    nx = 6
+    eq = lambda a, b: torch.equal(torch.nan_to_num(a.double(), nan=-1.0), torch.nan_to_num(b.double(), nan=-1.0))
+    for a in range(5):
+        assert eq(r[0]["after"][a][..., nx - 1], r[1]["before"][a][..., 1])
+        assert eq(r[1]["after"][a][..., 0], r[0]["before"][a][..., nx - 2])
+        assert eq(r[0]["after"][a][..., : nx - 1], r[0]["before"][a][..., : nx - 1])
+        assert eq(r[1]["after"][a][..., 1:], r[1]["before"][a][..., 1:])
