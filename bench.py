@@ -10,7 +10,7 @@ N>1 (torchrun): weak scaling, one 256^3 block per GPU, block decomposition with
 the halo exchange of configs[4] between advection! and move_particles!.
 
 Prints ONE JSON line (see DESIGN.md "Measurement" for every key).
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n CELLS]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells CELLS]
 """
 from __future__ import annotations
 
@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="cells per dimension per GPU (headline: 256)")
+    ap.add_argument("--cells", dest="n", type=int, default=256, help="cells per dimension per GPU (headline: 256)")
     ap.add_argument("--cpu-n", type=int, default=64, help="cells per dimension of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -197,6 +197,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     topo = CartesianTopology.create(world, 3, rank)
     n = args.n
@@ -331,10 +332,12 @@ def run_ours(args):
             "config": {"workload": workload_name(n, world), "cells_per_gpu": n ** 3, "live_particles_per_gpu": int(nlive_mean),
                        "migrant_fraction": round(f_mig, 4), "move_path": move_path, "dropped_per_step": dropped, "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
                        "topology": list(topo.dims)},
-            "gpu_launches": args.steps * (1 + 28 + 1 + 1 + (6 * sum(1 for d in topo.dims if d > 1) if world > 1 else 0)),
+            # per step: advect 1; move (plan path) classify 1 + plan 27 + finalize 1 + scan 2 + set 1 + gather 1 + scatter 1;
+            # p2g 2 (cell + node); phase ratios 1; halo: 2 pack + 2 unpack per decomposed dimension
+            "gpu_launches": args.steps * (1 + 34 + 2 + 1 + (4 * sum(1 for d in topo.dims if d > 1) if world > 1 else 0)),
             "phase_ms": per_phase,
-            "roofline": {"bound": "hbm", "kernel": {"advect": "k_advect<3,RK2,fast,uniform>", "move": "k_move_classify + 27 x k_move_sweep",
-                                                     "p2g": "k_p2g<3>", "phase_ratios": "k_phase<3,2>"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"advect": "k_advect_tile<3,RK2,uniform>", "move": "k_move_classify2 + 27 x k_move_plan + k_move_gather + k_move_scatter",
+                                                     "p2g": "k_p2g_cell<3,fastw> + k_p2g_node<3>", "phase_ratios": "k_phase<3,2>"}[dom],
                          "achieved": kernel_gbs[dom], "peak": peak, "unit": "GB/s", "frac": kernel_gbs[dom] / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_particle": ab, "per_phase_GBps": kernel_gbs,
