@@ -49,7 +49,7 @@ __device__ __forceinline__ void jp_code_dir(int code, int *dv) {
 // reference's seeded bisection puts it; anything else (on a vertex, further away) is
 // left to the direct sweeps.
 template <int N>
-__global__ void __launch_bounds__(256) k_move_classify2(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
+__global__ void __launch_bounds__(256, 3) k_move_classify2(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
                                                         unsigned int *complex_flag) {
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
@@ -181,7 +181,7 @@ struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 #define JP_MV_U 4
 #define JP_MV_A 4      // arrays handled per register batch (coords + fields); more arrays loop again
 template <int N>
-__global__ void __launch_bounds__(256) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* staging stride */) {
+__global__ void __launch_bounds__(256, 3) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* staging stride */) {
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t lv = ok ? ws.leave[c] : 0;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) k_move_gather(JpGrid g, MovePlanWs ws, Mo
 
 // ---- E. scatter: arrivals from staging, NaN into vacated slots, mask bytes
 template <int N>
-__global__ void __launch_bounds__(256) k_move_scatter(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index, const double *__restrict__ stage, int64_t M) {
+__global__ void __launch_bounds__(256, 3) k_move_scatter(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index, const double *__restrict__ stage, int64_t M) {
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t amask = ok ? ws.arrmask[c] : 0, lmask = ok ? ws.leave[c] : 0;

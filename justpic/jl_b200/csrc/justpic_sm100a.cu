@@ -429,8 +429,19 @@ __global__ void __launch_bounds__(256) k_p2g(JpGrid g, CPtr3 co, const uint8_t *
 // reference's (k, j, i) order.  Same terms as the reference, fixed order, but the
 // association is (cell sums) + ... instead of one running chain: results agree with
 // the reference to a few ulp (stated tolerance 1e-12), not bit-for-bit.
+// reciprocal to <= 2 ulp: MUFU seed + two Newton steps (no correctly-rounded fix-up, no
+// special-case branch).  Only used by JP_P2G_TWOPASS_FASTW, whose contract is the 1e-12 tolerance.
+__device__ __forceinline__ double jp_rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
 template <int N, bool FASTW>
-__global__ void __launch_bounds__(256) k_p2g_cell(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, const double *__restrict__ Fp,
+__global__ void __launch_bounds__(256, 3) k_p2g_cell(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, const double *__restrict__ Fp,
                                                   double *__restrict__ PW, double *__restrict__ PWF) {
     constexpr int NQ = N == 2 ? 4 : 8;
     constexpr int U = 4;                       // slots per batch: loads of a batch are issued together
@@ -469,7 +480,7 @@ __global__ void __launch_bounds__(256) k_p2g_cell(JpGrid g, CPtr3 co, const uint
                     double ss = d2[0][q & 1] + d2[1][(q >> 1) & 1];
                     if (N == 3) ss = ss + d2[2][(q >> 2) & 1];
                     double wi;
-                    if (FASTW) wi = 1.0 / ss;
+                    if (FASTW) wi = jp_rcp_fast(ss);
                     else { const double dist = sqrt(ss); wi = 1.0 / (dist * dist); }
                     aw[q] += wi;
                     awf[q] = fma(wi, ff[u], awf[q]);
