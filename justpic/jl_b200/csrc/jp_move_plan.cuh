@@ -44,81 +44,135 @@ __device__ __forceinline__ void jp_code_dir(int code, int *dv) {
 }
 
 // ---- A. classify
-// Destination by comparisons against the four vertices around the storage cell:
-// a particle strictly inside (xv[j], xv[j+1]) for j in {i-1, i, i+1} is exactly where the
-// reference's seeded bisection puts it; anything else (on a vertex, further away) is
-// left to the direct sweeps.
+// Phase 1 (thread = cell, slot-synchronous, coalesced): strict isincell test of every live
+// particle -> leave word.  Phase 2: the warp's leavers (~40 % of the particles) are compacted
+// through a shared-memory ring and classified 32 at a time at full lane occupancy:
+// destination by comparisons against the four vertices around the storage cell -- a particle
+// strictly inside (xv[j], xv[j+1]) for j in {i-1, i, i+1} is exactly where the reference's
+// seeded bisection puts it; anything else (on a vertex, further away) is left to the direct
+// sweeps.  Codes are staged as bytes in shared memory ([cell][k], k = rank of the slot among
+// the cell's leavers) and written out as packed 8-byte words.
+struct ClsGeom { double am, a, b, bp, dx, lo, hi; };
+__device__ __forceinline__ ClsGeom jp_cls_geom(const JpGrid &g, int d, int i) {
+    const double *xv = g.xv[d];
+    ClsGeom q;
+    q.a = xv[i]; q.b = xv[i + 1];
+    q.am = i > 0 ? xv[i - 1] : NAN;
+    q.bp = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
+    q.dx = jp_d_of(xv, g.uniform, i);
+    q.lo = xv[0]; q.hi = xv[g.n[d]];
+    return q;
+}
+// one dimension of the destination search; returns false when the planner cannot express it
+__device__ __forceinline__ bool jp_cls_dim(const ClsGeom &q, int uniform, double pd, int &dv, bool &dest_ok) {
+    double lower, dxd;
+    if (q.a < pd && pd < q.b) { dv = 0; lower = q.a; dxd = uniform ? q.dx : q.b - q.a; }
+    else if (q.am < pd && pd < q.a) { dv = -1; lower = q.am; dxd = uniform ? q.dx : q.a - q.am; }
+    else if (q.b < pd && pd < q.bp) { dv = 1; lower = q.b; dxd = uniform ? q.dx : q.bp - q.b; }
+    else { dv = 0; return false; }                   // on a vertex or more than one cell away
+    dest_ok = dest_ok && (lower < pd) && (pd < lower + dxd);
+    return true;
+}
+
 template <int N>
 __global__ void __launch_bounds__(256, 3) k_move_classify2(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
                                                         unsigned int *complex_flag) {
+    __shared__ uint64_t lv_sm[JP_BY][32];
+    __shared__ __align__(8) uint8_t code_sm[JP_BY][32][JP_MAX_SLOTS];
+    __shared__ uint16_t ring_sm[JP_BY][128];
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
+    const int lane = threadIdx.x, w = threadIdx.y;
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
-    uint64_t lv = 0, codew = 0;
-    int nl = 0;
-    unsigned cplx = 0;     // reason bits: 1 far, 2 same cell (tie), 4 fails isincell in destination
-    double am[3], a[3], b[3], bp[3], dx[3], lo[3], hi[3];
-    if (ok)
-        for (int d = 0; d < N; d++) {
-            const double *xv = g.xv[d];
-            const int i = ci[d];
-            a[d] = xv[i]; b[d] = xv[i + 1];
-            am[d] = i > 0 ? xv[i - 1] : NAN;
-            bp[d] = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
-            dx[d] = jp_d_of(xv, g.uniform, i);
-            lo[d] = xv[0]; hi[d] = xv[g.n[d]];
-        }
-    for (int s = 0; s < g.S; s++) {
-        const bool live = (m >> s) & 1ull;
-        if (!__any_sync(0xffffffffu, live)) continue;
-        if (live) {
-            const int64_t e = c + (int64_t)s * g.C;
-            double p[3];
+    // ---- phase 1: leave word
+    uint64_t lv = 0;
+    {
+        double a[3], ub[3];
+        if (ok)
+            for (int d = 0; d < N; d++) { a[d] = g.xv[d][ci[d]]; ub[d] = a[d] + jp_d_of(g.xv[d], g.uniform, ci[d]); }
+        for (int s0 = 0; s0 < g.S; s0 += 4) {
+            const unsigned bits = (unsigned)(m >> s0) & 15u;
+            if (!__any_sync(0xffffffffu, bits != 0)) continue;
+            double p[4][3];
 #pragma unroll
-            for (int d = 0; d < N; d++) p[d] = co.p[d][e];
-            bool incell = true;
+            for (int u = 0; u < 4; u++)
 #pragma unroll
-            for (int d = 0; d < N; d++) incell = incell & (a[d] < p[d]) & (p[d] < a[d] + dx[d]);
-            if (!incell) {
-                lv |= 1ull << s;
-                bool indom = true;
+                for (int d = 0; d < N; d++) p[u][d] = ((bits >> u) & 1u) ? co.p[d][c + (int64_t)(s0 + u) * g.C] : 0.0;
 #pragma unroll
-                for (int d = 0; d < N; d++) indom = indom && (lo[d] < p[d] && p[d] < hi[d]);
-                int code = JP_CODE_DELETE;
-                if (indom) {
-                    int dv[3] = {0, 0, 0};
-                    bool far = false, dest_ok = true;
+            for (int u = 0; u < 4; u++) {
+                bool in = true;
 #pragma unroll
-                    for (int d = 0; d < N; d++) {
-                        const double pd = p[d];
-                        double lower, dxd;
-                        if (a[d] < pd && pd < b[d]) { dv[d] = 0; lower = a[d]; dxd = g.uniform ? dx[d] : b[d] - a[d]; }
-                        else if (am[d] < pd && pd < a[d]) { dv[d] = -1; lower = am[d]; dxd = g.uniform ? dx[d] : a[d] - am[d]; }
-                        else if (b[d] < pd && pd < bp[d]) { dv[d] = 1; lower = b[d]; dxd = g.uniform ? dx[d] : bp[d] - b[d]; }
-                        else { far = true; lower = a[d]; dxd = dx[d]; }        // on a vertex or more than one cell away
-                        dest_ok = dest_ok && (lower < pd) && (pd < lower + dxd);
-                    }
-                    const bool same = dv[0] == 0 && dv[1] == 0 && (N == 2 || dv[2] == 0);
-                    if (far || same || !dest_ok) cplx |= (far ? 1u : 0u) | ((same && !far) ? 2u : 0u) | ((!dest_ok && !far) ? 4u : 0u);
-                    else code = jp_dir_code(dv, N);
-                }
-                codew |= (uint64_t)code << (5 * (nl % 12));
-                nl++;
-                if (nl % 12 == 0) { ws.code[(int64_t)(nl / 12 - 1) * g.C + c] = codew; codew = 0; }
+                for (int d = 0; d < N; d++) in = in & (a[d] < p[u][d]) & (p[u][d] < ub[d]);
+                if (((bits >> u) & 1u) && !in) lv |= 1ull << (s0 + u);
             }
         }
     }
-    if (ok) {
-        ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
-        if (nl % 12 != 0) ws.code[(int64_t)(nl / 12) * g.C + c] = codew;
+    lv_sm[w][lane] = lv;
+    if (ok) { ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv; }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, lv != 0)) return;
+    // ---- phase 2: compacted leavers
+    const int x0 = blockIdx.x * JP_BX;
+    ClsGeom gy = jp_cls_geom(g, 1, min(ci[1], g.n[1] - 1)), gz;
+    if (N == 3) gz = jp_cls_geom(g, 2, ci[2]);
+    const int64_t crow = (int64_t)g.n[0] * (ci[1] + (N == 3 ? (int64_t)g.n[1] * ci[2] : 0));
+    unsigned cplx = 0;     // reason bits: 1 far / on a vertex, 2 same cell (ulp gap), 4 fails isincell in destination
+    const unsigned lt = (1u << lane) - 1u;
+    int head = 0, tail = 0;
+    for (int s = 0; s <= g.S; s++) {
+        if (s < g.S) {
+            const bool l = (lv >> s) & 1ull;
+            const unsigned bal = __ballot_sync(0xffffffffu, l);
+            if (l) ring_sm[w][(tail + __popc(bal & lt)) & 127] = (uint16_t)((s << 5) | lane);
+            tail += __popc(bal);
+            __syncwarp();
+        }
+        while (tail - head >= 32 || (s == g.S && tail > head)) {
+            const int k = head + lane;
+            if (k < tail) {
+                const int ent = ring_sm[w][k & 127];
+                const int sl = ent >> 5, l = ent & 31;
+                const int cx = x0 + l;
+                const int64_t e = crow + cx + (int64_t)sl * g.C;
+                double p[3];
+#pragma unroll
+                for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+                const ClsGeom gx = jp_cls_geom(g, 0, cx);
+                bool indom = (gx.lo < p[0] && p[0] < gx.hi) && (gy.lo < p[1] && p[1] < gy.hi);
+                if (N == 3) indom = indom && (gz.lo < p[2] && p[2] < gz.hi);
+                int code = JP_CODE_DELETE;
+                if (indom) {
+                    int dv[3] = {0, 0, 0};
+                    bool dest_ok = true;
+                    bool near = jp_cls_dim(gx, g.uniform, p[0], dv[0], dest_ok);
+                    near = jp_cls_dim(gy, g.uniform, p[1], dv[1], dest_ok) && near;
+                    if (N == 3) near = jp_cls_dim(gz, g.uniform, p[2], dv[2], dest_ok) && near;
+                    const bool same = dv[0] == 0 && dv[1] == 0 && dv[2] == 0;
+                    if (!near) cplx |= 1u;
+                    else if (same) cplx |= 2u;
+                    else if (!dest_ok) cplx |= 4u;
+                    else code = jp_dir_code(dv, N);
+                }
+                const int kk = __popcll(lv_sm[w][l] & ((1ull << sl) - 1));
+                code_sm[w][l][kk] = (uint8_t)code;
+            }
+            head += 32;
+            __syncwarp();
+        }
+    }
+    // ---- packed code words (8 byte-codes per word), one plane per 8 leavers
+    if (lv) {
+        const int nl = __popcll(lv);
+        const uint64_t *cw = reinterpret_cast<const uint64_t *>(&code_sm[w][lane][0]);
+        for (int q = 0; q * 8 < nl; q++) ws.code[(int64_t)q * g.C + c] = cw[q];
     }
     const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
-    if (wc && threadIdx.x == 0) atomicOr(complex_flag, wc);
+    if (wc && lane == 0) atomicOr(complex_flag, wc);
 }
 
 // ---- B. one colour of the plan (thread = source cell; 8-byte words only).
 // Literal slot logic of move_kernel! (src/Particles/move_safe.jl:72-125) on the occupancy
-// words; the slot given to the k-th leaver goes to res (7 bits: slot | placed << 6).
+// words; the slot given to the k-th leaver goes to res (one byte: slot | placed << 6).
 template <int N>
 __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
                                                    long long *stats) {
@@ -139,9 +193,11 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
     while (lv) {
         const int ip = __ffsll((long long)lv) - 1;
         lv &= lv - 1;
-        if (k % 12 == 0) codew = ws.code[(int64_t)(k / 12) * g.C + c];
-        if (k % 9 == 0 && k > 0) { ws.res[(int64_t)(k / 9 - 1) * g.C + c] = resw; resw = 0; }
-        const int code = (int)((codew >> (5 * (k % 12))) & 31);
+        if ((k & 7) == 0) {
+            codew = ws.code[(int64_t)(k >> 3) * g.C + c];
+            if (k > 0) { ws.res[(int64_t)((k >> 3) - 1) * g.C + c] = resw; resw = 0; }
+        }
+        const int code = (int)((codew >> (8 * (k & 7))) & 255);
         const int kk = k++;
         occ_c &= ~(1ull << ip);
         if (code == JP_CODE_DELETE) { n_deleted++; continue; }
@@ -154,10 +210,10 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
         const int fs = __ffsll((long long)freebits) - 1;
         cursor = fs;
         ws.occ[c2] = o2 | (1ull << fs);
-        resw |= (uint64_t)(fs | 64) << (7 * (kk % 9));
+        resw |= (uint64_t)(fs | 64) << (8 * (kk & 7));
     }
     ws.occ[c] = occ_c;
-    ws.res[(int64_t)((k - 1) / 9) * g.C + c] = resw;
+    ws.res[(int64_t)((k - 1) >> 3) * g.C + c] = resw;
     if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
     if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);
 }
@@ -181,13 +237,13 @@ struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 #define JP_MV_U 4
 #define JP_MV_A 4      // arrays handled per register batch (coords + fields); more arrays loop again
 template <int N>
-__global__ void __launch_bounds__(256, 3) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* staging stride */) {
+__global__ void __launch_bounds__(256, 3) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* unused */) {
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t lv = ok ? ws.leave[c] : 0;
     if (!__any_sync(0xffffffffu, lv != 0)) return;
     uint64_t codew = 0, resw = 0;
-    int codepl = -1, respl = -1;
+    int respl = -1;
     for (int s0 = 0; s0 < g.S; s0 += JP_MV_U) {
         const unsigned bits = (unsigned)(lv >> s0) & ((1u << JP_MV_U) - 1u);
         if (!__any_sync(0xffffffffu, bits != 0)) continue;
@@ -199,12 +255,11 @@ __global__ void __launch_bounds__(256, 3) k_move_gather(JpGrid g, MovePlanWs ws,
             act[u] = false; pos[u] = 0; e[u] = c + (int64_t)s * g.C;
             if ((bits >> u) & 1u) {
                 const int k = __popcll(lv & ((1ull << s) - 1));
-                if (k / 9 != respl) { respl = k / 9; resw = ws.res[(int64_t)respl * g.C + c]; }
-                const int r = (int)((resw >> (7 * (k % 9))) & 127);
+                if ((k >> 3) != respl) { respl = k >> 3; resw = ws.res[(int64_t)respl * g.C + c]; codew = ws.code[(int64_t)respl * g.C + c]; }
+                const int r = (int)((resw >> (8 * (k & 7))) & 255);
                 if (r & 64) {
                     const int fs = r & 63;
-                    if (k / 12 != codepl) { codepl = k / 12; codew = ws.code[(int64_t)codepl * g.C + c]; }
-                    const int code = (int)((codew >> (5 * (k % 12))) & 31);
+                    const int code = (int)((codew >> (8 * (k & 7))) & 255);
                     int dv[3];
                     jp_code_dir(code, dv);
                     const int64_t c2 = c + dv[0] + (int64_t)g.n[0] * (dv[1] + (N == 3 ? (int64_t)g.n[1] * dv[2] : 0));
@@ -213,18 +268,23 @@ __global__ void __launch_bounds__(256, 3) k_move_gather(JpGrid g, MovePlanWs ws,
                 }
             }
         }
-        for (int a0 = 0; a0 < arrs.n; a0 += JP_MV_A) {
+        // staging is array-of-structs: one migrant = AS consecutive doubles (AS = n rounded up to 4,
+        // padding written too), so every touched 32-byte sector is written completely (no fill read)
+        const int AS = (arrs.n + 3) & ~3;
+        for (int a0 = 0; a0 < AS; a0 += JP_MV_A) {
             double v[JP_MV_U][JP_MV_A];
 #pragma unroll
             for (int u = 0; u < JP_MV_U; u++)
 #pragma unroll
                 for (int a = 0; a < JP_MV_A; a++)
-                    if (act[u] && a0 + a < arrs.n) v[u][a] = arrs.a[a0 + a][e[u]];
+                    v[u][a] = (act[u] && a0 + a < arrs.n) ? arrs.a[a0 + a][e[u]] : 0.0;
 #pragma unroll
             for (int u = 0; u < JP_MV_U; u++)
-#pragma unroll
-                for (int a = 0; a < JP_MV_A; a++)
-                    if (act[u] && a0 + a < arrs.n) stage[(int64_t)(a0 + a) * M + pos[u]] = v[u][a];
+                if (act[u]) {
+                    double2 *dst = reinterpret_cast<double2 *>(stage + pos[u] * AS + a0);
+                    dst[0] = make_double2(v[u][0], v[u][1]);
+                    dst[1] = make_double2(v[u][2], v[u][3]);
+                }
         }
     }
 }
@@ -245,13 +305,14 @@ __global__ void __launch_bounds__(256, 3) k_move_scatter(JpGrid g, MovePlanWs ws
         int64_t pos[JP_MV_U];
 #pragma unroll
         for (int u = 0; u < JP_MV_U; u++) pos[u] = base + __popcll(amask & ((1ull << (s0 + u)) - 1));
+        const int AS = (arrs.n + 3) & ~3;
         for (int a0 = 0; a0 < arrs.n; a0 += JP_MV_A) {
             double v[JP_MV_U][JP_MV_A];
 #pragma unroll
             for (int u = 0; u < JP_MV_U; u++)
 #pragma unroll
                 for (int a = 0; a < JP_MV_A; a++)
-                    if (a0 + a < arrs.n && ((chb >> u) & 1u)) v[u][a] = ((arb >> u) & 1u) ? stage[(int64_t)(a0 + a) * M + pos[u]] : NAN;
+                    if (a0 + a < arrs.n && ((chb >> u) & 1u)) v[u][a] = ((arb >> u) & 1u) ? stage[pos[u] * AS + a0 + a] : NAN;
 #pragma unroll
             for (int u = 0; u < JP_MV_U; u++)
 #pragma unroll

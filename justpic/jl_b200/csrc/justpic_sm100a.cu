@@ -38,8 +38,8 @@ struct MovePlanWs {
     uint64_t *occ;        // [C] running occupancy (plan) -> final occupancy
     uint64_t *occ0;       // [C] occupancy before the move
     uint64_t *leave;      // [C] slots vacated by the move (original leavers)
-    uint64_t *code;       // [ceil(S/12)][C] packed 5-bit destination codes of the leavers, slot order
-    uint64_t *res;        // [ceil(S/9)][C] packed 7-bit results (dest slot | placed << 6), slot order
+    uint64_t *code;       // [ceil(S/8)][C] destination codes of the leavers, one byte each, slot order
+    uint64_t *res;        // [ceil(S/8)][C] results (dest slot | placed << 6), one byte per leaver, slot order
     uint64_t *arrmask;    // [C] slots receiving an arrival
     uint32_t *cnt;        // [C+1] arrivals per cell
     uint32_t *off;        // [C+1] exclusive scan of cnt (off[C] = total)
@@ -748,8 +748,8 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
 static int move_plan_alloc(jp_ctx *ctx) {
     const JpGrid &g = ctx->g;
     if (ctx->mp.code) return JP_OK;
-    JP_CUDA(cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * (size_t)((g.S + 11) / 12) * g.C));
-    JP_CUDA(cudaMalloc(&ctx->mp.res, sizeof(uint64_t) * (size_t)((g.S + 8) / 9) * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * (size_t)((g.S + 7) / 8) * g.C));
+    JP_CUDA(cudaMalloc(&ctx->mp.res, sizeof(uint64_t) * (size_t)((g.S + 7) / 8) * g.C));
     JP_CUDA(cudaMalloc(&ctx->mp.occ0, sizeof(uint64_t) * g.C));
     JP_CUDA(cudaMalloc(&ctx->mp.arrmask, sizeof(uint64_t) * g.C));
     JP_CUDA(cudaMalloc(&ctx->mp.cnt, sizeof(uint32_t) * (g.C + 1)));
@@ -815,7 +815,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     MoveArrays arrs; arrs.n = 0;
     for (int d = 0; d < N; d++) arrs.a[arrs.n++] = p->coords[d];
     for (int i = 0; i < a.n; i++) arrs.a[arrs.n++] = a.a[i];
-    const size_t need = M * (size_t)arrs.n;
+    const size_t need = M * (size_t)((arrs.n + 3) & ~3);        // array-of-structs staging, stride padded to 4 doubles
     if (need > ctx->stage_elems) {
         if (ctx->stage) JP_CUDA(cudaFree(ctx->stage));
         ctx->stage = nullptr; ctx->stage_elems = 0;
