@@ -50,7 +50,10 @@ struct jp_ctx {
     JpGrid g;             // device pointers
     void *gridmem;        // one allocation holding all grid vectors
     uint64_t *occ, *leave;  // [C] occupancy / leave words (move, inject)
-    uint8_t *flag;        // [C] inject candidate flags
+    uint8_t *inbox;       // [C] 1: every live particle of the cell lies in its closed box (inject)
+    int *inj_list;        // [2^N][cap] cells to inject into, per colour
+    unsigned int *inj_count;  // [8]
+    int64_t inj_cap;
     long long *stats;     // device counters: [0..2] move, [3] inject
     double *p2g_ws;       // [2 * 2^N * C] per-cell partial sums of the two-pass particle2grid (lazy)
     int p2g_mode;         // JP_P2G_EXACT / JP_P2G_TWOPASS / JP_P2G_TWOPASS_FASTW
@@ -305,43 +308,184 @@ __global__ void __launch_bounds__(256) k_clean(JpGrid g, Ptr3 co, uint8_t *index
     }
 }
 
-// inject_particles! pass A: flag the cells the reference would inject into
+// inject_particles! pass A (thread = cell, coalesced): occupancy word + "would the reference
+// inject here?" -> the cell is appended to the work list of its colour (order within a colour
+// is irrelevant: same-colour cells only read their neighbours, which have other colours).
 template <int N>
-__global__ void __launch_bounds__(256) k_inject_classify(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, int min_xq, uint8_t *flag) {
+__global__ void __launch_bounds__(256) k_inject_classify(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, int min_xq,
+                                                         uint64_t *occ, uint8_t *inbox, int *list, unsigned int *count, int64_t cap) {
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
-    double vq[3], dq[3];
+    double vq[3], ub[3], hi[3];
     if (ok)
-        for (int d = 0; d < N; d++) { vq[d] = g.xv[d][ci[d]]; dq[d] = jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; }
+        for (int d = 0; d < N; d++) { vq[d] = g.xv[d][ci[d]]; ub[d] = vq[d] + jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; hi[d] = g.xv[d][ci[d] + 1]; }
     int nq0 = 0;
-    for (int s = 0; s < g.S; s++) {
-        const bool live = (m >> s) & 1ull;
-        if (!__any_sync(0xffffffffu, live)) continue;
-        if (live) {
-            const int64_t e = c + (int64_t)s * g.C;
-            double p[3];
+    bool allin = true;       // every live particle lies in the closed box [xv[i], xv[i+1]]^N (lets the donor search prune this cell)
+    for (int s0 = 0; s0 < g.S; s0 += 4) {
+        const unsigned bits = (unsigned)(m >> s0) & 15u;
+        if (!__any_sync(0xffffffffu, bits != 0)) continue;
+        double p[4][3];
 #pragma unroll
-            for (int d = 0; d < N; d++) p[d] = co.p[d][e];
-            nq0 += jp_isincell<N>(p, vq, dq) ? 1 : 0;
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int d = 0; d < N; d++) p[u][d] = ((bits >> u) & 1u) ? co.p[d][c + (int64_t)(s0 + u) * g.C] : NAN;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            bool in = (bits >> u) & 1u;
+#pragma unroll
+            for (int d = 0; d < N; d++) in = in && (vq[d] < p[u][d]) && (p[u][d] < ub[d]);
+            nq0 += in ? 1 : 0;
+            if ((bits >> u) & 1u) {
+#pragma unroll
+                for (int d = 0; d < N; d++) allin = allin && (vq[d] <= p[u][d]) && (p[u][d] <= hi[d]);
+            }
         }
     }
-    if (ok) flag[c] = jp_inject_candidate(nq0, __popcll(m), g.S, min_xq) ? 1 : 0;
+    if (ok) {
+        occ[c] = m;
+        inbox[c] = allin ? 1 : 0;
+        if (jp_inject_candidate(nq0, __popcll(m), g.S, min_xq)) {
+            const int col = (N == 3 ? ((ci[0] & 1) * 4 + (ci[1] & 1) * 2 + (ci[2] & 1)) : ((ci[0] & 1) * 2 + (ci[1] & 1)));
+            const unsigned pos = atomicAdd(&count[col], 1u);
+            list[(int64_t)col * cap + pos] = (int)c;
+        }
+    }
 }
 
-// inject_particles! pass B: one colour of the 2^N sweeps, flagged cells only
+// inject_particles! pass B: one colour of the 2^N sweeps, ONE WARP per listed cell.
+// Literal _inject_particles! (src/Particles/injection.jl:68-131): quadrant counts by ballot
+// over the cell's slots, new particles in ascending free slots, and the nearest-donor search
+// (index_min_distance, :330-393) spread over the lanes -- 3^N cells x S slots candidates,
+// reduced with the lexicographic key (distance, visiting order) so that the winner is the
+// candidate the reference's serial "strictly smaller" scan would keep.
 template <int N>
-__global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, const uint8_t *__restrict__ flag,
-                                                      int min_xcell, uint64_t seed, uint32_t step, int ox, int oy, int oz, long long *stats) {
-    int ci[3];
-    ci[0] = 2 * (blockIdx.x * JP_BX + threadIdx.x) + ox;
-    ci[1] = 2 * (blockIdx.y * JP_BY + threadIdx.y) + oy;
-    ci[2] = N == 3 ? 2 * blockIdx.z + oz : 0;
-    if (ci[0] >= g.n[0] || ci[1] >= g.n[1] || (N == 3 && ci[2] >= g.n[2])) return;
-    const int64_t c = jp_cell_lin<N>(g, ci);
-    if (!flag[c]) return;
-    const int inj = jp_inject_cell<N>(g, co.p, index, args, min_xcell, seed, step, c, ci);
-    if (inj) atomicAdd((unsigned long long *)&stats[3], (unsigned long long)inj);
+__global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ,
+                                                      uint8_t *inbox, const int *__restrict__ list, const unsigned int *__restrict__ count,
+                                                      int min_xcell, uint64_t seed, uint32_t step, long long *stats) {
+    const int lane = threadIdx.x & 31;
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    const unsigned n = *count;
+    const int S = g.S, NQ = N == 2 ? 4 : 8;
+    const int min_xq = (min_xcell + NQ - 1) / NQ;
+    const uint64_t smask = S == 64 ? ~0ull : ((1ull << S) - 1);
+    const int nx = g.n[0], ny = g.n[1], nz = N == 3 ? g.n[2] : 1;
+    for (unsigned t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n; t += nwarps) {
+        const int64_t c = list[t];
+        int ci[3];
+        jp_cell_ijk<N>(g, c, ci);
+        uint64_t occ_c = occ[c];
+        double p[2][3];
+        bool live[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int s = lane + 32 * h;
+            live[h] = s < S && ((occ_c >> s) & 1ull);
+#pragma unroll
+            for (int d = 0; d < N; d++) p[h][d] = live[h] ? co.p[d][c + (int64_t)s * g.C] : NAN;
+        }
+        double xvc[3], dq[3];
+#pragma unroll
+        for (int d = 0; d < N; d++) { xvc[d] = g.xv[d][ci[d]]; dq[d] = jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; }
+        int injected = 0;
+#pragma unroll 1
+        for (int iq = 0; iq < NQ; iq++) {
+            double vq[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) vq[d] = xvc[d] + dq[d] * (double)((iq >> d) & 1);
+            int num = 0;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const bool in = live[h] && jp_isincell<N>(p[h], vq, dq);
+                num += __popc(__ballot_sync(0xffffffffu, in));
+            }
+            if (num >= min_xq) break;
+            uint64_t freem = ~occ_c & smask;
+            while (freem) {
+                const int i = __ffsll((long long)freem) - 1;
+                freem &= freem - 1;
+                num++;
+                double r[3], pn[3];
+                jp_rand3(seed, 1u, step, (uint32_t)c, (uint32_t)i, r);
+#pragma unroll
+                for (int d = 0; d < N; d++) pn[d] = vq[d] + dq[d] * fma(0.95, r[d], 0.05);
+                const int64_t e = c + (int64_t)i * g.C;
+                if (lane == 0) {
+                    bool inside = true;
+#pragma unroll
+                    for (int d = 0; d < N; d++) {
+                        co.p[d][e] = pn[d];
+                        inside = inside && (g.xv[d][ci[d]] <= pn[d]) && (pn[d] <= g.xv[d][ci[d] + 1]);
+                    }
+                    index[e] = 1;
+                    if (!inside) inbox[c] = 0;       // keep the pruning flag truthful for later colours
+                }
+                occ_c |= 1ull << i;
+                if ((i & 31) == lane) {
+                    const int h = i >> 5;
+                    if (h == 0) { live[0] = true; for (int d = 0; d < N; d++) p[0][d] = pn[d]; }
+                    else        { live[1] = true; for (int d = 0; d < N; d++) p[1][d] = pn[d]; }
+                }
+                injected++;
+                // nearest live particle in the 3^N neighbourhood.  The winner is the minimum of the
+                // key (distance, visiting order of the reference), so cells may be evaluated in any
+                // order: own cell first, then the others, skipping a cell when every particle it
+                // holds is known to lie in its closed box (inbox) and the box is farther than the
+                // best distance so far (all IEEE operations involved are monotonic, so the computed
+                // box distance never exceeds the computed distance of a particle inside the box).
+                double best_d = INFINITY;
+                int best_ord = 0x7fffffff;
+                long long best_e = -1;
+#pragma unroll 1
+                for (int it = 0; it < (N == 3 ? 27 : 9); it++) {
+                    const int self = N == 3 ? 13 : 4;
+                    const int nidx = it == 0 ? self : (it <= self ? it - 1 : it);      // own cell first
+                    const int ii = ci[0] + nidx % 3 - 1, jj = ci[1] + (nidx / 3) % 3 - 1, kk = N == 3 ? ci[2] + nidx / 9 - 1 : 0;
+                    if (ii < 0 || jj < 0 || kk < 0 || ii >= nx || jj >= ny || kk >= nz) continue;
+                    const int64_t c2 = ii + (int64_t)nx * (jj + (int64_t)ny * kk);
+                    if (c2 != c && inbox[c2]) {
+                        const int cc[3] = {ii, jj, kk};
+                        double bx[3];
+#pragma unroll
+                        for (int d = 0; d < N; d++) {
+                            const double lo = g.xv[d][cc[d]], hi = g.xv[d][cc[d] + 1];
+                            bx[d] = pn[d] < lo ? lo : (pn[d] > hi ? hi : pn[d]);      // nearest point of the box
+                        }
+                        if (jp_distance<N>(bx, pn) > best_d) continue;
+                    }
+                    const uint64_t o2 = c2 == c ? occ_c : occ[c2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int s = lane + 32 * h;
+                        if (s < S && ((o2 >> s) & 1ull) && !(c2 == c && s == i)) {
+                            double q[3];
+                            if (c2 == c) { for (int d = 0; d < N; d++) q[d] = p[h][d]; }
+                            else { for (int d = 0; d < N; d++) q[d] = co.p[d][c2 + (int64_t)s * g.C]; }
+                            const double dist = jp_distance<N>(q, pn);
+                            const int ord = nidx * 64 + s;
+                            if (dist < best_d || (dist == best_d && ord < best_ord)) { best_d = dist; best_ord = ord; best_e = c2 + (int64_t)s * g.C; }
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const double od = __shfl_xor_sync(0xffffffffu, best_d, off);
+                        const int oo = __shfl_xor_sync(0xffffffffu, best_ord, off);
+                        const long long oe = __shfl_xor_sync(0xffffffffu, best_e, off);
+                        if (od < best_d || (od == best_d && oo < best_ord)) { best_d = od; best_ord = oo; best_e = oe; }
+                    }
+                }
+                if (best_e >= 0 && lane == 0)
+                    for (int a = 0; a < args.n; a++) args.a[a][e] = args.a[a][best_e];
+                __syncwarp();
+                if (num >= min_xq) break;
+            }
+        }
+        if (lane == 0) {
+            occ[c] = occ_c;
+            if (injected) atomicAdd((unsigned long long *)&stats[3], (unsigned long long)injected);
+        }
+        __syncwarp();
+    }
 }
 
 // grid2particle!
@@ -624,11 +768,14 @@ extern "C" int jp_ctx_create(const jp_grid_desc *d, int device, jp_ctx **out) {
     if (e == cudaSuccess) e = cudaMemcpy(dm, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->occ, g.C * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->leave, g.C * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->flag, g.C);
+    ctx->inj_cap = (int64_t)((g.n[0] + 1) / 2) * ((g.n[1] + 1) / 2) * ((g.n[2] + 1) / 2);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->inj_list, sizeof(int) * 8 * ctx->inj_cap);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->inj_count, 8 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->inbox, g.C);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->stats, 8 * sizeof(long long));
     if (e == cudaSuccess) e = cudaMemset(ctx->stats, 0, 8 * sizeof(long long));
     if (e != cudaSuccess) {
-        cudaFree(dm); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->flag); cudaFree(ctx->stats);
+        cudaFree(dm); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->inj_list); cudaFree(ctx->inj_count); cudaFree(ctx->inbox); cudaFree(ctx->stats);
         free(ctx);
         return jp_fail(JP_ERR_CUDA, "jp_ctx_create: %s", cudaGetErrorString(e));
     }
@@ -643,7 +790,7 @@ extern "C" int jp_ctx_create(const jp_grid_desc *d, int device, jp_ctx **out) {
 extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->flag); cudaFree(ctx->stats);
+    cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->inj_list); cudaFree(ctx->inj_count); cudaFree(ctx->inbox); cudaFree(ctx->stats);
     cudaFree(ctx->p2g_ws);
     cudaFree(ctx->mp.code); cudaFree(ctx->mp.res); cudaFree(ctx->mp.occ0); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
     cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage);
@@ -890,17 +1037,17 @@ extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args
     const int NQ = g.ndim == 2 ? 4 : 8;
     const int min_xq = (min_xcell + NQ - 1) / NQ;
     JP_CUDA(cudaMemsetAsync(ctx->stats + 3, 0, sizeof(long long), st));
-    if (g.ndim == 2) k_inject_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->flag);
-    else             k_inject_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->flag);
+    if ((int64_t)g.C >= (1ll << 31)) return jp_fail(JP_ERR_UNSUPPORTED, "jp_inject: more than 2^31 cells");
+    JP_CUDA(cudaMemsetAsync(ctx->inj_count, 0, 8 * sizeof(unsigned int), st));
+    if (g.ndim == 2) k_inject_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
+    else             k_inject_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
     JP_CHECK_LAUNCH();
-    const int ncx = (g.n[0] + 1) / 2, ncy = (g.n[1] + 1) / 2, ncz = g.ndim == 3 ? (g.n[2] + 1) / 2 : 1;
-    const dim3 sg = tile_grid(ncx, ncy, ncz);
-    for (int ox = 0; ox < 2; ox++)
-        for (int oy = 0; oy < 2; oy++)
-            for (int oz = 0; oz < (g.ndim == 3 ? 2 : 1); oz++) {
-                if (g.ndim == 2) k_inject_sweep<2><<<sg, blk, 0, st>>>(g, co, p->index, a, ctx->flag, min_xcell, seed, step, ox, oy, oz, ctx->stats);
-                else             k_inject_sweep<3><<<sg, blk, 0, st>>>(g, co, p->index, a, ctx->flag, min_xcell, seed, step, ox, oy, oz, ctx->stats);
-            }
+    // colour order of the reference: offset_i outermost (src/Particles/injection.jl:30-49)
+    const int ncol = g.ndim == 3 ? 8 : 4;
+    for (int col = 0; col < ncol; col++) {
+        if (g.ndim == 2) k_inject_sweep<2><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats);
+        else             k_inject_sweep<3><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats);
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
