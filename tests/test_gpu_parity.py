@@ -353,3 +353,22 @@ def test_full_size_invariants(cfg):
     J.phase_ratios_center(pr, p, ph)
     s = pr.center.sum(dim=0)
     assert bool(torch.allclose(s, torch.ones_like(s), rtol=1e-13))
+
+
+def test_unsupported_and_invalid_arguments():
+    """Error behaviour across the boundary: status codes -> exceptions, nothing crashes."""
+    J = jp()
+    gr = make_grids(6, 2, True)
+    with pytest.raises(J._cabi.JustPICError):            # max_xcell > 64: JP_ERR_UNSUPPORTED
+        J.init_particles(J.CUDABackend, 8, 80, 4, *gr.grid_vel)
+    t = Twin(2, 6, True)
+    many = J.init_cell_arrays(t.p, 17)
+    with pytest.raises(ValueError):                      # more than JP_MAX_ARGS fields in one call
+        J.move_particles(t.p, many)
+    with pytest.raises(ValueError):
+        J.particle2grid(torch.zeros(7 * 7, device="cuda", dtype=torch.float64), many[0], t.p, mode="bogus")
+    with pytest.raises(ValueError):                      # wrong dtype
+        J.grid2particle(many[0].float(), torch.zeros(7 * 7, device="cuda", dtype=torch.float64), t.p)
+    pr = J.PhaseRatios(J.CUDABackend, 40, gr.n)          # more than JP_MAX_PHASES
+    with pytest.raises(J._cabi.JustPICError):
+        J.phase_ratios_center(pr, t.p, many[0])
