@@ -18,14 +18,47 @@
 //     routine (jp_interp_velocity_literal), so results are bitwise those of the
 //     literal code in every case.
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include "jp_core.h"
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers --------------------------------------
+struct AdvTmaMaps { CUtensorMap m[3]; };
+
+__device__ __forceinline__ void adv_mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void adv_mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void adv_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_LOOP;\n\t}"
+        ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void adv_tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                   "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void adv_tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)),
+                   "r"(x), "r"(y) : "memory");
+}
 
 template <int N> struct AdvTile {
     static constexpr int TX = 32;
     static constexpr int TY = N == 3 ? 4 : 8;
     static constexpr int TZ = N == 3 ? 2 : 1;
-    static constexpr int EX = TX + 4, EY = TY + 4, EZ = N == 3 ? TZ + 4 : 1;   // staged nodes per dim
-    static constexpr int VOL = EX * EY * EZ;
+    // staged nodes per dim: one node below the brick in y/z; TWO below in x so that the box starts
+    // on an even node -- TMA needs the box origin 16-byte aligned in the innermost dimension
+    static constexpr int OX = 2;
+    static constexpr int EX = TX + 6, EY = TY + 4, EZ = N == 3 ? TZ + 4 : 1;
+    static constexpr int VOL = ((EX * EY * EZ + 15) / 16) * 16;                 // tile pitch: multiple of 128 bytes
     static constexpr int NW = TY * TZ;                                          // warps per CTA
 };
 
@@ -34,7 +67,7 @@ template <int N> struct AdvSmem {
     using T = AdvTile<N>;
     static constexpr int V_OFF = 0;                       // N tiles of VOL doubles
     static constexpr int XV_OFF = N * T::VOL;             // per dim: EX/EY/EZ entries (xv), padded to 40
-    static constexpr int VEC = 40;
+    static constexpr int VEC = 40;                        // >= EX
     static constexpr int XG_OFF = XV_OFF + 3 * VEC;
     static constexpr int IXV_OFF = XG_OFF + 3 * VEC;
     static constexpr int IXG_OFF = IXV_OFF + 3 * VEC;
@@ -101,23 +134,47 @@ __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__rest
 
 template <int N, int SCHEME, bool UNIFORM>
 __global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
-                                                                     double alpha, double dt) {
+                                                                     double alpha, double dt,
+                                                                     const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                                                                     const __grid_constant__ CUtensorMap tm2, int tma_mask) {
     using T = AdvTile<N>;
     using L = AdvSmem<N>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA destinations: 128-byte aligned (VOL*8 is a multiple of 128)
     double *sm = reinterpret_cast<double *>(smem_raw);
     uint16_t *wl_all = reinterpret_cast<uint16_t *>(smem_raw + sizeof(double) * L::NDOUBLES);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // brick origin (cells) and first staged node (one below)
     const int b0[3] = {(int)blockIdx.x * T::TX, (int)blockIdx.y * T::TY, N == 3 ? (int)blockIdx.z * T::TZ : 0};
-    const int c0[3] = {b0[0] - 1, b0[1] - 1, N == 3 ? b0[2] - 1 : 0};
+    const int c0[3] = {b0[0] - T::OX, b0[1] - 1, N == 3 ? b0[2] - 1 : 0};
 
-    // ---- 1. stage velocity stencils and grid-vector segments
+    // ---- 1. stage velocity stencils and grid-vector segments.
+    // Components whose array meets the TMA constraints (16-byte aligned base and row pitch) are
+    // fetched as ONE 3-D (2-D) box per component by cp.async.bulk.tensor, out-of-range nodes
+    // zero-filled by the hardware, completion signalled on an mbarrier; the others (e.g. Vx, whose
+    // leading extent n+1 is odd) by cooperative coalesced loads.
+    __shared__ __align__(8) uint64_t tma_bar;
+    if (tma_mask) {
+        if (tid == 0) adv_mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            adv_mbar_expect_tx(&tma_bar, (unsigned)(__popc(tma_mask) * T::EX * T::EY * T::EZ * sizeof(double)));
+            // (descriptors are addressed statically: they must stay in kernel-parameter space)
+            if (N == 3) {
+                if (tma_mask & 1) adv_tma_load_3d(sm + L::V_OFF + 0 * T::VOL, &tm0, &tma_bar, c0[0], c0[1], c0[2]);
+                if (tma_mask & 2) adv_tma_load_3d(sm + L::V_OFF + 1 * T::VOL, &tm1, &tma_bar, c0[0], c0[1], c0[2]);
+                if (tma_mask & 4) adv_tma_load_3d(sm + L::V_OFF + 2 * T::VOL, &tm2, &tma_bar, c0[0], c0[1], c0[2]);
+            } else {
+                if (tma_mask & 1) adv_tma_load_2d(sm + L::V_OFF + 0 * T::VOL, &tm0, &tma_bar, c0[0], c0[1]);
+                if (tma_mask & 2) adv_tma_load_2d(sm + L::V_OFF + 1 * T::VOL, &tm1, &tma_bar, c0[0], c0[1]);
+            }
+        }
+    }
     for (int c = 0; c < N; c++) {
+        if ((tma_mask >> c) & 1) continue;
         const double *__restrict__ F = V.p[c];
         const int n0 = g.nvel[c][0], n1 = g.nvel[c][1], n2 = N == 3 ? g.nvel[c][2] : 1;
-        for (int t = tid; t < T::VOL; t += T::NW * 32) {
+        for (int t = tid; t < T::EX * T::EY * T::EZ; t += T::NW * 32) {
             const int ix = t % T::EX, iy = (t / T::EX) % T::EY, iz = t / (T::EX * T::EY);
             const int gx = c0[0] + ix, gy = c0[1] + iy, gz = N == 3 ? c0[2] + iz : 0;
             double val = 0.0;
@@ -152,6 +209,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, P
 #pragma unroll 8
         for (int s = 0; s < g.S; s++) m |= (uint64_t)(ip[(int64_t)s * g.C] != 0) << s;
     }
+    if (tma_mask) adv_mbar_wait(&tma_bar, 0);   // TMA boxes have landed
     __syncthreads();                      // stencils staged by all warps
 
     // ---- 3. ballot the occupancy masks slot by slot into a small ring of compacted
@@ -174,7 +232,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, P
                 const int ent = ring[k & (L::RING - 1)];
                 const int sl = ent >> 5, l = ent & 31;
                 const int64_t e = crow + b0[0] + l + (int64_t)sl * g.C;
-                const int r0[3] = {l + 1, wy + 1, wz + 1};
+                const int r0[3] = {l + T::OX, wy + 1, wz + 1};
                 const int cell1[3] = {b0[0] + l + 1, cy + 1, cz + 1};
                 double p0[3], k1[3], k2[3], q[3], pn[3];
 #pragma unroll

@@ -839,6 +839,45 @@ extern "C" int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxc
     return JP_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link against libcuda)
+typedef CUresult (*jp_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static jp_encode_tiled_fn jp_get_encode_tiled() {
+    static jp_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (getenv("JP_NO_TMA") == nullptr &&
+            cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (jp_encode_tiled_fn)p;
+    }
+    return fn;
+}
+
+// Tensor maps for the velocity components that satisfy the TMA constraints; returns the component mask.
+template <int N>
+static int build_advect_tma(const JpGrid &g, CPtr3 V, AdvTmaMaps &maps) {
+    using T = AdvTile<N>;
+    memset(&maps, 0, sizeof(maps));
+    jp_encode_tiled_fn enc = jp_get_encode_tiled();
+    if (!enc) return 0;
+    int mask = 0;
+    for (int c = 0; c < N; c++) {
+        const cuuint64_t dims[3] = {(cuuint64_t)g.nvel[c][0], (cuuint64_t)g.nvel[c][1], (cuuint64_t)(N == 3 ? g.nvel[c][2] : 1)};
+        const cuuint64_t strides[2] = {dims[0] * 8, dims[0] * dims[1] * 8};        // bytes, dims 1..rank-1
+        if (((uintptr_t)V.p[c] & 15) || (strides[0] & 15) || (N == 3 && (strides[1] & 15))) continue;
+        const cuuint32_t box[3] = {(cuuint32_t)T::EX, (cuuint32_t)T::EY, (cuuint32_t)T::EZ};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&maps.m[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, N, (void *)V.p[c], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            mask |= 1 << c;
+    }
+    return mask;
+}
+
 template <int N, int SCHEME, bool UNIFORM>
 static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
     using T = AdvTile<N>;
@@ -849,8 +888,10 @@ static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co,
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    AdvTmaMaps maps;
+    const int tma_mask = build_advect_tma<N>(g, V, maps);
     const dim3 grd((g.n[0] + T::TX - 1) / T::TX, (g.n[1] + T::TY - 1) / T::TY, N == 3 ? (g.n[2] + T::TZ - 1) / T::TZ : 1);
-    k_advect_tile<N, SCHEME, UNIFORM><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt);
+    k_advect_tile<N, SCHEME, UNIFORM><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask);
     return cudaSuccess;
 }
 
