@@ -621,6 +621,129 @@ int jpo_phase_ratios_center(const jpo_grid *g, const double *const *coords, doub
     return 0;
 }
 
+/* accumulate_weight / phase_ratio_weights inner step: w .+ x .* (phase == j), x*false = strong zero */
+static inline void acc_phase(double *w, int K, double x, double ph) {
+    for (int k = 0; k < K; k++) w[k] = w[k] + (ph == (double)(k + 1) ? x : copysign(0.0, x));
+}
+
+/* ---- phase_ratios_vertex! (src/PhaseRatios/vertices.jl:4-107) ---------------
+ * ratios: CellArray over the vertex grid, element (node, phase k) at node + k*NN.
+ * Loop order: offset_i (x) OUTERMOST ... offset_k innermost; half-cell test with >=;
+ * NaNs (vertices with no particle in range) are left as they are. */
+int jpo_phase_ratios_vertex(const jpo_grid *g, const double *const *coords, double *ratios, const double *phases, int K) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1], nz = N == 3 ? g->n[2] : 0;
+    const int64_t NN = (int64_t)(nx + 1) * (ny + 1) * (N == 3 ? nz + 1 : 1);
+    if (K > 64) return -1;
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t nd = 0; nd < NN; nd++) {
+        int I[3] = {(int)(nd % (nx + 1)), (int)((nd / (nx + 1)) % (ny + 1)), (int)(nd / ((int64_t)(nx + 1) * (ny + 1)))};
+        double xv[3] = {g->xv[0][I[0]], g->xv[1][I[1]], N == 3 ? g->xv[2][I[2]] : 0.0};
+        double w[64];
+        for (int k = 0; k < K; k++) w[k] = 0.0;
+        for (int oi = -1; oi <= 0; oi++) {
+            int ic = I[0] + oi;
+            if (ic < 0 || ic >= nx) continue;
+            for (int oj = -1; oj <= 0; oj++) {
+                int jc = I[1] + oj;
+                if (jc < 0 || jc >= ny) continue;
+                for (int ok = (N == 3 ? -1 : 0); ok <= 0; ok++) {
+                    int kc = N == 3 ? I[2] + ok : 0;
+                    if (N == 3 && (kc < 0 || kc >= nz)) continue;
+                    int cc[3] = {ic, jc, kc};
+                    double di[3];
+                    for (int d = 0; d < N; d++) di[d] = d_of(g->xv[d], g->uniform, cc[d]);
+                    const int64_t c = ic + (int64_t)nx * (jc + (int64_t)ny * kc);
+                    for (int s = 0; s < g->S; s++) {
+                        const int64_t e = c + (int64_t)s * C;
+                        double p[3];
+                        int nan = 0, out = 0;
+                        for (int d = 0; d < N; d++) { p[d] = coords[d][e]; nan |= isnan(p[d]); }
+                        if (nan) continue;
+                        for (int d = 0; d < N; d++) if (fabs(p[d] - xv[d]) >= di[d] / 2) { out = 1; break; }
+                        if (out) continue;
+                        acc_phase(w, K, bilinear_weight(N, xv, p, di), phases[e]);
+                    }
+                }
+            }
+        }
+        double sum = w[0];
+        for (int k = 1; k < K; k++) sum = sum + w[k];
+        const double inv = 1.0 / sum;
+        for (int k = 0; k < K; k++) ratios[nd + (int64_t)k * NN] = w[k] * inv;
+    }
+    return 0;
+}
+
+/* ---- phase_ratios_face! (src/PhaseRatios/midpoints.jl:3-82) -----------------
+ * dim = 0/1/2 (:x/:y/:z).  ratios: CellArray over the face grid (n + e_dim), element
+ * (face node, k) at node + k*NF.  Work-item = cell I: face I+e_dim from the cells I and
+ * min(I+e_dim, n) (the last cell is visited twice, as in the reference), plus the low
+ * boundary face when I[dim] == 1.  NaN (no particle in range) -> 0. */
+int jpo_phase_ratios_face(const jpo_grid *g, const double *const *coords, double *ratios, const double *phases, int K, int dim) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1], nz = N == 3 ? g->n[2] : 1;
+    int nf[3] = {nx + (dim == 0), ny + (dim == 1), nz + (N == 3 && dim == 2)};
+    const int64_t NF = (int64_t)nf[0] * nf[1] * nf[2];
+    if (K > 64 || dim < 0 || dim >= N) return -1;
+    int off[3] = {dim == 0, dim == 1, dim == 2};
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c0 = 0; c0 < C; c0++) {
+        int I[3] = {(int)(c0 % nx), (int)((c0 / nx) % ny), (int)(c0 / ((int64_t)nx * ny))};
+        double di[3], cen[3], face[3], w[64];
+        for (int d = 0; d < N; d++) {
+            di[d] = d_of(g->xv[d], g->uniform, I[d]);
+            cen[d] = g->xc[d][I[d]];
+            face[d] = cen[d] + di[d] * (double)off[d] / 2;
+        }
+        for (int k = 0; k < K; k++) w[k] = 0.0;
+        for (int pass = 0; pass < 2; pass++) {
+            int cc[3];
+            for (int d = 0; d < 3; d++) { cc[d] = I[d] + (pass ? off[d] : 0); if (cc[d] > g->n[d] - 1 && d < N) cc[d] = g->n[d] - 1; }
+            if (N == 2) cc[2] = 0;
+            for (int d = 0; d < N; d++) di[d] = d_of(g->xv[d], g->uniform, cc[d]);       /* `di` is reassigned (outer variable) */
+            const int64_t c = cc[0] + (int64_t)nx * (cc[1] + (int64_t)ny * cc[2]);
+            for (int s = 0; s < g->S; s++) {
+                const int64_t e = c + (int64_t)s * C;
+                double p[3];
+                int nan = 0, in = 1;
+                for (int d = 0; d < N; d++) { p[d] = coords[d][e]; nan |= isnan(p[d]); }
+                if (nan) continue;
+                for (int d = 0; d < N; d++) in &= fabs(p[d] - face[d]) <= di[d] / 2;
+                if (!in) continue;
+                acc_phase(w, K, bilinear_weight(N, face, p, di), phases[e]);
+            }
+        }
+        double sum = w[0];
+        for (int k = 1; k < K; k++) sum = sum + w[k];
+        double inv = 1.0 / sum;
+        const int64_t fo = (I[0] + off[0]) + (int64_t)nf[0] * ((I[1] + off[1]) + (int64_t)nf[1] * (I[2] + off[2]));
+        for (int k = 0; k < K; k++) { double v = w[k] * inv; ratios[fo + (int64_t)k * NF] = isnan(v) ? 0.0 : v; }
+        if (I[dim] == 0) {                                     /* isboundary(offsets, I): low boundary face */
+            for (int d = 0; d < N; d++) face[d] = cen[d] - di[d] * (double)off[d] / 2;    /* di = last assigned above */
+            for (int k = 0; k < K; k++) w[k] = 0.0;
+            for (int s = 0; s < g->S; s++) {
+                const int64_t e = c0 + (int64_t)s * C;
+                double p[3];
+                int nan = 0, in = 1;
+                for (int d = 0; d < N; d++) { p[d] = coords[d][e]; nan |= isnan(p[d]); }
+                if (nan) continue;
+                for (int d = 0; d < N; d++) in &= fabs(p[d] - face[d]) <= di[d] / 2;
+                if (!in) continue;
+                acc_phase(w, K, bilinear_weight(N, face, p, di), phases[e]);
+            }
+            sum = w[0];
+            for (int k = 1; k < K; k++) sum = sum + w[k];
+            inv = 1.0 / sum;
+            const int64_t fb = I[0] + (int64_t)nf[0] * (I[1] + (int64_t)nf[1] * I[2]);
+            for (int k = 0; k < K; k++) { double v = w[k] * inv; ratios[fb + (int64_t)k * NF] = isnan(v) ? 0.0 : v; }
+        }
+    }
+    return 0;
+}
+
 /* ---- update_cell_halo! semantics for ONE array on ONE axis (test helper) ---
  * ImplicitGlobalGrid.update_halo! with overlap 2 / halowidth 1
  * (src/CellArrays/ImplicitGlobalGrid.jl:36-41): my plane 2 -> left nbr's plane

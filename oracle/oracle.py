@@ -137,6 +137,12 @@ class Oracle:
     def particle2centroid(self, coords, Fc, Fp):
         return lib().jpo_particle2centroid(C.byref(self.g), _pp(coords), _dp(Fc), _dp(Fp))
 
+    def phase_ratios_vertex(self, coords, ratios, phases, K):
+        return lib().jpo_phase_ratios_vertex(C.byref(self.g), _pp(coords), _dp(ratios), _dp(phases), int(K))
+
+    def phase_ratios_face(self, coords, ratios, phases, K, dim):
+        return lib().jpo_phase_ratios_face(C.byref(self.g), _pp(coords), _dp(ratios), _dp(phases), int(K), int(dim))
+
     def phase_ratios_center(self, coords, ratios, phases, K):
         return lib().jpo_phase_ratios_center(C.byref(self.g), _pp(coords), _dp(ratios), _dp(phases), int(K))
 
