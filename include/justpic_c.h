@@ -47,7 +47,10 @@ typedef enum {
 } jp_status;
 
 typedef enum { JP_EULER = 0, JP_RK2 = 1, JP_RK4 = 2 } jp_scheme;
-typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2 } jp_option;
+/* JP_OPT_ADVECT_AFFINE (0/1, default 1): let the tiled advection kernel regenerate grid coordinates as
+ * fma(i, dx, x0) when jp_ctx_create verified that this reproduces EVERY stored entry bit for bit
+ * (results are identical either way; 0 forces the table look-ups, used by the parity tests). */
+typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3 } jp_option;
 typedef enum { JP_MOVE_AUTO = 0, JP_MOVE_DIRECT = 1 } jp_move_mode;
 typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;
 
@@ -82,6 +85,7 @@ void jp_ctx_destroy(jp_ctx *ctx);
 const char *jp_last_error(void);
 int  jp_version(void);
 int  jp_set_option(jp_ctx *ctx, int32_t option, int32_t value);
+int  jp_get_option(const jp_ctx *ctx, int32_t option, int32_t *value);   /* effective value (e.g. AFFINE = option && detected) */
 
 /* init_particles(backend, nxcell, max_xcell, min_xcell, xi_vel...)
  * (src/Particles/particles_utils.jl:108-166, kernel fill_coords_index! :168-194).

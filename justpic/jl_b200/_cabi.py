@@ -8,14 +8,18 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "libjustpic_sm100a.so"
+# JUSTPIC_LIB: developer override used by tools/ to A/B two builds of the SAME library
+LIB_PATH = Path(os.environ["JUSTPIC_LIB"]) if os.environ.get("JUSTPIC_LIB") else HERE / "libjustpic_sm100a.so"
 
 JP_MAX_ARGS = 16
 JP_MAX_SLOTS = 64
 JP_MAX_PHASES = 32
 JP_OPT_P2G_MODE = 1
 JP_OPT_MOVE_MODE = 2
+JP_OPT_ADVECT_AFFINE = 3
 JP_MOVE_AUTO, JP_MOVE_DIRECT = 0, 1
 JP_P2G_EXACT, JP_P2G_TWOPASS, JP_P2G_TWOPASS_FASTW = 0, 1, 2
 
@@ -48,6 +52,7 @@ SYMBOLS = {
     "jp_last_error": (C.c_char_p, []),
     "jp_version": (C.c_int, []),
     "jp_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "jp_get_option": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "jp_init_particles": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_uint64, C.c_void_p]),
     "jp_advect": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
                             C.POINTER(C.c_void_p), C.c_double, C.c_void_p]),

@@ -35,7 +35,7 @@ import torch
 from . import _cabi
 
 __all__ = [
-    "CUDABackend", "LinRange", "expand_range", "add_ghost_nodes",
+    "CUDABackend", "LinRange", "StepRange", "expand_range", "add_ghost_nodes",
     "Euler", "RungeKutta2", "RungeKutta4",
     "Particles", "PhaseRatios",
     "init_particles", "init_cell_arrays", "cell_array",
@@ -85,12 +85,25 @@ class LinRange:
         return np.asarray(self)[i]
 
 
+class StepRange(LinRange):
+    """Julia ``range(start, stop, length=len)`` (``StepRangeLen`` with twice-precision arithmetic):
+    element i is the correctly rounded value of ``start + i*(stop-start)/(len-1)``, e.g. exact
+    multiples of 2^-k on power-of-two grids (the README's grids, README.md:24-48), whereas
+    ``LinRange`` rounds ``(1-t)*start + t*stop`` term by term.  Same *range* code path as LinRange."""
+
+    def __array__(self, dtype=None, copy=None):
+        from fractions import Fraction
+        a, b, d = Fraction(self.start), Fraction(self.stop), max(self.len - 1, 1)
+        out = np.array([float(a + (b - a) * i / d) for i in range(self.len)], dtype=np.float64)
+        return out if dtype is None else out.astype(dtype)
+
+
 def expand_range(x: LinRange) -> LinRange:
     """``expand_range`` of the reference scripts/tests (e.g.
     scripts/temperature_advection3D.jl:12-19): one ghost node on either side."""
     a = np.asarray(x)
     dx = a[1] - a[0]
-    return LinRange(a.min() - dx, a.max() + dx, len(a) + 2)
+    return type(x)(a.min() - dx, a.max() + dx, len(a) + 2)
 
 
 def add_ghost_nodes(x, dx, origin=None) -> np.ndarray:
@@ -312,9 +325,13 @@ def _args(args, p: Particles):
 
 
 # --------------------------------------------------------------------------- hot path
-def advection(particles: Particles, method, V, dt: float) -> None:
-    """``advection!(particles, method, V, dt)`` (src/Particles/Advection/advection.jl:21-62)."""
+def advection(particles: Particles, method, V, dt: float, affine: Optional[bool] = None) -> None:
+    """``advection!(particles, method, V, dt)`` (src/Particles/Advection/advection.jl:21-62).
+    ``affine=False`` forces grid-coordinate table look-ups even when the grid vectors were verified
+    to be exactly affine (identical results; the parity tests run both)."""
     p = particles
+    if affine is not None:
+        _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_ADVECT_AFFINE, 1 if affine else 0), "jp_set_option")
     V = tuple(V)
     if len(V) != p.ndim:
         raise ValueError("V must hold one staggered array per dimension")
@@ -326,6 +343,15 @@ def advection(particles: Particles, method, V, dt: float) -> None:
         _cabi.check(lib.jp_advect(C.c_void_p(p._ctx), C.byref(pc), method.scheme, float(method.alpha),
                                   _ptr_array(V), float(dt), _stream()), "advection")
         _done()
+
+
+def advect_affine_level(particles: Particles) -> int:
+    """0: the tiled advection kernel looks grid coordinates up; 1: it regenerates vertex coordinates
+    arithmetically; 2: ghosted-centre coordinates too (vectors verified exactly affine at context
+    creation and the option not switched off)."""
+    v = C.c_int32(0)
+    _cabi.check(_cabi.load().jp_get_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_ADVECT_AFFINE, C.byref(v)), "jp_get_option")
+    return int(v.value)
 
 
 def move_particles(particles: Particles, args=(), mode: Optional[str] = None) -> None:

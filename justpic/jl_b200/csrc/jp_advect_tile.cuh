@@ -52,37 +52,57 @@ __device__ __forceinline__ void adv_tma_load_2d(void *smem_dst, const CUtensorMa
 
 template <int N> struct AdvTile {
     static constexpr int TX = 32;
-    static constexpr int TY = N == 3 ? 4 : 8;
-    static constexpr int TZ = N == 3 ? 2 : 1;
+#ifndef JP_ADV_TPSM
+#define JP_ADV_TPSM 768      // resident threads per SM the register budget is sized for
+#endif
+#ifndef JP_ADV_TY
+#define JP_ADV_TY 4
+#define JP_ADV_TZ 2
+#define JP_ADV_EX 38
+#endif
+    static constexpr int TY = N == 3 ? JP_ADV_TY : 8;
+    static constexpr int TZ = N == 3 ? JP_ADV_TZ : 1;
     // staged nodes per dim: one node below the brick in y/z; TWO below in x so that the box starts
-    // on an even node -- TMA needs the box origin 16-byte aligned in the innermost dimension
+    // on an even node -- TMA needs the box origin 16-byte aligned in the innermost dimension.
+    // The x extent (needed: TX + 5) is padded to 48 so that the row pitch is a multiple of 16 doubles:
+    // every stencil row then starts on bank 0 and a lane's bank depends on its x index only.
     static constexpr int OX = 2;
-    static constexpr int EX = TX + 6, EY = TY + 4, EZ = N == 3 ? TZ + 4 : 1;
+    static constexpr int EX = N == 3 ? JP_ADV_EX : 40, EY = TY + 4, EZ = N == 3 ? TZ + 4 : 1;
     static constexpr int VOL = ((EX * EY * EZ + 15) / 16) * 16;                 // tile pitch: multiple of 128 bytes
     static constexpr int NW = TY * TZ;                                          // warps per CTA
 };
 
 // shared-memory layout (doubles first, then the uint16 work lists)
-template <int N> struct AdvSmem {
+template <int N, bool UNIFORM> struct AdvSmem {
     using T = AdvTile<N>;
     static constexpr int V_OFF = 0;                       // N tiles of VOL doubles
-    static constexpr int XV_OFF = N * T::VOL;             // per dim: EX/EY/EZ entries (xv), padded to 40
-    static constexpr int VEC = 40;                        // >= EX
+    static constexpr int VEC = 40;                        // grid-vector segment per dim (needed: TX + 6)
+    static constexpr int XV_OFF = N * T::VOL;
     static constexpr int XG_OFF = XV_OFF + 3 * VEC;
-    static constexpr int IXV_OFF = XG_OFF + 3 * VEC;
+    static constexpr int IXV_OFF = XG_OFF + 3 * VEC;      // reciprocal spacings: non-uniform grids only
     static constexpr int IXG_OFF = IXV_OFF + 3 * VEC;
-    static constexpr int NDOUBLES = IXG_OFF + 3 * VEC;
-    static constexpr int RING = 128;                       // per-warp ring of compacted (slot, cell) entries
-    static size_t bytes(int) { return sizeof(double) * NDOUBLES + sizeof(uint16_t) * T::NW * RING; }
+    static constexpr int NDOUBLES = UNIFORM ? IXV_OFF : IXG_OFF + 3 * VEC;
+    static constexpr int RING = 128;                      // per-warp ring of compacted (slot, cell) entries
+    static constexpr size_t BYTES = sizeof(double) * NDOUBLES + sizeof(uint16_t) * T::NW * RING;
 };
 
 // velocity at p from the staged stencils; r0[d] = tile-relative index of the seed
 // (storage) cell, c0[d] = global index of the tile's first staged node.
-template <int N, bool UNIFORM>
+// AFFINE (implies UNIFORM; 1: vertex vectors, 2: vertex and ghosted-centre vectors): grid coordinates
+// are regenerated as fma(i, dx, x0) -- verified on the host to reproduce every stored entry bit for
+// bit -- instead of being loaded from shared memory:
+// the kernel is bound by LDS return bandwidth (128 B/clk/SM) and 30 of its 78 loads per particle
+// were grid-vector entries.
+template <int N, bool UNIFORM, int AFFINE>
 __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *__restrict__ sm, const int *c0, const int *r0,
-                                                const double *p, double *vout) {
+                                                const double *gd0, const double *p, double *vout, unsigned amask) {
     using T = AdvTile<N>;
-    using L = AdvSmem<N>;
+    using L = AdvSmem<N, UNIFORM>;
+    // Straight-line code: a lane that cannot be served from the tile (tie with a grid node, NaN, more
+    // than one cell from its seed, outside the domain) only raises `bad` and is redone by the literal
+    // routine afterwards.  Divergent early exits made the compiler run the rest of the stage once per
+    // path (stage 2 was issued twice per batch at ~16 active lanes).
+    bool bad = false;
     int iv[3], ig[3];
     double tv[3], tg[3];
 #pragma unroll
@@ -91,21 +111,29 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
         const double *xg = sm + L::XG_OFF + d * L::VEC;
         const double pd = p[d];
         int r = r0[d];
-        double a = xv[r], b = xv[r + 1];
-        if (!(a < pd && pd < b)) {
-            if (pd > b) r += 1; else if (pd < a) r -= 1; else return false;
+        double gd = AFFINE ? gd0[d] : 0.0;                    // (double)(global index of node r)
+        double a, b;
+        if (AFFINE) { a = fma(gd, g.aff_dv[d], g.aff_v0[d]); b = fma(gd + 1.0, g.aff_dv[d], g.aff_v0[d]); }
+        else { a = xv[r]; b = xv[r + 1]; }
+        const bool up = pd > b, dn = pd < a;
+        if (__any_sync(amask, up || dn)) {          // warp-uniform: stage positions that left the seed cell
+            r += (up ? 1 : 0) - (dn ? 1 : 0);
+            if (AFFINE) {
+                gd += (up ? 1.0 : 0.0) - (dn ? 1.0 : 0.0);
+                a = fma(gd, g.aff_dv[d], g.aff_v0[d]); b = fma(gd + 1.0, g.aff_dv[d], g.aff_v0[d]);
+            } else { a = xv[r]; b = xv[r + 1]; }
             const int gi = c0[d] + r;
-            if (gi < 0 || gi >= g.n[d]) return false;
-            a = xv[r]; b = xv[r + 1];
-            if (!(a < pd && pd < b)) return false;
+            bad = bad || gi < 0 || gi >= g.n[d];
         }
+        bad = bad || !(a < pd && pd < b);                     // also catches ties and NaN
         iv[d] = r;
         tv[d] = (pd - a) * (UNIFORM ? g.inv_dv[d] : sm[L::IXV_OFF + d * L::VEC + r]);
-        const double m = xg[r + 1];
-        if (pd == m) return false;
+        const double m = AFFINE == 2 ? fma(gd + 1.0, g.aff_dg[d], g.aff_g0[d]) : xg[r + 1];
+        bad = bad || pd == m;
         const bool lower = pd < m;
         ig[d] = lower ? r : r + 1;
-        tg[d] = (pd - (lower ? xg[r] : m)) * (UNIFORM ? g.inv_dg[d] : sm[L::IXG_OFF + d * L::VEC + ig[d]]);
+        const double gl = AFFINE == 2 ? fma(gd, g.aff_dg[d], g.aff_g0[d]) : xg[r];
+        tg[d] = (pd - (lower ? gl : m)) * (UNIFORM ? g.inv_dg[d] : sm[L::IXG_OFF + d * L::VEC + ig[d]]);
     }
 #pragma unroll
     for (int c = 0; c < N; c++) {
@@ -122,23 +150,23 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
         }
         vout[c] = jp_lerp<N>(v, t);
     }
-    return true;
+    return !bad;
 }
 
-template <int N, bool UNIFORM>
+template <int N, bool UNIFORM, int AFFINE>
 __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__restrict__ sm, const double *const *V, const int *c0,
-                                           const int *r0, const int *cell1, const double *p, double *vout) {
-    if (adv_interp_tile<N, UNIFORM>(g, sm, c0, r0, p, vout)) return;
+                                           const int *r0, const double *gd0, const int *cell1, const double *p, double *vout, unsigned amask) {
+    if (adv_interp_tile<N, UNIFORM, AFFINE>(g, sm, c0, r0, gd0, p, vout, amask)) return;
     jp_interp_velocity_literal<N>(g, V, p, cell1, vout);
 }
 
-template <int N, int SCHEME, bool UNIFORM>
-__global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
+template <int N, int SCHEME, bool UNIFORM, int AFFINE>
+__global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 768) / (AdvTile<N>::NW * 32)) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
                                                                      double alpha, double dt,
                                                                      const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                                                                      const __grid_constant__ CUtensorMap tm2, int tma_mask) {
     using T = AdvTile<N>;
-    using L = AdvSmem<N>;
+    using L = AdvSmem<N, UNIFORM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA destinations: 128-byte aligned (VOL*8 is a multiple of 128)
     double *sm = reinterpret_cast<double *>(smem_raw);
     uint16_t *wl_all = reinterpret_cast<uint16_t *>(smem_raw + sizeof(double) * L::NDOUBLES);
@@ -212,32 +240,52 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, P
     if (tma_mask) adv_mbar_wait(&tma_bar, 0);   // TMA boxes have landed
     __syncthreads();                      // stencils staged by all warps
 
-    // ---- 3. ballot the occupancy masks slot by slot into a small ring of compacted
-    //         (slot, cell) entries and consume it 32 live particles at a time
-    uint16_t *ring = wl_all + warp * L::RING;
-    const unsigned lt = (1u << lane) - 1u;
+    // ---- 3. compaction + integration.  Slot planes are ~50 % full, so live (slot, cell) entries are
+    //         ballot-compacted into a small shared-memory ring and integrated 32 at a time.  The two
+    //         HALF-warps compact independently (lanes 0-15 <-> cells 0-15 of the x-run, 16-31 <-> 16-31):
+    //         a 64-bit LDS is served per half-warp, and with all 16 lanes of a half inside a 16-cell
+    //         window (stencil rows are bank-aligned, EX = 0 mod 16) their words fall in distinct banks;
+    //         compacting across the whole warp spreads a half over up to 32 cells and two lanes 16 cells
+    //         apart collide on every stencil load.
+    constexpr int RH = L::RING / 2;
+    // this half-warp's ring, addressed through a 32-bit shared-window address (one register, no generic->shared math per access)
+    const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(wl_all + warp * L::RING + (lane >> 4) * RH);
+    const unsigned lth = ((1u << (lane & 15)) - 1u) << (lane & 16);             // lower lanes of my half
     const double *Vp[3] = {V.p[0], V.p[1], V.p[2]};
-    int head = 0, tail = 0;
-    for (int s = 0; s <= g.S; s++) {
-        if (s < g.S) {
-            const bool live = (m >> s) & 1ull;
+    const bool hi = lane >> 4;
+    int head0 = 0, tail0 = 0, head1 = 0, tail1 = 0, q = 0;
+    for (;;) {
+        // produce until both halves hold a full batch (or one ring is about to fill up)
+        while (q < g.S && (tail0 - head0 < 16 || tail1 - head1 < 16) && tail0 - head0 <= RH - 16 && tail1 - head1 <= RH - 16) {
+            const bool live = (m >> q) & 1ull;
             const unsigned bal = __ballot_sync(0xffffffffu, live);
-            if (live) ring[(tail + __popc(bal & lt)) & (L::RING - 1)] = (uint16_t)((s << 5) | lane);
-            tail += __popc(bal);
-            __syncwarp();
+            if (live) {
+                const unsigned pos = ((hi ? tail1 : tail0) + __popc(bal & lth)) & (RH - 1);
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(ring_sa + 2u * pos), "h"((unsigned short)((q << 5) | lane)) : "memory");
+            }
+            tail0 += __popc(bal & 0xffffu);
+            tail1 += __popc(bal >> 16);
+            q++;
         }
-        while (tail - head >= 32 || (s == g.S && tail > head)) {
-            const int k = head + lane;
+        const int head = hi ? head1 : head0, tail = hi ? tail1 : tail0;
+        if (tail0 == head0 && tail1 == head1) break;
+        __syncwarp();
+        {
+            const int k = head + (lane & 15);
+            const unsigned amask = __ballot_sync(0xffffffffu, k < tail);
             if (k < tail) {
-                const int ent = ring[k & (L::RING - 1)];
+                unsigned short ent16;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ent16) : "r"(ring_sa + 2u * (unsigned)(k & (RH - 1))) : "memory");
+                const int ent = ent16;
                 const int sl = ent >> 5, l = ent & 31;
                 const int64_t e = crow + b0[0] + l + (int64_t)sl * g.C;
                 const int r0[3] = {l + T::OX, wy + 1, wz + 1};
                 const int cell1[3] = {b0[0] + l + 1, cy + 1, cz + 1};
-                double p0[3], k1[3], k2[3], q[3], pn[3];
+                const double gd0[3] = {(double)(b0[0] + l), (double)cy, (double)cz};     // global index of the seed cell's lower node
+                double p0[3], k1[3], k2[3], qq[3], pn[3];
 #pragma unroll
                 for (int d = 0; d < N; d++) p0[d] = co.p[d][e];
-                adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, p0, k1);
+                adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, p0, k1, amask);
                 if (SCHEME == 0) {
                     const double cdt = 1.0 * dt;
 #pragma unroll
@@ -245,8 +293,8 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, P
                 } else if (SCHEME == 1) {
                     const double cdt = (1.0 * alpha) * dt;
 #pragma unroll
-                    for (int d = 0; d < N; d++) q[d] = fma(cdt, k1[d], p0[d]);
-                    adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k2);
+                    for (int d = 0; d < N; d++) qq[d] = fma(cdt, k1[d], p0[d]);
+                    adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, qq, k2, amask);
                     if (alpha == 0.5) {
 #pragma unroll
                         for (int d = 0; d < N; d++) pn[d] = fma(1.0 * dt, k2[d], p0[d]);
@@ -258,23 +306,24 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32) k_advect_tile(JpGrid g, P
                 } else {
                     double k3[3], k4[3];
 #pragma unroll
-                    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k1[d] / 2;
-                    adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k2);
+                    for (int d = 0; d < N; d++) qq[d] = p0[d] + dt * k1[d] / 2;
+                    adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, qq, k2, amask);
 #pragma unroll
-                    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k2[d] / 2;
-                    adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k3);
+                    for (int d = 0; d < N; d++) qq[d] = p0[d] + dt * k2[d] / 2;
+                    adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, qq, k3, amask);
 #pragma unroll
-                    for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k3[d];
-                    adv_interp<N, UNIFORM>(g, sm, Vp, c0, r0, cell1, q, k4);
+                    for (int d = 0; d < N; d++) qq[d] = p0[d] + dt * k3[d];
+                    adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, qq, k4, amask);
 #pragma unroll
                     for (int d = 0; d < N; d++) pn[d] = p0[d] + dt * (((k1[d] + 2 * k2[d]) + 2 * k3[d]) + k4[d]) / 6;
                 }
 #pragma unroll
                 for (int d = 0; d < N; d++) co.p[d][e] = pn[d];
             }
-            head += 32;
-            __syncwarp();
+            head0 = min(head0 + 16, tail0);
+            head1 = min(head1 + 16, tail1);
         }
+        __syncwarp();
     }
 }
 

@@ -38,6 +38,11 @@ struct JpGrid {
     const double *ixg[3];      // 1/diff(xg)   (n+1)
     double inv_dv[3], inv_dg[3];  // uniform: 1/(x[1]-x[0])
     int32_t fast;              // 1: every (comp,dim) is V or G and xg[i] < xv[i] < xg[i+1] for all i
+    // 1: checked on the host for EVERY entry, bit for bit:  xv[d][i] == fma(i, aff_dv[d], aff_v0[d])  and
+    //    xg[d][j] == fma(j, aff_dg[d], aff_g0[d])  -- the tiled advection kernel then regenerates grid
+    //    coordinates in registers instead of loading them (same bits by construction)
+    int32_t affine;
+    double aff_v0[3], aff_dv[3], aff_g0[3], aff_dg[3];
 };
 
 struct JpArgs {               // particle fields carried along by move/inject/clean

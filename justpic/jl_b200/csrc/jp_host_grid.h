@@ -54,6 +54,20 @@ static inline const char *jp_grid_build(const jp_grid_desc *d, JpGrid &g, std::v
             if (!(d->xv[dim][i] < d->xv[dim][i + 1])) fast = 0;
     }
     g.fast = fast;
+    // exactly-affine grid vectors (e.g. a range over a power-of-two cell count): every stored entry must
+    // equal fma(i, x[1]-x[0], x[0]) bit for bit.  affine = 1: all vertex vectors; 2: ghosted-centre vectors too
+    int aff_v = fast && g.uniform, aff_g = 1;
+    for (int dim = 0; dim < N && aff_v; dim++) {
+        const double *xv = d->xv[dim], *xg = hxg[dim];
+        const double dv = xv[1] - xv[0];
+        for (int i = 0; i <= d->n[dim] && aff_v; i++) if (xv[i] != fma((double)i, dv, xv[0])) aff_v = 0;
+        g.aff_v0[dim] = xv[0]; g.aff_dv[dim] = dv;
+        if (!xg) { aff_g = 0; continue; }
+        const double dg = xg[1] - xg[0];
+        for (int i = 0; i <= d->n[dim] + 1 && aff_g; i++) if (xg[i] != fma((double)i, dg, xg[0])) aff_g = 0;
+        g.aff_g0[dim] = xg[0]; g.aff_dg[dim] = dg;
+    }
+    g.affine = aff_v ? (aff_g ? 2 : 1) : 0;
     h.clear();
     auto push = [&](const double *x, int n) { size_t off = h.size(); h.insert(h.end(), x, x + n); return off; };
     for (int dim = 0; dim < N; dim++) {

@@ -58,6 +58,7 @@ struct jp_ctx {
     double *p2g_ws;       // [2 * 2^N * C] per-cell partial sums of the two-pass particle2grid (lazy)
     int p2g_mode;         // JP_P2G_EXACT / JP_P2G_TWOPASS / JP_P2G_TWOPASS_FASTW
     int move_mode;        // JP_MOVE_AUTO (plan/gather/scatter, direct sweeps on ties) / JP_MOVE_DIRECT
+    int affine_detected;  // grid vectors are exactly affine (jp_grid_build); g.affine = detected && option
     int last_move_path;   // 0 = plan, 1 = direct (diagnostics)
     int last_complex;     // reason bits of the last classification (diagnostics)
     MovePlanWs mp;        // plan workspace (lazy); occ/leave alias the fields above
@@ -782,6 +783,7 @@ extern "C" int jp_ctx_create(const jp_grid_desc *d, int device, jp_ctx **out) {
     ctx->gridmem = dm;
     jp_grid_rebase(g, off, dm);
     ctx->g = g;
+    ctx->affine_detected = g.affine;
     ctx->p2g_mode = JP_P2G_TWOPASS_FASTW;
     *out = ctx;
     return JP_OK;
@@ -878,28 +880,30 @@ static int build_advect_tma(const JpGrid &g, CPtr3 V, AdvTmaMaps &maps) {
     return mask;
 }
 
-template <int N, int SCHEME, bool UNIFORM>
+template <int N, int SCHEME, bool UNIFORM, int AFFINE>
 static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
     using T = AdvTile<N>;
-    const size_t smem = AdvSmem<N>::bytes(g.S);
+    const size_t smem = AdvSmem<N, UNIFORM>::BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdvSmem<N>::bytes(JP_MAX_SLOTS));
+        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdvSmem<N, UNIFORM>::BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     AdvTmaMaps maps;
     const int tma_mask = build_advect_tma<N>(g, V, maps);
     const dim3 grd((g.n[0] + T::TX - 1) / T::TX, (g.n[1] + T::TY - 1) / T::TY, N == 3 ? (g.n[2] + T::TZ - 1) / T::TZ : 1);
-    k_advect_tile<N, SCHEME, UNIFORM><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask);
+    k_advect_tile<N, SCHEME, UNIFORM, AFFINE><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask);
     return cudaSuccess;
 }
 
 template <int N, int SCHEME>
 static cudaError_t launch_advect(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
     if (jp_standard_staggering(g)) {
-        return g.uniform ? launch_advect_tile<N, SCHEME, true>(g, st, co, index, V, alpha, dt)
-                         : launch_advect_tile<N, SCHEME, false>(g, st, co, index, V, alpha, dt);
+        if (g.uniform && g.affine == 2) return launch_advect_tile<N, SCHEME, true, 2>(g, st, co, index, V, alpha, dt);
+        if (g.uniform && g.affine == 1) return launch_advect_tile<N, SCHEME, true, 1>(g, st, co, index, V, alpha, dt);
+        return g.uniform ? launch_advect_tile<N, SCHEME, true, 0>(g, st, co, index, V, alpha, dt)
+                         : launch_advect_tile<N, SCHEME, false, 0>(g, st, co, index, V, alpha, dt);
     }
     if (g.fast) {
         if (g.uniform) k_advect<N, SCHEME, true, true><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
@@ -1136,7 +1140,16 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_set_option: null context");
     if (option == JP_OPT_MOVE_MODE && (value == JP_MOVE_AUTO || value == JP_MOVE_DIRECT)) { ctx->move_mode = value; return JP_OK; }
     if (option == JP_OPT_P2G_MODE && (value == JP_P2G_EXACT || value == JP_P2G_TWOPASS || value == JP_P2G_TWOPASS_FASTW)) { ctx->p2g_mode = value; return JP_OK; }
+    if (option == JP_OPT_ADVECT_AFFINE && (value == 0 || value == 1)) { ctx->g.affine = value ? ctx->affine_detected : 0; return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
+}
+
+extern "C" int jp_get_option(const jp_ctx *ctx, int32_t option, int32_t *value) {
+    if (!ctx || !value) return jp_fail(JP_ERR_INVALID, "jp_get_option: null argument");
+    if (option == JP_OPT_MOVE_MODE) { *value = ctx->move_mode; return JP_OK; }
+    if (option == JP_OPT_P2G_MODE) { *value = ctx->p2g_mode; return JP_OK; }
+    if (option == JP_OPT_ADVECT_AFFINE) { *value = ctx->g.affine; return JP_OK; }
+    return jp_fail(JP_ERR_INVALID, "jp_get_option: unknown option");
 }
 
 extern "C" int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, const double *Fp, void *stream) {

@@ -8,10 +8,10 @@ from types import SimpleNamespace
 
 import numpy as np
 
-from justpic.jl_b200.api import LinRange, expand_range
+from justpic.jl_b200.api import LinRange, StepRange, expand_range
 
 
-def make_grids(n, ndim, uniform=True, L=1.0, stretch=0.0):
+def make_grids(n, ndim, uniform=True, L=1.0, stretch=0.0, exact=False):
     """n cells per dim (int or tuple).  uniform -> LinRange grids (range path);
     else array grids (vector path), optionally stretched (non-uniform)."""
     ns = (n,) * ndim if isinstance(n, int) else tuple(n)
@@ -19,9 +19,10 @@ def make_grids(n, ndim, uniform=True, L=1.0, stretch=0.0):
     for d in range(ndim):
         nd = ns[d]
         if uniform:
-            v = LinRange(0.0, L, nd + 1)
+            R = StepRange if exact else LinRange      # exact: Julia range() (correctly rounded entries)
+            v = R(0.0, L, nd + 1)
             dx = v[1] - v[0]
-            c = LinRange(0.0 + dx / 2, L - dx / 2, nd)
+            c = R(0.0 + dx / 2, L - dx / 2, nd)
             g = expand_range(c)
         else:
             xi = np.asarray(LinRange(0.0, 1.0, nd + 1))

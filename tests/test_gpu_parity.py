@@ -56,9 +56,9 @@ def assert_close(gpu, ref, what, rtol=RTOL):
 class Twin:
     """The same problem on the GPU (public API) and in the oracle."""
 
-    def __init__(self, ndim, n, uniform=True, stretch=0.3, nxcell=12, max_xcell=24, min_xcell=8, seed=7):
+    def __init__(self, ndim, n, uniform=True, stretch=0.3, nxcell=12, max_xcell=24, min_xcell=8, seed=7, exact=False):
         J = jp()
-        self.gr = gr = make_grids(n, ndim, uniform=uniform, stretch=stretch)
+        self.gr = gr = make_grids(n, ndim, uniform=uniform, stretch=stretch, exact=exact)
         grids = gr.grid_vel if uniform else gr.xi_vel
         self.p = J.init_particles(J.CUDABackend, nxcell, max_xcell, min_xcell, *grids, seed=seed)
         self.o = Oracle(gr.xvi, gr.xci, gr.xi_vel, self.p.max_xcell, uniform)
@@ -101,6 +101,28 @@ def test_advection(g, method):
         J.advection(t.p, m[0], Vd, dt)
         t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
         t.check_state(f"advection {method} cfl {cfl}")
+
+
+@pytest.mark.parametrize("g", [(2, 32, True), (3, 16, True), (3, (32, 8, 16), True)], ids=ids)
+@pytest.mark.parametrize("method", ["euler", "rk2", "rk2_23", "rk4"])
+@pytest.mark.parametrize("affine", [2, 1, 0])
+def test_advection_affine_grids(g, method, affine):
+    """Power-of-two grids: vertex vectors are exactly affine (level 1); with Julia range() centres the
+    ghosted-centre vectors are too (level 2).  The tiled kernel regenerates such coordinates as
+    fma(i, dx, x0) or looks them up (level 0); all must equal the oracle bit for bit."""
+    J = jp()
+    t = Twin(*g, exact=(affine == 2))
+    V = stream_velocity(t.gr)
+    Vd = [dev(v) for v in V]
+    m = {"euler": (J.Euler(), 0, 0.0), "rk2": (J.RungeKutta2(), 1, 0.5), "rk2_23": (J.RungeKutta2(2 / 3), 1, 2 / 3),
+         "rk4": (J.RungeKutta4(), 2, 0.0)}[method]
+    for cfl in (0.5, 1.6):
+        dt = cfl_dt(t.gr, V, cfl)
+        J.advection(t.p, m[0], Vd, dt, affine=affine > 0)
+        assert J.advect_affine_level(t.p) == affine
+        t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
+        t.check_state(f"advection {method} cfl {cfl} affine={affine}")
+        J.move_particles(t.p); t.o.move(t.co, t.idx, [])
 
 
 @pytest.mark.parametrize("g", GRIDS, ids=ids)
