@@ -75,7 +75,7 @@ __device__ __forceinline__ bool jp_cls_dim(const ClsGeom &q, int uniform, double
 }
 
 template <int N>
-__global__ void __launch_bounds__(256, 3) k_move_classify2(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
+__global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify2(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
                                                         unsigned int *complex_flag) {
     __shared__ uint64_t lv_sm[JP_BY][32];
     __shared__ __align__(8) uint8_t code_sm[JP_BY][32][JP_MAX_SLOTS];
@@ -237,7 +237,7 @@ struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 #define JP_MV_U 4
 #define JP_MV_A 4      // arrays handled per register batch (coords + fields); more arrays loop again
 template <int N>
-__global__ void __launch_bounds__(256, 3) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* unused */) {
+__global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* unused */) {
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t lv = ok ? ws.leave[c] : 0;
@@ -289,9 +289,12 @@ __global__ void __launch_bounds__(256, 3) k_move_gather(JpGrid g, MovePlanWs ws,
     }
 }
 
-// ---- E. scatter: arrivals from staging, NaN into vacated slots, mask bytes
+// ---- E. scatter: arrivals from staging, NaN into vacated slots, mask bytes.
+// (Measured: walking each thread's own arrivals in rank order instead -- more loads in flight, but every
+// 8-byte store then goes to the L2 alone instead of merged with its x-neighbours' stores to the same
+// 32-byte sector -- is 3x SLOWER; the slot-synchronous order stays.)
 template <int N>
-__global__ void __launch_bounds__(256, 3) k_move_scatter(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index, const double *__restrict__ stage, int64_t M) {
+__global__ void __launch_bounds__(256, JP_MINB_SCATTER) k_move_scatter(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index, const double *__restrict__ stage, int64_t M) {
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t amask = ok ? ws.arrmask[c] : 0, lmask = ok ? ws.leave[c] : 0;

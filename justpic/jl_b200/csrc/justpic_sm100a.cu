@@ -77,6 +77,20 @@ struct CPtr3 { const double *p[3]; };
 // thread <-> cell mapping shared by all cell kernels: 32 x 8 tiles, z = blockIdx.z
 #define JP_BX 32
 #define JP_BY 8
+// resident 256-thread CTAs per SM each streaming kernel sizes its registers for (measured on B200:
+// classify / gather gain from occupancy, scatter and the two-pass particle2grid from registers)
+#ifndef JP_MINB_CLASSIFY
+#define JP_MINB_CLASSIFY 4
+#endif
+#ifndef JP_MINB_GATHER
+#define JP_MINB_GATHER 4
+#endif
+#ifndef JP_MINB_SCATTER
+#define JP_MINB_SCATTER 3
+#endif
+#ifndef JP_MINB_P2G
+#define JP_MINB_P2G 2
+#endif
 template <int N>
 __device__ __forceinline__ bool tile_cell(const JpGrid &g, int *ci, int64_t &c) {
     ci[0] = blockIdx.x * JP_BX + threadIdx.x;
@@ -586,7 +600,7 @@ __device__ __forceinline__ double jp_rcp_fast(double x) {
 }
 
 template <int N, bool FASTW>
-__global__ void __launch_bounds__(256, 3) k_p2g_cell(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, const double *__restrict__ Fp,
+__global__ void __launch_bounds__(256, JP_MINB_P2G) k_p2g_cell(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, const double *__restrict__ Fp,
                                                   double *__restrict__ PW, double *__restrict__ PWF) {
     constexpr int NQ = N == 2 ? 4 : 8;
     constexpr int U = 4;                       // slots per batch: loads of a batch are issued together
