@@ -150,6 +150,26 @@ int jp_particle2centroid(jp_ctx *ctx, const jp_particles *p, double *Fc, const d
 int jp_phase_ratios_center(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases,
                            int32_t K, void *stream);
 
+/* phase_ratios_vertex!(phase_ratios, particles, phases) (src/PhaseRatios/vertices.jl:4-107).
+ * ratios: CellArray over the vertex grid (n+1 per dim), element (node, k) at node + k*NN.  Every
+ * particle of the 2^N adjacent cells within (strictly less than) half a cell of the vertex
+ * contributes; a vertex with none keeps the reference's NaN (0 * inv(0)). */
+int jp_phase_ratios_vertex(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases,
+                           int32_t K, void *stream);
+
+/* phase_ratios_face!(phase_face, particles, phases, dimension) (src/PhaseRatios/midpoints.jl:3-82).
+ * dim = 0/1/2 for :x/:y/:z.  ratios: CellArray over the face grid n + e_dim (the Vx/Vy/Vz fields of
+ * PhaseRatios, constructors.jl:41-43), element (node, k) at node + k*NF; NaN (no particle in range) -> 0. */
+int jp_phase_ratios_face(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases,
+                         int32_t K, int32_t dim, void *stream);
+
+/* phase_ratios_midpoint!(phase_midpoint, particles, phases, dimension) (src/PhaseRatios/midpoints.jl:115-242),
+ * 3-D only.  plane = 0/1/2 for :xy/:yz/:xz, midpoint grid n + offsets with offsets (1,1,0)/(0,1,1)/(1,0,1)
+ * (the xy/yz/xz fields of PhaseRatios, constructors.jl:44-46); NaN -> 0.  The boundary branch is the
+ * reference's, quirks included (see oracle/justpic_oracle.c). */
+int jp_phase_ratios_midpoint(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases,
+                             int32_t K, int32_t plane, void *stream);
+
 /* update_cell_halo! building blocks (src/CellArrays/ImplicitGlobalGrid.jl:36-41):
  * gather / scatter one cell-plane (all S slots) of every listed CellArray into /
  * from one contiguous device buffer; the transport between ranks (NCCL

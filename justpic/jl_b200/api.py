@@ -41,7 +41,8 @@ __all__ = [
     "init_particles", "init_cell_arrays", "cell_array",
     "advection", "move_particles", "inject_particles", "clean_particles",
     "grid2particle", "centroid2particle", "particle2grid", "particle2centroid",
-    "phase_ratios_center", "set_synchronous",
+    "phase_ratios_center", "phase_ratios_vertex", "phase_ratios_face", "phase_ratios_midpoint",
+    "update_phase_ratios", "set_synchronous",
 ]
 
 
@@ -470,14 +471,87 @@ def particle2centroid(F, Fp, particles: Particles) -> None:
 
 @dataclass
 class PhaseRatios:
-    """``PhaseRatios(backend, nphases, ni)`` (src/PhaseRatios/constructors.jl:18-47).  Only the
-    ``center`` field is on the hot path; vertex/face/midpoint ratios are listed as "next"."""
-    center: torch.Tensor
-    nphases: int
+    """``PhaseRatios(backend, nphases, ni)`` (src/PhaseRatios/constructors.jl:18-47): CellArrays
+    ``center`` (n), ``vertex`` (n+1), ``Vx/Vy[/Vz]`` (faces) and, in 3-D, ``yz/xz/xy`` (edge
+    midpoints); in 2-D the last four are 1-cell dummies as in the reference."""
 
     def __init__(self, backend, nphases: int, ni: Sequence[int], device=None):
+        ni = tuple(int(n) for n in ni)
         self.nphases = int(nphases)
-        self.center = cell_array(0.0, (nphases,), ni, device=device)
+        self.ni = ni
+        mk = lambda dims: cell_array(0.0, (nphases,), dims, device=device)
+        self.center = mk(ni)
+        self.vertex = mk(tuple(n + 1 for n in ni))
+        face = lambda d: tuple(n + (1 if i == d else 0) for i, n in enumerate(ni))
+        self.Vx, self.Vy = mk(face(0)), mk(face(1))
+        if len(ni) == 3:
+            nx, ny, nz = ni
+            self.Vz = mk(face(2))
+            self.yz, self.xz, self.xy = mk((nx, ny + 1, nz + 1)), mk((nx + 1, ny, nz + 1)), mk((nx + 1, ny + 1, nz))
+        else:
+            self.Vz = self.yz = self.xz = self.xy = mk((1, 1))
+
+
+_FACE_DIM = {"x": 0, "y": 1, "z": 2}
+_MID_PLANE = {"xy": 0, "yz": 1, "xz": 2}
+
+
+def _phase_call(fn_name, who, ratios, p, phases, K, nelem, *extra):
+    r = _field(ratios, p, K * nelem, who)
+    ph = _pfield(phases, p, "phases")
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        fn = getattr(_cabi.load(), fn_name)
+        _cabi.check(fn(C.c_void_p(p._ctx), C.byref(pc), C.c_void_p(r.data_ptr()), C.c_void_p(ph.data_ptr()), K,
+                       *extra, _stream()), who)
+        _done()
+
+
+def phase_ratios_vertex(phase_ratios: PhaseRatios, particles: Particles, phases: torch.Tensor) -> None:
+    """``phase_ratios_vertex!(phase_ratios, particles, phases)`` (src/PhaseRatios/vertices.jl:4-13)."""
+    p = particles
+    _phase_call("jp_phase_ratios_vertex", "phase_ratios_vertex", phase_ratios.vertex, p, phases, phase_ratios.nphases,
+                int(np.prod([n + 1 for n in p.ncells])))
+
+
+def phase_ratios_face(phase_face: torch.Tensor, particles: Particles, phases: torch.Tensor, dimension: str) -> None:
+    """``phase_ratios_face!(phase_face, particles, phases, dimension)`` (src/PhaseRatios/midpoints.jl:3-24);
+    ``dimension`` is ``"x"``, ``"y"`` or ``"z"`` (the reference's ``:x/:y/:z``)."""
+    p = particles
+    d = _FACE_DIM.get(str(dimension).lstrip(":"))
+    if d is None or d >= p.ndim:
+        raise ValueError("dimension must be :x, :y or :z")
+    K = int(phase_face.shape[0])
+    nelem = int(np.prod([n + (1 if i == d else 0) for i, n in enumerate(p.ncells)]))
+    _phase_call("jp_phase_ratios_face", "phase_ratios_face", phase_face, p, phases, K, nelem, d)
+
+
+def phase_ratios_midpoint(phase_midpoint: torch.Tensor, particles: Particles, phases: torch.Tensor, dimension: str) -> None:
+    """``phase_ratios_midpoint!(phase_midpoint, particles, phases, dimension)`` (src/PhaseRatios/midpoints.jl:115-126),
+    3-D only; ``dimension`` is ``"xy"``, ``"yz"`` or ``"xz"``."""
+    p = particles
+    pl = _MID_PLANE.get(str(dimension).lstrip(":"))
+    if pl is None or p.ndim != 3:
+        raise ValueError("Unknown dimensions. Valid dimensions are :xy, :yz, :xz")
+    off = {0: (1, 1, 0), 1: (0, 1, 1), 2: (1, 0, 1)}[pl]
+    K = int(phase_midpoint.shape[0])
+    nelem = int(np.prod([n + o for n, o in zip(p.ncells, off)]))
+    _phase_call("jp_phase_ratios_midpoint", "phase_ratios_midpoint", phase_midpoint, p, phases, K, nelem, pl)
+
+
+def update_phase_ratios(phase_ratios: PhaseRatios, particles: Particles, phases: torch.Tensor) -> None:
+    """``update_phase_ratios!(phase_ratios, particles, phases)`` (src/PhaseRatios/utils.jl:15-41): centres,
+    vertices, velocity nodes and (3-D) edge midpoints, in the reference's order."""
+    pr, p = phase_ratios, particles
+    phase_ratios_center(pr, p, phases)
+    phase_ratios_vertex(pr, p, phases)
+    phase_ratios_face(pr.Vx, p, phases, "x")
+    phase_ratios_face(pr.Vy, p, phases, "y")
+    if p.ndim == 3:
+        phase_ratios_face(pr.Vz, p, phases, "z")
+        phase_ratios_midpoint(pr.xy, p, phases, "xy")
+        phase_ratios_midpoint(pr.yz, p, phases, "yz")
+        phase_ratios_midpoint(pr.xz, p, phases, "xz")
 
 
 def phase_ratios_center(phase_ratios: PhaseRatios, particles: Particles, phases: torch.Tensor) -> None:

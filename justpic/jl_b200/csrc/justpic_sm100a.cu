@@ -741,6 +741,8 @@ __global__ void __launch_bounds__(256, KMAX <= 8 ? 3 : 1) k_phase(JpGrid g, CPtr
     for (int k = 0; k < KMAX; k++) if (k < K) ratios[c + (int64_t)k * g.C] = w[k] * inv;
 }
 
+#include "jp_phase_ratios.cuh"
+
 // update_cell_halo! pack / unpack of one cell-plane
 struct HaloArrs { double *a[JP_MAX_ARGS + 3]; int n; };
 template <bool PACK>
@@ -1216,6 +1218,50 @@ extern "C" int jp_phase_ratios_center(jp_ctx *ctx, const jp_particles *p, double
     if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_center: 1 <= nphases <= 32 required");
     if (g.ndim == 2) launch_phase<2>(g, grd, blk, st, cco, ratios, phases, K);
     else             launch_phase<3>(g, grd, blk, st, cco, ratios, phases, K);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+// K-dispatch shared by the vertex / face / midpoint launchers
+#define JP_PHASE_DISPATCH(KERNEL, NTPL, GRID, ...)                                              \
+    do {                                                                                        \
+        if (K <= 2) KERNEL<NTPL 2><<<GRID, blk, 0, st>>>(__VA_ARGS__);                          \
+        else if (K <= 4) KERNEL<NTPL 4><<<GRID, blk, 0, st>>>(__VA_ARGS__);                     \
+        else if (K <= 8) KERNEL<NTPL 8><<<GRID, blk, 0, st>>>(__VA_ARGS__);                     \
+        else if (K <= 16) KERNEL<NTPL 16><<<GRID, blk, 0, st>>>(__VA_ARGS__);                   \
+        else KERNEL<NTPL 32><<<GRID, blk, 0, st>>>(__VA_ARGS__);                                \
+    } while (0)
+#define JP_COMMA ,
+
+extern "C" int jp_phase_ratios_vertex(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases, int32_t K, void *stream) {
+    PREP("jp_phase_ratios_vertex");
+    if (!ratios || !phases) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_vertex: null field");
+    if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_vertex: 1 <= nphases <= 32 required");
+    const dim3 ng = tile_grid(g.n[0] + 1, g.n[1] + 1, g.ndim == 3 ? g.n[2] + 1 : 1);
+    if (g.ndim == 2) JP_PHASE_DISPATCH(k_phase_vertex, 2 JP_COMMA, ng, g, cco, ratios, phases, K);
+    else             JP_PHASE_DISPATCH(k_phase_vertex, 3 JP_COMMA, ng, g, cco, ratios, phases, K);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_phase_ratios_face(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases, int32_t K, int32_t dim, void *stream) {
+    PREP("jp_phase_ratios_face");
+    if (!ratios || !phases) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_face: null field");
+    if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_face: 1 <= nphases <= 32 required");
+    if (dim < 0 || dim >= g.ndim) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_face: dimension must be :x, :y or :z");
+    if (g.ndim == 2) JP_PHASE_DISPATCH(k_phase_face, 2 JP_COMMA, grd, g, cco, ratios, phases, K, dim);
+    else             JP_PHASE_DISPATCH(k_phase_face, 3 JP_COMMA, grd, g, cco, ratios, phases, K, dim);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_phase_ratios_midpoint(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases, int32_t K, int32_t plane, void *stream) {
+    PREP("jp_phase_ratios_midpoint");
+    if (!ratios || !phases) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_midpoint: null field");
+    if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_midpoint: 1 <= nphases <= 32 required");
+    if (g.ndim != 3) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_midpoint: 3-D only");
+    if (plane < 0 || plane > 2) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_midpoint: Unknown dimensions. Valid dimensions are :xy, :yz, :xz");
+    JP_PHASE_DISPATCH(k_phase_midpoint, , grd, g, cco, ratios, phases, K, plane);
     JP_CHECK_LAUNCH();
     return JP_OK;
 }

@@ -744,6 +744,88 @@ int jpo_phase_ratios_face(const jpo_grid *g, const double *const *coords, double
     return 0;
 }
 
+/* ---- phase_ratios_midpoint! (src/PhaseRatios/midpoints.jl:115-242), 3-D only --------
+ * plane = 0/1/2 for :xy/:yz/:xz, offsets (1,1,0)/(0,1,1)/(1,0,1).  ratios: CellArray over the
+ * midpoint grid nm = n + offsets, element (node, k) at node + k*NM.  Work-item = cell I:
+ * general case accumulates the cells I + offsets.*mask, mask in ((1,0,0),(0,1,0),(0,0,1),(1,1,1)),
+ * clamped to the grid (so clamped cells are visited more than once), `di` reassigned per
+ * visited cell; NaN -> 0.  Boundary branch (any offsets[i]*I[i] == 1, 1-based): literal,
+ * including its quirks -- the `x === false` skip never fires for Ints, and the midpoint is
+ * centre - (di*offsets*flip)/2 with flip = -lastboundary_offset (0 or -1), i.e. the cell
+ * CENTRE in every direction that is not the last boundary. */
+static void midpoint_accumulate(const jpo_grid *g, const double *const *coords, const double *phases, int K,
+                                const int *I, const int *off, const double *mid, double *w) {
+    static const int MASK[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 1}};
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    for (int k = 0; k < K; k++) w[k] = 0.0;
+    for (int m = 0; m < 4; m++) {
+        int cc[3];
+        double di[3];
+        for (int d = 0; d < 3; d++) {
+            cc[d] = I[d] + off[d] * MASK[m][d];
+            if (cc[d] > g->n[d] - 1) cc[d] = g->n[d] - 1;
+            di[d] = d_of(g->xv[d], g->uniform, cc[d]);
+        }
+        const int64_t c = cc[0] + (int64_t)nx * (cc[1] + (int64_t)ny * cc[2]);
+        for (int s = 0; s < g->S; s++) {
+            const int64_t e = c + (int64_t)s * C;
+            double p[3];
+            int nan = 0, in = 1;
+            for (int d = 0; d < 3; d++) { p[d] = coords[d][e]; nan |= isnan(p[d]); }
+            if (nan) continue;
+            for (int d = 0; d < 3; d++) in &= fabs(p[d] - mid[d]) <= di[d] / 2;
+            if (!in) continue;
+            acc_phase(w, K, bilinear_weight(3, mid, p, di), phases[e]);
+        }
+    }
+}
+
+int jpo_phase_ratios_midpoint(const jpo_grid *g, const double *const *coords, double *ratios, const double *phases, int K, int plane) {
+    if (g->ndim != 3 || K > 64 || plane < 0 || plane > 2) return -1;
+    static const int OFF[3][3] = {{1, 1, 0}, {0, 1, 1}, {1, 0, 1}};
+    const int *off = OFF[plane];
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    const int nm[3] = {g->n[0] + off[0], g->n[1] + off[1], g->n[2] + off[2]};
+    const int64_t NM = (int64_t)nm[0] * nm[1] * nm[2];
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c0 = 0; c0 < C; c0++) {
+        int I[3] = {(int)(c0 % nx), (int)((c0 / nx) % ny), (int)(c0 / ((int64_t)nx * ny))};
+        double di[3], cen[3], mid[3], w[64];
+        for (int d = 0; d < 3; d++) {
+            di[d] = d_of(g->xv[d], g->uniform, I[d]);
+            cen[d] = g->xc[d][I[d]];
+            mid[d] = cen[d] + di[d] * (double)off[d] / 2;
+        }
+        midpoint_accumulate(g, coords, phases, K, I, off, mid, w);
+        double sum = w[0];
+        for (int k = 1; k < K; k++) sum = sum + w[k];
+        double inv = 1.0 / sum;
+        const int64_t mo = (I[0] + off[0]) + (int64_t)nm[0] * ((I[1] + off[1]) + (int64_t)nm[1] * (I[2] + off[2]));
+        for (int k = 0; k < K; k++) { double v = w[k] * inv; ratios[mo + (int64_t)k * NM] = isnan(v) ? 0.0 : v; }
+        int boundary = 0;
+        for (int d = 0; d < 3; d++) boundary |= (off[d] * (I[d] + 1) == 1);
+        if (boundary) {
+            int ob[3];
+            for (int d = 0; d < 3; d++) ob[d] = (g->n[d] == off[d] * (I[d] + 1));
+            for (int d = 0; d < 3; d++) {
+                const double dI = d_of(g->xv[d], g->uniform, I[d]);
+                mid[d] = cen[d] - ((dI * (double)off[d]) * (double)(-ob[d])) / 2;
+            }
+            midpoint_accumulate(g, coords, phases, K, I, off, mid, w);
+            sum = w[0];
+            for (int k = 1; k < K; k++) sum = sum + w[k];
+            inv = 1.0 / sum;
+            for (int pass = 0; pass < 2; pass++) {
+                const int64_t mb = (I[0] + pass * ob[0]) + (int64_t)nm[0] * ((I[1] + pass * ob[1]) + (int64_t)nm[1] * (I[2] + pass * ob[2]));
+                for (int k = 0; k < K; k++) { double v = w[k] * inv; ratios[mb + (int64_t)k * NM] = isnan(v) ? 0.0 : v; }
+            }
+        }
+    }
+    return 0;
+}
+
 /* ---- update_cell_halo! semantics for ONE array on ONE axis (test helper) ---
  * ImplicitGlobalGrid.update_halo! with overlap 2 / halowidth 1
  * (src/CellArrays/ImplicitGlobalGrid.jl:36-41): my plane 2 -> left nbr's plane

@@ -143,6 +143,9 @@ class Oracle:
     def phase_ratios_face(self, coords, ratios, phases, K, dim):
         return lib().jpo_phase_ratios_face(C.byref(self.g), _pp(coords), _dp(ratios), _dp(phases), int(K), int(dim))
 
+    def phase_ratios_midpoint(self, coords, ratios, phases, K, plane):
+        return lib().jpo_phase_ratios_midpoint(C.byref(self.g), _pp(coords), _dp(ratios), _dp(phases), int(K), int(plane))
+
     def phase_ratios_center(self, coords, ratios, phases, K):
         return lib().jpo_phase_ratios_center(C.byref(self.g), _pp(coords), _dp(ratios), _dp(phases), int(K))
 
