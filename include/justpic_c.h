@@ -117,6 +117,14 @@ int jp_last_move_path(const jp_ctx *ctx);
 int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs,
               int32_t min_xcell, uint64_t seed, uint32_t step, void *stream);
 /* Number of particles injected by the last jp_inject.  Synchronises `stream`. */
+/* inject_particles_phase!(particles, particles_phases, args, fields) (src/Particles/injection.jl:146-325):
+ * every quadrant of every cell is examined (2^N colour sweeps as jp_inject); a new particle takes the
+ * PHASE of its nearest live neighbour (index_min_distance, :330-393) and args[j] is interpolated from the
+ * grid field fields[j] at the new position, clamped to the extrema of the interpolation stencil:
+ * field_kind[j] = 1: centre field (n per dim; shifted/clamped centre cell, :295-305), 0: vertex field
+ * (n+1 per dim; the storage cell, :307-311).  Counter-based RNG keyed (seed, purpose 2, step, cell, slot). */
+int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phases, double *const *args, const double *const *fields,
+                    const int32_t *field_kind, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream);
 int jp_inject_stats(jp_ctx *ctx, int64_t *out, void *stream);
 
 /* clean_particles!(particles, grid, args) (src/Particles/move_safe.jl:289-320). */

@@ -61,6 +61,8 @@ SYMBOLS = {
     "jp_last_move_path": (C.c_int, [C.c_void_p]),
     "jp_inject": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
                             C.c_uint64, C.c_uint32, C.c_void_p]),
+    "jp_inject_phase": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p]),
     "jp_inject_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "jp_clean": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "jp_grid2particle": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),

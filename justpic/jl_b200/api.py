@@ -39,7 +39,7 @@ __all__ = [
     "Euler", "RungeKutta2", "RungeKutta4",
     "Particles", "PhaseRatios",
     "init_particles", "init_cell_arrays", "cell_array",
-    "advection", "move_particles", "inject_particles", "clean_particles",
+    "advection", "move_particles", "inject_particles", "inject_particles_phase", "clean_particles",
     "grid2particle", "centroid2particle", "particle2grid", "particle2centroid",
     "phase_ratios_center", "phase_ratios_vertex", "phase_ratios_face", "phase_ratios_midpoint",
     "update_phase_ratios", "set_synchronous",
@@ -406,6 +406,35 @@ def inject_particles(particles: Particles, args=(), step: Optional[int] = None) 
     with torch.cuda.device(p.device):
         _cabi.check(_cabi.load().jp_inject(C.c_void_p(p._ctx), C.byref(pc), _ptr_array(args), len(args), p.min_xcell,
                                            C.c_uint64(p.seed), C.c_uint32(int(step)), _stream()), "inject_particles")
+        _done()
+
+
+def inject_particles_phase(particles: Particles, particles_phases: torch.Tensor, args=(), fields=(), step: Optional[int] = None) -> None:
+    """``inject_particles_phase!(particles, particles_phases, args, fields)`` (src/Particles/injection.jl:146-200):
+    new particles take the phase of their nearest neighbour and ``args[j]`` is interpolated from the grid
+    field ``fields[j]`` (a centre field if it has one value per cell, else a vertex field), clamped to the
+    extrema of the interpolation stencil.  RNG stream as in ``inject_particles``."""
+    p = particles
+    args = _args(args, p)
+    fields = tuple(fields)
+    if len(fields) != len(args):
+        raise ValueError("inject_particles_phase: one grid field per particle field")
+    ph = _pfield(particles_phases, p, "particles_phases")
+    ncell, nvert = int(np.prod(p.ncells)), _nodes(p, 1)
+    kinds = (C.c_int32 * max(len(args), 1))()
+    for j, f in enumerate(fields):
+        if not isinstance(f, torch.Tensor) or f.numel() not in (ncell, nvert):
+            raise ValueError(f"fields[{j}]: expected a centre ({ncell}) or vertex ({nvert}) field")
+        kinds[j] = 1 if f.numel() == ncell else 0
+        _field(f, p, f.numel(), f"fields[{j}]")
+    if step is None:
+        step = p._inject_step
+        p._inject_step += 1
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_inject_phase(C.c_void_p(p._ctx), C.byref(pc), C.c_void_p(ph.data_ptr()), _ptr_array(args),
+                                                 _ptr_array(fields), kinds, len(args), p.min_xcell, C.c_uint64(p.seed),
+                                                 C.c_uint32(int(step)), _stream()), "inject_particles_phase")
         _done()
 
 

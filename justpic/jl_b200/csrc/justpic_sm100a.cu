@@ -326,16 +326,17 @@ __global__ void __launch_bounds__(256) k_clean(JpGrid g, Ptr3 co, uint8_t *index
 // inject_particles! pass A (thread = cell, coalesced): occupancy word + "would the reference
 // inject here?" -> the cell is appended to the work list of its colour (order within a colour
 // is irrelevant: same-colour cells only read their neighbours, which have other colours).
-template <int N>
+template <int N, bool PHASE>
 __global__ void __launch_bounds__(256) k_inject_classify(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, int min_xq,
                                                          uint64_t *occ, uint8_t *inbox, int *list, unsigned int *count, int64_t cap) {
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
-    double vq[3], ub[3], hi[3];
+    double vq[3], ub[3], hi[3], dqv[3];
     if (ok)
-        for (int d = 0; d < N; d++) { vq[d] = g.xv[d][ci[d]]; ub[d] = vq[d] + jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; hi[d] = g.xv[d][ci[d] + 1]; }
+        for (int d = 0; d < N; d++) { vq[d] = g.xv[d][ci[d]]; dqv[d] = jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; ub[d] = vq[d] + dqv[d]; hi[d] = g.xv[d][ci[d] + 1]; }
     int nq0 = 0;
+    uint64_t nq = 0;         // PHASE: live particles strictly inside each of the 2^N quadrants, one byte per quadrant
     bool allin = true;       // every live particle lies in the closed box [xv[i], xv[i+1]]^N (lets the donor search prune this cell)
     for (int s0 = 0; s0 < g.S; s0 += 4) {
         const unsigned bits = (unsigned)(m >> s0) & 15u;
@@ -351,6 +352,20 @@ __global__ void __launch_bounds__(256) k_inject_classify(JpGrid g, CPtr3 co, con
 #pragma unroll
             for (int d = 0; d < N; d++) in = in && (vq[d] < p[u][d]) && (p[u][d] < ub[d]);
             nq0 += in ? 1 : 0;
+            if (PHASE && ((bits >> u) & 1u)) {
+                // quadrant (b_x, b_y[, b_z]): vertex vq = xv + dq*b, strict isincell(p, vq, dq) per dimension
+                int q = 0;
+                bool inq = true;
+#pragma unroll
+                for (int d = 0; d < N; d++) {
+                    const double dq = dqv[d];
+                    const double mid = vq[d] + dq * 1.0;
+                    const bool lo = (vq[d] < p[u][d]) && (p[u][d] < vq[d] + dq), hi = (mid < p[u][d]) && (p[u][d] < mid + dq);
+                    inq = inq && (lo || hi);
+                    q |= (hi ? 1 : 0) << d;
+                }
+                if (inq) nq += 1ull << (8 * q);
+            }
             if ((bits >> u) & 1u) {
 #pragma unroll
                 for (int d = 0; d < N; d++) allin = allin && (vq[d] <= p[u][d]) && (p[u][d] <= hi[d]);
@@ -360,7 +375,14 @@ __global__ void __launch_bounds__(256) k_inject_classify(JpGrid g, CPtr3 co, con
     if (ok) {
         occ[c] = m;
         inbox[c] = allin ? 1 : 0;
-        if (jp_inject_candidate(nq0, __popcll(m), g.S, min_xq)) {
+        bool cand = jp_inject_candidate(nq0, __popcll(m), g.S, min_xq);
+        if (PHASE) {                                  // every quadrant is examined (injection.jl:271 `continue`)
+            bool deficient = false;
+#pragma unroll
+            for (int q = 0; q < (N == 2 ? 4 : 8); q++) deficient = deficient || (int)((nq >> (8 * q)) & 255) < min_xq;
+            cand = deficient && __popcll(m) < g.S;
+        }
+        if (cand) {
             const int col = (N == 3 ? ((ci[0] & 1) * 4 + (ci[1] & 1) * 2 + (ci[2] & 1)) : ((ci[0] & 1) * 2 + (ci[1] & 1)));
             const unsigned pos = atomicAdd(&count[col], 1u);
             list[(int64_t)col * cap + pos] = (int)c;
@@ -374,10 +396,45 @@ __global__ void __launch_bounds__(256) k_inject_classify(JpGrid g, CPtr3 co, con
 // (index_min_distance, :330-393) spread over the lanes -- 3^N cells x S slots candidates,
 // reduced with the lexicographic key (distance, visiting order) so that the winner is the
 // candidate the reference's serial "strictly smaller" scan would keep.
+// PHASE = inject_particles_phase! (src/Particles/injection.jl:146-325): every quadrant is examined, the
+// nearest particle donates only its phase id, and args[j] is interpolated from the grid field
+// fields[j] at the new position, clamped to the extrema of its interpolation stencil.
+struct InjPhase { double *phases; const double *fields[JP_MAX_ARGS]; int32_t fkind[JP_MAX_ARGS]; };
+
 template <int N>
+__device__ __forceinline__ double jp_inject_field(const JpGrid &g, const double *__restrict__ F, int kind, const int *ci,
+                                                  const double *xcc, const double *dcell, const double *pn) {
+    int ic[3] = {0, 0, 0};
+    double t[3], v[8];
+    int64_t s1, s2;
+    if (kind == 1) {                                   // centre field: shifted_index + clamp(., 1, n-1) (injection.jl:295-299)
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            int i1 = ci[d] + 1;
+            if (pn[d] < xcc[d]) i1 -= 1;
+            const int hi1 = g.n[d] - 1;
+            if (i1 > hi1) i1 = hi1; else if (i1 < 1) i1 = 1;
+            ic[d] = i1 - 1;
+            t[d] = (pn[d] - g.xc[d][ic[d]]) * (1.0 / jp_d_of(g.xc[d], g.uniform, ic[d]));
+        }
+        s1 = g.n[0]; s2 = (int64_t)g.n[0] * g.n[1];
+    } else {                                           // vertex field of the storage cell (injection.jl:307-311)
+#pragma unroll
+        for (int d = 0; d < N; d++) { ic[d] = ci[d]; t[d] = (pn[d] - g.xv[d][ci[d]]) * (1.0 / dcell[d]); }
+        s1 = g.n[0] + 1; s2 = (int64_t)(g.n[0] + 1) * (g.n[1] + 1);
+    }
+    jp_corners<N>(F, ic[0] + s1 * ic[1] + (N == 3 ? s2 * ic[2] : 0), s1, s2, v);
+    const double tmp = jp_lerp<N>(v, t);
+    double lo = v[0], hi = v[0];
+#pragma unroll
+    for (int q = 1; q < (N == 2 ? 4 : 8); q++) { lo = v[q] < lo ? v[q] : lo; hi = v[q] > hi ? v[q] : hi; }
+    return tmp > hi ? hi : (tmp < lo ? lo : tmp);
+}
+
+template <int N, bool PHASE>
 __global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ,
                                                       uint8_t *inbox, const int *__restrict__ list, const unsigned int *__restrict__ count,
-                                                      int min_xcell, uint64_t seed, uint32_t step, long long *stats) {
+                                                      int min_xcell, uint64_t seed, uint32_t step, long long *stats, InjPhase ph) {
     const int lane = threadIdx.x & 31;
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
     const unsigned n = *count;
@@ -414,14 +471,14 @@ __global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t
                 const bool in = live[h] && jp_isincell<N>(p[h], vq, dq);
                 num += __popc(__ballot_sync(0xffffffffu, in));
             }
-            if (num >= min_xq) break;
+            if (num >= min_xq) { if (PHASE) continue; else break; }
             uint64_t freem = ~occ_c & smask;
             while (freem) {
                 const int i = __ffsll((long long)freem) - 1;
                 freem &= freem - 1;
                 num++;
                 double r[3], pn[3];
-                jp_rand3(seed, 1u, step, (uint32_t)c, (uint32_t)i, r);
+                jp_rand3(seed, PHASE ? 2u : 1u, step, (uint32_t)c, (uint32_t)i, r);
 #pragma unroll
                 for (int d = 0; d < N; d++) pn[d] = vq[d] + dq[d] * fma(0.95, r[d], 0.05);
                 const int64_t e = c + (int64_t)i * g.C;
@@ -489,7 +546,15 @@ __global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t
                         if (od < best_d || (od == best_d && oo < best_ord)) { best_d = od; best_ord = oo; best_e = oe; }
                     }
                 }
-                if (best_e >= 0 && lane == 0)
+                if (PHASE) {
+                    if (best_e >= 0 && lane == 0) ph.phases[e] = ph.phases[best_e];
+                    if (lane < args.n) {                       // one lane per particle field
+                        double xcc[3], dcell[3];
+#pragma unroll
+                        for (int d = 0; d < N; d++) { dcell[d] = jp_d_of(g.xv[d], g.uniform, ci[d]); xcc[d] = (xvc[d] + dq[d] * 0.0) + dq[d]; }
+                        args.a[lane][e] = jp_inject_field<N>(g, ph.fields[lane], ph.fkind[lane], ci, xcc, dcell, pn);
+                    }
+                } else if (best_e >= 0 && lane == 0)
                     for (int a = 0; a < args.n; a++) args.a[a][e] = args.a[a][best_e];
                 __syncwarp();
                 if (num >= min_xq) break;
@@ -1100,14 +1165,47 @@ extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args
     JP_CUDA(cudaMemsetAsync(ctx->stats + 3, 0, sizeof(long long), st));
     if ((int64_t)g.C >= (1ll << 31)) return jp_fail(JP_ERR_UNSUPPORTED, "jp_inject: more than 2^31 cells");
     JP_CUDA(cudaMemsetAsync(ctx->inj_count, 0, 8 * sizeof(unsigned int), st));
-    if (g.ndim == 2) k_inject_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
-    else             k_inject_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
+    if (g.ndim == 2) k_inject_classify<2, false><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
+    else             k_inject_classify<3, false><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
     JP_CHECK_LAUNCH();
     // colour order of the reference: offset_i outermost (src/Particles/injection.jl:30-49)
     const int ncol = g.ndim == 3 ? 8 : 4;
     for (int col = 0; col < ncol; col++) {
-        if (g.ndim == 2) k_inject_sweep<2><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats);
-        else             k_inject_sweep<3><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats);
+        if (g.ndim == 2) k_inject_sweep<2, false><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, InjPhase());
+        else             k_inject_sweep<3, false><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, InjPhase());
+    }
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phases, double *const *args, const double *const *fields,
+                               const int32_t *field_kind, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream) {
+    PREP("jp_inject_phase");
+    JpArgs a;
+    int rc = pack_args(args, nargs, a, "jp_inject_phase");
+    if (rc) return rc;
+    if (!phases) return jp_fail(JP_ERR_INVALID, "jp_inject_phase: null phase array");
+    if (step >= (1u << 31)) return jp_fail(JP_ERR_INVALID, "jp_inject_phase: step must be < 2^31");
+    if ((int64_t)g.C >= (1ll << 31)) return jp_fail(JP_ERR_UNSUPPORTED, "jp_inject_phase: more than 2^31 cells");
+    InjPhase ph;
+    memset(&ph, 0, sizeof(ph));
+    ph.phases = phases;
+    for (int j = 0; j < nargs; j++) {
+        if (!fields || !fields[j] || !field_kind) return jp_fail(JP_ERR_INVALID, "jp_inject_phase: null grid field");
+        if (field_kind[j] != 0 && field_kind[j] != 1) return jp_fail(JP_ERR_INVALID, "jp_inject_phase: field kind must be 0 (vertex) or 1 (centre)");
+        ph.fields[j] = fields[j]; ph.fkind[j] = field_kind[j];
+    }
+    const int NQ = g.ndim == 2 ? 4 : 8;
+    const int min_xq = (min_xcell + NQ - 1) / NQ;
+    JP_CUDA(cudaMemsetAsync(ctx->stats + 3, 0, sizeof(long long), st));
+    JP_CUDA(cudaMemsetAsync(ctx->inj_count, 0, 8 * sizeof(unsigned int), st));
+    if (g.ndim == 2) k_inject_classify<2, true><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
+    else             k_inject_classify<3, true><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
+    JP_CHECK_LAUNCH();
+    const int ncol = g.ndim == 3 ? 8 : 4;
+    for (int col = 0; col < ncol; col++) {
+        if (g.ndim == 2) k_inject_sweep<2, true><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
+        else             k_inject_sweep<3, true><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
     }
     JP_CHECK_LAUNCH();
     return JP_OK;

@@ -451,6 +451,130 @@ int jpo_inject(const jpo_grid *g, double *const *coords, uint8_t *index, double 
     return 0;
 }
 
+/* ---- inject_particles_phase! (src/Particles/injection.jl:146-325) -------------------------
+ * Differences from inject_particles!: EVERY quadrant is examined (`continue`, :271, instead of the
+ * `break` of :100); the nearest particle (index_min_distance, looked up BEFORE the new particle is
+ * marked live, :283) only donates its PHASE; the other particle fields args[j] are interpolated
+ * from grid fields[j] at the new position and clamped to the extrema of the interpolation stencil:
+ * centre fields (size == cells, :295-305) from the cell-centre grid with the shifted / clamped cell
+ * index of centroid2particle, everything else (:307-311) as a vertex field of the storage cell.
+ * fkind[j]: 1 = centre field (n), 0 = vertex field (n+1).  RNG purpose 2. */
+static inline double clamp_julia(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+static void inject_phase_cell(const jpo_grid *g, double *const *coords, uint8_t *index, double *phases, double *const *args,
+                              const double *const *fields, const int *fkind, int nargs, int min_xcell, uint64_t seed,
+                              uint32_t step, const int *ci, int64_t *n_injected) {
+    const int N = g->ndim, S = g->S, NQ = N == 2 ? 4 : 8;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1], nz = N == 3 ? g->n[2] : 1;
+    const int64_t c = ci[0] + (int64_t)nx * (ci[1] + (int64_t)ny * (N == 3 ? ci[2] : 0));
+    double xvc[3], dcell[3], dq[3], xcc[3];
+    for (int d = 0; d < N; d++) {
+        xvc[d] = g->xv[d][ci[d]];
+        dcell[d] = d_of(g->xv[d], g->uniform, ci[d]);
+        dq[d] = dcell[d] / 2;
+        xcc[d] = (xvc[d] + dq[d] * 0.0) + dq[d];          /* xvi_quadrants[1] .+ di_quadrant */
+    }
+    const int min_xq = (min_xcell + NQ - 1) / NQ;
+    for (int iq = 0; iq < NQ; iq++) {
+        double vq[3];
+        for (int d = 0; d < N; d++) vq[d] = xvc[d] + dq[d] * (double)((iq >> d) & 1);
+        int num = 0;
+        for (int i = 0; i < S; i++) {
+            const int64_t e = c + (int64_t)i * C;
+            if (!index[e]) continue;
+            int in = 1;
+            for (int d = 0; d < N; d++) { double p = coords[d][e]; in &= (vq[d] < p) & (p < vq[d] + dq[d]); }
+            num += in;
+        }
+        if (num >= min_xq) continue;
+        for (int i = 0; i < S; i++) {
+            const int64_t e = c + (int64_t)i * C;
+            if (index[e]) continue;
+            num++;
+            double r[3], pn[3];
+            jpo_rand3(seed, 2u, step, (uint32_t)c, (uint32_t)i, r);
+            for (int d = 0; d < N; d++) pn[d] = vq[d] + dq[d] * fma(0.95, r[d], 0.05);
+            /* phase of the nearest live particle in the 3^N neighbourhood (k,j,i outer, slot inner, strict <) */
+            double dmin = INFINITY; int64_t emin = -1;
+            for (int kk = (N == 3 ? ci[2] - 1 : 0); kk <= (N == 3 ? ci[2] + 1 : 0); kk++)
+                for (int jj = ci[1] - 1; jj <= ci[1] + 1; jj++)
+                    for (int ii = ci[0] - 1; ii <= ci[0] + 1; ii++) {
+                        if (ii < 0 || jj < 0 || kk < 0 || ii >= nx || jj >= ny || kk >= nz) continue;
+                        const int64_t c2 = ii + (int64_t)nx * (jj + (int64_t)ny * kk);
+                        for (int ip = 0; ip < S; ip++) {
+                            if (c2 == c && ip == i) continue;
+                            const int64_t e2 = c2 + (int64_t)ip * C;
+                            if (!index[e2]) continue;
+                            double s = 0;
+                            for (int d = 0; d < N; d++) {
+                                double del = coords[d][e2] - pn[d];
+                                s = d == 0 ? del * del : s + del * del;
+                            }
+                            double dist = sqrt(s);
+                            if (dist < dmin) { dmin = dist; emin = e2; }
+                        }
+                    }
+            if (emin >= 0) phases[e] = phases[emin];       /* no live donor: the reference indexes slot 0 (UB); left untouched */
+            for (int d = 0; d < N; d++) coords[d][e] = pn[d];
+            index[e] = 1;
+            (*n_injected)++;
+            for (int a = 0; a < nargs; a++) {
+                const double *F = fields[a];
+                int ic[3] = {0, 0, 0};
+                double t[3], v[8];
+                int64_t s1, s2;
+                if (fkind[a] == 1) {
+                    for (int d = 0; d < N; d++) {
+                        int i1 = ci[d] + 1;                 /* 1-based */
+                        if (pn[d] < xcc[d]) i1 -= 1;
+                        const int hi1 = g->n[d] - 1;
+                        if (i1 > hi1) i1 = hi1;             /* clamp(x, 1, sz-1): x > hi first */
+                        else if (i1 < 1) i1 = 1;
+                        ic[d] = i1 - 1;
+                        t[d] = (pn[d] - g->xc[d][ic[d]]) * (1.0 / d_of(g->xc[d], g->uniform, ic[d]));
+                    }
+                    s1 = nx; s2 = (int64_t)nx * ny;
+                } else {
+                    for (int d = 0; d < N; d++) { ic[d] = ci[d]; t[d] = (pn[d] - g->xv[d][ci[d]]) * (1.0 / dcell[d]); }
+                    s1 = nx + 1; s2 = (int64_t)(nx + 1) * (ny + 1);
+                }
+                const int64_t b = ic[0] + s1 * ic[1] + (N == 3 ? s2 * ic[2] : 0);
+                v[0] = F[b]; v[1] = F[b + 1]; v[2] = F[b + s1]; v[3] = F[b + s1 + 1];
+                if (N == 3) { v[4] = F[b + s2]; v[5] = F[b + s2 + 1]; v[6] = F[b + s2 + s1]; v[7] = F[b + s2 + s1 + 1]; }
+                const double tmp = N == 2 ? lerp2(v, t) : lerp3(v, t);
+                double lo = v[0], hi = v[0];
+                for (int q = 1; q < (N == 2 ? 4 : 8); q++) { lo = v[q] < lo ? v[q] : lo; hi = v[q] > hi ? v[q] : hi; }
+                args[a][e] = clamp_julia(tmp, lo, hi);
+            }
+            if (num >= min_xq) break;
+        }
+    }
+}
+
+int jpo_inject_phase(const jpo_grid *g, double *const *coords, uint8_t *index, double *phases, double *const *args,
+                     const double *const *fields, const int *fkind, int nargs, int min_xcell, uint64_t seed, uint32_t step,
+                     int64_t *n_injected_out) {
+    const int N = g->ndim;
+    int ncol[3] = {(g->n[0] + 1) / 2, (g->n[1] + 1) / 2, N == 3 ? (g->n[2] + 1) / 2 : 1};
+    int64_t injected = 0;
+    const int oz_max = N == 3 ? 2 : 1;
+    for (int ox = 0; ox < 2; ox++)
+        for (int oy = 0; oy < 2; oy++)
+            for (int oz = 0; oz < oz_max; oz++) {
+                const int64_t nt = (int64_t)ncol[0] * ncol[1] * ncol[2];
+#pragma omp parallel for schedule(static) reduction(+ : injected) if (g_threads > 1)
+                for (int64_t t = 0; t < nt; t++) {
+                    int I = (int)(t % ncol[0]), J = (int)((t / ncol[0]) % ncol[1]), K = (int)(t / ((int64_t)ncol[0] * ncol[1]));
+                    int ci[3] = {2 * I + ox, 2 * J + oy, N == 3 ? 2 * K + oz : 0};
+                    if (ci[0] >= g->n[0] || ci[1] >= g->n[1] || (N == 3 && ci[2] >= g->n[2])) continue;
+                    inject_phase_cell(g, coords, index, phases, args, fields, fkind, nargs, min_xcell, seed, step, ci, &injected);
+                }
+            }
+    if (n_injected_out) *n_injected_out = injected;
+    return 0;
+}
+
 /* ---- grid2particle! (src/Interpolations/grid_to_particle.jl:26-82, :265-273;
  *      field_corners src/Interpolations/utils.jl:98-118) -------------------- */
 int jpo_grid2particle(const jpo_grid *g, const double *const *coords, const uint8_t *index, double *Fp, const double *F) {

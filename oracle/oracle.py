@@ -125,6 +125,15 @@ class Oracle:
         assert rc == 0
         return int(n.value)
 
+    def inject_phase(self, coords, index, phases, args, fields, fkind, min_xcell, seed, step):
+        n = C.c_int64()
+        kinds = (C.c_int * max(len(args), 1))(*[int(k) for k in fkind])
+        rc = lib().jpo_inject_phase(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _dp(phases), _pp(args),
+                                    _pp(fields), kinds, len(args), int(min_xcell), C.c_uint64(int(seed)), C.c_uint32(int(step)),
+                                    C.byref(n))
+        assert rc == 0
+        return int(n.value)
+
     def grid2particle(self, coords, index, Fp, F):
         return lib().jpo_grid2particle(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _dp(Fp), _dp(F))
 
