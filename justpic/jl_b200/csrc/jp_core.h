@@ -43,6 +43,8 @@ struct JpGrid {
     //    coordinates in registers instead of loading them (same bits by construction)
     int32_t affine;
     double aff_v0[3], aff_dv[3], aff_g0[3], aff_dg[3];
+    double dom_lo[3], dom_hi[3];   // xv[d][0], xv[d][n]  (kernel-parameter constants instead of per-thread loads)
+    double dxv0[3];                // xv[d][1] - xv[d][0]  (the scalar spacing of range grids)
 };
 
 struct JpArgs {               // particle fields carried along by move/inject/clean

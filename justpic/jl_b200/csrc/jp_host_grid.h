@@ -68,6 +68,10 @@ static inline const char *jp_grid_build(const jp_grid_desc *d, JpGrid &g, std::v
         g.aff_g0[dim] = xg[0]; g.aff_dg[dim] = dg;
     }
     g.affine = aff_v ? (aff_g ? 2 : 1) : 0;
+    for (int dim = 0; dim < N; dim++) {
+        g.dom_lo[dim] = d->xv[dim][0]; g.dom_hi[dim] = d->xv[dim][d->n[dim]];
+        g.dxv0[dim] = d->xv[dim][1] - d->xv[dim][0];
+    }
     h.clear();
     auto push = [&](const double *x, int n) { size_t off = h.size(); h.insert(h.end(), x, x + n); return off; };
     for (int dim = 0; dim < N; dim++) {

@@ -170,6 +170,84 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify2(JpGrid
     if (wc && lane == 0) atomicOr(complex_flag, wc);
 }
 
+// ---- A'. single-pass classify: every live particle is classified where it is loaded (no second
+// look at the leavers, no shared memory): the strict isincell test, the domain test and the
+// destination search share their comparisons, and since thread = cell walks its slots in order the
+// k-th leaver's code byte is simply shifted into the thread's own code word.  k_move_classify2
+// re-read the coordinates of the ~38 % leavers; with 4 CTAs/SM resident that second look missed the
+// L2 and cost 40 % extra DRAM traffic at 256^3 (27.7 GB read for 19.3 GB of coordinates).
+template <int N>
+__global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
+                                                                         unsigned int *complex_flag) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    // the four vertices around the cell per dimension (NaN outside the grid: comparisons fail)
+    double am[3], a[3], b[3], bp[3];
+    if (ok) {
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            const double *xv = g.xv[d];
+            const int i = ci[d];
+            a[d] = xv[i]; b[d] = xv[i + 1];
+            am[d] = i > 0 ? xv[i - 1] : NAN;
+            bp[d] = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
+        }
+    }
+    uint64_t lv = 0, codew = 0;
+    int k = 0;
+    unsigned cplx = 0;     // reason bits: 1 far / on a vertex, 2 same cell (ulp gap), 4 fails isincell in destination
+    constexpr int U = 2;
+    for (int s0 = 0; s0 < g.S; s0 += U) {
+        const unsigned bits = (unsigned)(m >> s0) & ((1u << U) - 1u);
+        if (!__any_sync(0xffffffffu, bits != 0)) continue;
+        double p[U][3];
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int d = 0; d < N; d++) p[u][d] = ((bits >> u) & 1u) ? co.p[d][c + (int64_t)(s0 + u) * g.C] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!((bits >> u) & 1u)) continue;
+            // isincell (strict, upper edge fl(a + dx)), domain test, destination by comparisons with the
+            // four vertices; dx = scalar spacing on range grids, the cell's own spacing on vector grids
+            bool in = true, indom = true, near = true, dest_ok = true;
+            int dv[3] = {0, 0, 0};
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                const double pd = p[u][d];
+                const double dx0 = g.uniform ? g.dxv0[d] : b[d] - a[d];
+                in = in & (a[d] < pd) & (pd < a[d] + dx0);
+                indom = indom & (g.dom_lo[d] < pd) & (pd < g.dom_hi[d]);
+                double lower, dxd;
+                if (a[d] < pd && pd < b[d]) { dv[d] = 0; lower = a[d]; dxd = dx0; }
+                else if (am[d] < pd && pd < a[d]) { dv[d] = -1; lower = am[d]; dxd = g.uniform ? g.dxv0[d] : a[d] - am[d]; }
+                else if (b[d] < pd && pd < bp[d]) { dv[d] = 1; lower = b[d]; dxd = g.uniform ? g.dxv0[d] : bp[d] - b[d]; }
+                else { near = false; lower = a[d]; dxd = dx0; }
+                dest_ok = dest_ok & (pd < lower + dxd);
+            }
+            if (in) continue;
+            lv |= 1ull << (s0 + u);
+            int code = JP_CODE_DELETE;
+            if (indom) {
+                const bool same = dv[0] == 0 && dv[1] == 0 && dv[2] == 0;
+                if (!near) cplx |= 1u;
+                else if (same) cplx |= 2u;
+                else if (!dest_ok) cplx |= 4u;
+                else code = jp_dir_code(dv, N);
+            }
+            codew |= (uint64_t)code << (8 * (k & 7));
+            if ((++k & 7) == 0) { ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
+        }
+    }
+    if (ok) {
+        ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
+        if (k & 7) ws.code[(int64_t)(k >> 3) * g.C + c] = codew;
+    }
+    const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
+    if (wc && threadIdx.x == 0) atomicOr(complex_flag, wc);
+}
+
 // ---- B. one colour of the plan (thread = source cell; 8-byte words only).
 // Literal slot logic of move_kernel! (src/Particles/move_safe.jl:72-125) on the occupancy
 // words; the slot given to the k-th leaver goes to res (one byte: slot | placed << 6).

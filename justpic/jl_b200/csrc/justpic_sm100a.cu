@@ -1053,7 +1053,9 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     auto mark = [&]() { if (timing) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); nev++; } };
     mark();
     JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
-    k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
+    static const bool cls2 = getenv("JP_MOVE_CLASSIFY2") != nullptr;       // developer A/B switch
+    if (cls2) k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
+    else      k_move_classify3<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
     JP_CHECK_LAUNCH();
     JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->mp_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     JP_CUDA(cudaStreamSynchronize(st));
