@@ -47,6 +47,7 @@ typedef enum {
 } jp_status;
 
 typedef enum { JP_EULER = 0, JP_RK2 = 1, JP_RK4 = 2 } jp_scheme;
+typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_interp;
 /* JP_OPT_ADVECT_AFFINE (0/1, default 1): let the tiled advection kernel regenerate grid coordinates as
  * fma(i, dx, x0) when jp_ctx_create verified that this reproduces EVERY stored entry bit for bit
  * (results are identical either way; 0 forces the table look-ups, used by the parity tests). */
@@ -98,6 +99,13 @@ int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxcell, uint64
  * V[comp] are the staggered velocity arrays with extents nvel[comp][0..ndim). */
 int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha,
               const double *const *V, double dt, void *stream);
+
+/* advection_LinP!(particles, method, V, dt) (src/Particles/Advection/advection_LinP.jl:12-391) and
+ * advection_MQS!(particles, method, V, dt) (advection_MQS.jl:16-124, src/Interpolations/MQS.jl):
+ * same integrators, velocity reconstructed with the LinP / MQS interpolant where the interpolation
+ * cell is interior (linear elsewhere).  interp = JP_INTERP_LINP / JP_INTERP_MQS (LINEAR = jp_advect). */
+int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha,
+                     const double *const *V, double dt, int32_t interp, void *stream);
 
 /* move_particles!(particles, args) (src/Particles/move_safe.jl:21-125).
  * Slot assignment bit-exact with the reference's 3^N colour sweeps (for displacements

@@ -56,6 +56,8 @@ SYMBOLS = {
     "jp_init_particles": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_uint64, C.c_void_p]),
     "jp_advect": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
                             C.POINTER(C.c_void_p), C.c_double, C.c_void_p]),
+    "jp_advect_interp": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
+                                   C.POINTER(C.c_void_p), C.c_double, C.c_int32, C.c_void_p]),
     "jp_move": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "jp_move_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "jp_last_move_path": (C.c_int, [C.c_void_p]),

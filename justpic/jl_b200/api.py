@@ -39,7 +39,7 @@ __all__ = [
     "Euler", "RungeKutta2", "RungeKutta4",
     "Particles", "PhaseRatios",
     "init_particles", "init_cell_arrays", "cell_array",
-    "advection", "move_particles", "inject_particles", "inject_particles_phase", "clean_particles",
+    "advection", "advection_LinP", "advection_MQS", "move_particles", "inject_particles", "inject_particles_phase", "clean_particles",
     "grid2particle", "centroid2particle", "particle2grid", "particle2centroid",
     "phase_ratios_center", "phase_ratios_vertex", "phase_ratios_face", "phase_ratios_midpoint",
     "update_phase_ratios", "set_synchronous",
@@ -344,6 +344,30 @@ def advection(particles: Particles, method, V, dt: float, affine: Optional[bool]
         _cabi.check(lib.jp_advect(C.c_void_p(p._ctx), C.byref(pc), method.scheme, float(method.alpha),
                                   _ptr_array(V), float(dt), _stream()), "advection")
         _done()
+
+
+def _advection_interp(particles: Particles, method, V, dt: float, interp: int, who: str) -> None:
+    p = particles
+    V = tuple(V)
+    if len(V) != p.ndim:
+        raise ValueError("V must hold one staggered array per dimension")
+    for c, v in enumerate(V):
+        _field(v, p, int(np.prod([len(x) for x in p.xi_vel[c]])), f"V[{c}]")
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_advect_interp(C.c_void_p(p._ctx), C.byref(pc), method.scheme, float(method.alpha),
+                                                  _ptr_array(V), float(dt), interp, _stream()), who)
+        _done()
+
+
+def advection_LinP(particles: Particles, method, V, dt: float) -> None:
+    """``advection_LinP!(particles, method, V, dt)`` (src/Particles/Advection/advection_LinP.jl:12-26)."""
+    _advection_interp(particles, method, V, dt, 1, "advection_LinP")
+
+
+def advection_MQS(particles: Particles, method, V, dt: float) -> None:
+    """``advection_MQS!(particles, method, V, dt)`` (src/Particles/Advection/advection_MQS.jl:16-29)."""
+    _advection_interp(particles, method, V, dt, 2, "advection_MQS")
 
 
 def advect_affine_level(particles: Particles) -> int:

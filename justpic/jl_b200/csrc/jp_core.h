@@ -119,6 +119,122 @@ JP_HD void jp_interp_velocity_literal(const JpGrid &g, const double *const *V, c
     }
 }
 
+// ---------------------------------------------------------------------------
+// advection_MQS! / advection_LinP! interpolants (src/Interpolations/MQS.jl,
+// src/Particles/Advection/advection_LinP.jl:96-391, advection_MQS.jl:96-124): the linear
+// interpolant of interp_velocity2particle plus a correction when the interpolation cell is interior
+// (1 < idx < size(F) - 1 in every direction).  Literal, quirks included (see oracle/justpic_oracle.c).
+template <int N> JP_HD double jp_Fat(const double *F, const int32_t *nF, int i1, int j1, int k1) {   // 1-based
+    return F[(i1 - 1) + (int64_t)nF[0] * ((j1 - 1) + (N == 3 ? (int64_t)nF[1] * (k1 - 1) : 0))];
+}
+// quadratic correction of one edge (v0e, v1e) at tq with the outer nodes on either side
+JP_HD double jp_mqs_edge(double v0e, double v1e, double tq, double outer_lo, double outer_hi) {
+    const double l = jp_lerp1(tq, v0e, v1e);
+    const bool low = tq < 0.5;
+    const double a = low ? outer_lo : v0e, b = low ? v0e : v1e, c = low ? v1e : outer_hi;
+    return l + (0.5 * ((tq - 0.5) * (tq - 0.5))) * (fma(-2.0, b, a) + c);
+}
+template <int N> JP_HD double jp_mqs(const double *F, const int32_t *nF, int comp, const int *idx1, const double *v, const double *t) {
+    const int i = idx1[0], j = idx1[1], k = N == 3 ? idx1[2] : 1;
+    if (N == 2) {
+        if (comp == 0)
+            return jp_lerp1(t[1], jp_mqs_edge(v[0], v[1], t[0], jp_Fat<N>(F, nF, i - 1, j, 1), jp_Fat<N>(F, nF, i + 2, j, 1)),
+                            jp_mqs_edge(v[2], v[3], t[0], jp_Fat<N>(F, nF, i - 1, j + 1, 1), jp_Fat<N>(F, nF, i + 2, j + 1, 1)));
+        return jp_lerp1(t[0], jp_mqs_edge(v[0], v[2], t[1], jp_Fat<N>(F, nF, i, j - 1, 1), jp_Fat<N>(F, nF, i, j + 2, 1)),
+                        jp_mqs_edge(v[1], v[3], t[1], jp_Fat<N>(F, nF, i + 1, j - 1, 1), jp_Fat<N>(F, nF, i + 1, j + 2, 1)));
+    }
+    double f[2];
+    for (int h = 0; h < 2; h++) {
+        if (comp == 0) {            // MQS-x of v[1:4] / v[5:8], outer nodes of BOTH taken in plane k (MQS.jl:62-70, :80-108)
+            const double *w = v + 4 * h;
+            f[h] = jp_lerp1(t[1], jp_mqs_edge(w[0], w[1], t[0], jp_Fat<N>(F, nF, i - 1, j, k), jp_Fat<N>(F, nF, i + 2, j, k)),
+                            jp_mqs_edge(w[2], w[3], t[0], jp_Fat<N>(F, nF, i - 1, j + 1, k), jp_Fat<N>(F, nF, i + 2, j + 1, k)));
+        } else if (comp == 1) {     // MQS-y (MQS.jl:110-133)
+            const double *w = v + 4 * h;
+            f[h] = jp_lerp1(t[0], jp_mqs_edge(w[0], w[2], t[1], jp_Fat<N>(F, nF, i, j - 1, k), jp_Fat<N>(F, nF, i, j + 2, k)),
+                            jp_mqs_edge(w[1], w[3], t[1], jp_Fat<N>(F, nF, i + 1, j - 1, k), jp_Fat<N>(F, nF, i + 1, j + 2, k)));
+        } else {                    // MQS-z: front (v1,v2,v5,v6) / back (v3,v4,v7,v8) with (t1,t3), same j, correction along x (MQS.jl:73-78, :135-158)
+            const double w[4] = {v[2 * h], v[2 * h + 1], v[4 + 2 * h], v[4 + 2 * h + 1]};
+            f[h] = jp_lerp1(t[2], jp_mqs_edge(w[0], w[1], t[0], jp_Fat<N>(F, nF, i - 1, j, k), jp_Fat<N>(F, nF, i + 2, j, k)),
+                            jp_mqs_edge(w[2], w[3], t[0], jp_Fat<N>(F, nF, i - 1, j, k + 1), jp_Fat<N>(F, nF, i + 2, j, k + 1)));
+        }
+    }
+    return comp == 2 ? jp_lerp1(t[1], f[0], f[1]) : jp_lerp1(t[2], f[0], f[1]);
+}
+JP_HD int jp_clampi(int x, int lo, int hi) { return x > hi ? hi : (x < lo ? lo : x); }
+template <int N> JP_HD double jp_linp(const double *F, const int32_t *nF, int comp, const int *idx1, const double *xc, const double *dxi,
+                                      const double *p, double VL) {
+    int ijk[3] = {idx1[0], idx1[1], N == 3 ? idx1[2] : 1};
+    ijk[comp] += p[comp] > xc[comp] + dxi[comp] / 2 ? 1 : 0;                  // offset_LinP (advection_LinP.jl:345-347)
+    // augment_offset (:364-391): three offsets (-1, 0, 1) along `comp`; the two transverse directions take
+    // (0|1): rows (1,1,1), (2,2,2), (3,1,3), (4,2,4) of (offset_i, offset_j, offset_k)
+    const int ta = comp == 0 ? 1 : 0, tb = comp == 2 ? 1 : 2;                // transverse dims, lower first
+    const int nrow = N == 2 ? 2 : 4;
+    double av[8];
+    for (int r = 0; r < nrow; r++) {
+        // bit pattern of the tables: offset_j rows (0,1,0,1) [used as rows 1,2,1,2], offset_k / offset_i rows (0,0,1,1)
+        int o[3] = {0, 0, 0};
+        if (comp == 0) { o[1] = r & 1; o[2] = r >> 1; }
+        else if (comp == 1) { o[0] = r & 1; o[2] = r >> 1; }
+        else { o[0] = r >> 1; o[1] = r & 1; }
+        (void)ta; (void)tb;
+        double f[3];
+        for (int m = 0; m < 3; m++) {
+            int q[3] = {ijk[0] + o[0], ijk[1] + o[1], ijk[2] + o[2]};
+            q[comp] = ijk[comp] + (m - 1);
+            f[m] = jp_Fat<N>(F, nF, jp_clampi(q[0], 1, nF[0]), jp_clampi(q[1], 1, nF[1]), N == 3 ? jp_clampi(q[2], 1, nF[2]) : 1);
+        }
+        av[2 * r] = (f[0] + f[1]) / 2;
+        av[2 * r + 1] = (f[2] + f[1]) / 2;
+    }
+    double FP[8];
+    if (comp == 0) { for (int q = 0; q < 2 * nrow; q++) FP[q] = av[q]; }
+    else {                                                                  // swap_F (:212-216, :335-340)
+        FP[0] = av[0]; FP[1] = av[2]; FP[2] = av[1]; FP[3] = av[3];
+        if (N == 3) { FP[4] = av[4]; FP[5] = av[6]; FP[6] = av[5]; FP[7] = av[7]; }
+    }
+    double tP[3];
+    for (int d = 0; d < N; d++) {
+        double x = xc[d];
+        if (d == comp) x = xc[d] + ((double)(1 - 2 * (p[d] < xc[d] + dxi[d] / 2 ? 1 : 0)) * dxi[d]) / 2;   // correct_xci_to_pressure_point
+        tP[d] = (p[d] - x) * (1.0 / dxi[d]);
+    }
+    const double VP = jp_lerp<N>(FP, tP);
+    const double A = 2.0 / 3.0;
+    return A * VL + (1 - A) * VP;
+}
+
+// interp_velocity2particle_LinP / _MQS: INTERP = 1 LinP, 2 MQS (0 = the linear interpolant)
+template <int N, int INTERP>
+JP_HD void jp_interp_velocity_hi(const JpGrid &g, const double *const *V, const double *p, const int *cell1, double *vout) {
+    for (int c = 0; c < N; c++) {
+        bool ok = true;
+        for (int d = 0; d < N; d++) {
+            const double *x = g.xvel[c][d];
+            if (!(x[0] <= p[d] && p[d] <= x[g.nvel[c][d] - 1])) { ok = false; break; }
+        }
+        if (!ok) { vout[c] = INFINITY; continue; }
+        int idx[3] = {1, 1, 1};
+        double t[3], xcn[3], dxi[3];
+        bool interior = true;
+        for (int d = 0; d < N; d++) {
+            const double *x = g.xvel[c][d];
+            idx[d] = jp_bisect1(p[d], x, g.nvel[c][d], cell1[d]);
+            xcn[d] = x[idx[d] - 1];
+            dxi[d] = jp_d_of(x, g.uniform, idx[d] - 1);
+            t[d] = (p[d] - xcn[d]) * (1.0 / dxi[d]);
+            interior = interior && 1 < idx[d] && idx[d] < g.nvel[c][d] - 1;
+        }
+        const int64_t s1 = g.nvel[c][0], s2 = (int64_t)g.nvel[c][0] * g.nvel[c][1];
+        double v[8];
+        jp_corners<N>(V[c], (idx[0] - 1) + s1 * (idx[1] - 1) + (N == 3 ? s2 * (idx[2] - 1) : 0), s1, s2, v);
+        const double VL = jp_lerp<N>(v, t);
+        if (INTERP == 0 || !interior) vout[c] = VL;
+        else if (INTERP == 2) vout[c] = jp_mqs<N>(V[c], g.nvel[c], c, idx, v, t);
+        else vout[c] = jp_linp<N>(V[c], g.nvel[c], c, idx, xcn, dxi, p, VL);
+    }
+}
+
 // Fast path.  Preconditions (g.fast): every xvel[comp][dim] is the vertex
 // vector ("V") or the ghosted-centre vector ("G") of that dim, and
 // xg[i] < xv[i] < xg[i+1] for every vertex i.  For a particle STRICTLY inside a
@@ -209,6 +325,38 @@ JP_HD void jp_advect_particle(const JpGrid &g, double alpha, const double *const
         jp_interp_velocity<N, FAST, UNIFORM>(g, V, q, cell1, k3);
         for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k3[d];
         jp_interp_velocity<N, FAST, UNIFORM>(g, V, q, cell1, k4);
+        for (int d = 0; d < N; d++) pout[d] = p0[d] + dt * (((k1[d] + 2 * k2[d]) + 2 * k3[d]) + k4[d]) / 6;
+    }
+}
+
+// advection_LinP! / advection_MQS!: same integrators (advect_particle with interpolation_fn,
+// src/Particles/Advection/Euler.jl, RK2.jl:28-54, RK4.jl), other interpolant
+template <int N, int SCHEME, int INTERP>
+JP_HD void jp_advect_particle_hi(const JpGrid &g, double alpha, const double *const *V, double dt,
+                                 const int *cell1, const double *p0, double *pout) {
+    double k1[3], k2[3], q[3];
+    jp_interp_velocity_hi<N, INTERP>(g, V, p0, cell1, k1);
+    if (SCHEME == 0) {
+        const double c = 1.0 * dt;
+        for (int d = 0; d < N; d++) pout[d] = fma(c, k1[d], p0[d]);
+    } else if (SCHEME == 1) {
+        const double c = (1.0 * alpha) * dt;
+        for (int d = 0; d < N; d++) q[d] = fma(c, k1[d], p0[d]);
+        jp_interp_velocity_hi<N, INTERP>(g, V, q, cell1, k2);
+        if (alpha == 0.5) {
+            for (int d = 0; d < N; d++) pout[d] = fma(1.0 * dt, k2[d], p0[d]);
+        } else {
+            const double b = 0.5 * (1.0 / alpha), a = 1.0 - b;
+            for (int d = 0; d < N; d++) pout[d] = fma(1.0 * dt, fma(b, k2[d], a * k1[d]), p0[d]);
+        }
+    } else {
+        double k3[3], k4[3];
+        for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k1[d] / 2;
+        jp_interp_velocity_hi<N, INTERP>(g, V, q, cell1, k2);
+        for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k2[d] / 2;
+        jp_interp_velocity_hi<N, INTERP>(g, V, q, cell1, k3);
+        for (int d = 0; d < N; d++) q[d] = p0[d] + dt * k3[d];
+        jp_interp_velocity_hi<N, INTERP>(g, V, q, cell1, k4);
         for (int d = 0; d < N; d++) pout[d] = p0[d] + dt * (((k1[d] + 2 * k2[d]) + 2 * k3[d]) + k4[d]) / 6;
     }
 }

@@ -145,6 +145,28 @@ __global__ void __launch_bounds__(256) k_advect(JpGrid g, Ptr3 co, const uint8_t
     }
 }
 
+// advection_LinP! / advection_MQS!: same thread <-> cell sweep, literal LinP / MQS interpolants
+template <int N, int SCHEME, int INTERP>
+__global__ void __launch_bounds__(256) k_advect_hi(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V, double alpha, double dt) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    const int cell1[3] = {ci[0] + 1, ci[1] + 1, ci[2] + 1};
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        if (live) {
+            const int64_t e = c + (int64_t)s * g.C;
+            double p0[3], p1[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) p0[d] = co.p[d][e];
+            jp_advect_particle_hi<N, SCHEME, INTERP>(g, alpha, V.p, dt, cell1, p0, p1);
+#pragma unroll
+            for (int d = 0; d < N; d++) co.p[d][e] = p1[d];
+        }
+    }
+}
+
 // move_particles! pass A: occupancy + leave words (order-free, coalesced)
 template <int N>
 __global__ void __launch_bounds__(256) k_move_classify(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, uint64_t *occ, uint64_t *leave) {
@@ -1014,6 +1036,37 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
         else le = launch_advect<3, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
     }
     if (le != cudaSuccess) return jp_fail(JP_ERR_CUDA, "jp_advect: %s", cudaGetErrorString(le));
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+template <int N, int INTERP>
+static void launch_advect_hi(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, int scheme, double alpha, double dt) {
+    if (scheme == 0) k_advect_hi<N, 0, INTERP><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
+    else if (scheme == 1) k_advect_hi<N, 1, INTERP><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
+    else k_advect_hi<N, 2, INTERP><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
+}
+
+extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt,
+                                int32_t interp, void *stream) {
+    if (interp == JP_INTERP_LINEAR) return jp_advect(ctx, p, scheme, alpha, V, dt, stream);
+    PREP("jp_advect_interp");
+    if (interp != JP_INTERP_LINP && interp != JP_INTERP_MQS) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: unknown interpolant");
+    if (!V) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: null velocity tuple");
+    CPtr3 v = {{nullptr, nullptr, nullptr}};
+    for (int d = 0; d < g.ndim; d++) {
+        if (!V[d]) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: null velocity component");
+        v.p[d] = V[d];
+    }
+    if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: Only 0 < alpha < 1 is supported");
+    if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: unknown integrator");
+    if (g.ndim == 2) {
+        if (interp == JP_INTERP_LINP) launch_advect_hi<2, 1>(g, grd, blk, st, co, p->index, v, scheme, alpha, dt);
+        else                          launch_advect_hi<2, 2>(g, grd, blk, st, co, p->index, v, scheme, alpha, dt);
+    } else {
+        if (interp == JP_INTERP_LINP) launch_advect_hi<3, 1>(g, grd, blk, st, co, p->index, v, scheme, alpha, dt);
+        else                          launch_advect_hi<3, 2>(g, grd, blk, st, co, p->index, v, scheme, alpha, dt);
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }

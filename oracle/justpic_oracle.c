@@ -124,8 +124,114 @@ void jpo_second_stage(double alpha, double dt, int n, const double *v0, const do
     }
 }
 
+/* ---- MQS (src/Interpolations/MQS.jl:1-158) and LinP (src/Particles/Advection/advection_LinP.jl:96-391)
+ * velocity reconstructions.  F: column-major array of component `comp` (0-based), sizes nF; idx1: 1-based
+ * corrected cell indices on that component's grid; v: the 2^N corners; t: normalised coordinates.
+ * Both are literal, including the reference's quirks: the 3-D MQS takes the outer stencil nodes of its
+ * "top"/"back" face from the SAME k (j) plane as the "bottom"/"front" one, the z-component's MQS
+ * correction runs along x, and LinP's 3-D z-component corner tuple is ordered as the code orders it. */
+static inline double Fat(const double *F, const int *nF, int N, int i1, int j1, int k1) {   /* 1-based */
+    return F[(i1 - 1) + (int64_t)nF[0] * ((j1 - 1) + (N == 3 ? (int64_t)nF[1] * (k1 - 1) : 0))];
+}
+/* one 4-corner MQS sweep: v = (a0, a1 | b0, b1), quadratic correction along the first pair direction.
+ * lo/hi outer nodes of the two edges are passed in (already fetched from F). */
+static inline double mqs_edge(double v0e, double v1e, double tq, double outer_lo, double outer_hi) {
+    const double half = 0.5;
+    const double l = lerp1(tq, v0e, v1e);
+    double a, b, c;
+    if (tq < half) { a = outer_lo; b = v0e; c = v1e; } else { a = v0e; b = v1e; c = outer_hi; }
+    const double corr = (half * ((tq - half) * (tq - half))) * (fma(-2.0, b, a) + c);
+    return l + corr;
+}
+static double mqs_eval(const double *F, const int *nF, int N, int comp, const int *idx1, const double *v, const double *t) {
+    const int i = idx1[0], j = idx1[1], k = N == 3 ? idx1[2] : 1;
+    if (N == 2) {
+        if (comp == 0) {
+            double e0 = mqs_edge(v[0], v[1], t[0], Fat(F, nF, N, i - 1, j, 1), Fat(F, nF, N, i + 2, j, 1));
+            double e1 = mqs_edge(v[2], v[3], t[0], Fat(F, nF, N, i - 1, j + 1, 1), Fat(F, nF, N, i + 2, j + 1, 1));
+            return lerp1(t[1], e0, e1);
+        }
+        double e0 = mqs_edge(v[0], v[2], t[1], Fat(F, nF, N, i, j - 1, 1), Fat(F, nF, N, i, j + 2, 1));
+        double e1 = mqs_edge(v[1], v[3], t[1], Fat(F, nF, N, i + 1, j - 1, 1), Fat(F, nF, N, i + 1, j + 2, 1));
+        return lerp1(t[0], e0, e1);
+    }
+    if (comp == 0) {            /* MQS-x on v[1:4] and v[5:8], both with plane k; lerp in t3 */
+        double f[2];
+        for (int h = 0; h < 2; h++) {
+            const double *w = v + 4 * h;
+            double e0 = mqs_edge(w[0], w[1], t[0], Fat(F, nF, N, i - 1, j, k), Fat(F, nF, N, i + 2, j, k));
+            double e1 = mqs_edge(w[2], w[3], t[0], Fat(F, nF, N, i - 1, j + 1, k), Fat(F, nF, N, i + 2, j + 1, k));
+            f[h] = lerp1(t[1], e0, e1);
+        }
+        return lerp1(t[2], f[0], f[1]);
+    }
+    if (comp == 1) {            /* MQS-y on v[1:4] and v[5:8], both with plane k */
+        double f[2];
+        for (int h = 0; h < 2; h++) {
+            const double *w = v + 4 * h;
+            double e0 = mqs_edge(w[0], w[2], t[1], Fat(F, nF, N, i, j - 1, k), Fat(F, nF, N, i, j + 2, k));
+            double e1 = mqs_edge(w[1], w[3], t[1], Fat(F, nF, N, i + 1, j - 1, k), Fat(F, nF, N, i + 1, j + 2, k));
+            f[h] = lerp1(t[0], e0, e1);
+        }
+        return lerp1(t[2], f[0], f[1]);
+    }
+    /* MQS-z: front = (v1,v2,v5,v6), back = (v3,v4,v7,v8), each with (t1,t3) and the SAME j; correction along x */
+    double f[2];
+    for (int h = 0; h < 2; h++) {
+        const double w[4] = {v[2 * h], v[2 * h + 1], v[4 + 2 * h], v[4 + 2 * h + 1]};
+        double e0 = mqs_edge(w[0], w[1], t[0], Fat(F, nF, N, i - 1, j, k), Fat(F, nF, N, i + 2, j, k));
+        double e1 = mqs_edge(w[2], w[3], t[0], Fat(F, nF, N, i - 1, j, k + 1), Fat(F, nF, N, i + 2, j, k + 1));
+        f[h] = lerp1(t[2], e0, e1);
+    }
+    return lerp1(t[1], f[0], f[1]);
+}
+
+static inline int clampi(int x, int lo, int hi) { return x > hi ? hi : (x < lo ? lo : x); }
+static double linp_eval(const double *F, const int *nF, int N, int comp, const int *idx1, const double *xc /* cell corner coords */,
+                        const double *dxi, const double *p, double VL) {
+    /* augment_offset(Val(comp+1)): rows of three offsets per direction */
+    static const int T3[3] = {-1, 0, 1};
+    int offI[4][3], offJ[4][3], offK[4][3];
+    for (int r = 0; r < 4; r++)
+        for (int m = 0; m < 3; m++) {
+            const int bj = (r & 1), bk = (r >> 1);           /* rows: (0,0), (1,0), (0,1), (1,1) pattern of the tables */
+            if (comp == 0)      { offI[r][m] = T3[m]; offJ[r][m] = bj;    offK[r][m] = bk; }
+            else if (comp == 1) { offI[r][m] = bj;    offJ[r][m] = T3[m]; offK[r][m] = bk; }
+            else                { offI[r][m] = bk;    offJ[r][m] = bj;    offK[r][m] = T3[m]; }
+        }
+    int i = idx1[0], j = idx1[1], k = N == 3 ? idx1[2] : 1;
+    if (comp == 0) i += p[0] > xc[0] + dxi[0] / 2;
+    if (comp == 1) j += p[1] > xc[1] + dxi[1] / 2;
+    if (comp == 2) k += p[2] > xc[2] + dxi[2] / 2;
+    /* rows used: 2-D (1,1),(2,2); 3-D (1,1,1),(2,2,2),(3,1,3),(4,2,4) (1-based rows of offset_i, offset_j, offset_k) */
+    static const int RI[4] = {0, 1, 2, 3}, RJ[4] = {0, 1, 0, 1}, RK[4] = {0, 1, 2, 3};
+    const int nrow = N == 2 ? 2 : 4;
+    double av[8];
+    for (int r = 0; r < nrow; r++) {
+        double f[3];
+        for (int m = 0; m < 3; m++)
+            f[m] = Fat(F, nF, N, clampi(i + offI[RI[r]][m], 1, nF[0]), clampi(j + offJ[RJ[r]][m], 1, nF[1]),
+                       N == 3 ? clampi(k + offK[RK[r]][m], 1, nF[2]) : 1);
+        av[2 * r] = (f[0] + f[1]) / 2;
+        av[2 * r + 1] = (f[2] + f[1]) / 2;
+    }
+    double FP[8];
+    if (comp == 0) { for (int q = 0; q < 2 * nrow; q++) FP[q] = av[q]; }
+    else if (N == 2) { FP[0] = av[0]; FP[1] = av[2]; FP[2] = av[1]; FP[3] = av[3]; }
+    else { FP[0] = av[0]; FP[1] = av[2]; FP[2] = av[1]; FP[3] = av[3]; FP[4] = av[4]; FP[5] = av[6]; FP[6] = av[5]; FP[7] = av[7]; }
+    double xP[3], tP[3];
+    for (int d = 0; d < N; d++) xP[d] = xc[d];
+    const int off = 1 - 2 * (p[comp] < xc[comp] + dxi[comp] / 2);
+    xP[comp] = xc[comp] + ((double)off * dxi[comp]) / 2;
+    for (int d = 0; d < N; d++) tP[d] = (p[d] - xP[d]) * (1.0 / dxi[d]);
+    const double VP = N == 2 ? lerp2(FP, tP) : lerp3(FP, tP);
+    const double A = 2.0 / 3.0;
+    return A * VL + (1 - A) * VP;
+}
+
 /* ---- interp_velocity2particle (src/Particles/Advection/advection.jl:93-148,
  *      src/Advection/advection.jl:3-47, src/Interpolations/utils.jl:54-58) -- */
+static int g_interp = 0;      /* 0 linear (advection!), 1 LinP (advection_LinP!), 2 MQS (advection_MQS!) */
 static inline void interp_velocity(const jpo_grid *g, const double *const *V, const double *p,
                                    const int *cell1 /* 1-based storage cell */, double *vout) {
     const int N = g->ndim;
@@ -148,15 +254,27 @@ static inline void interp_velocity(const jpo_grid *g, const double *const *V, co
         const double *F = V[c];
         const int64_t s1 = g->nvel[c][0], s2 = (int64_t)g->nvel[c][0] * g->nvel[c][1];
         const int64_t b = (idx[0] - 1) + s1 * (idx[1] - 1) + (N == 3 ? s2 * (idx[2] - 1) : 0);
-        if (N == 2) {
-            double v[4] = {F[b], F[b + 1], F[b + s1], F[b + s1 + 1]};
-            vout[c] = lerp2(v, t);
-        } else {
-            double v[8] = {F[b], F[b + 1], F[b + s1], F[b + s1 + 1],
-                           F[b + s2], F[b + s2 + 1], F[b + s2 + s1], F[b + s2 + s1 + 1]};
-            vout[c] = lerp3(v, t);
-        }
+        double v[8] = {F[b], F[b + 1], F[b + s1], F[b + s1 + 1], 0, 0, 0, 0};
+        if (N == 3) { v[4] = F[b + s2]; v[5] = F[b + s2 + 1]; v[6] = F[b + s2 + s1]; v[7] = F[b + s2 + s1 + 1]; }
+        const double VL = N == 2 ? lerp2(v, t) : lerp3(v, t);
+        vout[c] = VL;
+        if (g_interp == 0) continue;
+        /* interior test: all(1 .< indices .< size(F) .- 1)  (advection_LinP.jl:113, advection_MQS.jl:117) */
+        int interior = 1;
+        for (int d = 0; d < N; d++) interior &= (1 < idx[d]) & (idx[d] < g->nvel[c][d] - 1);
+        if (!interior) continue;
+        if (g_interp == 2) { vout[c] = mqs_eval(F, g->nvel[c], N, c, idx, v, t); continue; }
+        double xcn[3], dxi[3];
+        for (int d = 0; d < N; d++) { xcn[d] = g->xvel[c][d][idx[d] - 1]; dxi[d] = d_of(g->xvel[c][d], g->uniform, idx[d] - 1); }
+        vout[c] = linp_eval(F, g->nvel[c], N, c, idx, xcn, dxi, p, VL);
     }
+}
+/* single-point entry for the tests: velocity at p seeded from the 1-based cell cell1 */
+void jpo_interp_velocity(const jpo_grid *g, const double *const *V, const double *p, const int *cell1, int interp, double *vout) {
+    const int save = g_interp;
+    g_interp = interp;
+    interp_velocity(g, V, p, cell1, vout);
+    g_interp = save;
 }
 
 /* ---- advect_particle (src/Particles/Advection/Euler.jl:1-20, RK2.jl:1-26,
@@ -185,6 +303,17 @@ static inline void advect_particle(const jpo_grid *g, int scheme, double alpha, 
 }
 
 /* advection! (src/Particles/Advection/advection.jl:35-91) */
+int jpo_advect(const jpo_grid *g, double *const *coords, const uint8_t *index, int scheme, double alpha,
+               const double *const *V, double dt);
+/* advection_LinP! / advection_MQS! (advection_LinP.jl:12-91, advection_MQS.jl:16-91): same drivers, other interpolant */
+int jpo_advect_interp(const jpo_grid *g, double *const *coords, const uint8_t *index, int scheme, double alpha,
+                      const double *const *V, double dt, int interp) {
+    if (interp < 0 || interp > 2) return -1;
+    g_interp = interp;
+    const int rc = jpo_advect(g, coords, index, scheme, alpha, V, dt);
+    g_interp = 0;
+    return rc;
+}
 int jpo_advect(const jpo_grid *g, double *const *coords, const uint8_t *index, int scheme, double alpha,
                const double *const *V, double dt) {
     const int N = g->ndim;

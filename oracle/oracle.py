@@ -109,6 +109,18 @@ class Oracle:
         return lib().jpo_advect(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), int(scheme),
                                 C.c_double(alpha), _pp(V), C.c_double(dt))
 
+    def advect_interp(self, coords, index, scheme, alpha, V, dt, interp):
+        """interp: 1 = advection_LinP!, 2 = advection_MQS!"""
+        return lib().jpo_advect_interp(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), int(scheme),
+                                       C.c_double(alpha), _pp(V), C.c_double(dt), int(interp))
+
+    def interp_velocity(self, V, p, cell1, interp):
+        out = np.zeros(self.N)
+        pp = np.ascontiguousarray(p, dtype=np.float64)
+        cc = (C.c_int * 3)(*([int(c) for c in cell1] + [1] * (3 - len(cell1))))
+        lib().jpo_interp_velocity(C.byref(self.g), _pp(V), _dp(pp), cc, int(interp), _dp(out))
+        return out
+
     def move(self, coords, index, args):
         st = (C.c_int64 * 3)()
         rc = lib().jpo_move(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args), st)
