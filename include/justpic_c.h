@@ -158,6 +158,22 @@ int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const d
  *    (k, j, i, slot) order: bit-exact with the reference, reads every particle 2^N times. */
 int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, const double *Fp, void *stream);
 
+/* grid2particle_flip!(Fp, xvi, F, F0, particles; alpha) (src/Interpolations/grid_to_particle.jl:125-173):
+ * Fp <- muladd(F_pic, alpha, (Fp + (F_pic - F0_pic)) * (1 - alpha)), F_pic / F0_pic = vertex fields F / F0
+ * interpolated with the spacing grid_size(xvi) (the minimum spacing per dimension, utils.jl:61-63). */
+int jp_grid2particle_flip(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *F, const double *F0,
+                          double alpha, void *stream);
+
+/* subgrid_diffusion!(pT, T_grid, dT_grid, subgrid_arrays, particles, dt; d) and subgrid_diffusion_centroid!
+ * (src/Physics/subgrid_diffusion.jl:55-143).  pT0 / pdT / dt0 / dT_subgrid are the fields of
+ * SubgridDiffusionCellArrays (:17-33): particle CellArrays [C*S] and a vertex (centroid = 0) or centre
+ * (centroid = 1) grid array.  dT_grid is read at I + 1 (one ghost node on the low side, :137), its extents
+ * are dT_extents[0..ndim).  Same sequence of operations as the reference's seven launches, fused into two
+ * particle passes around particle2grid!/particle2centroid!; uses exp(), so the stated 1e-12 applies. */
+int jp_subgrid_diffusion(jp_ctx *ctx, const jp_particles *p, double *pT, const double *T_grid, const double *dT_grid,
+                         const int32_t *dT_extents, double *pT0, double *pdT, const double *dt0, double *dT_subgrid,
+                         double dt, double d, int32_t centroid, void *stream);
+
 /* particle2centroid!(F, Fp, particles) (src/Interpolations/particle_to_grid_centroid.jl:10-99). */
 int jp_particle2centroid(jp_ctx *ctx, const jp_particles *p, double *Fc, const double *Fp, void *stream);
 
@@ -182,7 +198,7 @@ int jp_phase_ratios_face(jp_ctx *ctx, const jp_particles *p, double *ratios, con
 /* phase_ratios_midpoint!(phase_midpoint, particles, phases, dimension) (src/PhaseRatios/midpoints.jl:115-242),
  * 3-D only.  plane = 0/1/2 for :xy/:yz/:xz, midpoint grid n + offsets with offsets (1,1,0)/(0,1,1)/(1,0,1)
  * (the xy/yz/xz fields of PhaseRatios, constructors.jl:44-46); NaN -> 0.  The boundary branch is the
- * reference's, quirks included (see oracle/justpic_oracle.c). */
+ * reference's, quirks included (listed in DESIGN.md). */
 int jp_phase_ratios_midpoint(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases,
                              int32_t K, int32_t plane, void *stream);
 

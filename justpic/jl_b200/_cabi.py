@@ -68,6 +68,11 @@ SYMBOLS = {
     "jp_inject_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "jp_clean": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "jp_grid2particle": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jp_grid2particle_flip": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                        C.c_void_p]),
+    "jp_subgrid_diffusion": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int32,
+                                       C.c_void_p]),
     "jp_centroid2particle": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),
     "jp_particle2grid": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),
     "jp_particle2centroid": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -40,7 +40,8 @@ __all__ = [
     "Particles", "PhaseRatios",
     "init_particles", "init_cell_arrays", "cell_array",
     "advection", "advection_LinP", "advection_MQS", "move_particles", "inject_particles", "inject_particles_phase", "clean_particles",
-    "grid2particle", "centroid2particle", "particle2grid", "particle2centroid",
+    "grid2particle", "grid2particle_flip", "centroid2particle", "particle2grid", "particle2centroid",
+    "SubgridDiffusionCellArrays", "subgrid_diffusion", "subgrid_diffusion_centroid",
     "phase_ratios_center", "phase_ratios_vertex", "phase_ratios_face", "phase_ratios_midpoint",
     "update_phase_ratios", "set_synchronous",
 ]
@@ -493,6 +494,65 @@ def grid2particle(Fp, F, particles: Particles) -> None:
     """``grid2particle!(Fp, F, particles)`` (src/Interpolations/grid_to_particle.jl:26-35)."""
     _call5("jp_grid2particle", particles, _pfield(Fp, particles, "Fp"), _field(F, particles, _nodes(particles, 1), "F"),
            "grid2particle")
+
+
+def grid2particle_flip(Fp, xvi, F, F0, particles: Particles, alpha: float = 0.0) -> None:
+    """``grid2particle_flip!(Fp, xvi, F, F0, particles; α = 0.0)`` (src/Interpolations/grid_to_particle.jl:125-138):
+    PIC/FLIP blend (α = 1 pure PIC, α = 0 pure FLIP).  ``xvi`` must be the particles' vertex grid (or None)."""
+    p = particles
+    Fp = _pfield(Fp, p, "Fp")
+    F = _field(F, p, _nodes(p, 1), "F")
+    F0 = _field(F0, p, _nodes(p, 1), "F0")
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_grid2particle_flip(C.c_void_p(p._ctx), C.byref(pc), C.c_void_p(Fp.data_ptr()),
+                                                       C.c_void_p(F.data_ptr()), C.c_void_p(F0.data_ptr()), float(alpha), _stream()),
+                    "grid2particle_flip")
+        _done()
+
+
+class SubgridDiffusionCellArrays:
+    """``SubgridDiffusionCellArrays(particles; loc = :vertex)`` (src/Physics/subgrid_diffusion.jl:13-33): scratch
+    CellArrays ``pT0``, ``pΔT`` (``pdT``), ``dt₀`` (``dt0``) and the grid-sized ``ΔT_subgrid`` (``dT_subgrid``)."""
+
+    def __init__(self, particles: Particles, loc: str = "vertex"):
+        loc = str(loc).lstrip(":")
+        if loc not in ("vertex", "center"):
+            raise ValueError("loc must be :vertex or :center")
+        self.loc = loc
+        self.pdT, self.pT0, self.dt0 = init_cell_arrays(particles, 3)
+        plus = 1 if loc == "vertex" else 0
+        self.dT_subgrid = torch.zeros(tuple(reversed([n + plus for n in particles.ncells])), dtype=torch.float64,
+                                      device=particles.device)
+
+
+def _subgrid(pT, T_grid, dT_grid, sa: SubgridDiffusionCellArrays, p: Particles, dt, d, centroid, who):
+    plus = 0 if centroid else 1
+    if sa.loc != ("center" if centroid else "vertex"):
+        raise ValueError(f"{who}: subgrid arrays were allocated for loc = :{sa.loc}")
+    pT = _pfield(pT, p, "pT")
+    T_grid = _field(T_grid, p, _nodes(p, plus), "T_grid")
+    if not isinstance(dT_grid, torch.Tensor) or dT_grid.dtype != torch.float64 or not dT_grid.is_contiguous() or dT_grid.dim() != p.ndim:
+        raise ValueError("dT_grid: expected a contiguous float64 grid array")
+    ext = (C.c_int32 * 3)(*(list(reversed(dT_grid.shape)) + [1] * (3 - p.ndim)))
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_subgrid_diffusion(
+            C.c_void_p(p._ctx), C.byref(pc), C.c_void_p(pT.data_ptr()), C.c_void_p(T_grid.data_ptr()), C.c_void_p(dT_grid.data_ptr()),
+            ext, C.c_void_p(sa.pT0.data_ptr()), C.c_void_p(sa.pdT.data_ptr()), C.c_void_p(sa.dt0.data_ptr()),
+            C.c_void_p(sa.dT_subgrid.data_ptr()), float(dt), float(d), 1 if centroid else 0, _stream()), who)
+        _done()
+
+
+def subgrid_diffusion(pT, T_grid, dT_grid, subgrid_arrays, particles: Particles, dt: float, d: float = 1.0) -> None:
+    """``subgrid_diffusion!(pT, T_grid, ΔT_grid, subgrid_arrays, particles, dt; d = 1.0)``
+    (src/Physics/subgrid_diffusion.jl:55-78): vertex-grid subgrid diffusion correction of particle temperatures."""
+    _subgrid(pT, T_grid, dT_grid, subgrid_arrays, particles, dt, d, False, "subgrid_diffusion")
+
+
+def subgrid_diffusion_centroid(pT, T_grid, dT_grid, subgrid_arrays, particles: Particles, dt: float, d: float = 1.0) -> None:
+    """``subgrid_diffusion_centroid!`` (src/Physics/subgrid_diffusion.jl:88-113): cell-centre variant."""
+    _subgrid(pT, T_grid, dT_grid, subgrid_arrays, particles, dt, d, True, "subgrid_diffusion_centroid")
 
 
 def centroid2particle(Fp, F, particles: Particles) -> None:

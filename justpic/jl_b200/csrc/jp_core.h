@@ -45,6 +45,7 @@ struct JpGrid {
     double aff_v0[3], aff_dv[3], aff_g0[3], aff_dg[3];
     double dom_lo[3], dom_hi[3];   // xv[d][0], xv[d][n]  (kernel-parameter constants instead of per-thread loads)
     double dxv0[3];                // xv[d][1] - xv[d][0]  (the scalar spacing of range grids)
+    double inv_dmin_v[3];          // inv(grid_size(xvi)) = 1 / abs(minimum(diff(xv)))  (grid2particle_flip!)
 };
 
 struct JpArgs {               // particle fields carried along by move/inject/clean
@@ -123,7 +124,7 @@ JP_HD void jp_interp_velocity_literal(const JpGrid &g, const double *const *V, c
 // advection_MQS! / advection_LinP! interpolants (src/Interpolations/MQS.jl,
 // src/Particles/Advection/advection_LinP.jl:96-391, advection_MQS.jl:96-124): the linear
 // interpolant of interp_velocity2particle plus a correction when the interpolation cell is interior
-// (1 < idx < size(F) - 1 in every direction).  Literal, quirks included (see oracle/justpic_oracle.c).
+// (1 < idx < size(F) - 1 in every direction).  Literal, quirks included (listed in DESIGN.md).
 template <int N> JP_HD double jp_Fat(const double *F, const int32_t *nF, int i1, int j1, int k1) {   // 1-based
     return F[(i1 - 1) + (int64_t)nF[0] * ((j1 - 1) + (N == 3 ? (int64_t)nF[1] * (k1 - 1) : 0))];
 }

@@ -71,6 +71,9 @@ static inline const char *jp_grid_build(const jp_grid_desc *d, JpGrid &g, std::v
     for (int dim = 0; dim < N; dim++) {
         g.dom_lo[dim] = d->xv[dim][0]; g.dom_hi[dim] = d->xv[dim][d->n[dim]];
         g.dxv0[dim] = d->xv[dim][1] - d->xv[dim][0];
+        double m = d->xv[dim][1] - d->xv[dim][0];
+        for (int i = 1; i < d->n[dim]; i++) { const double q = d->xv[dim][i + 1] - d->xv[dim][i]; m = q < m ? q : m; }
+        g.inv_dmin_v[dim] = 1.0 / fabs(m);
     }
     h.clear();
     auto push = [&](const double *x, int n) { size_t off = h.size(); h.insert(h.end(), x, x + n); return off; };

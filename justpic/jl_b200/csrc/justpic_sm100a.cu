@@ -615,6 +615,112 @@ __global__ void __launch_bounds__(256) k_g2p(JpGrid g, CPtr3 co, const uint8_t *
     }
 }
 
+// grid2particle_flip! (src/Interpolations/grid_to_particle.jl:125-173): PIC/FLIP blend; spacing = grid_size(xvi)
+template <int N>
+__global__ void __launch_bounds__(256) k_g2p_flip(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, double *__restrict__ Fp,
+                                                  const double *__restrict__ F, const double *__restrict__ F0, double alpha) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    double v[8], v0[8], xcorner[3], idx[3];
+    if (ok) {
+        const int64_t s1 = g.n[0] + 1, s2 = (int64_t)(g.n[0] + 1) * (g.n[1] + 1);
+        const int64_t b = ci[0] + s1 * ci[1] + (N == 3 ? s2 * ci[2] : 0);
+        jp_corners<N>(F, b, s1, s2, v);
+        jp_corners<N>(F0, b, s1, s2, v0);
+        for (int d = 0; d < N; d++) { xcorner[d] = g.xv[d][ci[d]]; idx[d] = g.inv_dmin_v[d]; }
+    }
+    for (int s = 0; s < g.S; s++) {
+        const bool live = (m >> s) & 1ull;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        if (live) {
+            const int64_t e = c + (int64_t)s * g.C;
+            double p[3];
+#pragma unroll
+            for (int d = 0; d < N; d++) p[d] = co.p[d][e];
+            const double Fpic = jp_g2p<N>(v, xcorner, idx, p), F0pic = jp_g2p<N>(v0, xcorner, idx, p);
+            const double Fflip = Fp[e] + (Fpic - F0pic);
+            Fp[e] = fma(Fpic, alpha, Fflip * (1.0 - alpha));
+        }
+    }
+}
+
+// ---- subgrid_diffusion! (src/Physics/subgrid_diffusion.jl:55-143), fused into two particle passes:
+// pass 1 = memcopy_cellarray_kernel! (all slots) + grid2particle!/centroid2particle!(pT, T_grid) +
+//          subgrid_diffusion_kernel! (live slots);   [particle2grid!/particle2centroid! and the grid kernel run in between]
+// pass 2 = grid2particle!/centroid2particle!(pdT, dT_subgrid) + update_particle_temperature_kernel! (all slots).
+// Per-slot results are those of the reference's separate kernels (same operations on the same values);
+// each slot is read and written once per pass instead of once per kernel.
+template <int N, bool CENTROID>
+__global__ void __launch_bounds__(256) k_subgrid_pass1(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, double *__restrict__ pT,
+                                                       double *__restrict__ pT0, double *__restrict__ pdT, const double *__restrict__ dt0,
+                                                       const double *__restrict__ Tg, double d, double dt) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    if (!ok) return;
+    double v[8], xcorner[3], idx[3];
+    if (!CENTROID) {
+        const int64_t s1 = g.n[0] + 1, s2 = (int64_t)(g.n[0] + 1) * (g.n[1] + 1);
+        jp_corners<N>(Tg, ci[0] + s1 * ci[1] + (N == 3 ? s2 * ci[2] : 0), s1, s2, v);
+        for (int dd = 0; dd < N; dd++) { xcorner[dd] = g.xv[dd][ci[dd]]; idx[dd] = 1.0 / jp_d_of(g.xv[dd], g.uniform, ci[dd]); }
+    }
+    for (int s = 0; s < g.S; s++) {
+        const int64_t e = c + (int64_t)s * g.C;
+        const double told = pT[e];
+        double t0 = told;                                            // memcopy: pT0 <- pT (every slot)
+        double p[3];
+        bool nan = false;
+#pragma unroll
+        for (int dd = 0; dd < N; dd++) { p[dd] = co.p[dd][e]; nan |= isnan(p[dd]); }
+        const bool live = index[e] != 0;
+        // grid2particle! uses the mask, centroid2particle! the NaN test (centroid_to_particle.jl:36)
+        double tnew = told;
+        if (CENTROID ? !nan : live) { tnew = CENTROID ? jp_c2p<N>(g, Tg, ci, p) : jp_g2p<N>(v, xcorner, idx, p); pT[e] = tnew; }
+        if (live) {                                                  // subgrid_diffusion_kernel! (:119-133)
+            const double q = dt0[e];
+            const double den = isnan(q) ? q : (q > 1.0e-9 ? q : 1.0e-9);
+            const double dTi = (tnew - t0) * (1 - exp(-d * dt / den));
+            t0 = t0 + dTi;
+            pdT[e] = dTi;
+        }
+        pT0[e] = t0;
+    }
+}
+
+template <int N, bool CENTROID>
+__global__ void __launch_bounds__(256) k_subgrid_pass2(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, double *__restrict__ pT,
+                                                       const double *__restrict__ pT0, double *__restrict__ pdT, const double *__restrict__ dTs) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    if (!ok) return;
+    double v[8], xcorner[3], idx[3];
+    if (!CENTROID) {
+        const int64_t s1 = g.n[0] + 1, s2 = (int64_t)(g.n[0] + 1) * (g.n[1] + 1);
+        jp_corners<N>(dTs, ci[0] + s1 * ci[1] + (N == 3 ? s2 * ci[2] : 0), s1, s2, v);
+        for (int dd = 0; dd < N; dd++) { xcorner[dd] = g.xv[dd][ci[dd]]; idx[dd] = 1.0 / jp_d_of(g.xv[dd], g.uniform, ci[dd]); }
+    }
+    for (int s = 0; s < g.S; s++) {
+        const int64_t e = c + (int64_t)s * g.C;
+        double p[3];
+        bool nan = false;
+#pragma unroll
+        for (int dd = 0; dd < N; dd++) { p[dd] = co.p[dd][e]; nan |= isnan(p[dd]); }
+        double dTi = pdT[e];
+        if (CENTROID ? !nan : index[e] != 0) { dTi = CENTROID ? jp_c2p<N>(g, dTs, ci, p) : jp_g2p<N>(v, xcorner, idx, p); pdT[e] = dTi; }
+        pT[e] = pT0[e] + dTi;                                        // update_particle_temperature_kernel! (every slot)
+    }
+}
+
+// update_dT_subgrid_kernel! (:135-138): dTsubgrid[I] = dT[I + 1] - dTsubgrid[I]
+template <int N>
+__global__ void __launch_bounds__(256) k_update_dT_subgrid(double *__restrict__ dTs, const double *__restrict__ dT, int n0, int n1, int n2, int m0, int m1) {
+    const int i = blockIdx.x * JP_BX + threadIdx.x, j = blockIdx.y * JP_BY + threadIdx.y, k = N == 3 ? blockIdx.z : 0;
+    if (i >= n0 || j >= n1 || k >= n2) return;
+    const int64_t a = i + (int64_t)n0 * (j + (int64_t)n1 * k);
+    const int64_t b = (i + 1) + (int64_t)m0 * ((j + 1) + (N == 3 ? (int64_t)m1 * (k + 1) : 0));
+    dTs[a] = dT[b] - dTs[a];
+}
+
 // centroid2particle!: liveness = !any(isnan, coords)  (the reference does not read the mask here)
 template <int N>
 __global__ void __launch_bounds__(256) k_c2p(JpGrid g, CPtr3 co, double *__restrict__ Fp, const double *__restrict__ Fc) {
@@ -1292,6 +1398,49 @@ extern "C" int jp_grid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, 
     if (!Fp || !F) return jp_fail(JP_ERR_INVALID, "jp_grid2particle: null field");
     if (g.ndim == 2) k_g2p<2><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F);
     else             k_g2p<3><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_grid2particle_flip(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *F, const double *F0, double alpha, void *stream) {
+    PREP("jp_grid2particle_flip");
+    if (!Fp || !F || !F0) return jp_fail(JP_ERR_INVALID, "jp_grid2particle_flip: null field");
+    if (g.ndim == 2) k_g2p_flip<2><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F, F0, alpha);
+    else             k_g2p_flip<3><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F, F0, alpha);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+// subgrid_diffusion!(pT, T_grid, dT_grid, subgrid_arrays, particles, dt; d) / subgrid_diffusion_centroid!
+extern "C" int jp_subgrid_diffusion(jp_ctx *ctx, const jp_particles *p, double *pT, const double *T_grid, const double *dT_grid,
+                                    const int32_t *dT_extents, double *pT0, double *pdT, const double *dt0, double *dT_subgrid,
+                                    double dt, double d, int32_t centroid, void *stream) {
+    PREP("jp_subgrid_diffusion");
+    if (!pT || !T_grid || !dT_grid || !dT_extents || !pT0 || !pdT || !dt0 || !dT_subgrid) return jp_fail(JP_ERR_INVALID, "jp_subgrid_diffusion: null argument");
+    const int plus = centroid ? 0 : 1;
+    const int n0 = g.n[0] + plus, n1 = g.n[1] + plus, n2 = g.ndim == 3 ? g.n[2] + plus : 1;
+    for (int dd = 0; dd < g.ndim; dd++)
+        if (dT_extents[dd] < (dd == 0 ? n0 : dd == 1 ? n1 : n2) + 1) return jp_fail(JP_ERR_INVALID, "jp_subgrid_diffusion: dT_grid needs one more node than dT_subgrid per dimension (it is read at I + 1)");
+    if (g.ndim == 2) {
+        if (centroid) k_subgrid_pass1<2, true><<<grd, blk, 0, st>>>(g, cco, p->index, pT, pT0, pdT, dt0, T_grid, d, dt);
+        else          k_subgrid_pass1<2, false><<<grd, blk, 0, st>>>(g, cco, p->index, pT, pT0, pdT, dt0, T_grid, d, dt);
+    } else {
+        if (centroid) k_subgrid_pass1<3, true><<<grd, blk, 0, st>>>(g, cco, p->index, pT, pT0, pdT, dt0, T_grid, d, dt);
+        else          k_subgrid_pass1<3, false><<<grd, blk, 0, st>>>(g, cco, p->index, pT, pT0, pdT, dt0, T_grid, d, dt);
+    }
+    JP_CHECK_LAUNCH();
+    int rc = centroid ? jp_particle2centroid(ctx, p, dT_subgrid, pdT, stream) : jp_particle2grid(ctx, p, dT_subgrid, pdT, stream);
+    if (rc) return rc;
+    const dim3 ng = tile_grid(n0, n1, n2);
+    if (g.ndim == 2) k_update_dT_subgrid<2><<<ng, blk, 0, st>>>(dT_subgrid, dT_grid, n0, n1, n2, dT_extents[0], dT_extents[1]);
+    else             k_update_dT_subgrid<3><<<ng, blk, 0, st>>>(dT_subgrid, dT_grid, n0, n1, n2, dT_extents[0], dT_extents[1]);
+    if (g.ndim == 2) {
+        if (centroid) k_subgrid_pass2<2, true><<<grd, blk, 0, st>>>(g, cco, p->index, pT, pT0, pdT, dT_subgrid);
+        else          k_subgrid_pass2<2, false><<<grd, blk, 0, st>>>(g, cco, p->index, pT, pT0, pdT, dT_subgrid);
+    } else {
+        if (centroid) k_subgrid_pass2<3, true><<<grd, blk, 0, st>>>(g, cco, p->index, pT, pT0, pdT, dT_subgrid);
+        else          k_subgrid_pass2<3, false><<<grd, blk, 0, st>>>(g, cco, p->index, pT, pT0, pdT, dT_subgrid);
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }

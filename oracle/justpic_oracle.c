@@ -730,6 +730,76 @@ int jpo_grid2particle(const jpo_grid *g, const double *const *coords, const uint
     return 0;
 }
 
+/* ---- grid2particle_flip! (src/Interpolations/grid_to_particle.jl:125-173): PIC/FLIP blend.
+ * di = grid_size(xvi) = abs(minimum(diff(x))) per dimension -- a SCALAR even on vector grids
+ * (src/Interpolations/utils.jl:61-63); t = (p - xv[idx]) * inv(di);
+ * Fp = muladd(F_pic, alpha, (Fp + (F_pic - F0_pic)) * (1 - alpha)). */
+int jpo_grid2particle_flip(const jpo_grid *g, const double *const *coords, const uint8_t *index, double *Fp, const double *F,
+                           const double *F0, double alpha) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    const int nx = g->n[0], ny = g->n[1];
+    const int64_t s1 = nx + 1, s2 = (int64_t)(nx + 1) * (ny + 1);
+    double idi[3];
+    for (int d = 0; d < N; d++) {
+        double m = g->xv[d][1] - g->xv[d][0];
+        for (int i = 1; i < g->n[d]; i++) { double q = g->xv[d][i + 1] - g->xv[d][i]; m = q < m ? q : m; }
+        idi[d] = 1.0 / fabs(m);
+    }
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t c = 0; c < C; c++) {
+        int ci[3] = {(int)(c % nx), (int)((c / nx) % ny), (int)(c / ((int64_t)nx * ny))};
+        const int64_t b = ci[0] + s1 * ci[1] + (N == 3 ? s2 * ci[2] : 0);
+        double v[8], v0[8];
+        for (int q = 0; q < (N == 2 ? 4 : 8); q++) {
+            const int64_t o = b + (q & 1) + ((q >> 1) & 1) * s1 + ((q >> 2) & 1) * s2;
+            v[q] = F[o]; v0[q] = F0[o];
+        }
+        for (int s = 0; s < g->S; s++) {
+            const int64_t e = c + (int64_t)s * C;
+            if (!index[e]) continue;
+            double t[3];
+            for (int d = 0; d < N; d++) t[d] = (coords[d][e] - g->xv[d][ci[d]]) * idi[d];
+            const double Fpic = N == 2 ? lerp2(v, t) : lerp3(v, t);
+            const double F0pic = N == 2 ? lerp2(v0, t) : lerp3(v0, t);
+            const double Fflip = Fp[e] + (Fpic - F0pic);
+            Fp[e] = fma(Fpic, alpha, Fflip * (1.0 - alpha));
+        }
+    }
+    return 0;
+}
+
+/* ---- subgrid_diffusion! building blocks (src/Physics/subgrid_diffusion.jl:55-143).
+ * The driver is a composition: memcopy (all slots) -> grid2particle! -> subgrid_diffusion_kernel! (live
+ * slots) -> particle2grid! -> update_dT_subgrid_kernel! (grid) -> grid2particle! -> update_particle_
+ * temperature_kernel! (all slots).  The three elementwise kernels are restated here; the drivers
+ * (vertex and centroid variants) are composed in oracle.py from these and the interpolation kernels.
+ * exp() is libm's: against CUDA's exp the stated 1e-12 tolerance applies (not bit-exactness). */
+void jpo_subgrid_kernel(const jpo_grid *g, const uint8_t *index, const double *pT, double *pT0, double *pdT, const double *dt0,
+                        double d, double dt) {
+    const int64_t tot = NCELLS(g) * g->S;
+#pragma omp parallel for schedule(static) if (g_threads > 1)
+    for (int64_t e = 0; e < tot; e++) {
+        if (!index[e]) continue;
+        const double den = dt0[e] > 1.0e-9 ? dt0[e] : 1.0e-9;          /* max(dt0, dt_floor); NaN dt0 -> NaN as in Julia's max */
+        const double denj = isnan(dt0[e]) ? dt0[e] : den;
+        const double dTi = (pT[e] - pT0[e]) * (1 - exp(-d * dt / denj));
+        pT0[e] = pT0[e] + dTi;
+        pdT[e] = dTi;
+    }
+}
+/* dTsubgrid[I] = dT[I + 1] - dTsubgrid[I]: dT carries one ghost node on the low side of every dimension */
+void jpo_update_dT_subgrid(int N, const int *nsub /* extents of dTsubgrid */, const int *ndT /* extents of dT */, double *dTsub, const double *dT) {
+    const int n2 = N == 3 ? nsub[2] : 1;
+    for (int k = 0; k < n2; k++)
+        for (int j = 0; j < nsub[1]; j++)
+            for (int i = 0; i < nsub[0]; i++) {
+                const int64_t a = i + (int64_t)nsub[0] * (j + (int64_t)nsub[1] * k);
+                const int64_t b = (i + 1) + (int64_t)ndT[0] * ((j + 1) + (N == 3 ? (int64_t)ndT[1] * (k + 1) : 0));
+                dTsub[a] = dT[b] - dTsub[a];
+            }
+}
+
 /* ---- centroid2particle! (src/Interpolations/centroid_to_particle.jl:13-76) - */
 int jpo_centroid2particle(const jpo_grid *g, const double *const *coords, double *Fp, const double *Fc) {
     const int N = g->ndim;

@@ -149,6 +149,33 @@ class Oracle:
     def grid2particle(self, coords, index, Fp, F):
         return lib().jpo_grid2particle(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _dp(Fp), _dp(F))
 
+    def grid2particle_flip(self, coords, index, Fp, F, F0, alpha):
+        return lib().jpo_grid2particle_flip(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _dp(Fp), _dp(F), _dp(F0),
+                                            C.c_double(alpha))
+
+    def subgrid_diffusion(self, coords, index, pT, T_grid, dT_grid, pT0, pdT, dt0, dT_subgrid, dt, d=1.0, centroid=False):
+        """subgrid_diffusion! / subgrid_diffusion_centroid! (src/Physics/subgrid_diffusion.jl:55-113), composed
+        from the restated kernels exactly as the reference composes them."""
+        pT0[...] = pT                                                                       # memcopy_cellarray_kernel!
+        if centroid:
+            self.centroid2particle(coords, pT, T_grid)
+        else:
+            self.grid2particle(coords, index, pT, T_grid)
+        lib().jpo_subgrid_kernel(C.byref(self.g), index.ctypes.data_as(C.c_void_p), _dp(pT), _dp(pT0), _dp(pdT), _dp(dt0),
+                                 C.c_double(d), C.c_double(dt))
+        if centroid:
+            self.particle2centroid(coords, dT_subgrid, pdT)
+        else:
+            self.particle2grid(coords, index, dT_subgrid, pdT)
+        nsub = (C.c_int * 3)(*(list(reversed(dT_subgrid.shape)) + [1] * (3 - dT_subgrid.ndim)))
+        ndt = (C.c_int * 3)(*(list(reversed(dT_grid.shape)) + [1] * (3 - dT_grid.ndim)))
+        lib().jpo_update_dT_subgrid(self.N, nsub, ndt, _dp(dT_subgrid), _dp(dT_grid))         # update_ΔT_subgrid_kernel!
+        if centroid:
+            self.centroid2particle(coords, pdT, dT_subgrid)
+        else:
+            self.grid2particle(coords, index, pdT, dT_subgrid)
+        pT[...] = pT0 + pdT                                                                 # update_particle_temperature_kernel!
+
     def centroid2particle(self, coords, Fp, Fc):
         return lib().jpo_centroid2particle(C.byref(self.g), _pp(coords), _dp(Fp), _dp(Fc))
 
