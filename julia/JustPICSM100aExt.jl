@@ -158,6 +158,85 @@ function JustPIC.phase_ratios_center!(pr::JustPIC.PhaseRatios{CUDABackend}, p::P
     done()
 end
 
+# ---- section 8 "next" rows ------------------------------------------------------------------------
+const FACE_DIM = Dict(:x => 0, :y => 1, :z => 2)
+const MID_PLANE = Dict(:xy => 0, :yz => 1, :xz => 2)
+const PhaseCall = (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, Int32, Ptr{Cvoid})
+const PhaseCallDim = (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, Int32, Int32, Ptr{Cvoid})
+
+# phase_ratios_vertex!(phase_ratios, particles, phases)            src/PhaseRatios/vertices.jl:4-13
+function JustPIC.phase_ratios_vertex!(pr::JustPIC.PhaseRatios{CUDABackend}, p::Particles{CUDABackend}, phases)
+    check(ccall((:jp_phase_ratios_vertex, libjustpic), Cint, PhaseCall,
+                context(p), jp(p), cptr(pr.vertex), cptr(phases), Int32(JustPIC.numphases(pr)), stream()), "phase_ratios_vertex!")
+    done()
+end
+
+# phase_ratios_face!(phase_face, particles, phases, dimension)      src/PhaseRatios/midpoints.jl:3-24
+function JustPIC.phase_ratios_face!(face::CellArray, p::Particles{CUDABackend}, phases, dimension::Symbol)
+    haskey(FACE_DIM, dimension) || throw(ArgumentError("dimension must be :x, :y or :z"))
+    check(ccall((:jp_phase_ratios_face, libjustpic), Cint, PhaseCallDim,
+                context(p), jp(p), cptr(face), cptr(phases), Int32(JustPIC.nphases(face)), Int32(FACE_DIM[dimension]), stream()),
+          "phase_ratios_face!")
+    done()
+end
+
+# phase_ratios_midpoint!(phase_midpoint, particles, phases, dimension)   src/PhaseRatios/midpoints.jl:115-126
+function JustPIC.phase_ratios_midpoint!(mid::CellArray, p::Particles{CUDABackend}, phases, dimension::Symbol)
+    haskey(MID_PLANE, dimension) || throw("Unknown dimensions. Valid dimensions are :xy, :yz, :xz")
+    check(ccall((:jp_phase_ratios_midpoint, libjustpic), Cint, PhaseCallDim,
+                context(p), jp(p), cptr(mid), cptr(phases), Int32(JustPIC.nphases(mid)), Int32(MID_PLANE[dimension]), stream()),
+          "phase_ratios_midpoint!")
+    done()
+end
+# update_phase_ratios! (src/PhaseRatios/utils.jl:15-41) is the reference's own composition of the calls above.
+
+# inject_particles_phase!(particles, particles_phases, args, fields, grid, grid_center, di, di_center)   src/Particles/injection.jl:153-200
+function JustPIC.inject_particles_phase!(p::Particles{CUDABackend, N}, phases, args, fields, grid::NTuple{N}, grid_center, di, di_center) where {N}
+    seed, step = UInt64(42), INJECT_STEP[]
+    INJECT_STEP[] += UInt32(1)
+    ptrs = argptrs(args)
+    fptrs = CuPtr{Float64}[pointer(f) for f in fields]
+    kinds = Int32[size(f) == size(p.index) ? 1 : 0 for f in fields]        # centre field iff one value per cell (:295)
+    check(ccall((:jp_inject_phase, libjustpic), Cint,
+                (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, Ptr{CuPtr{Float64}}, Ptr{CuPtr{Float64}}, Ptr{Int32}, Int32, Int32, UInt64, UInt32, Ptr{Cvoid}),
+                context(p), jp(p), cptr(phases), ptrs, fptrs, kinds, Int32(length(ptrs)), Int32(p.min_xcell), seed, UInt32(step), stream()),
+          "inject_particles_phase!")
+    done()
+end
+
+# advection_LinP! / advection_MQS!(particles, method, V, grid_vi, dt, dxi)   advection_LinP.jl:28-60, advection_MQS.jl:31-60
+for (fn, interp) in ((:advection_LinP!, 1), (:advection_MQS!, 2))
+    @eval function JustPIC.$fn(p::Particles{CUDABackend, N}, method::AbstractAdvectionIntegrator, V, grid_vi::NTuple{N, NTuple{N}}, dt, dxi) where {N}
+        s, α = scheme(method)
+        Vp = CuPtr{Float64}[pointer(v) for v in V]
+        check(ccall((:jp_advect_interp, libjustpic), Cint,
+                    (Ptr{Cvoid}, Ref{JpParticles}, Int32, Float64, Ptr{CuPtr{Float64}}, Float64, Int32, Ptr{Cvoid}),
+                    context(p), jp(p), s, α, Vp, Float64(dt), Int32($interp), stream()), $(string(fn)))
+        done()
+    end
+end
+
+# grid2particle_flip!(Fp, xvi, F, F0, particles; α)               src/Interpolations/grid_to_particle.jl:125-138
+function JustPIC.grid2particle_flip!(Fp::CellArray, xvi, F::CuArray, F0::CuArray, p::Particles{CUDABackend}; α = 0.0)
+    check(ccall((:jp_grid2particle_flip, libjustpic), Cint,
+                (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Float64, Ptr{Cvoid}),
+                context(p), jp(p), cptr(Fp), pointer(F), pointer(F0), Float64(α), stream()), "grid2particle_flip!")
+    done()
+end
+
+# subgrid_diffusion!(pT, T_grid, ΔT_grid, subgrid_arrays, particles, dt; d) / subgrid_diffusion_centroid!   src/Physics/subgrid_diffusion.jl:55-113
+for (fn, centroid) in ((:subgrid_diffusion!, 0), (:subgrid_diffusion_centroid!, 1))
+    @eval function JustPIC.$fn(pT::CellArray, T_grid::CuArray, ΔT_grid::CuArray, sa::JustPIC.SubgridDiffusionCellArrays, p::Particles{CUDABackend}, dt; d = 1.0)
+        ext = Int32[size(ΔT_grid)...]
+        check(ccall((:jp_subgrid_diffusion, libjustpic), Cint,
+                    (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Int32}, CuPtr{Float64}, CuPtr{Float64},
+                     CuPtr{Float64}, CuPtr{Float64}, Float64, Float64, Int32, Ptr{Cvoid}),
+                    context(p), jp(p), cptr(pT), pointer(T_grid), pointer(ΔT_grid), ext, cptr(sa.pT0), cptr(sa.pΔT), cptr(sa.dt₀),
+                    pointer(sa.ΔT_subgrid), Float64(dt), Float64(d), Int32($centroid), stream()), $(string(fn)))
+        done()
+    end
+end
+
 # init_particles: allocation stays in Julia (cell_array, src/launch.jl:101-108; the
 # CuCellArrays are owned by Julia), only the fill kernel (fill_coords_index!,
 # particles_utils.jl:168-194) is replaced.  Called from the tail of the reference's
