@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",            # no implicit FMA contraction; fma() is explicit (bit-exact contract)
-    "-diag-suppress", "550",  # "set but never used" from the PREP() prologue shared by all entry points
+    "-diag-suppress", "550,128",  # "set but never used" from the PREP() prologue shared by all entry points
     "-Xcompiler", "-fPIC", "-shared",
 ]
 

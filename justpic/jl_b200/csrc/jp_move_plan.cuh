@@ -197,7 +197,10 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
     uint64_t lv = 0, codew = 0;
     int k = 0;
     unsigned cplx = 0;     // reason bits: 1 far / on a vertex, 2 same cell (ulp gap), 4 fails isincell in destination
-    constexpr int U = 2;
+#ifndef JP_CLS_U
+#define JP_CLS_U 4
+#endif
+    constexpr int U = JP_CLS_U;
     for (int s0 = 0; s0 < g.S; s0 += U) {
         const unsigned bits = (unsigned)(m >> s0) & ((1u << U) - 1u);
         if (!__any_sync(0xffffffffu, bits != 0)) continue;
@@ -370,7 +373,8 @@ __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, M
 // ---- E. scatter: arrivals from staging, NaN into vacated slots, mask bytes.
 // (Measured: walking each thread's own arrivals in rank order instead -- more loads in flight, but every
 // 8-byte store then goes to the L2 alone instead of merged with its x-neighbours' stores to the same
-// 32-byte sector -- is 3x SLOWER; the slot-synchronous order stays.)
+// 32-byte sector -- is 3x SLOWER; the slot-synchronous order stays.  prefetch.global.L2 of the cell's
+// staging records ahead of the sweep: +4 % time; of the leavers' sectors in the gather: +80 %.)
 template <int N>
 __global__ void __launch_bounds__(256, JP_MINB_SCATTER) k_move_scatter(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index, const double *__restrict__ stage, int64_t M) {
     int ci[3]; int64_t c;

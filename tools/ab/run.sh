@@ -1,5 +1,3 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 export JP_MOVE_TIMING=1
-python tools/time_phases.py --cells 256 --steps 6 2>&1 | grep -E "^lib|^move|jp_move" | tail -3
-JUSTPIC_LIB=tools/ab/lib_C3.so python tools/time_phases.py --cells 256 --steps 6 2>&1 | grep -E "^lib|^move|jp_move" | tail -3
-JP_MOVE_CLASSIFY2=1 JUSTPIC_LIB=tools/ab/lib_C3.so python tools/time_phases.py --cells 256 --steps 6 2>&1 | grep -E "^lib|^move|jp_move" | tail -3
+for L in lib_P1 lib_P2 lib_P3; do echo $L; JUSTPIC_LIB=tools/ab/$L.so python tools/time_phases.py --cells 256 --steps 5 2>&1 | grep -E "jp_move|checksum" | tail -2; done
+python tools/time_phases.py --cells 256 --steps 5 2>&1 | grep -E "jp_move|checksum" | tail -2
