@@ -321,18 +321,22 @@ def test_api_errors():
 
 
 # ------------------------------------------------------------------ full-size properties
-@pytest.mark.parametrize("cfg", ["cfg1_2d_256", "cfg3_3d_128"])
+@pytest.mark.parametrize("cfg", ["cfg1_2d_256", "cfg2_2d_512_rk4", "cfg3_3d_128", "cfg4_3d_256"])
 def test_full_size_invariants(cfg):
     """BASELINE.json sizes: the oracle is too slow, so size-independent properties:
     count conservation (live = initial - dropped - deleted + injected), every live
     particle inside its cell, dead slots NaN, linear field reproduced by g2p, p2g of
     a constant field is that constant, phase ratios sum to 1, idempotent move."""
     J = jp()
-    ndim, n = (2, 256) if cfg == "cfg1_2d_256" else (3, 128)
+    ndim, n = {"cfg1_2d_256": (2, 256), "cfg2_2d_512_rk4": (2, 512), "cfg3_3d_128": (3, 128), "cfg4_3d_256": (3, 256)}[cfg]
+    if cfg == "cfg4_3d_256" and torch.cuda.mem_get_info()[1] < 100e9:
+        pytest.skip("needs ~80 GB of device memory")
     gr = make_grids(n, ndim, True)
     p = J.init_particles(J.CUDABackend, 24, 48, 12, *gr.grid_vel, seed=42)
-    V = stream_velocity(gr); Vd = [dev(v) for v in V]
+    rk4 = cfg == "cfg2_2d_512_rk4"                       # BASELINE configs[1]: rotation field, RK4, inject reseeding
+    V = rotation_velocity(gr) if rk4 else stream_velocity(gr); Vd = [dev(v) for v in V]
     dt = cfl_dt(gr, V, 0.75 if ndim == 2 else 0.5)
+    method = J.RungeKutta4() if rk4 else J.RungeKutta2()
     T = dev(vertex_field_linear(gr))
     pT, pc = J.init_cell_arrays(p, 2)
     J.grid2particle(pT, T, p)
@@ -340,7 +344,7 @@ def test_full_size_invariants(cfg):
     n_live = int(p.index.sum().item())
     assert n_live == 24 * int(np.prod(gr.n))
     for it in range(3):
-        J.advection(p, J.RungeKutta2(), Vd, dt)
+        J.advection(p, method, Vd, dt)
         J.move_particles(p, (pT, pc))
         moved, dropped, deleted = J.move_stats(p)
         J.inject_particles(p, (pT, pc), step=it)
@@ -356,12 +360,14 @@ def test_full_size_invariants(cfg):
         c = p.coords[d]
         assert bool((((c >= lo) & (c <= hi)) | ~live).all())
         assert bool((torch.isnan(c) == ~live).all())
-    # idempotence: a second move changes nothing
-    before = [c.clone() for c in p.coords]; ib = p.index.clone()
+    # idempotence: a second move changes nothing (checksums of position-weighted sums: no 20 GB clones at 256^3)
+    def digest():
+        w = torch.arange(p.index.shape[0], device="cuda", dtype=torch.float64).reshape(-1, *([1] * ndim)) + 1.0
+        return [float((torch.nan_to_num(c, nan=-7.0) * w).sum()) for c in p.coords] + [float((p.index.double() * w).sum())]
+    before = digest()
     J.move_particles(p, (pT, pc))
     assert J.move_stats(p) == (0, 0, 0)
-    assert all(torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0)) for a, b in zip(before, p.coords))
-    assert torch.equal(ib, p.index)
+    assert digest() == before
     # constant field survives p2g exactly up to rounding of the weighted mean
     F = torch.empty_like(T)
     J.particle2grid(F, pc, p)
