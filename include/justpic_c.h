@@ -51,7 +51,17 @@ typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_
 /* JP_OPT_ADVECT_AFFINE (0/1, default 1): let the tiled advection kernel regenerate grid coordinates as
  * fma(i, dx, x0) when jp_ctx_create verified that this reproduces EVERY stored entry bit for bit
  * (results are identical either way; 0 forces the table look-ups, used by the parity tests). */
-typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3 } jp_option;
+/* JP_OPT_MOVE_POLICY (default JP_MOVE_POLICY_REFERENCE): which free slot a migrant takes.
+ *   REFERENCE: the reference's rule, bit for bit -- first free slot >= a cursor that is carried over from one
+ *     migrant of a source cell to the next, across destination cells (src/Particles/move_safe.jl:114-118).
+ *     It spreads the particles of a cell over all max_xcell slots (slot planes ~50 % full).
+ *   COMPACT: NOT reference behaviour, opt-in -- the search starts at slot 0 for every migrant (the one
+ *     line `starting_point = free_idx` dropped).  Same particles in the same cells (up to fewer drops in
+ *     over-full cells), but in the lowest free slots: slot planes stay dense, so every streaming kernel
+ *     moves fewer dead-slot sectors.  Slot positions -- hence masks and summation order -- differ from the
+ *     reference's; checked against the oracle run with the same rule. */
+typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3, JP_OPT_MOVE_POLICY = 4 } jp_option;
+typedef enum { JP_MOVE_POLICY_REFERENCE = 0, JP_MOVE_POLICY_COMPACT = 1 } jp_move_policy;
 typedef enum { JP_MOVE_AUTO = 0, JP_MOVE_DIRECT = 1 } jp_move_mode;
 typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;
 

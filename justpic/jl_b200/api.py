@@ -53,6 +53,7 @@ class CUDABackend:
 
 _SYNC = False
 MOVE_MODE = "auto"      # module default for move_particles
+MOVE_POLICY = "reference"   # module default slot policy ("compact" is an opt-in deviation from the reference)
 P2G_MODE = "twopass_fastw"   # module default for particle2grid (see its docstring)
 
 
@@ -380,8 +381,11 @@ def advect_affine_level(particles: Particles) -> int:
     return int(v.value)
 
 
-def move_particles(particles: Particles, args=(), mode: Optional[str] = None) -> None:
+def move_particles(particles: Particles, args=(), mode: Optional[str] = None, policy: Optional[str] = None) -> None:
     """``move_particles!(particles, args)`` (src/Particles/move_safe.jl:21-49).
+    ``policy``: "reference" (default: the reference's free-slot rule, bit for bit) or "compact" (opt-in, NOT
+    reference behaviour: every migrant takes the lowest free slot of its destination, which keeps slot planes
+    dense; see JP_OPT_MOVE_POLICY in include/justpic_c.h).
     ``mode``: "auto" (default: sweeps planned on occupancy words + streaming payload passes,
     direct sweeps when a particle sits exactly on a face) or "direct" (always the literal
     sweeps on the particle arrays).  Both give the reference's slot assignment bit for bit."""
@@ -391,7 +395,12 @@ def move_particles(particles: Particles, args=(), mode: Optional[str] = None) ->
     m = (mode or MOVE_MODE).lower()
     if m not in ("auto", "direct"):
         raise ValueError("move_particles mode must be 'auto' or 'direct'")
+    pol = (policy or MOVE_POLICY).lower()
+    if pol not in ("reference", "compact"):
+        raise ValueError("move_particles policy must be 'reference' or 'compact'")
     with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_MOVE_POLICY,
+                                               _cabi.JP_MOVE_POLICY_COMPACT if pol == "compact" else _cabi.JP_MOVE_POLICY_REFERENCE), "jp_set_option")
         _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_MOVE_MODE,
                                                _cabi.JP_MOVE_AUTO if m == "auto" else _cabi.JP_MOVE_DIRECT), "jp_set_option")
         _cabi.check(_cabi.load().jp_move(C.c_void_p(p._ctx), C.byref(pc), _ptr_array(args), len(args), _stream()),

@@ -474,7 +474,7 @@ JP_HD bool jp_move_leaves(const JpGrid &g, const int *ci, const double *p) {
 // stats: [0] moved, [1] dropped, [2] deleted (accumulated by the caller).
 template <int N>
 JP_HD void jp_move_cell(const JpGrid &g, double *const *coords, uint8_t *index, const JpArgs &args,
-                        uint64_t *occ, uint64_t *leave, int64_t c, const int *ci, int *stats, int cursor = 0) {
+                        uint64_t *occ, uint64_t *leave, int64_t c, const int *ci, int *stats, int cursor = 0, bool compact = false) {
     uint64_t lv = leave[c];
     if (lv == 0) return;
     const int S = g.S;
@@ -513,7 +513,7 @@ JP_HD void jp_move_cell(const JpGrid &g, double *const *coords, uint8_t *index, 
 #else
         const int fs = __builtin_ctzll(freebits);
 #endif
-        cursor = fs;
+        if (!compact) cursor = fs;
         o2 |= 1ull << fs;
         const int64_t e2 = c2 + (int64_t)fs * g.C;
         index[e2] = 1;

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
 // words; the slot given to the k-th leaver goes to res (one byte: slot | placed << 6).
 template <int N>
 __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
-                                                   long long *stats) {
+                                                   long long *stats, int compact) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncol) return;
     int ci[3];
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
         const uint64_t freebits = ~o2 & smask & (~0ull << cursor);
         if (freebits == 0) { n_dropped++; continue; }
         const int fs = __ffsll((long long)freebits) - 1;
-        cursor = fs;
+        if (!compact) cursor = fs;            // JP_MOVE_POLICY_COMPACT: every search starts at slot 0
         ws.occ[c2] = o2 | (1ull << fs);
         resw |= (uint64_t)(fs | 64) << (8 * (kk & 7));
     }

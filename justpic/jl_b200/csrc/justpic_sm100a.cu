@@ -57,6 +57,7 @@ struct jp_ctx {
     long long *stats;     // device counters: [0..2] move, [3] inject
     double *p2g_ws;       // [2 * 2^N * C] per-cell partial sums of the two-pass particle2grid (lazy)
     int p2g_mode;         // JP_P2G_EXACT / JP_P2G_TWOPASS / JP_P2G_TWOPASS_FASTW
+    int move_policy;      // JP_MOVE_POLICY_REFERENCE (carried-over free-slot cursor) / JP_MOVE_POLICY_COMPACT
     int move_mode;        // JP_MOVE_AUTO (plan/gather/scatter, direct sweeps on ties) / JP_MOVE_DIRECT
     int affine_detected;  // grid vectors are exactly affine (jp_grid_build); g.affine = detected && option
     int last_move_path;   // 0 = plan, 1 = direct (diagnostics)
@@ -208,7 +209,7 @@ __device__ __forceinline__ int nth_set_bit64(uint64_t m, int i) {
 
 template <int N>
 __global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ, uint64_t *leave,
-                                                    int ox, int oy, int oz, int ncx, int ncy, int64_t ncol, long long *stats) {
+                                                    int ox, int oy, int oz, int ncx, int ncy, int64_t ncol, long long *stats, int compact) {
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= ncol) return;                                   // warp-uniform
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *
                 leave[c] = lv; occ[c] = occ_c;
                 int st[3] = {0, 0, 0};
                 // the cursor of the chunks already done carries over: emulate by a cursor-aware call
-                jp_move_cell<N>(g, co.p, index, args, occ, leave, c, ci, st, cursor);
+                jp_move_cell<N>(g, co.p, index, args, occ, leave, c, ci, st, cursor, compact != 0);
                 n_moved += st[0]; n_dropped += st[1]; n_deleted += st[2];
             }
             lv = 0;
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *
             const uint64_t freebits = ~o2 & smask & (~0ull << cursor);
             if (freebits == 0) { n_dropped++; continue; }
             const int fs = __ffsll((long long)freebits) - 1;
-            cursor = fs;
+            if (!compact) cursor = fs;
             if (c2 == c2k) my_occ = o2 | (1ull << fs);
             if (lane == k) my_fs = fs;
             n_moved++;
@@ -1227,7 +1228,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     for (int ox = 0; ox < 3; ox++)
         for (int oy = 0; oy < 3; oy++)
             for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
-                k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats);
+                k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
     const unsigned cblk = (unsigned)((g.C + 255) / 256);
     mark();
     k_move_finalize<N><<<cblk, 256, 0, st>>>(g, ctx->mp);
@@ -1296,8 +1297,8 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     for (int ox = 0; ox < 3; ox++)
         for (int oy = 0; oy < 3; oy++)
             for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {
-                if (g.ndim == 2) k_move_sweep<2><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats);
-                else             k_move_sweep<3><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats);
+                if (g.ndim == 2) k_move_sweep<2><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
+                else             k_move_sweep<3><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
             }
     JP_CHECK_LAUNCH();
     return JP_OK;
@@ -1458,6 +1459,7 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_set_option: null context");
     if (option == JP_OPT_MOVE_MODE && (value == JP_MOVE_AUTO || value == JP_MOVE_DIRECT)) { ctx->move_mode = value; return JP_OK; }
     if (option == JP_OPT_P2G_MODE && (value == JP_P2G_EXACT || value == JP_P2G_TWOPASS || value == JP_P2G_TWOPASS_FASTW)) { ctx->p2g_mode = value; return JP_OK; }
+    if (option == JP_OPT_MOVE_POLICY && (value == JP_MOVE_POLICY_REFERENCE || value == JP_MOVE_POLICY_COMPACT)) { ctx->move_policy = value; return JP_OK; }
     if (option == JP_OPT_ADVECT_AFFINE && (value == 0 || value == 1)) { ctx->g.affine = value ? ctx->affine_detected : 0; return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
 }
@@ -1467,6 +1469,7 @@ extern "C" int jp_get_option(const jp_ctx *ctx, int32_t option, int32_t *value) 
     if (option == JP_OPT_MOVE_MODE) { *value = ctx->move_mode; return JP_OK; }
     if (option == JP_OPT_P2G_MODE) { *value = ctx->p2g_mode; return JP_OK; }
     if (option == JP_OPT_ADVECT_AFFINE) { *value = ctx->g.affine; return JP_OK; }
+    if (option == JP_OPT_MOVE_POLICY) { *value = ctx->move_policy; return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_get_option: unknown option");
 }
 

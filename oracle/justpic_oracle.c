@@ -396,6 +396,14 @@ int jpo_init_particles(const jpo_grid *g, double *const *coords, uint8_t *index,
 /* ---- move_particles! (src/Particles/move_safe.jl:21-125; isincell
  *      src/Particles/utils.jl:7-15; indomain :199-206; find_free_memory
  *      :192-197) ------------------------------------------------------------ */
+/* Slot policy.  0 = the reference's: the free-slot search starts at `starting_point`, which is carried
+ * over from one migrant of the source cell to the next even when they go to DIFFERENT destination cells
+ * (move_safe.jl:114-118).  1 = "compact" (an OPTION of the library, not reference behaviour): the search
+ * starts at slot 0 for every migrant, i.e. the line `starting_point = free_idx` is dropped.  Everything
+ * else (sweep order, strict tests, drop when no slot is found) is unchanged. */
+static int g_move_compact = 0;
+void jpo_set_move_policy(int compact) { g_move_compact = compact ? 1 : 0; }
+
 static void move_cell(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs,
                       const int *ci /*0-based*/, int64_t *n_moved, int64_t *n_dropped, int64_t *n_deleted) {
     const int N = g->ndim, S = g->S;
@@ -439,7 +447,7 @@ static void move_cell(const jpo_grid *g, double *const *coords, uint8_t *index, 
         for (int i = starting_point; i < S; i++)
             if (!index[c2 + (int64_t)i * C]) { free_idx = i; break; }
         if (free_idx < 0) { (*n_dropped)++; continue; }
-        starting_point = free_idx;
+        if (!g_move_compact) starting_point = free_idx;
         const int64_t e2 = c2 + (int64_t)free_idx * C;
         index[e2] = 1;
         for (int d = 0; d < N; d++) coords[d][e2] = p[d];

@@ -121,6 +121,11 @@ class Oracle:
         lib().jpo_interp_velocity(C.byref(self.g), _pp(V), _dp(pp), cc, int(interp), _dp(out))
         return out
 
+    @staticmethod
+    def set_move_policy(compact: bool):
+        """False: the reference's carried-over free-slot cursor; True: the library's optional "compact" policy."""
+        lib().jpo_set_move_policy(1 if compact else 0)
+
     def move(self, coords, index, args):
         st = (C.c_int64 * 3)()
         rc = lib().jpo_move(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args), st)

@@ -178,6 +178,37 @@ def test_phase_ratios_center(g, K):
 
 
 @pytest.mark.parametrize("move_mode", ["auto", "direct"])
+@pytest.mark.parametrize("g", [(2, 24, True), (2, (19, 33), False), (3, 10, True), (3, (9, 7, 12), False)], ids=ids)
+def test_move_policy_compact(g, move_mode):
+    """JP_MOVE_POLICY_COMPACT (opt-in, not reference behaviour): bit-exact against the oracle run with the same
+    rule (free-slot search restarts at slot 0 for every migrant), and equivalent to the reference policy
+    in what a cell CONTAINS: same particles in the same cells (sorted per-cell coordinate multisets) whenever
+    nothing was dropped."""
+    J = jp()
+    t = Twin(*g, nxcell=12, max_xcell=24, min_xcell=8)
+    ref = Twin(*g, nxcell=12, max_xcell=24, min_xcell=8)            # same seed: identical start, reference policy
+    V = stream_velocity(t.gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(t.gr, V, 0.9)
+    pT, = J.init_cell_arrays(t.p, 1); J.grid2particle(pT, dev(vertex_field_linear(t.gr)), t.p)
+    opT = host(pT).copy(); rpT = host(pT).copy()
+    try:
+        for it in range(6):
+            J.advection(t.p, J.RungeKutta2(), Vd, dt)
+            t.o.advect(t.co, t.idx, 1, 0.5, V, dt); ref.o.advect(ref.co, ref.idx, 1, 0.5, V, dt)
+            J.move_particles(t.p, (pT,), mode=move_mode, policy="compact")
+            Oracle.set_move_policy(True); st = t.o.move(t.co, t.idx, [opT]); Oracle.set_move_policy(False)
+            rst = ref.o.move(ref.co, ref.idx, [rpT])
+            t.check_state(f"step {it} move_particles[{move_mode}, compact]", (pT,), (opT,))
+            assert J.move_stats(t.p) == st
+            if st[1] == 0 and rst[1] == 0:                            # nothing dropped: same content per cell
+                for d in range(t.gr.ndim):
+                    a = np.sort(np.nan_to_num(t.co[d], nan=np.inf), axis=0); b = np.sort(np.nan_to_num(ref.co[d], nan=np.inf), axis=0)
+                    assert np.array_equal(a, b), f"step {it}: cell contents differ between the policies (coords[{d}])"
+    finally:
+        Oracle.set_move_policy(False)
+
+
+@pytest.mark.parametrize("move_mode", ["auto", "direct"])
 @pytest.mark.parametrize("g", GRIDS + [(2, 17, True), (3, (7, 5, 6), True), (2, (40, 9), True)], ids=ids)
 def test_trajectory_advect_move_inject(g, move_mode):
     """L2 protocol: coupled steps; any divergence shows up at the first differing call.

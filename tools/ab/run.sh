@@ -1,3 +1,2 @@
-export JP_MOVE_TIMING=1
-for L in lib_P1 lib_P2 lib_P3; do echo $L; JUSTPIC_LIB=tools/ab/$L.so python tools/time_phases.py --cells 256 --steps 5 2>&1 | grep -E "jp_move|checksum" | tail -2; done
-python tools/time_phases.py --cells 256 --steps 5 2>&1 | grep -E "jp_move|checksum" | tail -2
+python -m pytest tests -m gpu -x -q -k "policy or trajectory" 2>&1 | tail -2
+for P in reference compact; do python tools/time_phases.py --cells 128 --steps 16 --policy $P 2>&1 | grep -E "^policy|^advect|^move|^p2g|^phase"; done
