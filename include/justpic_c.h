@@ -212,6 +212,16 @@ int jp_phase_ratios_face(jp_ctx *ctx, const jp_particles *p, double *ratios, con
 int jp_phase_ratios_midpoint(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases,
                              int32_t K, int32_t plane, void *stream);
 
+/* update_phase_ratios!(phase_ratios, particles, phases) (src/PhaseRatios/utils.jl:15-41): centre, vertex, the
+ * ndim face fields (Vx, Vy[, Vz]) and, in 3-D, the midpoint fields in the order xy, yz, xz.
+ * JP_PHASE_LITERAL: the reference's sequence of kernels, bit-exact.  JP_PHASE_FUSED: ONE pass over the particles
+ * accumulating per-cell partial sums for every node a cell touches + node-centric gathers in the reference's
+ * cell order (the low-boundary nodes still come from the literal boundary branches): same terms, associated
+ * as (cell sums) + ..., within the stated 1e-12; centre ratios stay bit-exact.  FUSED needs K <= 4 (else literal). */
+typedef enum { JP_PHASE_LITERAL = 0, JP_PHASE_FUSED = 1 } jp_phase_mode;
+int jp_update_phase_ratios(jp_ctx *ctx, const jp_particles *p, const double *phases, int32_t K, double *center, double *vertex,
+                           double *const *faces, double *const *midpoints, int32_t mode, void *stream);
+
 /* update_cell_halo! building blocks (src/CellArrays/ImplicitGlobalGrid.jl:36-41):
  * gather / scatter one cell-plane (all S slots) of every listed CellArray into /
  * from one contiguous device buffer; the transport between ranks (NCCL

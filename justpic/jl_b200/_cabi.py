@@ -86,6 +86,8 @@ SYMBOLS = {
                                        C.c_int32, C.c_void_p]),
     "jp_phase_ratios_midpoint": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_int32, C.c_void_p]),
+    "jp_update_phase_ratios": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "jp_halo_plane_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32]),
     "jp_halo_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p]),

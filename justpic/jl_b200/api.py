@@ -55,6 +55,7 @@ _SYNC = False
 MOVE_MODE = "auto"      # module default for move_particles
 MOVE_POLICY = "reference"   # module default slot policy ("compact" is an opt-in deviation from the reference)
 P2G_MODE = "twopass_fastw"   # module default for particle2grid (see its docstring)
+PHASE_MODE = "fused"         # module default for update_phase_ratios ("literal" = the reference's kernels, bit-exact)
 
 
 def set_synchronous(flag: bool) -> None:
@@ -661,19 +662,32 @@ def phase_ratios_midpoint(phase_midpoint: torch.Tensor, particles: Particles, ph
     _phase_call("jp_phase_ratios_midpoint", "phase_ratios_midpoint", phase_midpoint, p, phases, K, nelem, pl)
 
 
-def update_phase_ratios(phase_ratios: PhaseRatios, particles: Particles, phases: torch.Tensor) -> None:
+def update_phase_ratios(phase_ratios: PhaseRatios, particles: Particles, phases: torch.Tensor, mode: Optional[str] = None) -> None:
     """``update_phase_ratios!(phase_ratios, particles, phases)`` (src/PhaseRatios/utils.jl:15-41): centres,
-    vertices, velocity nodes and (3-D) edge midpoints, in the reference's order."""
+    vertices, velocity nodes and (3-D) edge midpoints.  ``mode``: "literal" (the reference's kernels one after the
+    other, bit-exact) or "fused" (default for up to 4 phases: one pass over the particles + node gathers, within the
+    stated 1e-12; ~10x faster)."""
     pr, p = phase_ratios, particles
-    phase_ratios_center(pr, p, phases)
-    phase_ratios_vertex(pr, p, phases)
-    phase_ratios_face(pr.Vx, p, phases, "x")
-    phase_ratios_face(pr.Vy, p, phases, "y")
-    if p.ndim == 3:
-        phase_ratios_face(pr.Vz, p, phases, "z")
-        phase_ratios_midpoint(pr.xy, p, phases, "xy")
-        phase_ratios_midpoint(pr.yz, p, phases, "yz")
-        phase_ratios_midpoint(pr.xz, p, phases, "xz")
+    m = (mode or PHASE_MODE).lower()
+    if m not in ("literal", "fused"):
+        raise ValueError("update_phase_ratios mode must be 'literal' or 'fused'")
+    K = pr.nphases
+    ph = _pfield(phases, p, "phases")
+    _field(pr.center, p, K * int(np.prod(p.ncells)), "phase_ratios.center")
+    _field(pr.vertex, p, K * _nodes(p, 1), "phase_ratios.vertex")
+    faces = (pr.Vx, pr.Vy, pr.Vz)[:p.ndim]
+    for d, f in enumerate(faces):
+        _field(f, p, K * int(np.prod([n + (1 if i == d else 0) for i, n in enumerate(p.ncells)])), "phase_ratios face field")
+    mids = (pr.xy, pr.yz, pr.xz) if p.ndim == 3 else ()
+    for off, f in zip(((1, 1, 0), (0, 1, 1), (1, 0, 1)), mids):
+        _field(f, p, K * int(np.prod([n + o for n, o in zip(p.ncells, off)])), "phase_ratios midpoint field")
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_update_phase_ratios(
+            C.c_void_p(p._ctx), C.byref(pc), C.c_void_p(ph.data_ptr()), K, C.c_void_p(pr.center.data_ptr()),
+            C.c_void_p(pr.vertex.data_ptr()), _ptr_array(faces), _ptr_array(mids) if mids else None,
+            1 if m == "fused" else 0, _stream()), "update_phase_ratios")
+        _done()
 
 
 def phase_ratios_center(phase_ratios: PhaseRatios, particles: Particles, phases: torch.Tensor) -> None:

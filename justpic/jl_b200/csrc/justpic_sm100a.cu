@@ -66,6 +66,7 @@ struct jp_ctx {
     unsigned int *mp_flag;   // device: "complex" flag
     void *cub_tmp; size_t cub_tmp_bytes;
     double *stage; size_t stage_elems;   // staging buffer (grow-only)
+    double *pr_ws; size_t pr_ws_elems;   // per-cell partial sums of the fused update_phase_ratios (lazy, grow-only)
     unsigned int *h_pinned;  // pinned host scratch for flag / totals
 };
 
@@ -1005,7 +1006,7 @@ extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->inj_list); cudaFree(ctx->inj_count); cudaFree(ctx->inbox); cudaFree(ctx->stats);
     cudaFree(ctx->p2g_ws);
     cudaFree(ctx->mp.code); cudaFree(ctx->mp.res); cudaFree(ctx->mp.occ0); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
-    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage);
+    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage); cudaFree(ctx->pr_ws);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     free(ctx);
 }
@@ -1554,8 +1555,8 @@ extern "C" int jp_phase_ratios_face(jp_ctx *ctx, const jp_particles *p, double *
     if (!ratios || !phases) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_face: null field");
     if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_face: 1 <= nphases <= 32 required");
     if (dim < 0 || dim >= g.ndim) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_face: dimension must be :x, :y or :z");
-    if (g.ndim == 2) JP_PHASE_DISPATCH(k_phase_face, 2 JP_COMMA, grd, g, cco, ratios, phases, K, dim);
-    else             JP_PHASE_DISPATCH(k_phase_face, 3 JP_COMMA, grd, g, cco, ratios, phases, K, dim);
+    if (g.ndim == 2) JP_PHASE_DISPATCH(k_phase_face, 2 JP_COMMA, grd, g, cco, ratios, phases, K, dim, false);
+    else             JP_PHASE_DISPATCH(k_phase_face, 3 JP_COMMA, grd, g, cco, ratios, phases, K, dim, false);
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1566,9 +1567,74 @@ extern "C" int jp_phase_ratios_midpoint(jp_ctx *ctx, const jp_particles *p, doub
     if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_midpoint: 1 <= nphases <= 32 required");
     if (g.ndim != 3) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_midpoint: 3-D only");
     if (plane < 0 || plane > 2) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_midpoint: Unknown dimensions. Valid dimensions are :xy, :yz, :xz");
-    JP_PHASE_DISPATCH(k_phase_midpoint, , grd, g, cco, ratios, phases, K, plane);
+    JP_PHASE_DISPATCH(k_phase_midpoint, , grd, g, cco, ratios, phases, K, plane, false);
     JP_CHECK_LAUNCH();
     return JP_OK;
+}
+
+// update_phase_ratios!(phase_ratios, particles, phases) (src/PhaseRatios/utils.jl:15-41) in one call.
+// mode JP_PHASE_LITERAL: the reference's sequence of kernels (bit-exact).  JP_PHASE_FUSED: one pass over the
+// particles + node gathers (csrc/jp_phase_ratios.cuh), within the stated 1e-12; needs K <= 4, else literal.
+template <int N, int KMAX>
+static int update_phase_ratios_fused(jp_ctx *ctx, const jp_particles *p, const double *phases, int K, double *center, double *vertex,
+                                     double *const *faces, double *const *mids, cudaStream_t st) {
+    using P = PhaseFused<N>;
+    const JpGrid &g = ctx->g;
+    const size_t need = (size_t)P::NT * K * g.C;
+    if (need > ctx->pr_ws_elems) {
+        if (ctx->pr_ws) JP_CUDA(cudaFree(ctx->pr_ws));
+        ctx->pr_ws = nullptr; ctx->pr_ws_elems = 0;
+        JP_CUDA(cudaMalloc(&ctx->pr_ws, need * sizeof(double)));
+        ctx->pr_ws_elems = need;
+    }
+    CPtr3 cco = {{p->coords[0], p->coords[1], p->coords[2]}};
+    const size_t smem = (size_t)P::NT * KMAX * P::THREADS * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        JP_CUDA(cudaFuncSetAttribute(k_phase_fused_cell<N, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const dim3 cblk(32, 4, 1), cgrd((g.n[0] + 31) / 32, (g.n[1] + 3) / 4, N == 3 ? g.n[2] : 1);
+    k_phase_fused_cell<N, KMAX><<<cgrd, cblk, smem, st>>>(g, cco, phases, K, center, ctx->pr_ws);
+    JP_CHECK_LAUNCH();
+    const dim3 blk(JP_BX, JP_BY, 1);
+    k_phase_fused_node<N, KMAX><<<tile_grid(g.n[0] + 1, g.n[1] + 1, N == 3 ? g.n[2] + 1 : 1), blk, 0, st>>>(g, ctx->pr_ws, vertex, K, 0, 0);
+    const dim3 grd = tile_grid(g.n[0], g.n[1], g.n[2]);
+    for (int d = 0; d < N; d++) {
+        const int nn[3] = {g.n[0] + (d == 0), g.n[1] + (d == 1), N == 3 ? g.n[2] + (d == 2) : 1};
+        k_phase_fused_node<N, KMAX><<<tile_grid(nn[0], nn[1], nn[2]), blk, 0, st>>>(g, ctx->pr_ws, faces[d], K, 1, d);
+        k_phase_face<N, KMAX><<<grd, blk, 0, st>>>(g, cco, faces[d], phases, K, d, true);          // low-boundary faces: literal branch
+    }
+    if (N == 3)
+        for (int pl = 0; pl < 3; pl++) {
+            const int off[3] = {pl != 1, pl != 2, pl != 0};
+            k_phase_fused_node<N, KMAX><<<tile_grid(g.n[0] + off[0], g.n[1] + off[1], g.n[2] + off[2]), blk, 0, st>>>(g, ctx->pr_ws, mids[pl], K, 2, pl);
+            k_phase_midpoint<KMAX><<<grd, blk, 0, st>>>(g, cco, mids[pl], phases, K, pl, true);    // low-boundary midpoints: literal branch
+        }
+    JP_CHECK_LAUNCH();
+    return JP_OK;
+}
+
+extern "C" int jp_update_phase_ratios(jp_ctx *ctx, const jp_particles *p, const double *phases, int32_t K, double *center, double *vertex,
+                                      double *const *faces, double *const *midpoints, int32_t mode, void *stream) {
+    PREP("jp_update_phase_ratios");
+    if (!phases || !center || !vertex || !faces) return jp_fail(JP_ERR_INVALID, "jp_update_phase_ratios: null field");
+    for (int d = 0; d < g.ndim; d++) if (!faces[d]) return jp_fail(JP_ERR_INVALID, "jp_update_phase_ratios: null face field");
+    if (g.ndim == 3) { if (!midpoints) return jp_fail(JP_ERR_INVALID, "jp_update_phase_ratios: null midpoint fields");
+                       for (int d = 0; d < 3; d++) if (!midpoints[d]) return jp_fail(JP_ERR_INVALID, "jp_update_phase_ratios: null midpoint field"); }
+    if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_update_phase_ratios: 1 <= nphases <= 32 required");
+    if (mode != JP_PHASE_LITERAL && mode != JP_PHASE_FUSED) return jp_fail(JP_ERR_INVALID, "jp_update_phase_ratios: unknown mode");
+    if (mode == JP_PHASE_FUSED && K <= 4) {
+        if (g.ndim == 2) return K <= 2 ? update_phase_ratios_fused<2, 2>(ctx, p, phases, K, center, vertex, faces, midpoints, st)
+                                       : update_phase_ratios_fused<2, 4>(ctx, p, phases, K, center, vertex, faces, midpoints, st);
+        return K <= 2 ? update_phase_ratios_fused<3, 2>(ctx, p, phases, K, center, vertex, faces, midpoints, st)
+                      : update_phase_ratios_fused<3, 4>(ctx, p, phases, K, center, vertex, faces, midpoints, st);
+    }
+    int rc = jp_phase_ratios_center(ctx, p, center, phases, K, stream);
+    if (!rc) rc = jp_phase_ratios_vertex(ctx, p, vertex, phases, K, stream);
+    for (int d = 0; d < g.ndim && !rc; d++) rc = jp_phase_ratios_face(ctx, p, faces[d], phases, K, d, stream);
+    if (g.ndim == 3) for (int pl = 0; pl < 3 && !rc; pl++) rc = jp_phase_ratios_midpoint(ctx, p, midpoints[pl], phases, K, pl, stream);
+    return rc;
 }
 
 static int64_t plane_cells(const JpGrid &g, int dim) {
