@@ -188,7 +188,19 @@ function JustPIC.phase_ratios_midpoint!(mid::CellArray, p::Particles{CUDABackend
           "phase_ratios_midpoint!")
     done()
 end
-# update_phase_ratios! (src/PhaseRatios/utils.jl:15-41) is the reference's own composition of the calls above.
+# update_phase_ratios!(phase_ratios, particles, phases)            src/PhaseRatios/utils.jl:15-41
+# one call for all outputs; JUSTPIC_PHASE_MODE = 0 literal kernels (bit-exact), 1 fused one-pass mode (1e-12, default)
+const PHASE_MODE = Ref{Int32}(parse(Int32, get(ENV, "JUSTPIC_PHASE_MODE", "1")))
+function JustPIC.update_phase_ratios!(pr::JustPIC.PhaseRatios{CUDABackend}, p::Particles{CUDABackend, N}, phases) where {N}
+    faces = CuPtr{Float64}[cptr(pr.Vx), cptr(pr.Vy)]
+    N == 3 && push!(faces, cptr(pr.Vz))
+    mids = N == 3 ? CuPtr{Float64}[cptr(pr.xy), cptr(pr.yz), cptr(pr.xz)] : CuPtr{Float64}[]
+    check(ccall((:jp_update_phase_ratios, libjustpic), Cint,
+                (Ptr{Cvoid}, Ref{JpParticles}, CuPtr{Float64}, Int32, CuPtr{Float64}, CuPtr{Float64}, Ptr{CuPtr{Float64}}, Ptr{CuPtr{Float64}}, Int32, Ptr{Cvoid}),
+                context(p), jp(p), cptr(phases), Int32(JustPIC.numphases(pr)), cptr(pr.center), cptr(pr.vertex), faces, mids, PHASE_MODE[], stream()),
+          "update_phase_ratios!")
+    done()
+end
 
 # inject_particles_phase!(particles, particles_phases, args, fields, grid, grid_center, di, di_center)   src/Particles/injection.jl:153-200
 function JustPIC.inject_particles_phase!(p::Particles{CUDABackend, N}, phases, args, fields, grid::NTuple{N}, grid_center, di, di_center) where {N}

@@ -85,13 +85,28 @@ __global__ void __launch_bounds__(256) k_phase_vertex(JpGrid g, CPtr3 co, double
     jp_phase_store<KMAX, false>(ratios, in + (int64_t)(nx + 1) * (jn + (N == 3 ? (int64_t)(ny + 1) * kn : 0)), NN, K, w);
 }
 
+// boundary_only launches (fused mode): threads enumerate only the cells of the plane ci[bdim] == 0 (dense 1-D grid,
+// so a warp holds 32 boundary cells instead of one); cells with ci[skipdim] == 0 are left to another launch.
+template <int N>
+__device__ __forceinline__ bool jp_plane_cell(const JpGrid &g, int bdim, int skipdim, int *ci, int64_t &c) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x * blockDim.y + threadIdx.y * blockDim.x + threadIdx.x;
+    const int d1 = bdim == 0 ? 1 : 0, d2 = bdim == 2 ? 1 : 2;                 // the two in-plane dimensions (d2 unused in 2-D)
+    const int n1 = g.n[d1], n2 = N == 3 ? g.n[d2] : 1;
+    if (t >= (int64_t)n1 * n2) return false;
+    ci[0] = ci[1] = ci[2] = 0;
+    ci[d1] = (int)(t % n1);
+    if (N == 3) ci[d2] = (int)(t / n1);
+    if (skipdim >= 0 && ci[skipdim] == 0) return false;
+    c = jp_cell_lin<N>(g, ci);
+    return true;
+}
+
 // ---- faces (velocity nodes): thread = cell I -> face I + e_dim (+ the low boundary face when I[dim] == 1)
 template <int N, int KMAX>
 __global__ void __launch_bounds__(256) k_phase_face(JpGrid g, CPtr3 co, double *__restrict__ ratios, const double *__restrict__ phases, int K, int dim,
                                                     bool boundary_only) {
     int ci[3]; int64_t c0;
-    if (!tile_cell<N>(g, ci, c0)) return;
-    if (boundary_only && ci[dim] != 0) return;              // fused mode: only the low-boundary faces are computed here
+    if (boundary_only ? !jp_plane_cell<N>(g, dim, -1, ci, c0) : !tile_cell<N>(g, ci, c0)) return;   // fused mode: only the low-boundary faces
     const int off[3] = {dim == 0, dim == 1, dim == 2};
     const int nf[3] = {g.n[0] + off[0], g.n[1] + off[1], (N == 3 ? g.n[2] : 1) + (N == 3 ? off[2] : 0)};
     const int64_t NF = (int64_t)nf[0] * nf[1] * nf[2];
@@ -144,11 +159,12 @@ __device__ __forceinline__ void jp_midpoint_accumulate(const JpGrid &g, const CP
 
 template <int KMAX>
 __global__ void __launch_bounds__(256) k_phase_midpoint(JpGrid g, CPtr3 co, double *__restrict__ ratios, const double *__restrict__ phases, int K, int plane,
-                                                        bool boundary_only) {
+                                                        int bdim, int skipdim) {
+    // bdim < 0: every cell (literal mode); else only the boundary plane ci[bdim] == 0 minus ci[skipdim] == 0 (fused mode)
+    const bool boundary_only = bdim >= 0;
     int ci[3]; int64_t c0;
-    if (!tile_cell<3>(g, ci, c0)) return;
+    if (boundary_only ? !jp_plane_cell<3>(g, bdim, skipdim, ci, c0) : !tile_cell<3>(g, ci, c0)) return;
     const int off[3] = {plane != 1, plane != 2, plane != 0};                    // xy (1,1,0), yz (0,1,1), xz (1,0,1)
-    if (boundary_only && !(off[0] * (ci[0] + 1) == 1 || off[1] * (ci[1] + 1) == 1 || off[2] * (ci[2] + 1) == 1)) return;
     const int nm[3] = {g.n[0] + off[0], g.n[1] + off[1], g.n[2] + off[2]};
     const int64_t NM = (int64_t)nm[0] * nm[1] * nm[2];
     double cen[3], mid[3], w[KMAX];
@@ -230,14 +246,24 @@ __global__ void __launch_bounds__(PhaseFused<N>::THREADS) k_phase_fused_cell(JpG
     double wc[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; k++) wc[k] = 0.0;
+    // software pipeline over the slots: the next slot's coordinates / phase are in flight while this one is processed
+    double pn[3] = {0.0, 0.0, 0.0}, phn = 0.0;
+#pragma unroll
+    for (int d = 0; d < N; d++) pn[d] = co.p[d][c];
+    phn = isnan(pn[0]) ? 0.0 : phases[c];
     for (int s = 0; s < g.S; s++) {
-        const int64_t e = c + (int64_t)s * g.C;
         double p[3];
         bool nan = false;
 #pragma unroll
-        for (int d = 0; d < N; d++) { p[d] = co.p[d][e]; nan |= isnan(p[d]); }
+        for (int d = 0; d < N; d++) { p[d] = pn[d]; nan |= isnan(p[d]); }
+        const double ph = phn;
+        if (s + 1 < g.S) {
+            const int64_t en = c + (int64_t)(s + 1) * g.C;
+#pragma unroll
+            for (int d = 0; d < N; d++) pn[d] = co.p[d][en];
+            phn = phases[en];
+        }
         if (isnan(p[0])) continue;                               // the centre kernel's liveness test (centers.jl / utils.jl:53)
-        const double ph = phases[e];
         double fC[3], fF[3][2], fV[3][2];
         bool pC[3], pF[3][2], pV[3][2];
 #pragma unroll

@@ -1567,7 +1567,7 @@ extern "C" int jp_phase_ratios_midpoint(jp_ctx *ctx, const jp_particles *p, doub
     if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_midpoint: 1 <= nphases <= 32 required");
     if (g.ndim != 3) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_midpoint: 3-D only");
     if (plane < 0 || plane > 2) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_midpoint: Unknown dimensions. Valid dimensions are :xy, :yz, :xz");
-    JP_PHASE_DISPATCH(k_phase_midpoint, , grd, g, cco, ratios, phases, K, plane, false);
+    JP_PHASE_DISPATCH(k_phase_midpoint, , grd, g, cco, ratios, phases, K, plane, -1, -1);
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1603,13 +1603,15 @@ static int update_phase_ratios_fused(jp_ctx *ctx, const jp_particles *p, const d
     for (int d = 0; d < N; d++) {
         const int nn[3] = {g.n[0] + (d == 0), g.n[1] + (d == 1), N == 3 ? g.n[2] + (d == 2) : 1};
         k_phase_fused_node<N, KMAX><<<tile_grid(nn[0], nn[1], nn[2]), blk, 0, st>>>(g, ctx->pr_ws, faces[d], K, 1, d);
-        k_phase_face<N, KMAX><<<grd, blk, 0, st>>>(g, cco, faces[d], phases, K, d, true);          // low-boundary faces: literal branch
+        k_phase_face<N, KMAX><<<(unsigned)((g.C / g.n[d] + 255) / 256), blk, 0, st>>>(g, cco, faces[d], phases, K, d, true);   // low-boundary faces: literal branch
     }
     if (N == 3)
         for (int pl = 0; pl < 3; pl++) {
             const int off[3] = {pl != 1, pl != 2, pl != 0};
             k_phase_fused_node<N, KMAX><<<tile_grid(g.n[0] + off[0], g.n[1] + off[1], g.n[2] + off[2]), blk, 0, st>>>(g, ctx->pr_ws, mids[pl], K, 2, pl);
-            k_phase_midpoint<KMAX><<<grd, blk, 0, st>>>(g, cco, mids[pl], phases, K, pl, true);    // low-boundary midpoints: literal branch
+            const int da = pl == 1 ? 1 : 0, db = pl == 0 ? 1 : 2;                                  // low-boundary midpoints: literal branch on the two planes
+            k_phase_midpoint<KMAX><<<(unsigned)((g.C / g.n[da] + 255) / 256), blk, 0, st>>>(g, cco, mids[pl], phases, K, pl, da, -1);
+            k_phase_midpoint<KMAX><<<(unsigned)((g.C / g.n[db] + 255) / 256), blk, 0, st>>>(g, cco, mids[pl], phases, K, pl, db, da);
         }
     JP_CHECK_LAUNCH();
     return JP_OK;
