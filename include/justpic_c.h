@@ -60,7 +60,19 @@ typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_
  *     over-full cells), but in the lowest free slots: slot planes stay dense, so every streaming kernel
  *     moves fewer dead-slot sectors.  Slot positions -- hence masks and summation order -- differ from the
  *     reference's; checked against the oracle run with the same rule. */
-typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3, JP_OPT_MOVE_POLICY = 4 } jp_option;
+/* JP_OPT_ADVECT_CLASSIFY (0/1, default 0): advection -> move hand-off.  With 1, jp_advect (tiled kernel:
+ *   standard staggering) also classifies every new position for the following move_particles! -- the
+ *   same comparisons jp_move makes, on the value being stored -- and leaves one byte per slot in a
+ *   library-owned plane; the next jp_move on the SAME coordinate / index arrays builds its plan from
+ *   those bytes instead of re-reading the coordinates (results bit-identical to option 0).  The bytes are
+ *   dropped by every library call that changes particles (init, inject, clean, another advect, move);
+ *   planes rewritten by jp_halo_unpack are re-classified from the coordinates.  The caller must not
+ *   modify coordinates or the index mask between the two calls by other means -- the reference's
+ *   time loops never do (advection! -> update_halo! -> move_particles!), but the library cannot see such
+ *   writes, hence opt-in.
+ * JP_OPT_LAST_CLASSIFY (jp_get_option only): 1 if the last planned jp_move used the hand-off bytes. */
+typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3, JP_OPT_MOVE_POLICY = 4,
+               JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6 } jp_option;
 typedef enum { JP_MOVE_POLICY_REFERENCE = 0, JP_MOVE_POLICY_COMPACT = 1 } jp_move_policy;
 typedef enum { JP_MOVE_AUTO = 0, JP_MOVE_DIRECT = 1 } jp_move_mode;
 typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;

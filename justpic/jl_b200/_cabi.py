@@ -21,6 +21,8 @@ JP_OPT_P2G_MODE = 1
 JP_OPT_MOVE_MODE = 2
 JP_OPT_ADVECT_AFFINE = 3
 JP_OPT_MOVE_POLICY = 4
+JP_OPT_ADVECT_CLASSIFY = 5
+JP_OPT_LAST_CLASSIFY = 6
 JP_MOVE_POLICY_REFERENCE, JP_MOVE_POLICY_COMPACT = 0, 1
 JP_MOVE_AUTO, JP_MOVE_DIRECT = 0, 1
 JP_P2G_EXACT, JP_P2G_TWOPASS, JP_P2G_TWOPASS_FASTW = 0, 1, 2

@@ -329,11 +329,18 @@ def _args(args, p: Particles):
 
 
 # --------------------------------------------------------------------------- hot path
-def advection(particles: Particles, method, V, dt: float, affine: Optional[bool] = None) -> None:
+def advection(particles: Particles, method, V, dt: float, affine: Optional[bool] = None,
+              classify: Optional[bool] = None) -> None:
     """``advection!(particles, method, V, dt)`` (src/Particles/Advection/advection.jl:21-62).
     ``affine=False`` forces grid-coordinate table look-ups even when the grid vectors were verified
-    to be exactly affine (identical results; the parity tests run both)."""
+    to be exactly affine (identical results; the parity tests run both).
+    ``classify=True`` switches on the advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY in
+    include/justpic_c.h; sticky per ``Particles``): the kernel also classifies every new position for the
+    following ``move_particles``, which then skips its own pass over the coordinates.  Results are
+    bit-identical; the caller must not write coordinates / index between the two calls by other means."""
     p = particles
+    if classify is not None:
+        _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_ADVECT_CLASSIFY, 1 if classify else 0), "jp_set_option")
     if affine is not None:
         _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_ADVECT_AFFINE, 1 if affine else 0), "jp_set_option")
     V = tuple(V)
@@ -420,6 +427,14 @@ def move_stats(particles: Particles) -> Tuple[int, int, int]:
 def last_move_path(particles: Particles) -> str:
     """"plan" or "direct": which implementation the last ``move_particles`` call took."""
     return "plan" if (_cabi.load().jp_last_move_path(C.c_void_p(particles._ctx)) & 0xff) == 0 else "direct"
+
+
+def last_move_classify(particles: Particles) -> str:
+    """"handoff" if the last planned ``move_particles`` built its plan from the bytes left by
+    ``advection(..., classify=True)``, "coords" if it classified the coordinates itself."""
+    v = C.c_int32(0)
+    _cabi.check(_cabi.load().jp_get_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_LAST_CLASSIFY, C.byref(v)), "jp_get_option")
+    return "handoff" if v.value else "coords"
 
 
 def last_move_reasons(particles: Particles) -> int:

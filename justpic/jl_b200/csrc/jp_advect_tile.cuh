@@ -160,11 +160,14 @@ __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__rest
     jp_interp_velocity_literal<N>(g, V, p, cell1, vout);
 }
 
-template <int N, int SCHEME, bool UNIFORM, int AFFINE>
+// HINT (JP_OPT_ADVECT_CLASSIFY): every new position is also classified for the following
+// move_particles! (jp_classify_particle on the value being stored, against the vertices already staged
+// in shared memory) and the byte goes to hint[element]; jp_move then skips its coordinate pass.
+template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
 __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 768) / (AdvTile<N>::NW * 32)) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
                                                                      double alpha, double dt,
                                                                      const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
-                                                                     const __grid_constant__ CUtensorMap tm2, int tma_mask) {
+                                                                     const __grid_constant__ CUtensorMap tm2, int tma_mask, uint8_t *__restrict__ hint) {
     using T = AdvTile<N>;
     using L = AdvSmem<N, UNIFORM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA destinations: 128-byte aligned (VOL*8 is a multiple of 128)
@@ -336,6 +339,16 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
                 }
 #pragma unroll
                 for (int d = 0; d < N; d++) co.p[d][e] = pn[d];
+                if (HINT) {
+                    // the staged vertex segments hold NaN outside the grid, exactly the convention of k_move_classify3
+                    double vm[3], va[3], vb[3], vp[3];
+#pragma unroll
+                    for (int d = 0; d < N; d++) {
+                        const double *xv = sm + L::XV_OFF + d * L::VEC + r0[d];
+                        vm[d] = xv[-1]; va[d] = xv[0]; vb[d] = xv[1]; vp[d] = xv[2];
+                    }
+                    hint[e] = (uint8_t)jp_classify_particle<N>(g, vm, va, vb, vp, pn);
+                }
             }
         }
         if (!any_next) break;

@@ -398,6 +398,43 @@ template <int N> JP_HD int64_t jp_cell_lin(const JpGrid &g, const int *ci) {
     return ci[0] + (int64_t)g.n[0] * (ci[1] + (N == 3 ? (int64_t)g.n[1] * ci[2] : 0));
 }
 
+// ---- move_particles! classification of ONE live particle (shared by k_move_classify3 and the
+// advection -> move hand-off of the tiled advection kernel, so both produce the same byte from the same
+// comparisons).  am/a/b/bp: the four vertices around the storage cell per dimension (NaN outside the
+// grid, so every comparison with them fails).  Returns
+//   JP_CLS_STAY         strictly inside its cell (isincell, upper edge fl(a + dx), move_safe.jl:93)
+//   0..26               left for the neighbour with that direction code (x fastest); 2-D codes use dz = 0
+//   JP_CODE_DELETE      left the domain (indomain, move_safe.jl:96-103)
+//   JP_CLS_CPLX + r     the planner cannot express it (r = 1: on a vertex / more than one cell away,
+//                       2: bisects back into its own cell (ulp gap), 3: fails isincell in its destination)
+#define JP_CODE_DELETE 27
+#define JP_CLS_STAY 28
+#define JP_CLS_CPLX 28
+template <int N>
+JP_HD int jp_classify_particle(const JpGrid &g, const double *am, const double *a, const double *b, const double *bp, const double *p) {
+    bool in = true, indom = true, near = true, dest_ok = true;
+    int dv[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+        const double pd = p[d];
+        const double dx0 = g.uniform ? g.dxv0[d] : b[d] - a[d];
+        in = in & (a[d] < pd) & (pd < a[d] + dx0);
+        indom = indom & (g.dom_lo[d] < pd) & (pd < g.dom_hi[d]);
+        double lower, dxd;
+        if (a[d] < pd && pd < b[d]) { dv[d] = 0; lower = a[d]; dxd = dx0; }
+        else if (am[d] < pd && pd < a[d]) { dv[d] = -1; lower = am[d]; dxd = g.uniform ? g.dxv0[d] : a[d] - am[d]; }
+        else if (b[d] < pd && pd < bp[d]) { dv[d] = 1; lower = b[d]; dxd = g.uniform ? g.dxv0[d] : bp[d] - b[d]; }
+        else { near = false; lower = a[d]; dxd = dx0; }
+        dest_ok = dest_ok & (pd < lower + dxd);
+    }
+    if (in) return JP_CLS_STAY;
+    if (!indom) return JP_CODE_DELETE;
+    if (!near) return JP_CLS_CPLX + 1;
+    if (dv[0] == 0 && dv[1] == 0 && dv[2] == 0) return JP_CLS_CPLX + 2;
+    if (!dest_ok) return JP_CLS_CPLX + 3;
+    return (dv[0] + 1) + 3 * (dv[1] + 1) + (N == 3 ? 9 * (dv[2] + 1) : 9);
+}
+
 // isincell (src/Particles/utils.jl:7-15): strict, upper edge = fl(xv + dx)
 template <int N> JP_HD bool jp_isincell(const double *p, const double *corner, const double *dx) {
     bool in = true;

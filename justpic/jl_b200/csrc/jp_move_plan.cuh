@@ -32,7 +32,7 @@
 #pragma once
 #include "jp_core.h"
 
-#define JP_CODE_DELETE 27
+// JP_CODE_DELETE / JP_CLS_STAY / JP_CLS_CPLX and jp_classify_particle live in jp_core.h
 
 // struct MovePlanWs is defined in justpic_sm100a.cu (it is a member of jp_ctx)
 
@@ -176,11 +176,18 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify2(JpGrid
 // k-th leaver's code byte is simply shifted into the thread's own code word.  k_move_classify2
 // re-read the coordinates of the ~38 % leavers; with 4 CTAs/SM resident that second look missed the
 // L2 and cost 40 % extra DRAM traffic at 256^3 (27.7 GB read for 19.3 GB of coordinates).
-template <int N>
+struct JpBox { int o[3], e[3]; };      // sub-box of cells (origin, extent) for the BOX instantiation
+template <int N, bool BOX>
 __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
-                                                                         unsigned int *complex_flag) {
+                                                                         unsigned int *complex_flag, JpBox box) {
     int ci[3]; int64_t c;
-    const bool ok = tile_cell<N>(g, ci, c);
+    bool ok;
+    if (BOX) {
+        const int lx = blockIdx.x * JP_BX + threadIdx.x, ly = blockIdx.y * JP_BY + threadIdx.y, lz = N == 3 ? blockIdx.z : 0;
+        ci[0] = box.o[0] + lx; ci[1] = box.o[1] + ly; ci[2] = N == 3 ? box.o[2] + lz : 0;
+        ok = lx < box.e[0] && ly < box.e[1] && ci[0] < g.n[0] && ci[1] < g.n[1] && (N == 2 || (lz < box.e[2] && ci[2] < g.n[2]));
+        c = ok ? jp_cell_lin<N>(g, ci) : 0;
+    } else ok = tile_cell<N>(g, ci, c);
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
     // the four vertices around the cell per dimension (NaN outside the grid: comparisons fail)
     double am[3], a[3], b[3], bp[3];
@@ -214,31 +221,49 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
             if (!((bits >> u) & 1u)) continue;
             // isincell (strict, upper edge fl(a + dx)), domain test, destination by comparisons with the
             // four vertices; dx = scalar spacing on range grids, the cell's own spacing on vector grids
-            bool in = true, indom = true, near = true, dest_ok = true;
-            int dv[3] = {0, 0, 0};
-#pragma unroll
-            for (int d = 0; d < N; d++) {
-                const double pd = p[u][d];
-                const double dx0 = g.uniform ? g.dxv0[d] : b[d] - a[d];
-                in = in & (a[d] < pd) & (pd < a[d] + dx0);
-                indom = indom & (g.dom_lo[d] < pd) & (pd < g.dom_hi[d]);
-                double lower, dxd;
-                if (a[d] < pd && pd < b[d]) { dv[d] = 0; lower = a[d]; dxd = dx0; }
-                else if (am[d] < pd && pd < a[d]) { dv[d] = -1; lower = am[d]; dxd = g.uniform ? g.dxv0[d] : a[d] - am[d]; }
-                else if (b[d] < pd && pd < bp[d]) { dv[d] = 1; lower = b[d]; dxd = g.uniform ? g.dxv0[d] : bp[d] - b[d]; }
-                else { near = false; lower = a[d]; dxd = dx0; }
-                dest_ok = dest_ok & (pd < lower + dxd);
-            }
-            if (in) continue;
+            int code = jp_classify_particle<N>(g, am, a, b, bp, p[u]);
+            if (code == JP_CLS_STAY) continue;
             lv |= 1ull << (s0 + u);
-            int code = JP_CODE_DELETE;
-            if (indom) {
-                const bool same = dv[0] == 0 && dv[1] == 0 && dv[2] == 0;
-                if (!near) cplx |= 1u;
-                else if (same) cplx |= 2u;
-                else if (!dest_ok) cplx |= 4u;
-                else code = jp_dir_code(dv, N);
-            }
+            if (code > JP_CLS_CPLX) { cplx |= 1u << (code - JP_CLS_CPLX - 1); code = JP_CODE_DELETE; }
+            codew |= (uint64_t)code << (8 * (k & 7));
+            if ((++k & 7) == 0) { ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
+        }
+    }
+    if (ok) {
+        ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
+        if (k & 7) ws.code[(int64_t)(k >> 3) * g.C + c] = codew;
+    }
+    const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
+    if (wc && threadIdx.x == 0) atomicOr(complex_flag, wc);
+}
+
+// ---- A''. classify from the advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY): the tiled advection
+// kernel already had every new position in registers and left its classification byte
+// (jp_classify_particle) in a plane laid out like `index`; this pass turns mask + bytes into the same
+// occupancy / leave / code words k_move_classify3 produces without touching the coordinates
+// (1.6 GB instead of 10.5 GB at 256^3).  Bytes of dead slots are stale and never read.
+template <int N>
+__global__ void __launch_bounds__(256, 4) k_move_classify_hint(JpGrid g, const uint8_t *__restrict__ index, const uint8_t *__restrict__ hint,
+                                                              MovePlanWs ws, unsigned int *complex_flag) {
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
+    uint64_t lv = 0, codew = 0;
+    int k = 0;
+    unsigned cplx = 0;
+    constexpr int U = 8;
+    for (int s0 = 0; s0 < g.S; s0 += U) {
+        const unsigned bits = (unsigned)(m >> s0) & ((1u << U) - 1u);
+        if (!__any_sync(0xffffffffu, bits != 0)) continue;
+        int h[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) h[u] = ((bits >> u) & 1u) ? (int)hint[c + (int64_t)(s0 + u) * g.C] : JP_CLS_STAY;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int code = h[u];
+            if (code == JP_CLS_STAY) continue;
+            lv |= 1ull << (s0 + u);
+            if (code > JP_CLS_CPLX) { cplx |= 1u << ((code - JP_CLS_CPLX - 1) & 3); code = JP_CODE_DELETE; }
             codew |= (uint64_t)code << (8 * (k & 7));
             if ((++k & 7) == 0) { ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
         }

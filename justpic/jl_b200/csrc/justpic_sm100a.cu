@@ -68,7 +68,18 @@ struct jp_ctx {
     double *stage; size_t stage_elems;   // staging buffer (grow-only)
     double *pr_ws; size_t pr_ws_elems;   // per-cell partial sums of the fused update_phase_ratios (lazy, grow-only)
     unsigned int *h_pinned;  // pinned host scratch for flag / totals
+    // advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY): classification bytes left by the tiled advection
+    // kernel, valid only for the coordinate / index arrays they were computed from and until the next
+    // library call that changes particles; planes rewritten by jp_halo_unpack are re-classified from the
+    // coordinates (hint_dirty)
+    int hint_opt;            // option value (default 0)
+    uint8_t *hint;           // [S][C] bytes, laid out like `index` (lazy)
+    int hint_valid;
+    const void *hint_key[4]; // coords[0..2], index the bytes belong to
+    int hint_ndirty; int hint_dirty[8][2];   // (dim, plane) rewritten since the hand-off
+    int last_classify;       // 0: coordinates (k_move_classify3), 1: hand-off bytes (diagnostics)
 };
+static inline void hint_invalidate(jp_ctx *ctx) { ctx->hint_valid = 0; ctx->hint_ndirty = 0; }
 
 struct Ptr3 { double *p[3]; };
 struct CPtr3 { const double *p[3]; };
@@ -1006,7 +1017,7 @@ extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->inj_list); cudaFree(ctx->inj_count); cudaFree(ctx->inbox); cudaFree(ctx->stats);
     cudaFree(ctx->p2g_ws);
     cudaFree(ctx->mp.code); cudaFree(ctx->mp.res); cudaFree(ctx->mp.occ0); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
-    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage); cudaFree(ctx->pr_ws);
+    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage); cudaFree(ctx->pr_ws); cudaFree(ctx->hint);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     free(ctx);
 }
@@ -1042,6 +1053,7 @@ static int pack_args(double *const *args, int nargs, JpArgs &out, const char *wh
 
 extern "C" int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxcell, uint64_t seed, void *stream) {
     PREP("jp_init_particles");
+    hint_invalidate(ctx);
     const int NQ = g.ndim == 2 ? 4 : 8;
     if (nxcell < 1) return jp_fail(JP_ERR_INVALID, "jp_init_particles: nxcell < 1");
     const int npq = (nxcell + NQ - 1) / NQ;
@@ -1091,30 +1103,39 @@ static int build_advect_tma(const JpGrid &g, CPtr3 V, AdvTmaMaps &maps) {
     return mask;
 }
 
-template <int N, int SCHEME, bool UNIFORM, int AFFINE>
-static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
+template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
+static cudaError_t launch_advect_tile_h(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, uint8_t *hint) {
     using T = AdvTile<N>;
     const size_t smem = AdvSmem<N, UNIFORM>::BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdvSmem<N, UNIFORM>::BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdvSmem<N, UNIFORM>::BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     AdvTmaMaps maps;
     const int tma_mask = build_advect_tma<N>(g, V, maps);
     const dim3 grd((g.n[0] + T::TX - 1) / T::TX, (g.n[1] + T::TY - 1) / T::TY, N == 3 ? (g.n[2] + T::TZ - 1) / T::TZ : 1);
-    k_advect_tile<N, SCHEME, UNIFORM, AFFINE><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask);
+    k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask, hint);
     return cudaSuccess;
 }
+template <int N, int SCHEME, bool UNIFORM, int AFFINE>
+static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, uint8_t *hint) {
+    return hint ? launch_advect_tile_h<N, SCHEME, UNIFORM, AFFINE, true>(g, st, co, index, V, alpha, dt, hint)
+                : launch_advect_tile_h<N, SCHEME, UNIFORM, AFFINE, false>(g, st, co, index, V, alpha, dt, nullptr);
+}
 
+// *hinted is set when the launch left classification bytes in `hint` (tiled kernel only)
 template <int N, int SCHEME>
-static cudaError_t launch_advect(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt) {
+static cudaError_t launch_advect(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt,
+                                 uint8_t *hint, bool *hinted) {
+    *hinted = false;
     if (jp_standard_staggering(g)) {
-        if (g.uniform && g.affine == 2) return launch_advect_tile<N, SCHEME, true, 2>(g, st, co, index, V, alpha, dt);
-        if (g.uniform && g.affine == 1) return launch_advect_tile<N, SCHEME, true, 1>(g, st, co, index, V, alpha, dt);
-        return g.uniform ? launch_advect_tile<N, SCHEME, true, 0>(g, st, co, index, V, alpha, dt)
-                         : launch_advect_tile<N, SCHEME, false, 0>(g, st, co, index, V, alpha, dt);
+        *hinted = hint != nullptr;
+        if (g.uniform && g.affine == 2) return launch_advect_tile<N, SCHEME, true, 2>(g, st, co, index, V, alpha, dt, hint);
+        if (g.uniform && g.affine == 1) return launch_advect_tile<N, SCHEME, true, 1>(g, st, co, index, V, alpha, dt, hint);
+        return g.uniform ? launch_advect_tile<N, SCHEME, true, 0>(g, st, co, index, V, alpha, dt, hint)
+                         : launch_advect_tile<N, SCHEME, false, 0>(g, st, co, index, V, alpha, dt, hint);
     }
     if (g.fast) {
         if (g.uniform) k_advect<N, SCHEME, true, true><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
@@ -1133,18 +1154,30 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
     }
     if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect: Only 0 < alpha < 1 is supported");
     if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect: unknown integrator");
+    hint_invalidate(ctx);
+    uint8_t *hint = nullptr;
+    if (ctx->hint_opt) {
+        if (!ctx->hint) JP_CUDA(cudaMalloc(&ctx->hint, (size_t)g.C * g.S));
+        hint = ctx->hint;
+    }
+    bool hinted = false;
     cudaError_t le;
     if (g.ndim == 2) {
-        if (scheme == 0) le = launch_advect<2, 0>(g, grd, blk, st, co, p->index, v, alpha, dt);
-        else if (scheme == 1) le = launch_advect<2, 1>(g, grd, blk, st, co, p->index, v, alpha, dt);
-        else le = launch_advect<2, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        if (scheme == 0) le = launch_advect<2, 0>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
+        else if (scheme == 1) le = launch_advect<2, 1>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
+        else le = launch_advect<2, 2>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
     } else {
-        if (scheme == 0) le = launch_advect<3, 0>(g, grd, blk, st, co, p->index, v, alpha, dt);
-        else if (scheme == 1) le = launch_advect<3, 1>(g, grd, blk, st, co, p->index, v, alpha, dt);
-        else le = launch_advect<3, 2>(g, grd, blk, st, co, p->index, v, alpha, dt);
+        if (scheme == 0) le = launch_advect<3, 0>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
+        else if (scheme == 1) le = launch_advect<3, 1>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
+        else le = launch_advect<3, 2>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
     }
     if (le != cudaSuccess) return jp_fail(JP_ERR_CUDA, "jp_advect: %s", cudaGetErrorString(le));
     JP_CHECK_LAUNCH();
+    if (hinted) {
+        ctx->hint_valid = 1;
+        for (int d = 0; d < 3; d++) ctx->hint_key[d] = d < g.ndim ? (const void *)p->coords[d] : nullptr;
+        ctx->hint_key[3] = p->index;
+    }
     return JP_OK;
 }
 
@@ -1159,6 +1192,7 @@ extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t sche
                                 int32_t interp, void *stream) {
     if (interp == JP_INTERP_LINEAR) return jp_advect(ctx, p, scheme, alpha, V, dt, stream);
     PREP("jp_advect_interp");
+    hint_invalidate(ctx);
     if (interp != JP_INTERP_LINP && interp != JP_INTERP_MQS) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: unknown interpolant");
     if (!V) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: null velocity tuple");
     CPtr3 v = {{nullptr, nullptr, nullptr}};
@@ -1215,8 +1249,21 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     mark();
     JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
     static const bool cls2 = getenv("JP_MOVE_CLASSIFY2") != nullptr;       // developer A/B switch
-    if (cls2) k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
-    else      k_move_classify3<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
+    const JpBox whole = {{0, 0, 0}, {g.n[0], g.n[1], g.n[2]}};
+    bool use_hint = ctx->hint_valid && ctx->hint && ctx->hint_key[3] == (const void *)p->index;
+    for (int d = 0; d < N; d++) use_hint = use_hint && ctx->hint_key[d] == (const void *)p->coords[d];
+    ctx->last_classify = use_hint ? 1 : 0;
+    if (use_hint) {
+        k_move_classify_hint<N><<<grd, blk, 0, st>>>(g, p->index, ctx->hint, ctx->mp, ctx->mp_flag);
+        for (int i = 0; i < ctx->hint_ndirty; i++) {        // planes rewritten by jp_halo_unpack: from the coordinates
+            JpBox bx = whole;
+            bx.o[ctx->hint_dirty[i][0]] = ctx->hint_dirty[i][1];
+            bx.e[ctx->hint_dirty[i][0]] = 1;
+            k_move_classify3<N, true><<<tile_grid(bx.e[0], bx.e[1], N == 3 ? bx.e[2] : 1), blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag, bx);
+        }
+    } else if (cls2) k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
+    else      k_move_classify3<N, false><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag, whole);
+    hint_invalidate(ctx);
     JP_CHECK_LAUNCH();
     JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->mp_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     JP_CUDA(cudaStreamSynchronize(st));
@@ -1289,6 +1336,7 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
         JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
     }
     ctx->last_move_path = 1;
+    hint_invalidate(ctx);
     if (g.ndim == 2) k_move_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
     else             k_move_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
     JP_CHECK_LAUNCH();
@@ -1319,6 +1367,7 @@ extern "C" int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream) {
 
 extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream) {
     PREP("jp_inject");
+    hint_invalidate(ctx);
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_inject");
     if (rc) return rc;
@@ -1344,6 +1393,7 @@ extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args
 extern "C" int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phases, double *const *args, const double *const *fields,
                                const int32_t *field_kind, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream) {
     PREP("jp_inject_phase");
+    hint_invalidate(ctx);
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_inject_phase");
     if (rc) return rc;
@@ -1386,6 +1436,7 @@ extern "C" int jp_inject_stats(jp_ctx *ctx, int64_t *out, void *stream) {
 
 extern "C" int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream) {
     PREP("jp_clean");
+    hint_invalidate(ctx);
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_clean");
     if (rc) return rc;
@@ -1462,6 +1513,7 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (option == JP_OPT_P2G_MODE && (value == JP_P2G_EXACT || value == JP_P2G_TWOPASS || value == JP_P2G_TWOPASS_FASTW)) { ctx->p2g_mode = value; return JP_OK; }
     if (option == JP_OPT_MOVE_POLICY && (value == JP_MOVE_POLICY_REFERENCE || value == JP_MOVE_POLICY_COMPACT)) { ctx->move_policy = value; return JP_OK; }
     if (option == JP_OPT_ADVECT_AFFINE && (value == 0 || value == 1)) { ctx->g.affine = value ? ctx->affine_detected : 0; return JP_OK; }
+    if (option == JP_OPT_ADVECT_CLASSIFY && (value == 0 || value == 1)) { ctx->hint_opt = value; hint_invalidate(ctx); return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
 }
 
@@ -1471,6 +1523,8 @@ extern "C" int jp_get_option(const jp_ctx *ctx, int32_t option, int32_t *value) 
     if (option == JP_OPT_P2G_MODE) { *value = ctx->p2g_mode; return JP_OK; }
     if (option == JP_OPT_ADVECT_AFFINE) { *value = ctx->g.affine; return JP_OK; }
     if (option == JP_OPT_MOVE_POLICY) { *value = ctx->move_policy; return JP_OK; }
+    if (option == JP_OPT_ADVECT_CLASSIFY) { *value = ctx->hint_opt; return JP_OK; }
+    if (option == JP_OPT_LAST_CLASSIFY) { *value = ctx->last_classify; return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_get_option: unknown option");
 }
 
@@ -1661,7 +1715,17 @@ static int halo_common(jp_ctx *ctx, int dim, int plane, double *const *arrays, i
     const int64_t total = (int64_t)(narrays + 1) * g.S * M;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (pack) k_halo<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
-    else      k_halo<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
+    else {
+        k_halo<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
+        if (ctx->hint_valid) {                     // the hand-off bytes of this plane are stale now
+            bool seen = false;
+            for (int i = 0; i < ctx->hint_ndirty; i++) seen = seen || (ctx->hint_dirty[i][0] == dim && ctx->hint_dirty[i][1] == plane);
+            if (!seen) {
+                if (ctx->hint_ndirty < 8) { ctx->hint_dirty[ctx->hint_ndirty][0] = dim; ctx->hint_dirty[ctx->hint_ndirty][1] = plane; ctx->hint_ndirty++; }
+                else hint_invalidate(ctx);
+            }
+        }
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }

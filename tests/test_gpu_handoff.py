@@ -1,0 +1,149 @@
+"""GPU parity of the advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY, include/justpic_c.h):
+`advection(..., classify=True)` leaves one classification byte per slot and the next
+`move_particles` plans from those bytes instead of re-reading the coordinates.  The results must
+be those of the reference's `move_particles!` (src/Particles/move_safe.jl:21-125) bit for bit --
+checked against the oracle exactly like the default path -- and the bytes must be dropped
+whenever the particles change in between."""
+import numpy as np
+import pytest
+import torch
+
+from tests.problems import cfl_dt, stream_velocity, vertex_field_linear
+from tests.test_gpu_parity import GRIDS, Twin, dev, host, ids, jp
+
+pytestmark = pytest.mark.gpu
+
+
+def _fields(J, t):
+    T = vertex_field_linear(t.gr)
+    pT, ph = J.init_cell_arrays(t.p, 2)
+    J.grid2particle(pT, dev(T), t.p)
+    opT = np.zeros_like(t.co[0]); t.o.grid2particle(t.co, t.idx, opT, T)
+    oph = np.where(t.idx > 0, 1.0 + (t.co[0] < t.co[-1]), 0.0)
+    ph.copy_(dev(oph))
+    return pT, ph, opT, oph
+
+
+@pytest.mark.parametrize("g", GRIDS + [(3, (40, 9, 6), True), (2, (70, 11), True)], ids=ids)
+def test_handoff_trajectory(g):
+    J = jp()
+    t = Twin(*g)
+    V = stream_velocity(t.gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(t.gr, V, 0.9)
+    pT, ph, opT, oph = _fields(J, t)
+    methods = [(J.RungeKutta2(), 1, 0.5), (J.RungeKutta4(), 2, 0.0), (J.RungeKutta2(2 / 3), 1, 2 / 3), (J.Euler(), 0, 0.0)]
+    for it in range(8):
+        m = methods[it % 4]
+        J.advection(t.p, m[0], Vd, dt, classify=True); t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
+        t.check_state(f"step {it} advection (hand-off on)")
+        J.move_particles(t.p, (pT, ph)); st = t.o.move(t.co, t.idx, [opT, oph])
+        t.check_state(f"step {it} move_particles from hand-off bytes", (pT, ph), (opT, oph))
+        assert J.move_stats(t.p) == st
+        assert J.last_move_path(t.p) == "plan" and J.last_move_classify(t.p) == "handoff"
+        J.inject_particles(t.p, (pT, ph), step=it); t.o.inject(t.co, t.idx, [opT, oph], t.min_xcell, t.seed, it)
+        t.check_state(f"step {it} inject_particles", (pT, ph), (opT, oph))
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_handoff_is_dropped_when_particles_change(ndim):
+    """inject / clean / a second advect / other arrays between the two calls: the bytes must not be used."""
+    J = jp()
+    t = Twin(ndim, 12 if ndim == 2 else 8, True)
+    V = stream_velocity(t.gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(t.gr, V, 0.7)
+    pT, ph, opT, oph = _fields(J, t)
+    # (a) inject in between
+    J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=True); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+    J.inject_particles(t.p, (pT, ph), step=0); t.o.inject(t.co, t.idx, [opT, oph], t.min_xcell, t.seed, 0)
+    J.move_particles(t.p, (pT, ph)); t.o.move(t.co, t.idx, [opT, oph])
+    assert J.last_move_classify(t.p) == "coords"
+    t.check_state("inject between advect and move", (pT, ph), (opT, oph))
+    # (b) two advects in a row: the bytes of the second one are the valid ones
+    J.advection(t.p, J.RungeKutta2(), Vd, dt); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+    J.advection(t.p, J.Euler(), Vd, 0.3 * dt); t.o.advect(t.co, t.idx, 0, 0.0, V, 0.3 * dt)
+    J.move_particles(t.p, (pT, ph)); t.o.move(t.co, t.idx, [opT, oph])
+    t.check_state("two advects then move", (pT, ph), (opT, oph))
+    # (c) a move consumes the bytes: a second move right after classifies the coordinates
+    J.advection(t.p, J.RungeKutta2(), Vd, dt); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+    J.move_particles(t.p, (pT, ph)); t.o.move(t.co, t.idx, [opT, oph])
+    assert J.last_move_classify(t.p) == "handoff"
+    J.move_particles(t.p, (pT, ph)); t.o.move(t.co, t.idx, [opT, oph])
+    assert J.last_move_classify(t.p) == "coords"
+    t.check_state("second move", (pT, ph), (opT, oph))
+    # (d) clean in between
+    J.advection(t.p, J.RungeKutta2(), Vd, dt); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+    J.clean_particles(t.p, None, (pT, ph)); t.o.clean(t.co, t.idx, [opT, oph])
+    J.move_particles(t.p, (pT, ph)); t.o.move(t.co, t.idx, [opT, oph])
+    assert J.last_move_classify(t.p) == "coords"
+    t.check_state("clean between advect and move", (pT, ph), (opT, oph))
+    # (e) switched off again
+    J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=False); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+    J.move_particles(t.p, (pT, ph)); t.o.move(t.co, t.idx, [opT, oph])
+    assert J.last_move_classify(t.p) == "coords"
+    t.check_state("hand-off off", (pT, ph), (opT, oph))
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_handoff_with_halo_unpack_in_between(ndim):
+    """The multi-GPU time loop: advection! -> update_halo! -> move_particles!.  Planes rewritten by
+    jp_halo_unpack are re-classified from the coordinates, the rest comes from the bytes."""
+    J = jp()
+    from justpic.jl_b200 import halo as H
+    n = 12 if ndim == 2 else (8, 6, 7)
+    t = Twin(ndim, n, True)
+    gr = t.gr
+    V = stream_velocity(gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(gr, V, 0.9)
+    pT, ph, opT, oph = _fields(J, t)
+    for it in range(3):
+        J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=True); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+        # periodic self-exchange in every dimension (what a 1-rank periodic topology does):
+        # plane 1 -> plane n-1 and plane n-2 -> plane 0, on the GPU through pack/unpack, on the host by slicing
+        arrays = [*t.p.coords, pT, ph]
+        oarrays = [*t.co, opT, oph]
+        for d in range(ndim):
+            nd = gr.n[d]
+            for src, dst in ((1, nd - 1), (nd - 2, 0)):
+                buf = torch.empty(H.plane_bytes(t.p.ncells, t.p.max_xcell, d, len(arrays)), dtype=torch.uint8, device="cuda")
+                H._cuda_pack(t.p, d, src, arrays, buf)
+                H._cuda_unpack(t.p, d, dst, arrays, buf)
+                ax = ndim - d                      # arrays are (S, [nz,] ny, nx)
+                for a in oarrays + [t.idx]:
+                    sl_src = [slice(None)] * a.ndim; sl_dst = [slice(None)] * a.ndim
+                    sl_src[ax] = src; sl_dst[ax] = dst
+                    a[tuple(sl_dst)] = a[tuple(sl_src)]
+        t.check_state(f"step {it} after self-exchange", (pT, ph), (opT, oph))
+        J.move_particles(t.p, (pT, ph)); st = t.o.move(t.co, t.idx, [opT, oph])
+        assert J.last_move_classify(t.p) == "handoff"
+        t.check_state(f"step {it} move after halo unpack", (pT, ph), (opT, oph))
+        assert J.move_stats(t.p) == st
+        J.inject_particles(t.p, (pT, ph), step=it); t.o.inject(t.co, t.idx, [opT, oph], t.min_xcell, t.seed, it)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_handoff_ties_fall_back_to_direct_sweeps(ndim):
+    """Particles that end an advection exactly on a face / outside the domain: the bytes carry the
+    'cannot plan' reason, the call takes the literal sweeps, results stay exact."""
+    J = jp()
+    t = Twin(ndim, 8, True, exact=True)
+    gr = t.gr
+    # zero velocity: positions stay where we put them -- on vertices, centres, outside
+    V = [np.zeros_like(v) for v in stream_velocity(gr)]; Vd = [dev(v) for v in V]
+    rng = np.random.default_rng(3)
+    live = np.argwhere(t.idx > 0)
+    for tt in live[rng.choice(len(live), size=len(live) // 4, replace=False)]:
+        for d in range(ndim):
+            if rng.random() < 0.5:
+                cell = tt[ndim - d]
+                cand = [gr.xvi[d][cell], gr.xvi[d][cell + 1], gr.xvi[d][min(cell + 2, gr.n[d])] - 1e-9, gr.xvi[d][max(cell - 1, 0)] + 1e-9]
+                t.co[d][tuple(tt)] = cand[rng.integers(len(cand))]
+    for d in range(ndim):
+        t.p.coords[d].copy_(dev(t.co[d]))
+    pT, = J.init_cell_arrays(t.p, 1)
+    opT = np.where(t.idx > 0, rng.random(t.idx.shape), 0.0); pT.copy_(dev(opT))
+    J.advection(t.p, J.RungeKutta2(), Vd, 1e-3, classify=True); t.o.advect(t.co, t.idx, 1, 0.5, V, 1e-3)
+    t.check_state("advection with zero velocity")
+    J.move_particles(t.p, (pT,)); st = t.o.move(t.co, t.idx, [opT])
+    assert J.last_move_classify(t.p) == "handoff" and J.last_move_path(t.p) == "direct"
+    t.check_state("move from tie positions", (pT,), (opT,))
+    assert J.move_stats(t.p) == st

@@ -16,6 +16,7 @@ ap.add_argument("--method", default="rk2")
 ap.add_argument("--exact", action="store_true", help="Julia range() grids (exactly affine centres)")
 ap.add_argument("--affine", type=int, default=1)
 ap.add_argument("--policy", default="reference", help="move slot policy: reference | compact")
+ap.add_argument("--classify", type=int, default=0, help="1: advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY)")
 a = ap.parse_args()
 gr = make_grids(a.cells, a.ndim, True, exact=a.exact)
 p = J.init_particles(J.CUDABackend, 24, 48, 12, *gr.grid_vel, seed=42)
@@ -33,7 +34,7 @@ names = ["advect", "move", "p2g", "phase"]
 rows = []
 for it in range(a.steps):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    ev[0].record(); J.advection(p, m, V, dt, affine=bool(a.affine))
+    ev[0].record(); J.advection(p, m, V, dt, affine=bool(a.affine), classify=(True if a.classify else None))
     ev[1].record(); J.move_particles(p, tuple(fields), policy=a.policy)
     ev[2].record(); J.particle2grid(T, fields[0], p)
     ev[3].record()
@@ -41,7 +42,7 @@ for it in range(a.steps):
     ev[4].record(); torch.cuda.synchronize()
     rows.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
 r = np.array(rows)
-print("policy", a.policy, "lib", os.environ.get("JUSTPIC_LIB", "default"), "affine", J.advect_affine_level(p) if hasattr(J, "advect_affine_level") else None, "cells", a.cells, "live", int(p.index.sum()))
+print("classify", a.classify, J.last_move_classify(p) if a.classify else "-", "policy", a.policy, "lib", os.environ.get("JUSTPIC_LIB", "default"), "affine", J.advect_affine_level(p) if hasattr(J, "advect_affine_level") else None, "cells", a.cells, "live", int(p.index.sum()))
 for i, n in enumerate(names):
     print(f"{n:8s}", " ".join(f"{x:7.3f}" for x in r[:, i]), f"| mean(last half) {r[len(r)//2:, i].mean():7.3f}")
 print("checksum", float(torch.nan_to_num(p.coords[0]).sum()), float(torch.nan_to_num(fields[0]).sum()), int(p.index.sum()))
