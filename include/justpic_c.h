@@ -246,6 +246,21 @@ int jp_halo_pack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays,
 int jp_halo_unpack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays, int32_t narrays,
                    uint8_t *index, const void *buf, void *stream);
 
+/* Array(CA) / Array(T, CA) and CuArray(CA) / CuArray(T, CA) for a CellArray
+ * (src/CellArrays/conversion.jl:19-43, ext/JustPICCUDAExt.jl:166-179; checkpoints, test/test_save_load.jl:120-173):
+ * the reference's permutedims(CA.data, (3, 2, 1)) between the device layout data[C, S, 1] (element
+ * (cell c, component s) at c + s*C) and the host layout data[1, S, C] (at s + c*S), with the element
+ * conversion of the typed forms (Float64 <-> Float32 by IEEE round-to-nearest as Julia's convert; Bool
+ * stays Bool).  src and dst are both DEVICE pointers of ncells*ncomp elements and must not alias: the
+ * shim copies dst to the host (JP_LAYOUT_TO_HOST) or uploads src first (JP_LAYOUT_TO_DEVICE).
+ * ncells = number of cells of that CellArray (n for particle fields / centres, n+1 per dim for vertex
+ * ratios, ...), ncomp = entries per cell (max_xcell, nphases, ...).  ctx may be NULL (a bare CellArray has
+ * no Particles): the launch then goes to the caller's current device. */
+typedef enum { JP_F64 = 0, JP_F32 = 1, JP_BOOL = 2 } jp_dtype;
+typedef enum { JP_LAYOUT_TO_HOST = 0, JP_LAYOUT_TO_DEVICE = 1 } jp_layout_direction;
+int jp_cellarray_permute(jp_ctx *ctx, const void *src, int32_t src_type, void *dst, int32_t dst_type,
+                         int64_t ncells, int32_t ncomp, int32_t direction, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,8 @@ JP_OPT_ADVECT_AFFINE = 3
 JP_OPT_MOVE_POLICY = 4
 JP_OPT_ADVECT_CLASSIFY = 5
 JP_OPT_LAST_CLASSIFY = 6
+JP_F64, JP_F32, JP_BOOL = 0, 1, 2
+JP_LAYOUT_TO_HOST, JP_LAYOUT_TO_DEVICE = 0, 1
 JP_MOVE_POLICY_REFERENCE, JP_MOVE_POLICY_COMPACT = 0, 1
 JP_MOVE_AUTO, JP_MOVE_DIRECT = 0, 1
 JP_P2G_EXACT, JP_P2G_TWOPASS, JP_P2G_TWOPASS_FASTW = 0, 1, 2
@@ -90,6 +92,8 @@ SYMBOLS = {
                                            C.c_int32, C.c_void_p]),
     "jp_update_phase_ratios": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "jp_cellarray_permute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_void_p]),
     "jp_halo_plane_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32]),
     "jp_halo_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p]),

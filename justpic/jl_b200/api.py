@@ -44,6 +44,7 @@ __all__ = [
     "SubgridDiffusionCellArrays", "subgrid_diffusion", "subgrid_diffusion_centroid",
     "phase_ratios_center", "phase_ratios_vertex", "phase_ratios_face", "phase_ratios_midpoint",
     "update_phase_ratios", "set_synchronous",
+    "Array", "CuArray", "HostParticles", "HostPhaseRatios", "last_move_classify",
 ]
 
 
@@ -716,3 +717,144 @@ def phase_ratios_center(phase_ratios: PhaseRatios, particles: Particles, phases:
         _cabi.check(_cabi.load().jp_phase_ratios_center(C.c_void_p(p._ctx), C.byref(pc), C.c_void_p(r.data_ptr()),
                                                         C.c_void_p(ph.data_ptr()), K, _stream()), "phase_ratios_center")
         _done()
+
+
+# --------------------------------------------------------------------------- Array(...) / CuArray(...)
+# Host images of the device containers, in the reference's CPU CellArray layout
+# (blocklength 1, data[1, S, C]: slot fastest; src/launch.jl:81): numpy arrays of shape
+# ([nz,] ny, nx, S) in C order.  Checkpoints written from them are what JLD2 stores in the reference
+# (src/IO/JLD2.jl saves Array(particles), test/test_save_load.jl:120-173).
+@dataclass
+class HostParticles:
+    """``Array(particles)``: the ``Particles{CPU}`` image of a device container (src/CellArrays/conversion.jl:45-69)."""
+    coords: Tuple[np.ndarray, ...]
+    index: np.ndarray
+    nxcell: int
+    max_xcell: int
+    min_xcell: int
+    np: int
+    di: SimpleNamespace
+    xci: Tuple[np.ndarray, ...]
+    xvi: Tuple[np.ndarray, ...]
+    xi_vel: Tuple[Tuple[np.ndarray, ...], ...]
+    uniform: bool
+    seed: int = 42
+    inject_step: int = 0
+
+
+@dataclass
+class HostPhaseRatios:
+    """``Array(phase_ratios)``: every field of ``PhaseRatios`` in the host layout."""
+    nphases: int
+    ni: Tuple[int, ...]
+    center: np.ndarray
+    vertex: np.ndarray
+    Vx: np.ndarray
+    Vy: np.ndarray
+    Vz: np.ndarray
+    yz: np.ndarray
+    xz: np.ndarray
+    xy: np.ndarray
+
+
+_PR_FIELDS = ("center", "vertex", "Vx", "Vy", "Vz", "yz", "xz", "xy")
+_TORCH_OF = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
+_JP_OF = {torch.float64: _cabi.JP_F64, torch.float32: _cabi.JP_F32, torch.uint8: _cabi.JP_BOOL, torch.bool: _cabi.JP_BOOL}
+
+
+def _eltype(T, src_dtype: torch.dtype) -> torch.dtype:
+    if src_dtype in (torch.uint8, torch.bool):
+        return src_dtype                                   # index stays Bool whatever T is (conversion.jl:50-51)
+    if T is None:
+        return src_dtype
+    dt = np.dtype(T)
+    if dt not in _TORCH_OF:
+        raise TypeError(f"{T} is not a supported CellArray element type (Float64 / Float32)")
+    return _TORCH_OF[dt]
+
+
+def _permute(src: torch.Tensor, dst: torch.Tensor, ncells: int, ncomp: int, direction: int, ctx=None) -> None:
+    with torch.cuda.device(src.device):
+        _cabi.check(_cabi.load().jp_cellarray_permute(C.c_void_p(ctx), C.c_void_p(src.data_ptr()), _JP_OF[src.dtype],
+                                                      C.c_void_p(dst.data_ptr()), _JP_OF[dst.dtype], ncells, ncomp, direction,
+                                                      _stream()), "jp_cellarray_permute")
+
+
+def _cellarray_to_host(t: torch.Tensor, T=None, ctx=None) -> np.ndarray:
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and t.dim() >= 2):
+        raise TypeError("Array(CellArray): expected a contiguous CUDA tensor of shape (ncomp, [nz,] ny, nx)")
+    if t.dtype not in _JP_OF:
+        raise TypeError(f"{t.dtype} is not a supported CellArray type.")
+    ncomp, cells = int(t.shape[0]), tuple(int(v) for v in t.shape[1:])
+    out = torch.empty((*cells, ncomp), dtype=_eltype(T, t.dtype), device=t.device)
+    _permute(t, out, int(np.prod(cells)), ncomp, _cabi.JP_LAYOUT_TO_HOST, ctx)
+    h = out.cpu().numpy()                                   # synchronises
+    return h.astype(np.bool_) if t.dtype in (torch.uint8, torch.bool) else h
+
+
+def _cellarray_to_device(a: np.ndarray, T=None, device=None, ctx=None) -> torch.Tensor:
+    a = np.ascontiguousarray(a)
+    if a.ndim < 2:
+        raise TypeError("CuArray(CellArray): expected a host array of shape ([nz,] ny, nx, ncomp)")
+    if a.dtype == np.bool_:
+        a = a.astype(np.uint8)
+    elif a.dtype not in _TORCH_OF:
+        raise TypeError(f"{a.dtype} is not a supported CellArray type.")
+    dev = torch.device(device or "cuda")
+    if dev.type != "cuda":
+        raise RuntimeError("justpic.jl_b200 has no CPU path: CuArray targets a CUDA device")
+    src = torch.from_numpy(a).to(dev)
+    cells, ncomp = tuple(a.shape[:-1]), int(a.shape[-1])
+    out = torch.empty((ncomp, *cells), dtype=_eltype(T, src.dtype), device=src.device)
+    _permute(src, out, int(np.prod(cells)), ncomp, _cabi.JP_LAYOUT_TO_DEVICE, ctx)
+    _done()
+    return out
+
+
+def Array(x, T=None):
+    """``Array(x)`` / ``Array(T, x)`` (src/CellArrays/conversion.jl:19-69) for a device CellArray (tensor of
+    shape ``(ncomp, [nz,] ny, nx)``), ``Particles`` or ``PhaseRatios``: the host image in the reference's CPU
+    CellArray layout (``permutedims(data, (3, 2, 1))``: shape ``([nz,] ny, nx, ncomp)``), optionally
+    converted to element type ``T`` (``index`` stays Bool).  The permutation runs on the device
+    (``jp_cellarray_permute``), the copy to the host is one contiguous transfer per array."""
+    if isinstance(x, (HostParticles, HostPhaseRatios, np.ndarray)):
+        return x                                            # already on the host (conversion.jl:24-29)
+    if isinstance(x, torch.Tensor):
+        return _cellarray_to_host(x, T)
+    if isinstance(x, Particles):
+        return HostParticles(tuple(_cellarray_to_host(c, T, x._ctx) for c in x.coords), _cellarray_to_host(x.index, None, x._ctx),
+                             x.nxcell, x.max_xcell, x.min_xcell, x.np, x.di, x.xci, x.xvi, x.xi_vel, x.uniform, x.seed,
+                             x._inject_step)
+    if isinstance(x, PhaseRatios):
+        return HostPhaseRatios(x.nphases, x.ni, *(_cellarray_to_host(getattr(x, f), T) for f in _PR_FIELDS))
+    raise TypeError(f"{type(x).__name__} is not a supported CellArray type.")
+
+
+def CuArray(x, T=None, device=None):
+    """``CuArray(x)`` / ``CuArray(T, x)`` (ext/JustPICCUDAExt.jl:51-187): the device container of a host image
+    produced by :func:`Array` (or loaded from a checkpoint).  ``Particles`` are rebuilt with a fresh library
+    context for the same grids; the kernels are fp64, so ``T`` other than Float64 is accepted for bare
+    CellArrays and ``PhaseRatios`` only."""
+    if isinstance(x, (Particles, PhaseRatios, torch.Tensor)):
+        return x                                            # already on the device (ext/JustPICCUDAExt.jl:181-182)
+    if isinstance(x, np.ndarray):
+        return _cellarray_to_device(x, T, device)
+    if isinstance(x, HostPhaseRatios):
+        pr = PhaseRatios.__new__(PhaseRatios)
+        pr.nphases, pr.ni = x.nphases, tuple(x.ni)
+        for f in _PR_FIELDS:
+            setattr(pr, f, _cellarray_to_device(getattr(x, f), T, device))
+        return pr
+    if isinstance(x, HostParticles):
+        if T is not None and np.dtype(T) != np.float64:
+            raise NotImplementedError("Particles on the device are Float64: the sm_100a kernels compute in fp64")
+        dev = torch.device(device or "cuda")
+        dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        dev = torch.device("cuda", dev_index)
+        ni = tuple(len(c) for c in x.xci)
+        ctx, keep = _make_ctx(len(ni), ni, x.max_xcell, x.uniform, x.xvi, x.xci, x.xi_vel, dev_index)
+        coords = tuple(_cellarray_to_device(c.astype(np.float64, copy=False), None, dev, ctx) for c in x.coords)
+        index = _cellarray_to_device(x.index, None, dev, ctx)
+        return Particles(coords, index, x.nxcell, x.max_xcell, x.min_xcell, x.np, x.di, x.xci, x.xvi, x.xi_vel, x.uniform,
+                         seed=x.seed, _ctx=ctx, _keep=keep, _inject_step=x.inject_step)
+    raise TypeError(f"{type(x).__name__} is not a supported CellArray type.")

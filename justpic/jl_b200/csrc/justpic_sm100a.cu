@@ -126,6 +126,7 @@ __device__ __forceinline__ uint64_t load_mask(const uint8_t *__restrict__ index,
 }
 
 #include "jp_move_plan.cuh"
+#include "jp_convert.cuh"
 
 // ---------------------------------------------------------------------------
 template <int N>
@@ -1734,4 +1735,29 @@ extern "C" int jp_halo_pack(jp_ctx *ctx, int32_t dim, int32_t plane, double *con
 }
 extern "C" int jp_halo_unpack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays, int32_t narrays, uint8_t *index, const void *buf, void *stream) {
     return halo_common(ctx, dim, plane, arrays, narrays, index, (void *)buf, stream, false);
+}
+
+// ---------------------------------------------------------------------------
+// Array(CellArray) / CuArray(CellArray) layout conversion (jp_convert.cuh)
+extern "C" int jp_cellarray_permute(jp_ctx *ctx, const void *src, int32_t src_type, void *dst, int32_t dst_type, int64_t ncells,
+                                    int32_t ncomp, int32_t direction, void *stream) {
+    if (!src || !dst) return jp_fail(JP_ERR_INVALID, "jp_cellarray_permute: null argument");
+    if (src == dst) return jp_fail(JP_ERR_INVALID, "jp_cellarray_permute: in-place conversion is not supported");
+    if (ncells < 0 || ncomp < 0) return jp_fail(JP_ERR_INVALID, "jp_cellarray_permute: negative extent");
+    if (direction != JP_LAYOUT_TO_HOST && direction != JP_LAYOUT_TO_DEVICE) return jp_fail(JP_ERR_INVALID, "jp_cellarray_permute: unknown direction");
+    const bool sb = src_type == JP_BOOL, db = dst_type == JP_BOOL;
+    if (src_type < JP_F64 || src_type > JP_BOOL || dst_type < JP_F64 || dst_type > JP_BOOL || sb != db)
+        return jp_fail(JP_ERR_UNSUPPORTED, "jp_cellarray_permute: element types must be Float64/Float32 (convertible) or Bool -> Bool");
+    if (ncells == 0 || ncomp == 0) return JP_OK;
+    if ((ncells + 31) / 32 > 2147483647LL) return jp_fail(JP_ERR_UNSUPPORTED, "jp_cellarray_permute: too many cells");
+    if (ctx) JP_CUDA(cudaSetDevice(ctx->device));       // no context: the caller's current device
+    cudaStream_t st = (cudaStream_t)stream;
+    const int th = direction == JP_LAYOUT_TO_HOST;
+    if (sb) launch_cellarray_permute<uint8_t, uint8_t>(src, dst, ncells, ncomp, th, st);
+    else if (src_type == JP_F64 && dst_type == JP_F64) launch_cellarray_permute<double, double>(src, dst, ncells, ncomp, th, st);
+    else if (src_type == JP_F64 && dst_type == JP_F32) launch_cellarray_permute<double, float>(src, dst, ncells, ncomp, th, st);
+    else if (src_type == JP_F32 && dst_type == JP_F64) launch_cellarray_permute<float, double>(src, dst, ncells, ncomp, th, st);
+    else launch_cellarray_permute<float, float>(src, dst, ncells, ncomp, th, st);
+    JP_CHECK_LAUNCH();
+    return JP_OK;
 }

@@ -228,3 +228,23 @@ def rand3(seed, purpose, step, cell, slot):
     r = np.empty(3)
     lib().jpo_rand3(C.c_uint64(int(seed)), C.c_uint32(purpose), C.c_uint32(step), C.c_uint32(cell), C.c_uint32(slot), _dp(r))
     return r
+
+
+# ---- Array(CellArray) / CuArray(CellArray) (src/CellArrays/conversion.jl:32-43,
+# ext/JustPICCUDAExt.jl:166-179): the device CellArray stores data[C, S, 1] (column-major: element
+# (cell c, component s) at c + s*C, ext/JustPICCUDAExt.jl:26-30), the host CellArray data[1, S, C]
+# (launch.jl:81); the conversion is permutedims(data, (3, 2, 1)) followed by copyto!, with
+# convert(T, .) per element for the typed forms.  In this package's array convention
+# (component axis first, then [nz,] ny, nx in C order) that is: move axis 0 to the end.
+def cellarray_to_host_layout(a: np.ndarray, T=None) -> np.ndarray:
+    out = np.ascontiguousarray(np.moveaxis(np.asarray(a), 0, -1))
+    if a.dtype in (np.uint8, np.bool_):
+        return out.astype(np.bool_)
+    return out.astype(T) if T is not None else out
+
+
+def cellarray_to_device_layout(a: np.ndarray, T=None) -> np.ndarray:
+    out = np.ascontiguousarray(np.moveaxis(np.asarray(a), -1, 0))
+    if a.dtype in (np.uint8, np.bool_):
+        return out.astype(np.uint8)
+    return out.astype(T) if T is not None else out
