@@ -62,14 +62,14 @@ typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_
  *     reference's; checked against the oracle run with the same rule. */
 /* JP_OPT_ADVECT_CLASSIFY (0/1, default 0): advection -> move hand-off.  With 1, jp_advect (tiled kernel:
  *   standard staggering) also classifies every new position for the following move_particles! -- the
- *   same comparisons jp_move makes, on the value being stored -- and leaves one byte per slot in a
- *   library-owned plane; the next jp_move on the SAME coordinate / index arrays builds its plan from
- *   those bytes instead of re-reading the coordinates (results bit-identical to option 0).  The bytes are
- *   dropped by every library call that changes particles (init, inject, clean, another advect, move);
- *   planes rewritten by jp_halo_unpack are re-classified from the coordinates.  The caller must not
- *   modify coordinates or the index mask between the two calls by other means -- the reference's
- *   time loops never do (advection! -> update_halo! -> move_particles!), but the library cannot see such
- *   writes, hence opt-in.
+ *   same comparisons jp_move makes, on the value being stored -- and writes the move plan's per-cell
+ *   occupancy / leave / destination-code words into the library workspace; the next jp_move on the SAME
+ *   coordinate / index arrays starts from those words instead of re-reading the coordinates (results
+ *   bit-identical to option 0).  The words are dropped by every library call that changes particles
+ *   (init, inject, clean, another advect, move); planes rewritten by jp_halo_unpack are re-classified
+ *   from the coordinates.  The caller must not modify coordinates or the index mask between the two
+ *   calls by other means -- the reference's time loops never do (advection! -> update_halo! ->
+ *   move_particles!), but the library cannot see such writes, hence opt-in.
  * JP_OPT_LAST_CLASSIFY (jp_get_option only): 1 if the last planned jp_move used the hand-off bytes. */
 typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3, JP_OPT_MOVE_POLICY = 4,
                JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6 } jp_option;

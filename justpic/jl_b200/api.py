@@ -431,7 +431,7 @@ def last_move_path(particles: Particles) -> str:
 
 
 def last_move_classify(particles: Particles) -> str:
-    """"handoff" if the last planned ``move_particles`` built its plan from the bytes left by
+    """"handoff" if the last planned ``move_particles`` built its plan from the words left by
     ``advection(..., classify=True)``, "coords" if it classified the coordinates itself."""
     v = C.c_int32(0)
     _cabi.check(_cabi.load().jp_get_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_LAST_CLASSIFY, C.byref(v)), "jp_get_option")

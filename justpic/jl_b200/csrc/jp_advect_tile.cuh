@@ -160,19 +160,24 @@ __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__rest
     jp_interp_velocity_literal<N>(g, V, p, cell1, vout);
 }
 
-// HINT (JP_OPT_ADVECT_CLASSIFY): every new position is also classified for the following
-// move_particles! (jp_classify_particle on the value being stored, against the vertices already staged
-// in shared memory) and the byte goes to hint[element]; jp_move then skips its coordinate pass.
+// HINT (JP_OPT_ADVECT_CLASSIFY, the advection -> move hand-off): every new position is also classified
+// for the following move_particles! -- jp_classify_fast / jp_classify_particle on the value being stored,
+// i.e. exactly what k_move_classify3 would compute from memory -- into a per-warp byte table in shared
+// memory ([slot][cell of the x-run]); when the warp has finished its x-run, lane = cell packs its leavers'
+// codes in slot order and writes the occupancy / leave / code words of the move plan itself.  jp_move then
+// starts at the plan kernels: no pass over the coordinates, no intermediate plane in HBM.
 template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
 __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 768) / (AdvTile<N>::NW * 32)) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
                                                                      double alpha, double dt,
                                                                      const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
-                                                                     const __grid_constant__ CUtensorMap tm2, int tma_mask, uint8_t *__restrict__ hint) {
+                                                                     const __grid_constant__ CUtensorMap tm2, int tma_mask, MovePlanWs ws,
+                                                                     unsigned int *complex_flag) {
     using T = AdvTile<N>;
     using L = AdvSmem<N, UNIFORM>;
     extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA destinations: 128-byte aligned (VOL*8 is a multiple of 128)
     double *sm = reinterpret_cast<double *>(smem_raw);
     uint16_t *wl_all = reinterpret_cast<uint16_t *>(smem_raw + sizeof(double) * L::NDOUBLES);
+    uint8_t *code_all = smem_raw + L::BYTES;                     // HINT: [warp][slot][32] classification bytes
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // brick origin (cells) and first staged node (one below)
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
     // software pipeline: the coordinates of batch b+1 are fetched before batch b is integrated, so the
     // global-load latency (27 % of the stall samples before) overlaps the ~450 instructions of a batch
     bool cur_valid = false;
-    int cur_l = 0;
+    int cur_l = 0;                     // ring entry: (slot << 5) | cell of the x-run
     int64_t cur_e = 0;
     double cur_p[3] = {0.0, 0.0, 0.0};
     for (;;) {
@@ -286,8 +291,8 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
         if (nxt_valid) {
             unsigned short ent16;
             asm volatile("ld.shared.u16 %0, [%1];" : "=h"(ent16) : "r"(ring_sa + 2u * (unsigned)(k & (RH - 1))) : "memory");
-            nxt_l = ent16 & 31;
-            nxt_e = crow + b0[0] + nxt_l + (int64_t)(ent16 >> 5) * g.C;
+            nxt_l = ent16;
+            nxt_e = crow + b0[0] + (ent16 & 31) + (int64_t)(ent16 >> 5) * g.C;
 #pragma unroll
             for (int d = 0; d < N; d++) nxt_p[d] = co.p[d][nxt_e];
         }
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
         {
             const unsigned amask = __ballot_sync(0xffffffffu, cur_valid);
             if (cur_valid) {
-                const int l = cur_l;
+                const int l = cur_l & 31;
                 const int64_t e = cur_e;
                 const int r0[3] = {l + T::OX, wy + 1, wz + 1};
                 const int cell1[3] = {b0[0] + l + 1, cy + 1, cz + 1};
@@ -340,14 +345,24 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
 #pragma unroll
                 for (int d = 0; d < N; d++) co.p[d][e] = pn[d];
                 if (HINT) {
-                    // the staged vertex segments hold NaN outside the grid, exactly the convention of k_move_classify3
-                    double vm[3], va[3], vb[3], vp[3];
+                    const double *xvs = sm + L::XV_OFF;
+                    double va[3];
 #pragma unroll
-                    for (int d = 0; d < N; d++) {
-                        const double *xv = sm + L::XV_OFF + d * L::VEC + r0[d];
-                        vm[d] = xv[-1]; va[d] = xv[0]; vb[d] = xv[1]; vp[d] = xv[2];
+                    for (int d = 0; d < N; d++) va[d] = AFFINE ? fma(gd0[d], g.aff_dv[d], g.aff_v0[d]) : xvs[d * L::VEC + r0[d]];
+                    const int ci3[3] = {b0[0] + l, cy, cz};
+                    int code = g.cls_fast ? jp_classify_fast<N>(g, ci3, va, pn) : -1;
+                    if (code < 0) {
+                        // within 1e-4 dx of a vertex, far away, NaN / Inf, or a vector grid: the exact comparisons.
+                        // The staged vertex segments hold NaN outside the grid, the convention of k_move_classify3.
+                        double vm[3], vb[3], vp[3];
+#pragma unroll
+                        for (int d = 0; d < N; d++) {
+                            const double *xv = xvs + d * L::VEC + r0[d];
+                            vm[d] = xv[-1]; va[d] = xv[0]; vb[d] = xv[1]; vp[d] = xv[2];
+                        }
+                        code = jp_classify_particle<N>(g, vm, va, vb, vp, pn);
                     }
-                    hint[e] = (uint8_t)jp_classify_particle<N>(g, vm, va, vb, vp, pn);
+                    code_all[(warp * g.S + (cur_l >> 5)) * 32 + l] = (uint8_t)code;
                 }
             }
         }
@@ -356,6 +371,31 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
 #pragma unroll
         for (int d = 0; d < N; d++) cur_p[d] = nxt_p[d];
         __syncwarp();
+    }
+    if (HINT) {
+        // ---- 4. lane = cell: the words k_move_classify3 would have produced (same packing, same order)
+        __syncwarp();
+        const int64_t c = crow + cx;
+        const uint8_t *cs = code_all + (warp * g.S) * 32 + lane;
+        uint64_t lv = 0, codew = 0;
+        int k = 0;
+        unsigned cplx = 0;
+        for (int s = 0; s < g.S; s++) {
+            int code = cs[s * 32];
+            const bool leaver = ((m >> s) & 1ull) && code != JP_CLS_STAY;
+            if (leaver) {
+                lv |= 1ull << s;
+                if (code > JP_CLS_CPLX) { cplx |= 1u << ((code - JP_CLS_CPLX - 1) & 3); code = JP_CODE_DELETE; }
+                codew |= (uint64_t)code << (8 * (k & 7));
+                if ((++k & 7) == 0) { ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
+            }
+        }
+        if (ok) {
+            ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
+            if (k & 7) ws.code[(int64_t)(k >> 3) * g.C + c] = codew;
+        }
+        const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
+        if (wc && lane == 0) atomicOr(complex_flag, wc);
     }
 }
 

@@ -46,6 +46,9 @@ struct JpGrid {
     double dom_lo[3], dom_hi[3];   // xv[d][0], xv[d][n]  (kernel-parameter constants instead of per-thread loads)
     double dxv0[3];                // xv[d][1] - xv[d][0]  (the scalar spacing of range grids)
     double inv_dmin_v[3];          // inv(grid_size(xvi)) = 1 / abs(minimum(diff(xv)))  (grid2particle_flip!)
+    // 1: range grid whose vertices were checked on the host to be affine within 1e-6 dx (and dx >> ulp of the
+    //    coordinates): jp_classify_fast may decide particles that are clearly inside a cell (see there)
+    int32_t cls_fast;
 };
 
 struct JpArgs {               // particle fields carried along by move/inject/clean
@@ -433,6 +436,35 @@ JP_HD int jp_classify_particle(const JpGrid &g, const double *am, const double *
     if (dv[0] == 0 && dv[1] == 0 && dv[2] == 0) return JP_CLS_CPLX + 2;
     if (!dest_ok) return JP_CLS_CPLX + 3;
     return (dv[0] + 1) + 3 * (dv[1] + 1) + (N == 3 ? 9 * (dv[2] + 1) : 9);
+}
+
+// Shortcut for jp_classify_particle on range grids (g.cls_fast): u = (p - a) / dx in single precision
+// locates the particle relative to its storage cell; when every coordinate is at least JP_CLS_EPS cell
+// widths away from a vertex, each strict comparison of jp_classify_particle is decided with a margin
+// (1e-4 dx) that is orders of magnitude above every rounding involved (u: < 2e-7; vertices vs. the affine
+// model: <= 1e-6 dx, checked by jp_grid_build; fl(a + dx), fl(lower + dx): 1 ulp), so the result is THE
+// SAME code.  Otherwise (within 1e-4 dx of a vertex, more than one cell away, NaN / Inf) it returns -1
+// and the caller evaluates jp_classify_particle.  ci = storage cell, a = its lower vertices.
+#define JP_CLS_EPS 1.0e-4f
+template <int N>
+JP_HD int jp_classify_fast(const JpGrid &g, const int *ci, const double *a, const double *p) {
+    bool sure = true, stay = true, del = false;
+    int code = N == 3 ? 0 : 9;
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+        const float u = (float)((p[d] - a[d]) * g.inv_dv[d]);
+        const bool in = u > JP_CLS_EPS && u < 1.0f - JP_CLS_EPS;
+        const bool lf = u > -1.0f + JP_CLS_EPS && u < -JP_CLS_EPS;
+        const bool rt = u > 1.0f + JP_CLS_EPS && u < 2.0f - JP_CLS_EPS;
+        sure = sure && (in || lf || rt);
+        stay = stay && in;
+        const int dv = (rt ? 1 : 0) - (lf ? 1 : 0);
+        const int cd = ci[d] + dv;
+        del = del || cd < 0 || cd >= g.n[d];       // the neighbour does not exist: p is outside the domain
+        code += (dv + 1) * (d == 0 ? 1 : d == 1 ? 3 : 9);
+    }
+    if (!sure) return -1;
+    return stay ? JP_CLS_STAY : del ? JP_CODE_DELETE : code;
 }
 
 // isincell (src/Particles/utils.jl:7-15): strict, upper edge = fl(xv + dx)

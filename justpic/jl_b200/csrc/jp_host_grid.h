@@ -75,6 +75,17 @@ static inline const char *jp_grid_build(const jp_grid_desc *d, JpGrid &g, std::v
         for (int i = 1; i < d->n[dim]; i++) { const double q = d->xv[dim][i + 1] - d->xv[dim][i]; m = q < m ? q : m; }
         g.inv_dmin_v[dim] = 1.0 / fabs(m);
     }
+    // jp_classify_fast precondition: range grid, vertices affine within 1e-6 dx, dx far above the ulp of the coordinates
+    int cf = g.uniform;
+    for (int dim = 0; dim < N && cf; dim++) {
+        const double *xv = d->xv[dim];
+        const double dx0 = xv[1] - xv[0];
+        const double amax = fmax(fabs(xv[0]), fabs(xv[d->n[dim]]));
+        if (!(dx0 > 0) || !(amax * 3.6e-15 <= 1e-6 * dx0)) { cf = 0; break; }
+        for (int i = 0; i <= d->n[dim]; i++)
+            if (!(fabs(xv[i] - (xv[0] + i * dx0)) <= 1e-6 * dx0)) { cf = 0; break; }
+    }
+    g.cls_fast = cf;
     h.clear();
     auto push = [&](const double *x, int n) { size_t off = h.size(); h.insert(h.end(), x, x + n); return off; };
     for (int dim = 0; dim < N; dim++) {

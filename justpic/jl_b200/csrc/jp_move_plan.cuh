@@ -221,49 +221,11 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
             if (!((bits >> u) & 1u)) continue;
             // isincell (strict, upper edge fl(a + dx)), domain test, destination by comparisons with the
             // four vertices; dx = scalar spacing on range grids, the cell's own spacing on vector grids
-            int code = jp_classify_particle<N>(g, am, a, b, bp, p[u]);
+            int code = g.cls_fast ? jp_classify_fast<N>(g, ci, a, p[u]) : -1;
+            if (code < 0) code = jp_classify_particle<N>(g, am, a, b, bp, p[u]);
             if (code == JP_CLS_STAY) continue;
             lv |= 1ull << (s0 + u);
             if (code > JP_CLS_CPLX) { cplx |= 1u << (code - JP_CLS_CPLX - 1); code = JP_CODE_DELETE; }
-            codew |= (uint64_t)code << (8 * (k & 7));
-            if ((++k & 7) == 0) { ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
-        }
-    }
-    if (ok) {
-        ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
-        if (k & 7) ws.code[(int64_t)(k >> 3) * g.C + c] = codew;
-    }
-    const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
-    if (wc && threadIdx.x == 0) atomicOr(complex_flag, wc);
-}
-
-// ---- A''. classify from the advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY): the tiled advection
-// kernel already had every new position in registers and left its classification byte
-// (jp_classify_particle) in a plane laid out like `index`; this pass turns mask + bytes into the same
-// occupancy / leave / code words k_move_classify3 produces without touching the coordinates
-// (1.6 GB instead of 10.5 GB at 256^3).  Bytes of dead slots are stale and never read.
-template <int N>
-__global__ void __launch_bounds__(256, 4) k_move_classify_hint(JpGrid g, const uint8_t *__restrict__ index, const uint8_t *__restrict__ hint,
-                                                              MovePlanWs ws, unsigned int *complex_flag) {
-    int ci[3]; int64_t c;
-    const bool ok = tile_cell<N>(g, ci, c);
-    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
-    uint64_t lv = 0, codew = 0;
-    int k = 0;
-    unsigned cplx = 0;
-    constexpr int U = 8;
-    for (int s0 = 0; s0 < g.S; s0 += U) {
-        const unsigned bits = (unsigned)(m >> s0) & ((1u << U) - 1u);
-        if (!__any_sync(0xffffffffu, bits != 0)) continue;
-        int h[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) h[u] = ((bits >> u) & 1u) ? (int)hint[c + (int64_t)(s0 + u) * g.C] : JP_CLS_STAY;
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            int code = h[u];
-            if (code == JP_CLS_STAY) continue;
-            lv |= 1ull << (s0 + u);
-            if (code > JP_CLS_CPLX) { cplx |= 1u << ((code - JP_CLS_CPLX - 1) & 3); code = JP_CODE_DELETE; }
             codew |= (uint64_t)code << (8 * (k & 7));
             if ((++k & 7) == 0) { ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
         }

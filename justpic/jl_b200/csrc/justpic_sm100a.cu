@@ -68,14 +68,13 @@ struct jp_ctx {
     double *stage; size_t stage_elems;   // staging buffer (grow-only)
     double *pr_ws; size_t pr_ws_elems;   // per-cell partial sums of the fused update_phase_ratios (lazy, grow-only)
     unsigned int *h_pinned;  // pinned host scratch for flag / totals
-    // advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY): classification bytes left by the tiled advection
-    // kernel, valid only for the coordinate / index arrays they were computed from and until the next
-    // library call that changes particles; planes rewritten by jp_halo_unpack are re-classified from the
-    // coordinates (hint_dirty)
+    // advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY): the tiled advection kernel leaves the move plan's
+    // classification words (what k_move_classify3 computes), valid only for the coordinate / index arrays
+    // they were computed from and until the next library call that changes particles or uses the occupancy
+    // words; planes rewritten by jp_halo_unpack are re-classified from the coordinates (hint_dirty)
     int hint_opt;            // option value (default 0)
-    uint8_t *hint;           // [S][C] bytes, laid out like `index` (lazy)
-    int hint_valid;
-    const void *hint_key[4]; // coords[0..2], index the bytes belong to
+    int hint_valid;          // mp.occ / occ0 / leave / code and mp_flag hold the classification of hint_key
+    const void *hint_key[4]; // coords[0..2], index the words belong to
     int hint_ndirty; int hint_dirty[8][2];   // (dim, plane) rewritten since the hand-off
     int last_classify;       // 0: coordinates (k_move_classify3), 1: hand-off bytes (diagnostics)
 };
@@ -1018,7 +1017,7 @@ extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->inj_list); cudaFree(ctx->inj_count); cudaFree(ctx->inbox); cudaFree(ctx->stats);
     cudaFree(ctx->p2g_ws);
     cudaFree(ctx->mp.code); cudaFree(ctx->mp.res); cudaFree(ctx->mp.occ0); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
-    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage); cudaFree(ctx->pr_ws); cudaFree(ctx->hint);
+    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage); cudaFree(ctx->pr_ws);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     free(ctx);
 }
@@ -1104,35 +1103,38 @@ static int build_advect_tma(const JpGrid &g, CPtr3 V, AdvTmaMaps &maps) {
     return mask;
 }
 
+static int move_plan_alloc(jp_ctx *ctx);
+struct AdvHandoff { MovePlanWs ws; unsigned int *flag; };        // flag == nullptr: no hand-off
 template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
-static cudaError_t launch_advect_tile_h(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, uint8_t *hint) {
+static cudaError_t launch_advect_tile_h(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, const AdvHandoff &ho) {
     using T = AdvTile<N>;
-    const size_t smem = AdvSmem<N, UNIFORM>::BYTES;
+    const size_t smem = AdvSmem<N, UNIFORM>::BYTES + (HINT ? (size_t)T::NW * g.S * 32 : 0);     // + the per-warp classification bytes
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdvSmem<N, UNIFORM>::BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(AdvSmem<N, UNIFORM>::BYTES + (HINT ? T::NW * JP_MAX_SLOTS * 32 : 0)));
         if (e != cudaSuccess) return e;
         configured = true;
     }
     AdvTmaMaps maps;
     const int tma_mask = build_advect_tma<N>(g, V, maps);
     const dim3 grd((g.n[0] + T::TX - 1) / T::TX, (g.n[1] + T::TY - 1) / T::TY, N == 3 ? (g.n[2] + T::TZ - 1) / T::TZ : 1);
-    k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask, hint);
+    k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask, ho.ws, ho.flag);
     return cudaSuccess;
 }
 template <int N, int SCHEME, bool UNIFORM, int AFFINE>
-static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, uint8_t *hint) {
-    return hint ? launch_advect_tile_h<N, SCHEME, UNIFORM, AFFINE, true>(g, st, co, index, V, alpha, dt, hint)
-                : launch_advect_tile_h<N, SCHEME, UNIFORM, AFFINE, false>(g, st, co, index, V, alpha, dt, nullptr);
+static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, const AdvHandoff &ho) {
+    return ho.flag ? launch_advect_tile_h<N, SCHEME, UNIFORM, AFFINE, true>(g, st, co, index, V, alpha, dt, ho)
+                   : launch_advect_tile_h<N, SCHEME, UNIFORM, AFFINE, false>(g, st, co, index, V, alpha, dt, ho);
 }
 
-// *hinted is set when the launch left classification bytes in `hint` (tiled kernel only)
+// *hinted is set when the launch left the move plan's classification words (tiled kernel only)
 template <int N, int SCHEME>
 static cudaError_t launch_advect(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt,
-                                 uint8_t *hint, bool *hinted) {
+                                 const AdvHandoff &hint, bool *hinted) {
     *hinted = false;
     if (jp_standard_staggering(g)) {
-        *hinted = hint != nullptr;
+        *hinted = hint.flag != nullptr;
         if (g.uniform && g.affine == 2) return launch_advect_tile<N, SCHEME, true, 2>(g, st, co, index, V, alpha, dt, hint);
         if (g.uniform && g.affine == 1) return launch_advect_tile<N, SCHEME, true, 1>(g, st, co, index, V, alpha, dt, hint);
         return g.uniform ? launch_advect_tile<N, SCHEME, true, 0>(g, st, co, index, V, alpha, dt, hint)
@@ -1156,10 +1158,13 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
     if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect: Only 0 < alpha < 1 is supported");
     if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect: unknown integrator");
     hint_invalidate(ctx);
-    uint8_t *hint = nullptr;
-    if (ctx->hint_opt) {
-        if (!ctx->hint) JP_CUDA(cudaMalloc(&ctx->hint, (size_t)g.C * g.S));
-        hint = ctx->hint;
+    AdvHandoff hint;
+    memset(&hint, 0, sizeof(hint));
+    if (ctx->hint_opt && jp_standard_staggering(g)) {
+        int rc = move_plan_alloc(ctx);
+        if (rc) return rc;
+        hint.ws = ctx->mp; hint.flag = ctx->mp_flag;
+        JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
     }
     bool hinted = false;
     cudaError_t le;
@@ -1248,22 +1253,24 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     int nev = 0;
     auto mark = [&]() { if (timing) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); nev++; } };
     mark();
-    JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
     static const bool cls2 = getenv("JP_MOVE_CLASSIFY2") != nullptr;       // developer A/B switch
     const JpBox whole = {{0, 0, 0}, {g.n[0], g.n[1], g.n[2]}};
-    bool use_hint = ctx->hint_valid && ctx->hint && ctx->hint_key[3] == (const void *)p->index;
+    bool use_hint = ctx->hint_valid && ctx->hint_key[3] == (const void *)p->index;
     for (int d = 0; d < N; d++) use_hint = use_hint && ctx->hint_key[d] == (const void *)p->coords[d];
     ctx->last_classify = use_hint ? 1 : 0;
     if (use_hint) {
-        k_move_classify_hint<N><<<grd, blk, 0, st>>>(g, p->index, ctx->hint, ctx->mp, ctx->mp_flag);
-        for (int i = 0; i < ctx->hint_ndirty; i++) {        // planes rewritten by jp_halo_unpack: from the coordinates
+        // the words (and the flag) were left by jp_advect; only planes rewritten by jp_halo_unpack are redone
+        for (int i = 0; i < ctx->hint_ndirty; i++) {
             JpBox bx = whole;
             bx.o[ctx->hint_dirty[i][0]] = ctx->hint_dirty[i][1];
             bx.e[ctx->hint_dirty[i][0]] = 1;
             k_move_classify3<N, true><<<tile_grid(bx.e[0], bx.e[1], N == 3 ? bx.e[2] : 1), blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag, bx);
         }
-    } else if (cls2) k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
-    else      k_move_classify3<N, false><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag, whole);
+    } else {
+        JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
+        if (cls2) k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
+        else      k_move_classify3<N, false><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag, whole);
+    }
     hint_invalidate(ctx);
     JP_CHECK_LAUNCH();
     JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->mp_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));

@@ -97,13 +97,15 @@ def test_handoff_with_halo_unpack_in_between(ndim):
     pT, ph, opT, oph = _fields(J, t)
     for it in range(3):
         J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=True); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
-        # periodic self-exchange in every dimension (what a 1-rank periodic topology does):
-        # plane 1 -> plane n-1 and plane n-2 -> plane 0, on the GPU through pack/unpack, on the host by slicing
+        # Rewrite the boundary planes through pack/unpack as update_halo! does (on the host by slicing).  The
+        # received planes hold particles of the ADJACENT plane (1 -> 0, n-2 -> n-1), i.e. particles one cell
+        # away from their storage cell as after a real exchange -- displacements > 1 cell are racy in the
+        # reference itself and only the serial oracle is deterministic for them.
         arrays = [*t.p.coords, pT, ph]
         oarrays = [*t.co, opT, oph]
         for d in range(ndim):
             nd = gr.n[d]
-            for src, dst in ((1, nd - 1), (nd - 2, 0)):
+            for src, dst in ((1, 0), (nd - 2, nd - 1)):
                 buf = torch.empty(H.plane_bytes(t.p.ncells, t.p.max_xcell, d, len(arrays)), dtype=torch.uint8, device="cuda")
                 H._cuda_pack(t.p, d, src, arrays, buf)
                 H._cuda_unpack(t.p, d, dst, arrays, buf)
