@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
                     for (int d = 0; d < N; d++) va[d] = AFFINE ? fma(gd0[d], g.aff_dv[d], g.aff_v0[d]) : xvs[d * L::VEC + r0[d]];
                     const int ci3[3] = {b0[0] + l, cy, cz};
                     int code = g.cls_fast ? jp_classify_fast<N>(g, ci3, va, pn) : -1;
-                    if (code < 0) {
+                    if (__any_sync(amask, code < 0) && code < 0) {
                         // within 1e-4 dx of a vertex, far away, NaN / Inf, or a vector grid: the exact comparisons.
                         // The staged vertex segments hold NaN outside the grid, the convention of k_move_classify3.
                         double vm[3], vb[3], vp[3];

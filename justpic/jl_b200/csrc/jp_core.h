@@ -448,23 +448,21 @@ JP_HD int jp_classify_particle(const JpGrid &g, const double *am, const double *
 #define JP_CLS_EPS 1.0e-4f
 template <int N>
 JP_HD int jp_classify_fast(const JpGrid &g, const int *ci, const double *a, const double *p) {
-    bool sure = true, stay = true, del = false;
-    int code = N == 3 ? 0 : 9;
+    bool sure = true, del = false;
+    int code = 13;                                         // direction (0, 0, 0); 2-D codes carry dz = 0
 #pragma unroll
     for (int d = 0; d < N; d++) {
         const float u = (float)((p[d] - a[d]) * g.inv_dv[d]);
-        const bool in = u > JP_CLS_EPS && u < 1.0f - JP_CLS_EPS;
-        const bool lf = u > -1.0f + JP_CLS_EPS && u < -JP_CLS_EPS;
-        const bool rt = u > 1.0f + JP_CLS_EPS && u < 2.0f - JP_CLS_EPS;
-        sure = sure && (in || lf || rt);
-        stay = stay && in;
-        const int dv = (rt ? 1 : 0) - (lf ? 1 : 0);
-        const int cd = ci[d] + dv;
-        del = del || cd < 0 || cd >= g.n[d];       // the neighbour does not exist: p is outside the domain
-        code += (dv + 1) * (d == 0 ? 1 : d == 1 ? 3 : 9);
+        const float kf = floorf(u);                        // -1 / 0 / +1: left neighbour / own cell / right neighbour
+        const float fr = u - kf;
+        const bool ok = fr > JP_CLS_EPS && fr < 1.0f - JP_CLS_EPS && fabsf(kf) <= 1.0f;   // false for NaN / Inf
+        sure = sure && ok;
+        const int dv = ok ? (int)kf : 0;
+        del = del || (unsigned)(ci[d] + dv) >= (unsigned)g.n[d];   // the neighbour does not exist: p is outside the domain
+        code += dv * (d == 0 ? 1 : d == 1 ? 3 : 9);
     }
     if (!sure) return -1;
-    return stay ? JP_CLS_STAY : del ? JP_CODE_DELETE : code;
+    return code == 13 ? JP_CLS_STAY : del ? JP_CODE_DELETE : code;
 }
 
 // isincell (src/Particles/utils.jl:7-15): strict, upper edge = fl(xv + dx)

@@ -189,17 +189,10 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
         c = ok ? jp_cell_lin<N>(g, ci) : 0;
     } else ok = tile_cell<N>(g, ci, c);
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
-    // the four vertices around the cell per dimension (NaN outside the grid: comparisons fail)
-    double am[3], a[3], b[3], bp[3];
+    double a[3] = {0.0, 0.0, 0.0};                      // lower vertices of the cell
     if (ok) {
 #pragma unroll
-        for (int d = 0; d < N; d++) {
-            const double *xv = g.xv[d];
-            const int i = ci[d];
-            a[d] = xv[i]; b[d] = xv[i + 1];
-            am[d] = i > 0 ? xv[i - 1] : NAN;
-            bp[d] = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
-        }
+        for (int d = 0; d < N; d++) a[d] = g.xv[d][ci[d]];
     }
     uint64_t lv = 0, codew = 0;
     int k = 0;
@@ -216,13 +209,38 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
         for (int u = 0; u < U; u++)
 #pragma unroll
             for (int d = 0; d < N; d++) p[u][d] = ((bits >> u) & 1u) ? co.p[d][c + (int64_t)(s0 + u) * g.C] : 0.0;
+        // range grids: single-precision pre-filter (jp_classify_fast), branch-free; the exact comparisons
+        // (isincell with upper edge fl(a + dx), domain test, destination among the four vertices) run only
+        // for batches holding a particle within 1e-4 dx of a vertex -- and always on vector grids
+        int codes[U];
+        bool unsure = false;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (!((bits >> u) & 1u)) continue;
-            // isincell (strict, upper edge fl(a + dx)), domain test, destination by comparisons with the
-            // four vertices; dx = scalar spacing on range grids, the cell's own spacing on vector grids
-            int code = g.cls_fast ? jp_classify_fast<N>(g, ci, a, p[u]) : -1;
-            if (code < 0) code = jp_classify_particle<N>(g, am, a, b, bp, p[u]);
+            const bool live = (bits >> u) & 1u;
+            const int cf = g.cls_fast ? jp_classify_fast<N>(g, ci, a, p[u]) : -1;
+            codes[u] = live ? cf : JP_CLS_STAY;
+            unsure = unsure || codes[u] < 0;
+        }
+        if (__any_sync(0xffffffffu, unsure)) {
+            if (unsure) {
+                // the four vertices around the cell per dimension (NaN outside the grid: comparisons fail)
+                double am[3], b[3], bp[3];
+#pragma unroll
+                for (int d = 0; d < N; d++) {
+                    const double *xv = g.xv[d];
+                    const int i = ci[d];
+                    b[d] = xv[i + 1];
+                    am[d] = i > 0 ? xv[i - 1] : NAN;
+                    bp[d] = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (codes[u] < 0) codes[u] = jp_classify_particle<N>(g, am, a, b, bp, p[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int code = codes[u];
             if (code == JP_CLS_STAY) continue;
             lv |= 1ull << (s0 + u);
             if (code > JP_CLS_CPLX) { cplx |= 1u << (code - JP_CLS_CPLX - 1); code = JP_CODE_DELETE; }

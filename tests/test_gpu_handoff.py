@@ -86,7 +86,12 @@ def test_handoff_is_dropped_when_particles_change(ndim):
 @pytest.mark.parametrize("ndim", [2, 3])
 def test_handoff_with_halo_unpack_in_between(ndim):
     """The multi-GPU time loop: advection! -> update_halo! -> move_particles!.  Planes rewritten by
-    jp_halo_unpack are re-classified from the coordinates, the rest comes from the bytes."""
+    jp_halo_unpack are re-classified from the coordinates, the rest comes from the words advect left.
+    The boundary planes are overwritten (through jp_halo_pack / jp_halo_unpack) with what they held BEFORE
+    the advection: every particle there is inside its cell again, while the hand-off says ~40 % of them
+    left -- a move that trusted the stale words would relocate particles that must stay.  (Planes holding
+    a neighbour's particles would do as well, but particles up to two cells from their halo cell take the
+    literal sweeps, which only the serial oracle makes deterministic.)"""
     J = jp()
     from justpic.jl_b200 import halo as H
     n = 12 if ndim == 2 else (8, 6, 7)
@@ -96,27 +101,25 @@ def test_handoff_with_halo_unpack_in_between(ndim):
     dt = cfl_dt(gr, V, 0.9)
     pT, ph, opT, oph = _fields(J, t)
     for it in range(3):
-        J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=True); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
-        # Rewrite the boundary planes through pack/unpack as update_halo! does (on the host by slicing).  The
-        # received planes hold particles of the ADJACENT plane (1 -> 0, n-2 -> n-1), i.e. particles one cell
-        # away from their storage cell as after a real exchange -- displacements > 1 cell are racy in the
-        # reference itself and only the serial oracle is deterministic for them.
         arrays = [*t.p.coords, pT, ph]
-        oarrays = [*t.co, opT, oph]
-        for d in range(ndim):
-            nd = gr.n[d]
-            for src, dst in ((1, 0), (nd - 2, nd - 1)):
-                buf = torch.empty(H.plane_bytes(t.p.ncells, t.p.max_xcell, d, len(arrays)), dtype=torch.uint8, device="cuda")
-                H._cuda_pack(t.p, d, src, arrays, buf)
-                H._cuda_unpack(t.p, d, dst, arrays, buf)
-                ax = ndim - d                      # arrays are (S, [nz,] ny, nx)
-                for a in oarrays + [t.idx]:
-                    sl_src = [slice(None)] * a.ndim; sl_dst = [slice(None)] * a.ndim
-                    sl_src[ax] = src; sl_dst[ax] = dst
-                    a[tuple(sl_dst)] = a[tuple(sl_src)]
-        t.check_state(f"step {it} after self-exchange", (pT, ph), (opT, oph))
+        oarrays = [*t.co, opT, oph, t.idx]
+        planes = [(d, pl) for d in range(ndim) for pl in (0, gr.n[d] - 1)]
+        bufs, saved = [], []
+        for d, pl in planes:
+            buf = torch.empty(H.plane_bytes(t.p.ncells, t.p.max_xcell, d, len(arrays)), dtype=torch.uint8, device="cuda")
+            H._cuda_pack(t.p, d, pl, arrays, buf)
+            bufs.append(buf)
+            sl = [slice(None)] * oarrays[0].ndim; sl[ndim - d] = pl          # arrays are (S, [nz,] ny, nx)
+            saved.append([a[tuple(sl)].copy() for a in oarrays])
+        J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=True); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+        for (d, pl), buf, sv in zip(planes, bufs, saved):
+            H._cuda_unpack(t.p, d, pl, arrays, buf)
+            sl = [slice(None)] * oarrays[0].ndim; sl[ndim - d] = pl
+            for a, v in zip(oarrays, sv):
+                a[tuple(sl)] = v
+        t.check_state(f"step {it} after restoring the boundary planes", (pT, ph), (opT, oph))
         J.move_particles(t.p, (pT, ph)); st = t.o.move(t.co, t.idx, [opT, oph])
-        assert J.last_move_classify(t.p) == "handoff"
+        assert J.last_move_classify(t.p) == "handoff" and J.last_move_path(t.p) == "plan"
         t.check_state(f"step {it} move after halo unpack", (pT, ph), (opT, oph))
         assert J.move_stats(t.p) == st
         J.inject_particles(t.p, (pT, ph), step=it); t.o.inject(t.co, t.idx, [opT, oph], t.min_xcell, t.seed, it)
