@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=64, help="cells per dimension of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--handoff", type=int, default=1, choices=[0, 1],
+                    help="1 (default): advection! also leaves move_particles!' classification words (JP_OPT_ADVECT_CLASSIFY, "
+                         "bit-identical results, see include/justpic_c.h); 0: move_particles! classifies the coordinates itself")
     return ap.parse_args()
 
 
@@ -227,7 +230,7 @@ def run_ours(args):
             if ev is not None:
                 ev[i].record()
         mark(0)
-        J.advection(p, rk2, V, dt)
+        J.advection(p, rk2, V, dt, classify=bool(args.handoff))
         mark(1)
         if world > 1:
             update_cell_halo(p, fields, topo, buffers=halo_buffers)
@@ -268,6 +271,7 @@ def run_ours(args):
     step()
     moved, dropped, deleted = J.move_stats(p)
     move_path = J.last_move_path(p)
+    move_classify = J.last_move_classify(p)
     f_mig = (moved + dropped + deleted) / max(live, 1)
     # particles processed per step ~ live count (changes by drops only); use mean of start/end
     updates = 0.5 * (live0 + live) * args.steps
@@ -379,11 +383,14 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, world), "cells_per_gpu": n ** 3, "live_particles_per_gpu": int(nlive_mean),
                        "migrant_fraction": round(f_mig, 4), "move_path": move_path, "dropped_per_step": dropped,
+                       "advect_move_handoff": bool(args.handoff), "move_classify": move_classify,
                        "p2g_mode": J.api.P2G_MODE, "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
                        "topology": list(topo.dims)},
-            # per step: advect 1; move (plan path) classify 1 + plan 27 + finalize 1 + scan 2 + set 1 + gather 1 + scatter 1;
-            # p2g 2 (cell + node); phase ratios 1; halo: 2 pack + 2 unpack per decomposed dimension
-            "gpu_launches": args.steps * (1 + 34 + 2 + 1 + (4 * sum(1 for d in topo.dims if d > 1) if world > 1 else 0)),
+            # per step: advect 1; move (plan path) classify 1 (hand-off: 0, + 1 per halo plane rewritten) + plan 27 +
+            # finalize 1 + scan 2 + set 1 + gather 1 + scatter 1; p2g 2 (cell + node); phase ratios 1;
+            # halo: 2 pack + 2 unpack per decomposed dimension
+            "gpu_launches": args.steps * (1 + 33 + (0 if args.handoff else 1) + 2 + 1
+                                          + ((4 + (2 if args.handoff else 0)) * sum(1 for d in topo.dims if d > 1) if world > 1 else 0)),
             "phase_ms": per_phase,
             # dominant single kernel: k_advect_tile (the advect phase is exactly one launch, so its
             # CUDA-event time is the kernel's duration); the move phase is longer but spans 34 launches
@@ -394,7 +401,9 @@ def run_ours(args):
                          "per_phase_frac": {k: v / peak for k, v in kernel_gbs.items()},
                          "step_GBps": step_bytes / (step_ms * 1e-3) / 1e9,
                          "step_frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                         "note": "advect is bound by shared-memory (LDS) bandwidth and fp64 issue, not HBM; see DESIGN.md 4.1"},
+                         "note": "advect is bound by instruction issue and shared-memory (LDS) latency, not HBM; with the hand-off it also "
+                                 "does move_particles!' classification (its 26 B/particle scan is no longer read) but is still "
+                                 "credited with the 51 B/particle of advection! only; see DESIGN.md 4.1-4.2"},
             "clocks": clocks,
         }
         if e2e:

@@ -1,6 +1,7 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_handoff.py -x -q 2>&1 | tail -5
-for c in 1 0; do JP_MOVE_TIMING=1 timeout 300 python tools/time_phases.py --cells 256 --steps 8 --classify $c > gpurun_out/tp_cls$c.log 2>&1; tail -7 gpurun_out/tp_cls$c.log | grep -E "advect|move|classify"; grep "jp_move" gpurun_out/tp_cls$c.log | tail -1; done
-for v in B C D; do JUSTPIC_LIB=tools/ab/var$v.so JP_MOVE_TIMING=1 timeout 300 python tools/time_phases.py --cells 256 --steps 8 > gpurun_out/tp_var$v.log 2>&1; echo "variant $v"; grep "jp_move" gpurun_out/tp_var$v.log | tail -1; grep checksum gpurun_out/tp_var$v.log; done
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+timeout 600 python tools/all_kernels.py --cells 64 2>&1 | tail -3
+timeout 1500 ncu --set full --clock-control none --profile-from-start off -f -o /tmp/all_128 python tools/all_kernels.py --cells 128 > gpurun_out/all_kernels_ncu.log 2>&1; tail -3 gpurun_out/all_kernels_ncu.log
+ncu -i /tmp/all_128.ncu-rep --page raw --csv > gpurun_out/r01f_all_kernels_128_raw.csv
+python profiles/kernel_table.py gpurun_out/r01f_all_kernels_128_raw.csv > gpurun_out/r01f_all_kernels_128_table.md; head -5 gpurun_out/r01f_all_kernels_128_table.md; wc -l gpurun_out/r01f_all_kernels_128_table.md
+ls -la /tmp/all_128.ncu-rep
