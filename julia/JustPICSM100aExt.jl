@@ -264,4 +264,41 @@ end
 # the transport between ranks stays with the host (MPI.Isend/Irecv of ONE packed
 # buffer per face, or NCCL as in justpic/jl_b200/halo.py).
 
+# Array(CA) / Array(T, CA) for a device CellArray                  src/CellArrays/conversion.jl:19-43
+# CuArray(CA) / CuArray(T, CA) for a host CellArray                ext/JustPICCUDAExt.jl:166-179
+# The reference permutes on the host side of the copy (permutedims(CA.data, (3, 2, 1)) allocates a second full
+# array); here the permutation (+ optional Float64 <-> Float32 conversion; Bool stays Bool) is one device
+# kernel into a scratch CuArray and the transfer is a single contiguous copy.
+const JP_DTYPE = Dict(Float64 => Int32(0), Float32 => Int32(1), Bool => Int32(2))
+function permute_layout!(dst::CuArray, src::CuArray, ncells::Integer, ncomp::Integer, to_host::Bool)
+    check(ccall((:jp_cellarray_permute, libjustpic), Cint,
+                (Ptr{Cvoid}, CuPtr{Cvoid}, Int32, CuPtr{Cvoid}, Int32, Int64, Int32, Int32, Ptr{Cvoid}),
+                C_NULL, pointer(src), JP_DTYPE[eltype(src)], pointer(dst), JP_DTYPE[eltype(dst)], Int64(ncells), Int32(ncomp),
+                Int32(to_host ? 0 : 1), stream()), "jp_cellarray_permute")
+    done()
+    return dst
+end
+function Base.Array(::Type{T}, CA::CellArray{<:Any, <:Any, 0, <:CuArray}) where {T <: Number}      # device -> host image
+    ni, S = size(CA), length(eltype(CA))
+    Td = eltype(eltype(CA)) === Bool ? Bool : T
+    tmp = permute_layout!(CuArray{Td}(undef, 1, S, prod(ni)), CA.data, prod(ni), S, true)
+    CA_cpu = JustPIC.CPU_CellArray(SVector{S, Td}, undef, ni)
+    copyto!(CA_cpu.data, tmp)
+    return CA_cpu
+end
+function CUDA.CuArray(::Type{T}, CA::CellArray{<:Any, <:Any, 1, <:Array}) where {T <: Number}       # host image -> device
+    ni, S = size(CA), length(eltype(CA))
+    Td = eltype(eltype(CA)) === Bool ? Bool : T
+    CA_gpu = CuCellArray(SVector{S, Td}, undef, ni...)
+    permute_layout!(CA_gpu.data, CuArray(CA.data), prod(ni), S, false)
+    return CA_gpu
+end
+
+# advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY = 5, include/justpic_c.h): advection! also leaves
+# move_particles!' classification words; results are bit-identical.  Opt-in because the library cannot see
+# writes to coords / index made between the two calls by other code: JUSTPIC_ADVECT_CLASSIFY=1.
+const ADVECT_CLASSIFY = Ref{Int32}(parse(Int32, get(ENV, "JUSTPIC_ADVECT_CLASSIFY", "0")))
+set_handoff!(p::Particles{CUDABackend}, on::Bool = ADVECT_CLASSIFY[] != 0) =
+    check(ccall((:jp_set_option, libjustpic), Cint, (Ptr{Cvoid}, Int32, Int32), context(p), Int32(5), Int32(on)), "jp_set_option")
+
 end # module
