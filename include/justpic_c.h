@@ -36,14 +36,16 @@ extern "C" {
 #endif
 
 #define JP_MAX_ARGS 16   /* particle fields carried by move/inject/clean/halo in one call */
-#define JP_MAX_SLOTS 64  /* max_xcell supported by the occupancy-word kernels */
+#define JP_MAX_SLOTS 64  /* max_xcell served by the occupancy-word kernels (the tuned path) */
+#define JP_MAX_SLOTS_WIDE 1024  /* largest max_xcell accepted: above JP_MAX_SLOTS the per-slot kernels run in 64-slot
+                                  chunks and move / inject take literal per-cell kernels (same results, not tuned) */
 #define JP_MAX_PHASES 32
 
 typedef enum {
     JP_OK = 0,
     JP_ERR_INVALID = -1,     /* bad argument (dims, null pointer, alpha out of (0,1), ...) */
     JP_ERR_CUDA = -2,        /* CUDA runtime error (message holds cudaGetErrorString) */
-    JP_ERR_UNSUPPORTED = -3  /* e.g. S > JP_MAX_SLOTS, nargs > JP_MAX_ARGS */
+    JP_ERR_UNSUPPORTED = -3  /* e.g. S > JP_MAX_SLOTS_WIDE, nargs > JP_MAX_ARGS */
 } jp_status;
 
 typedef enum { JP_EULER = 0, JP_RK2 = 1, JP_RK4 = 2 } jp_scheme;

@@ -15,7 +15,8 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["JUSTPIC_LIB"]) if os.environ.get("JUSTPIC_LIB") else HERE / "libjustpic_sm100a.so"
 
 JP_MAX_ARGS = 16
-JP_MAX_SLOTS = 64
+JP_MAX_SLOTS = 64          # occupancy-word kernels
+JP_MAX_SLOTS_WIDE = 1024   # largest max_xcell accepted (chunked launches + literal move / inject above 64)
 JP_MAX_PHASES = 32
 JP_OPT_P2G_MODE = 1
 JP_OPT_MOVE_MODE = 2

@@ -17,7 +17,8 @@
 #endif
 
 #define JP_MAX_ARGS 16
-#define JP_MAX_SLOTS 64
+#define JP_MAX_SLOTS 64          // occupancy-word kernels (one 64-bit mask per cell)
+#define JP_MAX_SLOTS_WIDE 1024   // max_xcell > 64: slot-chunked launches + literal per-cell move / inject kernels
 #define JP_MAX_PHASES 32
 
 // Grid tables.  Pointers are device pointers in the library and host pointers
@@ -601,6 +602,51 @@ JP_HD void jp_move_cell(const JpGrid &g, double *const *coords, uint8_t *index, 
     }
     occ[c] = occ_c;
     leave[c] = 0;
+}
+
+// max_xcell > JP_MAX_SLOTS ("wide" cells; the reference's own tests use max_xcell = 80 and 150,
+// test/test_2D.jl:437, test/test_3D.jl:369): one source cell of one colour sweep as the literal slot loop of
+// move_kernel! (src/Particles/move_safe.jl:72-125) on the index bytes themselves -- no occupancy words.
+// A particle re-slotted into its own cell at a higher slot, or into a cell whose sweep is still to come, is
+// met again by the loop exactly as in the reference.
+template <int N>
+JP_HD void jp_move_cell_wide(const JpGrid &g, double *const *coords, uint8_t *index, const JpArgs &args,
+                             int64_t c, const int *ci, int *stats, bool compact) {
+    const int S = g.S;
+    const int64_t C = g.C;
+    double lo[3], hi[3], corner[3], dx[3];
+    for (int d = 0; d < N; d++) {
+        lo[d] = g.xv[d][0]; hi[d] = g.xv[d][g.n[d]];
+        corner[d] = g.xv[d][ci[d]]; dx[d] = jp_d_of(g.xv[d], g.uniform, ci[d]);
+    }
+    int cursor = 0;                                   // starting_point - 1
+    for (int ip = 0; ip < S; ip++) {
+        const int64_t e = c + (int64_t)ip * C;
+        if (!index[e]) continue;
+        double p[3];
+        for (int d = 0; d < N; d++) p[d] = coords[d][e];
+        if (jp_isincell<N>(p, corner, dx)) continue;
+        bool indom = true;
+        for (int d = 0; d < N; d++) indom = indom && (lo[d] < p[d] && p[d] < hi[d]);
+        double cache[JP_MAX_ARGS];
+        for (int a = 0; a < args.n; a++) { cache[a] = args.a[a][e]; args.a[a][e] = NAN; }
+        for (int d = 0; d < N; d++) coords[d][e] = NAN;
+        index[e] = 0;
+        if (!indom) { stats[2]++; continue; }
+        int nc[3] = {0, 0, 0};
+        for (int d = 0; d < N; d++) nc[d] = jp_bisect1(p[d], g.xv[d], g.n[d] + 1, ci[d] + 1) - 1;
+        const int64_t c2 = jp_cell_lin<N>(g, nc);
+        int fs = -1;                                  // find_free_memory(starting_point, index, new_cell)
+        for (int i = cursor; i < S; i++)
+            if (!index[c2 + (int64_t)i * C]) { fs = i; break; }
+        if (fs < 0) { stats[1]++; continue; }
+        if (!compact) cursor = fs;
+        const int64_t e2 = c2 + (int64_t)fs * C;
+        index[e2] = 1;
+        for (int d = 0; d < N; d++) coords[d][e2] = p[d];
+        for (int a = 0; a < args.n; a++) args.a[a][e2] = cache[a];
+        stats[0]++;
+    }
 }
 
 // clean_particles! (src/Particles/move_safe.jl:289-320) for one live slot:

@@ -22,7 +22,7 @@ static inline bool jp_same_vec(const double *a, int na, const double *b, int nb)
 static inline const char *jp_grid_build(const jp_grid_desc *d, JpGrid &g, std::vector<double> &h, JpGridOffsets &o) {
     if (!d) return "null grid description";
     if (d->ndim != 2 && d->ndim != 3) return "ndim must be 2 or 3";
-    if (d->S < 1 || d->S > JP_MAX_SLOTS) return "need 1 <= max_xcell <= 64";
+    if (d->S < 1 || d->S > JP_MAX_SLOTS_WIDE) return "need 1 <= max_xcell <= 1024";
     const int N = d->ndim;
     for (int a = 0; a < N; a++) {
         if (d->n[a] < 2) return "need >= 2 cells per dimension";

@@ -603,6 +603,103 @@ __global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t
     }
 }
 
+// ---- max_xcell > JP_MAX_SLOTS ("wide" cells, e.g. the reference's tests with max_xcell = 80 / 150): move_particles! and
+// inject_particles!(_phase!) as literal per-cell kernels on the index bytes (thread = cell of the colour being swept).
+// Same results as the occupancy-word kernels (the GPU tests run both against the oracle); not tuned -- the word kernels
+// are the product path for every max_xcell <= 64.
+template <int N>
+__global__ void __launch_bounds__(128) k_move_sweep_wide(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, int ox, int oy, int oz, int ncx, int ncy,
+                                                         int64_t ncol, long long *stats, int compact) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncol) return;
+    int ci[3];
+    ci[0] = 3 * (int)(t % ncx) + ox;
+    ci[1] = 3 * (int)((t / ncx) % ncy) + oy;
+    ci[2] = N == 3 ? 3 * (int)(t / ((int64_t)ncx * ncy)) + oz : 0;
+    if (ci[0] >= g.n[0] || ci[1] >= g.n[1] || (N == 3 && ci[2] >= g.n[2])) return;
+    int st[3] = {0, 0, 0};
+    jp_move_cell_wide<N>(g, co.p, index, args, jp_cell_lin<N>(g, ci), ci, st, compact != 0);
+    if (st[0]) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)st[0]);
+    if (st[1]) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)st[1]);
+    if (st[2]) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)st[2]);
+}
+
+// literal _inject_particles_phase! (src/Particles/injection.jl:205-325) for one cell, serial
+template <int N>
+__device__ int jp_inject_phase_cell(const JpGrid &g, double *const *coords, uint8_t *index, const JpArgs &args, const InjPhase &ph,
+                                    int min_xcell, uint64_t seed, uint32_t step, int64_t c, const int *ci) {
+    const int S = g.S, NQ = N == 2 ? 4 : 8;
+    const int64_t C = g.C;
+    const int nx = g.n[0], ny = g.n[1], nz = N == 3 ? g.n[2] : 1;
+    double xvc[3], dq[3];
+    for (int d = 0; d < N; d++) { xvc[d] = g.xv[d][ci[d]]; dq[d] = jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; }
+    const int min_xq = (min_xcell + NQ - 1) / NQ;
+    int injected = 0;
+    for (int iq = 0; iq < NQ; iq++) {
+        double vq[3];
+        for (int d = 0; d < N; d++) vq[d] = xvc[d] + dq[d] * (double)((iq >> d) & 1);
+        int num = 0;
+        for (int i = 0; i < S; i++) {
+            const int64_t e = c + (int64_t)i * C;
+            if (!index[e]) continue;
+            double p[3];
+            for (int d = 0; d < N; d++) p[d] = coords[d][e];
+            num += jp_isincell<N>(p, vq, dq) ? 1 : 0;
+        }
+        if (num >= min_xq) continue;                      // every quadrant is examined (injection.jl:271)
+        for (int i = 0; i < S; i++) {
+            const int64_t e = c + (int64_t)i * C;
+            if (index[e]) continue;
+            num++;
+            double r[3], pn[3];
+            jp_rand3(seed, 2u, step, (uint32_t)c, (uint32_t)i, r);
+            for (int d = 0; d < N; d++) pn[d] = vq[d] + dq[d] * fma(0.95, r[d], 0.05);
+            for (int d = 0; d < N; d++) coords[d][e] = pn[d];
+            index[e] = 1;
+            injected++;
+            double dmin = INFINITY;
+            int64_t emin = -1;
+            for (int kk = (N == 3 ? ci[2] - 1 : 0); kk <= (N == 3 ? ci[2] + 1 : 0); kk++)
+                for (int jj = ci[1] - 1; jj <= ci[1] + 1; jj++)
+                    for (int ii = ci[0] - 1; ii <= ci[0] + 1; ii++) {
+                        if (ii < 0 || jj < 0 || kk < 0 || ii >= nx || jj >= ny || kk >= nz) continue;
+                        const int64_t c2 = ii + (int64_t)nx * (jj + (int64_t)ny * kk);
+                        for (int ip = 0; ip < S; ip++) {
+                            if (c2 == c && ip == i) continue;
+                            const int64_t e2 = c2 + (int64_t)ip * C;
+                            if (!index[e2]) continue;
+                            double q[3];
+                            for (int d = 0; d < N; d++) q[d] = coords[d][e2];
+                            const double dist = jp_distance<N>(q, pn);
+                            if (dist < dmin) { dmin = dist; emin = e2; }
+                        }
+                    }
+            if (emin >= 0) ph.phases[e] = ph.phases[emin];
+            double xcc[3], dcell[3];
+            for (int d = 0; d < N; d++) { dcell[d] = jp_d_of(g.xv[d], g.uniform, ci[d]); xcc[d] = (xvc[d] + dq[d] * 0.0) + dq[d]; }
+            for (int a = 0; a < args.n; a++) args.a[a][e] = jp_inject_field<N>(g, ph.fields[a], ph.fkind[a], ci, xcc, dcell, pn);
+            if (num >= min_xq) break;
+        }
+    }
+    return injected;
+}
+
+template <int N, bool PHASE>
+__global__ void __launch_bounds__(128) k_inject_wide(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
+                                                     int min_xcell, uint64_t seed, uint32_t step, long long *stats, InjPhase ph) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncol) return;
+    int ci[3];
+    ci[0] = 2 * (int)(t % ncx) + ox;
+    ci[1] = 2 * (int)((t / ncx) % ncy) + oy;
+    ci[2] = N == 3 ? 2 * (int)(t / ((int64_t)ncx * ncy)) + oz : 0;
+    if (ci[0] >= g.n[0] || ci[1] >= g.n[1] || (N == 3 && ci[2] >= g.n[2])) return;
+    const int64_t c = jp_cell_lin<N>(g, ci);
+    const int inj = PHASE ? jp_inject_phase_cell<N>(g, co.p, index, args, ph, min_xcell, seed, step, c, ci)
+                          : jp_inject_cell<N>(g, co.p, index, args, min_xcell, seed, step, c, ci);
+    if (inj) atomicAdd((unsigned long long *)&stats[3], (unsigned long long)inj);
+}
+
 // grid2particle!
 template <int N>
 __global__ void __launch_bounds__(256) k_g2p(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, double *__restrict__ Fp, const double *__restrict__ F) {
@@ -1051,6 +1148,22 @@ static int pack_args(double *const *args, int nargs, JpArgs &out, const char *wh
     const dim3 grd = tile_grid(g.n[0], g.n[1], g.n[2]);              \
     (void)co; (void)cco; (void)blk; (void)grd; (void)st;
 
+// max_xcell > JP_MAX_SLOTS: the per-slot kernels (advection, grid2particle, clean, ...) keep one 64-bit occupancy
+// mask per cell, so they are launched once per chunk of 64 slot planes -- slots [64k, 64k + 64) of a CellArray
+// are themselves a CellArray with the same cell stride, starting 64k*C elements further on.
+struct SlotChunk { JpGrid g; int64_t off; };
+static inline int jp_nchunks(const JpGrid &g) { return (g.S + JP_MAX_SLOTS - 1) / JP_MAX_SLOTS; }
+static inline SlotChunk jp_chunk(const JpGrid &g, int ch) {
+    SlotChunk k;
+    k.g = g;
+    k.g.S = g.S - JP_MAX_SLOTS * ch < JP_MAX_SLOTS ? g.S - JP_MAX_SLOTS * ch : JP_MAX_SLOTS;
+    k.off = (int64_t)JP_MAX_SLOTS * ch * g.C;
+    return k;
+}
+static inline Ptr3 jp_shift(Ptr3 a, int64_t off) { for (int d = 0; d < 3; d++) if (a.p[d]) a.p[d] += off; return a; }
+static inline CPtr3 jp_shift(CPtr3 a, int64_t off) { for (int d = 0; d < 3; d++) if (a.p[d]) a.p[d] += off; return a; }
+static inline JpArgs jp_shift(JpArgs a, int64_t off) { for (int i = 0; i < a.n; i++) a.a[i] += off; return a; }
+
 extern "C" int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxcell, uint64_t seed, void *stream) {
     PREP("jp_init_particles");
     hint_invalidate(ctx);
@@ -1160,24 +1273,29 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
     hint_invalidate(ctx);
     AdvHandoff hint;
     memset(&hint, 0, sizeof(hint));
-    if (ctx->hint_opt && jp_standard_staggering(g)) {
+    if (ctx->hint_opt && jp_standard_staggering(g) && g.S <= JP_MAX_SLOTS) {
         int rc = move_plan_alloc(ctx);
         if (rc) return rc;
         hint.ws = ctx->mp; hint.flag = ctx->mp_flag;
         JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
     }
     bool hinted = false;
-    cudaError_t le;
-    if (g.ndim == 2) {
-        if (scheme == 0) le = launch_advect<2, 0>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
-        else if (scheme == 1) le = launch_advect<2, 1>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
-        else le = launch_advect<2, 2>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
-    } else {
-        if (scheme == 0) le = launch_advect<3, 0>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
-        else if (scheme == 1) le = launch_advect<3, 1>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
-        else le = launch_advect<3, 2>(g, grd, blk, st, co, p->index, v, alpha, dt, hint, &hinted);
+    for (int ch = 0; ch < jp_nchunks(g); ch++) {          // one launch unless max_xcell > 64
+        const SlotChunk k = jp_chunk(g, ch);
+        const Ptr3 kc = jp_shift(co, k.off);
+        const uint8_t *ki = p->index + k.off;
+        cudaError_t le;
+        if (g.ndim == 2) {
+            if (scheme == 0) le = launch_advect<2, 0>(k.g, grd, blk, st, kc, ki, v, alpha, dt, hint, &hinted);
+            else if (scheme == 1) le = launch_advect<2, 1>(k.g, grd, blk, st, kc, ki, v, alpha, dt, hint, &hinted);
+            else le = launch_advect<2, 2>(k.g, grd, blk, st, kc, ki, v, alpha, dt, hint, &hinted);
+        } else {
+            if (scheme == 0) le = launch_advect<3, 0>(k.g, grd, blk, st, kc, ki, v, alpha, dt, hint, &hinted);
+            else if (scheme == 1) le = launch_advect<3, 1>(k.g, grd, blk, st, kc, ki, v, alpha, dt, hint, &hinted);
+            else le = launch_advect<3, 2>(k.g, grd, blk, st, kc, ki, v, alpha, dt, hint, &hinted);
+        }
+        if (le != cudaSuccess) return jp_fail(JP_ERR_CUDA, "jp_advect: %s", cudaGetErrorString(le));
     }
-    if (le != cudaSuccess) return jp_fail(JP_ERR_CUDA, "jp_advect: %s", cudaGetErrorString(le));
     JP_CHECK_LAUNCH();
     if (hinted) {
         ctx->hint_valid = 1;
@@ -1208,12 +1326,17 @@ extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t sche
     }
     if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: Only 0 < alpha < 1 is supported");
     if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: unknown integrator");
-    if (g.ndim == 2) {
-        if (interp == JP_INTERP_LINP) launch_advect_hi<2, 1>(g, grd, blk, st, co, p->index, v, scheme, alpha, dt);
-        else                          launch_advect_hi<2, 2>(g, grd, blk, st, co, p->index, v, scheme, alpha, dt);
-    } else {
-        if (interp == JP_INTERP_LINP) launch_advect_hi<3, 1>(g, grd, blk, st, co, p->index, v, scheme, alpha, dt);
-        else                          launch_advect_hi<3, 2>(g, grd, blk, st, co, p->index, v, scheme, alpha, dt);
+    for (int ch = 0; ch < jp_nchunks(g); ch++) {
+        const SlotChunk k = jp_chunk(g, ch);
+        const Ptr3 kc = jp_shift(co, k.off);
+        const uint8_t *ki = p->index + k.off;
+        if (g.ndim == 2) {
+            if (interp == JP_INTERP_LINP) launch_advect_hi<2, 1>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
+            else                          launch_advect_hi<2, 2>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
+        } else {
+            if (interp == JP_INTERP_LINP) launch_advect_hi<3, 1>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
+            else                          launch_advect_hi<3, 2>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
+        }
     }
     JP_CHECK_LAUNCH();
     return JP_OK;
@@ -1338,6 +1461,21 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     int rc = pack_args(args, nargs, a, "jp_move");
     if (rc) return rc;
     JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
+    if (g.S > JP_MAX_SLOTS) {                                // wide cells: literal per-cell sweeps on the index bytes
+        ctx->last_move_path = 1;
+        hint_invalidate(ctx);
+        const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = g.ndim == 3 ? (g.n[2] + 2) / 3 : 1;
+        const int64_t ncol = (int64_t)ncx * ncy * ncz;
+        const unsigned nblk = (unsigned)((ncol + 127) / 128);
+        for (int ox = 0; ox < 3; ox++)
+            for (int oy = 0; oy < 3; oy++)
+                for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {
+                    if (g.ndim == 2) k_move_sweep_wide<2><<<nblk, 128, 0, st>>>(g, co, p->index, a, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
+                    else             k_move_sweep_wide<3><<<nblk, 128, 0, st>>>(g, co, p->index, a, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
+                }
+        JP_CHECK_LAUNCH();
+        return JP_OK;
+    }
     if (ctx->move_mode == JP_MOVE_AUTO) {
         rc = g.ndim == 2 ? move_planned<2>(ctx, p, a, st) : move_planned<3>(ctx, p, a, st);
         if (rc <= 0) { ctx->last_move_path = 0; return rc; }
@@ -1373,6 +1511,21 @@ extern "C" int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream) {
     return JP_OK;
 }
 
+// wide cells (max_xcell > 64): 2^N colour sweeps of the literal per-cell routine, colour order of the reference
+template <bool PHASE>
+static void launch_inject_wide(const JpGrid &g, cudaStream_t st, Ptr3 co, uint8_t *index, const JpArgs &a, int min_xcell, uint64_t seed, uint32_t step,
+                               long long *stats, const InjPhase &ph) {
+    const int ncx = (g.n[0] + 1) / 2, ncy = (g.n[1] + 1) / 2, ncz = g.ndim == 3 ? (g.n[2] + 1) / 2 : 1;
+    const int64_t ncol = (int64_t)ncx * ncy * ncz;
+    const unsigned nblk = (unsigned)((ncol + 127) / 128);
+    for (int ox = 0; ox < 2; ox++)
+        for (int oy = 0; oy < 2; oy++)
+            for (int oz = 0; oz < (g.ndim == 3 ? 2 : 1); oz++) {
+                if (g.ndim == 2) k_inject_wide<2, PHASE><<<nblk, 128, 0, st>>>(g, co, index, a, ox, oy, oz, ncx, ncy, ncol, min_xcell, seed, step, stats, ph);
+                else             k_inject_wide<3, PHASE><<<nblk, 128, 0, st>>>(g, co, index, a, ox, oy, oz, ncx, ncy, ncol, min_xcell, seed, step, stats, ph);
+            }
+}
+
 extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream) {
     PREP("jp_inject");
     hint_invalidate(ctx);
@@ -1384,6 +1537,11 @@ extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args
     const int min_xq = (min_xcell + NQ - 1) / NQ;
     JP_CUDA(cudaMemsetAsync(ctx->stats + 3, 0, sizeof(long long), st));
     if ((int64_t)g.C >= (1ll << 31)) return jp_fail(JP_ERR_UNSUPPORTED, "jp_inject: more than 2^31 cells");
+    if (g.S > JP_MAX_SLOTS) {
+        launch_inject_wide<false>(g, st, co, p->index, a, min_xcell, seed, step, ctx->stats, InjPhase());
+        JP_CHECK_LAUNCH();
+        return JP_OK;
+    }
     JP_CUDA(cudaMemsetAsync(ctx->inj_count, 0, 8 * sizeof(unsigned int), st));
     if (g.ndim == 2) k_inject_classify<2, false><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
     else             k_inject_classify<3, false><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
@@ -1419,6 +1577,11 @@ extern "C" int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phase
     const int NQ = g.ndim == 2 ? 4 : 8;
     const int min_xq = (min_xcell + NQ - 1) / NQ;
     JP_CUDA(cudaMemsetAsync(ctx->stats + 3, 0, sizeof(long long), st));
+    if (g.S > JP_MAX_SLOTS) {
+        launch_inject_wide<true>(g, st, co, p->index, a, min_xcell, seed, step, ctx->stats, ph);
+        JP_CHECK_LAUNCH();
+        return JP_OK;
+    }
     JP_CUDA(cudaMemsetAsync(ctx->inj_count, 0, 8 * sizeof(unsigned int), st));
     if (g.ndim == 2) k_inject_classify<2, true><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
     else             k_inject_classify<3, true><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
@@ -1448,8 +1611,11 @@ extern "C" int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args,
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_clean");
     if (rc) return rc;
-    if (g.ndim == 2) k_clean<2><<<grd, blk, 0, st>>>(g, co, p->index, a);
-    else             k_clean<3><<<grd, blk, 0, st>>>(g, co, p->index, a);
+    for (int ch = 0; ch < jp_nchunks(g); ch++) {
+        const SlotChunk k = jp_chunk(g, ch);
+        if (g.ndim == 2) k_clean<2><<<grd, blk, 0, st>>>(k.g, jp_shift(co, k.off), p->index + k.off, jp_shift(a, k.off));
+        else             k_clean<3><<<grd, blk, 0, st>>>(k.g, jp_shift(co, k.off), p->index + k.off, jp_shift(a, k.off));
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1457,8 +1623,11 @@ extern "C" int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args,
 extern "C" int jp_grid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *F, void *stream) {
     PREP("jp_grid2particle");
     if (!Fp || !F) return jp_fail(JP_ERR_INVALID, "jp_grid2particle: null field");
-    if (g.ndim == 2) k_g2p<2><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F);
-    else             k_g2p<3><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F);
+    for (int ch = 0; ch < jp_nchunks(g); ch++) {
+        const SlotChunk k = jp_chunk(g, ch);
+        if (g.ndim == 2) k_g2p<2><<<grd, blk, 0, st>>>(k.g, jp_shift(cco, k.off), p->index + k.off, Fp + k.off, F);
+        else             k_g2p<3><<<grd, blk, 0, st>>>(k.g, jp_shift(cco, k.off), p->index + k.off, Fp + k.off, F);
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1466,8 +1635,11 @@ extern "C" int jp_grid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, 
 extern "C" int jp_grid2particle_flip(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *F, const double *F0, double alpha, void *stream) {
     PREP("jp_grid2particle_flip");
     if (!Fp || !F || !F0) return jp_fail(JP_ERR_INVALID, "jp_grid2particle_flip: null field");
-    if (g.ndim == 2) k_g2p_flip<2><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F, F0, alpha);
-    else             k_g2p_flip<3><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, F, F0, alpha);
+    for (int ch = 0; ch < jp_nchunks(g); ch++) {
+        const SlotChunk k = jp_chunk(g, ch);
+        if (g.ndim == 2) k_g2p_flip<2><<<grd, blk, 0, st>>>(k.g, jp_shift(cco, k.off), p->index + k.off, Fp + k.off, F, F0, alpha);
+        else             k_g2p_flip<3><<<grd, blk, 0, st>>>(k.g, jp_shift(cco, k.off), p->index + k.off, Fp + k.off, F, F0, alpha);
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1540,7 +1712,7 @@ extern "C" int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, c
     PREP("jp_particle2grid");
     if (!Fp || !F) return jp_fail(JP_ERR_INVALID, "jp_particle2grid: null field");
     const dim3 ng = tile_grid(g.n[0] + 1, g.n[1] + 1, g.ndim == 3 ? g.n[2] + 1 : 1);
-    if (ctx->p2g_mode == JP_P2G_EXACT) {
+    if (ctx->p2g_mode == JP_P2G_EXACT || g.S > JP_MAX_SLOTS) {     // the two-pass cell kernel keeps a 64-bit mask per cell
         if (g.ndim == 2) k_p2g<2><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
         else             k_p2g<3><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
     } else {

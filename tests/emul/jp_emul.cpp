@@ -78,6 +78,20 @@ extern "C" int jpe_advect(Emul *e, double *const *co, const uint8_t *index, int 
 template <int N>
 static void move_t(Emul *e, double *const *co, uint8_t *index, const JpArgs &args, int64_t *stats) {
     const JpGrid &g = e->g;
+    if (g.S > JP_MAX_SLOTS) {                // wide cells: k_move_sweep_wide, literal slot loop on the index bytes
+        int st[3] = {0, 0, 0};
+        for (int ox = 0; ox < 3; ox++)
+            for (int oy = 0; oy < 3; oy++)
+                for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
+                    for (int k = oz; k < g.n[2]; k += 3)
+                        for (int j = oy; j < g.n[1]; j += 3)
+                            for (int i = ox; i < g.n[0]; i += 3) {
+                                int ci[3] = {i, j, k};
+                                jp_move_cell_wide<N>(g, co, index, args, jp_cell_lin<N>(g, ci), ci, st, false);
+                            }
+        stats[0] = st[0]; stats[1] = st[1]; stats[2] = st[2];
+        return;
+    }
     // pass A: classify (k_move_classify)
     for (int64_t c = 0; c < g.C; c++) {
         int ci[3];
@@ -117,7 +131,8 @@ template <int N>
 static int64_t inject_t(Emul *e, double *const *co, uint8_t *index, const JpArgs &args, int min_xcell, uint64_t seed, uint32_t step) {
     const JpGrid &g = e->g;
     const int NQ = N == 2 ? 4 : 8, min_xq = (min_xcell + NQ - 1) / NQ;
-    for (int64_t c = 0; c < g.C; c++) {      // k_inject_classify
+    for (int64_t c = 0; c < g.C; c++) {      // k_inject_classify (wide cells, S > 64: k_inject_wide visits every cell)
+        if (g.S > JP_MAX_SLOTS) { e->flag[c] = 1; continue; }
         int ci[3];
         jp_cell_ijk<N>(g, c, ci);
         double vq[3], dq[3];

@@ -29,6 +29,8 @@ CASES = [
     (2, 17, True, 0.0, 12, 12, 6, 0.95),     # tight storage: drops
     (3, (7, 5, 6), True, 0.0, 16, 8, 8, 2.5),  # > 1-cell moves: literal fallback everywhere
     (2, (5, 33), True, 0.0, 64, 40, 20, 0.6),  # S = 64 (full occupancy word)
+    (2, (7, 9), True, 0.0, 80, 60, 50, 0.7),   # max_xcell > 64 (test/test_2D.jl:437): literal wide move / inject
+    (3, (4, 5, 3), False, 0.3, 150, 125, 100, 0.6),  # test/test_3D.jl:369,424
 ]
 
 

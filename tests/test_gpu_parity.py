@@ -418,8 +418,8 @@ def test_unsupported_and_invalid_arguments():
     """Error behaviour across the boundary: status codes -> exceptions, nothing crashes."""
     J = jp()
     gr = make_grids(6, 2, True)
-    with pytest.raises(J._cabi.JustPICError):            # max_xcell > 64: JP_ERR_UNSUPPORTED
-        J.init_particles(J.CUDABackend, 8, 80, 4, *gr.grid_vel)
+    with pytest.raises(J._cabi.JustPICError):            # max_xcell > JP_MAX_SLOTS_WIDE (1024): JP_ERR_UNSUPPORTED
+        J.init_particles(J.CUDABackend, 8, 1025, 4, *gr.grid_vel)
     t = Twin(2, 6, True)
     many = J.init_cell_arrays(t.p, 17)
     with pytest.raises(ValueError):                      # more than JP_MAX_ARGS fields in one call
@@ -431,3 +431,87 @@ def test_unsupported_and_invalid_arguments():
     pr = J.PhaseRatios(J.CUDABackend, 40, gr.n)          # more than JP_MAX_PHASES
     with pytest.raises(J._cabi.JustPICError):
         J.phase_ratios_center(pr, t.p, many[0])
+
+
+WIDE = [
+    # ndim, n, uniform, nxcell, max_xcell, min_xcell  -- the reference's own sizes above 64 slots
+    (2, (11, 9), True, 60, 80, 50),        # test/test_2D.jl:437
+    (3, (5, 4, 6), False, 125, 150, 100),  # test/test_3D.jl:369,424 (refined grid variant)
+    (3, (6, 5, 4), True, 40, 70, 32),      # second chunk only 6 slots wide
+]
+
+
+@pytest.mark.parametrize("w", WIDE, ids=lambda w: f"{w[0]}D-{w[1]}-{'range' if w[2] else 'vector'}-S{w[4]}")
+def test_wide_cells_max_xcell_above_64(w):
+    """max_xcell > 64 (JP_MAX_SLOTS): the per-slot kernels run in 64-slot chunks, move_particles! /
+    inject_particles!(_phase!) take the literal per-cell kernels, particle2grid! the exact kernel.  Every
+    entry point of a coupled run must still match the oracle bit for bit."""
+    J = jp()
+    ndim, n, uniform, nxcell, max_xcell, min_xcell = w
+    t = Twin(ndim, n, uniform=uniform, nxcell=nxcell, max_xcell=max_xcell, min_xcell=min_xcell)
+    assert t.p.max_xcell == max_xcell and t.idx.shape[0] == max_xcell
+    t.check_state("init_particles")
+    gr = t.gr
+    V = stream_velocity(gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(gr, V, 0.8)
+    T = vertex_field_linear(gr) + 0.25 * np.sin(7 * vertex_field_linear(gr, 0)); Tc = centre_field_linear(gr) ** 2
+    Td, Tcd = dev(T), dev(Tc)
+    pT, ph, pC = J.init_cell_arrays(t.p, 3)
+    opT = np.zeros_like(t.co[0]); opC = np.zeros_like(t.co[0])
+    J.grid2particle(pT, Td, t.p); t.o.grid2particle(t.co, t.idx, opT, T)
+    assert_same(pT, opT, "grid2particle")
+    J.centroid2particle(pC, Tcd, t.p); t.o.centroid2particle(t.co, opC, Tc)
+    assert_same(pC, opC, "centroid2particle")
+    oph = np.where(t.idx > 0, 1.0 + (t.co[0] < t.co[-1]), 0.0)
+    ph.copy_(dev(oph))
+    K = 2
+    pr = J.PhaseRatios(J.CUDABackend, K, gr.n)
+    methods = [(J.RungeKutta2(), 1, 0.5), (J.RungeKutta4(), 2, 0.0), (J.RungeKutta2(2 / 3), 1, 2 / 3), (J.Euler(), 0, 0.0)]
+    moved = injected = 0
+    for it in range(6):
+        m = methods[it % 4]
+        if it == 4:
+            J.advection_LinP(t.p, m[0], Vd, dt); assert t.o.advect_interp(t.co, t.idx, m[1], m[2], V, dt, 1) == 0
+        elif it == 5:
+            J.advection_MQS(t.p, m[0], Vd, dt); assert t.o.advect_interp(t.co, t.idx, m[1], m[2], V, dt, 2) == 0
+        else:
+            J.advection(t.p, m[0], Vd, dt); t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
+        t.check_state(f"step {it} advection")
+        J.move_particles(t.p, (pT, ph, pC)); st = t.o.move(t.co, t.idx, [opT, oph, opC])
+        t.check_state(f"step {it} move_particles", (pT, ph, pC), (opT, oph, opC))
+        assert J.move_stats(t.p) == st and J.last_move_path(t.p) == "direct"
+        moved += st[0]
+        if it % 2 == 0:
+            J.inject_particles(t.p, (pT, ph, pC), step=it); inj = t.o.inject(t.co, t.idx, [opT, oph, opC], min_xcell, t.seed, it)
+        else:
+            J.inject_particles_phase(t.p, ph, (pT, pC), (Td, Tcd), step=it)
+            inj = t.o.inject_phase(t.co, t.idx, oph, [opT, opC], [T, Tc], [0, 1], min_xcell, t.seed, it)
+        t.check_state(f"step {it} inject", (pT, ph, pC), (opT, oph, opC))
+        assert J.inject_stats(t.p) == inj
+        injected += inj
+        J.phase_ratios_center(pr, t.p, ph)
+        ratios = np.zeros(t.o.cell_shape(K)); t.o.phase_ratios_center(t.co, ratios, oph, K)
+        assert_same(pr.center, ratios, f"step {it} phase_ratios_center")
+    assert moved > 0 and injected > 0
+    Tg = torch.empty_like(Td); oT = np.empty_like(T)
+    t.o.particle2grid(t.co, t.idx, oT, opT)
+    for mode in ("exact", "twopass", "twopass_fastw"):
+        J.particle2grid(Tg, pT, t.p, mode=mode)
+        assert_same(Tg, oT, f"particle2grid[{mode}] (wide cells use the exact kernel)")
+    Tc2 = torch.empty_like(Tcd); oTc2 = np.empty_like(Tc)
+    J.particle2centroid(Tc2, pT, t.p); t.o.particle2centroid(t.co, oTc2, opT)
+    assert_same(Tc2, oTc2, "particle2centroid")
+    T0 = T * 0.5
+    J.grid2particle_flip(pT, None, Td, dev(T0), t.p, alpha=0.25); t.o.grid2particle_flip(t.co, t.idx, opT, T, T0, 0.25)
+    assert_same(pT, opT, "grid2particle_flip")
+    # push a few particles out of their cells, then clean_particles!
+    sh = t.co[0].copy(); live = t.idx > 0
+    sh[live] += np.where(np.arange(int(live.sum())) % 7 == 0, 1.5 * float(gr.xvi[0][1] - gr.xvi[0][0]), 0.0)
+    t.co[0][:] = sh; t.p.coords[0].copy_(dev(sh))
+    J.clean_particles(t.p, None, (pT, ph, pC)); t.o.clean(t.co, t.idx, [opT, oph, opC])
+    t.check_state("clean_particles", (pT, ph, pC), (opT, oph, opC))
+    # checkpoint layout round trip
+    h = J.Array(t.p); p2 = J.CuArray(h)
+    for d in range(ndim):
+        assert torch.equal(torch.nan_to_num(p2.coords[d], nan=-1.0), torch.nan_to_num(t.p.coords[d], nan=-1.0))
+    assert torch.equal(p2.index, t.p.index)

@@ -59,9 +59,11 @@ J.grid2particle_flip(pT, None, T, T0, p, alpha=0.25)
 J.centroid2particle(strain, Tc, p)
 J.particle2centroid(Tc, pT, p)
 sa = J.SubgridDiffusionCellArrays(p)
-J.subgrid_diffusion(pT, T, (T - T0).contiguous(), sa, p, dt)
+dTg = torch.zeros([n + 1 for n in T.shape], dtype=torch.float64, device="cuda")       # read at I + 1: one more node per dimension
+dTg[tuple(slice(1, None) for _ in T.shape)] = T - T0
+J.subgrid_diffusion(pT, T, dTg, sa, p, dt)
 sac = J.SubgridDiffusionCellArrays(p, loc="center")
-J.subgrid_diffusion_centroid(pT, Tc, torch.zeros_like(Tc), sac, p, dt)
+J.subgrid_diffusion_centroid(pT, Tc, torch.zeros([n + 1 for n in Tc.shape], dtype=torch.float64, device="cuda"), sac, p, dt)
 # --- phase ratios on every node family
 J.update_phase_ratios(pr, p, ph, mode="literal")
 J.update_phase_ratios(pr, p, ph, mode="fused")
