@@ -159,6 +159,14 @@ int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phases, double *
                     const int32_t *field_kind, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream);
 int jp_inject_stats(jp_ctx *ctx, int64_t *out, void *stream);
 
+/* force_injection!(particles, p_new, fields, values) (src/Particles/forced_injection.jl:16-79; reference tests
+ * test/test_2D.jl:301-384, test/test_3D.jl:279-333).  pnew[d]: [C*S] coordinate component d of the caller's candidate
+ * points, element (cell c, entry k) at c + k*C (the reference's p_new[I..., k]).  A cell injects iff its FIRST entry is
+ * not NaN in component 0 ("NaN marks empty input", :9, :36); then every free slot ip of the cell takes entry ip (the
+ * reference's counter c advances with the slot loop, :38-42), its mask is set and fields[j][slot] = values[j]. */
+int jp_force_injection(jp_ctx *ctx, const jp_particles *p, const double *const *pnew, double *const *fields, const double *values,
+                       int32_t nfields, void *stream);
+
 /* clean_particles!(particles, grid, args) (src/Particles/move_safe.jl:289-320). */
 int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream);
 

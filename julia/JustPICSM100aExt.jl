@@ -113,6 +113,22 @@ function JustPIC.inject_particles!(p::Particles{CUDABackend}, args, grid::NTuple
     done()
 end
 
+# force_injection!(particles, p_new, fields, values)     src/Particles/forced_injection.jl:16-29
+# p_new is an array of user points (anything with getindex / isnan): repacked once into N CellArray-shaped
+# coordinate arrays, NaN in component 1 marking an inactive point, which is what the library tests per cell.
+function JustPIC.force_injection!(p::Particles{CUDABackend}, p_new, fields::NTuple{NF, Any}, values::NTuple{NF, Any}) where {NF}
+    N = length(p.coords)
+    host = Array(p_new)
+    comps = ntuple(d -> CuArray(Float64[(d == 1 && isnan(q)) ? NaN : Float64(q[d]) for q in host]), N)
+    pn = CuPtr{Float64}[pointer(c) for c in comps]
+    f = argptrs(fields)
+    v = Float64[Float64(x) for x in values]
+    GC.@preserve comps check(ccall((:jp_force_injection, libjustpic), Cint,
+                (Ptr{Cvoid}, Ref{JpParticles}, Ptr{CuPtr{Float64}}, Ptr{CuPtr{Float64}}, Ptr{Float64}, Int32, Ptr{Cvoid}),
+                context(p), jp(p), pn, f, v, Int32(length(f)), stream()), "force_injection!")
+    done()
+end
+
 # clean_particles!(particles, grid, args)               src/Particles/move_safe.jl:289-295
 function JustPIC.clean_particles!(p::Particles{CUDABackend}, grid, args)
     a = argptrs(args)

@@ -74,6 +74,8 @@ SYMBOLS = {
                                   C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, C.c_void_p]),
     "jp_inject_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "jp_clean": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "jp_force_injection": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_double), C.c_int32, C.c_void_p]),
     "jp_grid2particle": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p]),
     "jp_grid2particle_flip": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_void_p]),

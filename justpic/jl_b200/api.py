@@ -39,7 +39,7 @@ __all__ = [
     "Euler", "RungeKutta2", "RungeKutta4",
     "Particles", "PhaseRatios",
     "init_particles", "init_cell_arrays", "cell_array",
-    "advection", "advection_LinP", "advection_MQS", "move_particles", "inject_particles", "inject_particles_phase", "clean_particles",
+    "advection", "advection_LinP", "advection_MQS", "move_particles", "inject_particles", "inject_particles_phase", "force_injection", "clean_particles",
     "grid2particle", "grid2particle_flip", "centroid2particle", "particle2grid", "particle2centroid",
     "SubgridDiffusionCellArrays", "subgrid_diffusion", "subgrid_diffusion_centroid",
     "phase_ratios_center", "phase_ratios_vertex", "phase_ratios_face", "phase_ratios_midpoint",
@@ -494,6 +494,28 @@ def inject_stats(particles: Particles) -> int:
     with torch.cuda.device(particles.device):
         _cabi.check(_cabi.load().jp_inject_stats(C.c_void_p(particles._ctx), C.byref(out), _stream()), "inject_stats")
     return int(out.value)
+
+
+def force_injection(particles: Particles, p_new, fields=(), values=()) -> None:
+    """``force_injection!(particles, p_new, fields, values)`` (src/Particles/forced_injection.jl:16-29): candidate points are
+    written straight into free slots, no nearest-neighbour search.  ``p_new``: one tensor per coordinate, CellArray-shaped like
+    ``particles.coords`` (entry k of cell I at ``[k, ..., I]``); a cell whose FIRST entry is NaN injects nothing ("NaN marks
+    empty input slots"), otherwise every free slot ip takes entry ip.  ``fields[j]`` of the filled slots is set to ``values[j]``."""
+    p = particles
+    fields = _args(fields, p)
+    values = tuple(float(v) for v in values)
+    if len(values) != len(fields):
+        raise ValueError("force_injection: one value per field")
+    p_new = tuple(p_new)
+    if len(p_new) != p.ndim:
+        raise ValueError(f"force_injection: p_new needs {p.ndim} coordinate arrays")
+    p_new = tuple(_pfield(t, p, f"p_new[{d}]") for d, t in enumerate(p_new))
+    vals = (C.c_double * max(len(values), 1))(*values)
+    pc = p._c()
+    with torch.cuda.device(p.device):
+        _cabi.check(_cabi.load().jp_force_injection(C.c_void_p(p._ctx), C.byref(pc), _ptr_array(p_new), _ptr_array(fields), vals,
+                                                    len(fields), _stream()), "force_injection")
+        _done()
 
 
 def clean_particles(particles: Particles, grid=None, args=()) -> None:

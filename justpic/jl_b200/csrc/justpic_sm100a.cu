@@ -335,6 +335,23 @@ __global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *
     }
 }
 
+// force_injection! (src/Particles/forced_injection.jl:32-79): thread = cell; entry ip of p_new goes to slot ip if it is free
+struct ForceVals { double v[JP_MAX_ARGS]; };
+template <int N>
+__global__ void __launch_bounds__(256) k_force_injection(JpGrid g, Ptr3 co, uint8_t *index, CPtr3 pnew, JpArgs fields, ForceVals vals) {
+    int ci[3]; int64_t c;
+    if (!tile_cell<N>(g, ci, c)) return;
+    if (isnan(pnew.p[0][c])) return;                       // !isnan(p_new[I..., begin])
+    for (int s = 0; s < g.S; s++) {
+        const int64_t e = c + (int64_t)s * g.C;
+        if (index[e]) continue;                            // doskip(index, ip, I...) || continue
+#pragma unroll
+        for (int d = 0; d < N; d++) co.p[d][e] = pnew.p[d][e];
+        index[e] = 1;
+        for (int a = 0; a < fields.n; a++) fields.a[a][e] = vals.v[a];
+    }
+}
+
 template <int N>
 __global__ void __launch_bounds__(256) k_clean(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args) {
     int ci[3]; int64_t c;
@@ -605,7 +622,7 @@ __global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t
 
 // ---- max_xcell > JP_MAX_SLOTS ("wide" cells, e.g. the reference's tests with max_xcell = 80 / 150): move_particles! and
 // inject_particles!(_phase!) as literal per-cell kernels on the index bytes (thread = cell of the colour being swept).
-// Same results as the occupancy-word kernels (the GPU tests run both against the oracle); not tuned -- the word kernels
+// Same results as the occupancy-word kernels (the GPU parity tests cover both); not tuned -- the word kernels
 // are the product path for every max_xcell <= 64.
 template <int N>
 __global__ void __launch_bounds__(128) k_move_sweep_wide(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, int ox, int oy, int oz, int ncx, int ncy,
@@ -1168,7 +1185,7 @@ extern "C" int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxc
     PREP("jp_init_particles");
     hint_invalidate(ctx);
     const int NQ = g.ndim == 2 ? 4 : 8;
-    if (nxcell < 1) return jp_fail(JP_ERR_INVALID, "jp_init_particles: nxcell < 1");
+    if (nxcell < 0) return jp_fail(JP_ERR_INVALID, "jp_init_particles: nxcell < 0");     // 0: empty container (test/test_2D.jl:302)
     const int npq = (nxcell + NQ - 1) / NQ;
     if (npq * NQ > g.S) return jp_fail(JP_ERR_INVALID, "jp_init_particles: nxcell (rounded up to a multiple of 2^N) exceeds max_xcell");
     if (g.ndim == 2) k_init<2><<<grd, blk, 0, st>>>(g, co, p->index, npq, seed);
@@ -1602,6 +1619,28 @@ extern "C" int jp_inject_stats(jp_ctx *ctx, int64_t *out, void *stream) {
     JP_CUDA(cudaMemcpyAsync(&h, ctx->stats + 3, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     JP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     *out = h;
+    return JP_OK;
+}
+
+extern "C" int jp_force_injection(jp_ctx *ctx, const jp_particles *p, const double *const *pnew, double *const *fields, const double *values,
+                                  int32_t nfields, void *stream) {
+    PREP("jp_force_injection");
+    hint_invalidate(ctx);
+    JpArgs f;
+    int rc = pack_args(fields, nfields, f, "jp_force_injection");
+    if (rc) return rc;
+    if (!pnew) return jp_fail(JP_ERR_INVALID, "jp_force_injection: null p_new");
+    CPtr3 pn = {{nullptr, nullptr, nullptr}};
+    for (int d = 0; d < g.ndim; d++) {
+        if (!pnew[d]) return jp_fail(JP_ERR_INVALID, "jp_force_injection: null p_new component");
+        pn.p[d] = pnew[d];
+    }
+    if (nfields > 0 && !values) return jp_fail(JP_ERR_INVALID, "jp_force_injection: null values");
+    ForceVals fv;
+    for (int a = 0; a < JP_MAX_ARGS; a++) fv.v[a] = a < nfields ? values[a] : 0.0;
+    if (g.ndim == 2) k_force_injection<2><<<grd, blk, 0, st>>>(g, co, p->index, pn, f, fv);
+    else             k_force_injection<3><<<grd, blk, 0, st>>>(g, co, p->index, pn, f, fv);
+    JP_CHECK_LAUNCH();
     return JP_OK;
 }
 

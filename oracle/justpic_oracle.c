@@ -479,6 +479,30 @@ int jpo_move(const jpo_grid *g, double *const *coords, uint8_t *index, double *c
     return 0;
 }
 
+/* ---- force_injection! (src/Particles/forced_injection.jl:16-79) -------------
+ * pnew[d][c + k*C] = component d of p_new[I..., k]; a cell injects iff its first entry is not NaN (:36, :60; the
+ * reference tests overload isnan for their point type, test/test_2D.jl:81); the helper counter `c` of :37-40 advances
+ * with the slot loop, so free slot ip always takes entry ip. */
+int jpo_force_injection(const jpo_grid *g, double *const *coords, uint8_t *index, const double *const *pnew, double *const *fields,
+                        const double *values, int nfields) {
+    const int N = g->ndim;
+    const int64_t C = NCELLS(g);
+    for (int64_t cell = 0; cell < C; cell++) {
+        if (isnan(pnew[0][cell])) continue;
+        int c = 0;
+        for (int ip = 0; ip < g->S; ip++) {
+            c += 1;
+            if (c > g->S) continue;
+            const int64_t e = cell + (int64_t)ip * C;
+            if (index[e]) continue;
+            for (int d = 0; d < N; d++) coords[d][e] = pnew[d][cell + (int64_t)(c - 1) * C];
+            index[e] = 1;
+            for (int a = 0; a < nfields; a++) fields[a][e] = values[a];
+        }
+    }
+    return 0;
+}
+
 /* ---- clean_particles! (src/Particles/move_safe.jl:289-320) ---------------- */
 int jpo_clean(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs) {
     const int N = g->ndim;

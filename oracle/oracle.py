@@ -135,6 +135,11 @@ class Oracle:
     def clean(self, coords, index, args):
         return lib().jpo_clean(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args))
 
+    def force_injection(self, coords, index, pnew, fields, values):
+        vals = (C.c_double * max(len(values), 1))(*[float(v) for v in values])
+        return lib().jpo_force_injection(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(pnew), _pp(fields), vals,
+                                         len(fields))
+
     def inject(self, coords, index, args, min_xcell, seed, step):
         n = C.c_int64()
         rc = lib().jpo_inject(C.byref(self.g), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args),
