@@ -320,7 +320,9 @@ struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 // ---- D. gather (source-centric, slot-synchronous => every source sector is read once, in
 // streaming order): payload of each placed leaver -> staging[off[dest] + rank of its slot].
 // Slots are handled in batches of U with all loads of a batch issued before the stores.
+#ifndef JP_MV_U
 #define JP_MV_U 4
+#endif
 #define JP_MV_A 4      // arrays handled per register batch (coords + fields); more arrays loop again
 template <int N>
 __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* unused */) {
