@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--handoff", type=int, default=1, choices=[0, 1],
                     help="1 (default): advection! also leaves move_particles!' classification words (JP_OPT_ADVECT_CLASSIFY, "
                          "bit-identical results, see include/justpic_c.h); 0: move_particles! classifies the coordinates itself")
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
+                    help="N > 1 only. 1 (default): advection! runs as shell + interior launches and update_cell_halo! travels on a side "
+                         "stream behind the interior launch (halo.advection_with_halo, bit-identical results); 0: advection!, then the exchange")
     return ap.parse_args()
 
 
@@ -190,7 +193,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import justpic.jl_b200 as J
-    from justpic.jl_b200.halo import CartesianTopology, update_cell_halo
+    from justpic.jl_b200.halo import CartesianTopology, update_cell_halo, advection_with_halo, join_halo
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -201,7 +204,14 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        opts = None
+        if args.overlap:
+            # the exchange runs behind the interior advection launch: NCCL's copy kernels must win SM slots as advection
+            # CTAs retire (high-priority stream) and fit into one such slot (256 threads per channel instead of 640)
+            os.environ.setdefault("NCCL_NTHREADS", "256")
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.is_high_priority_stream = True
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     topo = CartesianTopology.create(world, 3, rank)
     n = args.n
     gv = local_grids(n, topo.dims, topo.coords())
@@ -230,10 +240,17 @@ def run_ours(args):
             if ev is not None:
                 ev[i].record()
         mark(0)
-        J.advection(p, rk2, V, dt, classify=bool(args.handoff))
-        mark(1)
-        if world > 1:
-            update_cell_halo(p, fields, topo, buffers=halo_buffers)
+        if world > 1 and args.overlap:
+            # shell bricks -> [side stream: pack / NCCL / unpack] || interior bricks -> join: the "halo" phase below is what is
+            # left of the exchange after the interior launch has finished (the "advect" phase holds both launches)
+            advection_with_halo(p, rk2, V, dt, fields, topo, buffers=halo_buffers, classify=bool(args.handoff), join=False)
+            mark(1)
+            join_halo(p)
+        else:
+            J.advection(p, rk2, V, dt, classify=bool(args.handoff))
+            mark(1)
+            if world > 1:
+                update_cell_halo(p, fields, topo, buffers=halo_buffers)
         mark(2)
         J.move_particles(p, fields)
         mark(3)
@@ -384,12 +401,13 @@ def run_ours(args):
             "config": {"workload": workload_name(n, world), "cells_per_gpu": n ** 3, "live_particles_per_gpu": int(nlive_mean),
                        "migrant_fraction": round(f_mig, 4), "move_path": move_path, "dropped_per_step": dropped,
                        "advect_move_handoff": bool(args.handoff), "move_classify": move_classify,
+                       "halo_overlap": bool(world > 1 and args.overlap),
                        "p2g_mode": J.api.P2G_MODE, "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
                        "topology": list(topo.dims)},
             # per step: advect 1; move (plan path) classify 1 (hand-off: 0, + 1 per halo plane rewritten) + plan 27 +
             # finalize 1 + scan 2 + set 1 + gather 1 + scatter 1; p2g 2 (cell + node); phase ratios 1;
             # halo: 2 pack + 2 unpack per decomposed dimension
-            "gpu_launches": args.steps * (1 + 33 + (0 if args.handoff else 1) + 2 + 1
+            "gpu_launches": args.steps * ((2 if world > 1 and args.overlap else 1) + 33 + (0 if args.handoff else 1) + 2 + 1
                                           + ((4 + (2 if args.handoff else 0)) * sum(1 for d in topo.dims if d > 1) if world > 1 else 0)),
             "phase_ms": per_phase,
             # dominant single kernel: k_advect_tile (the advect phase is exactly one launch, so its

@@ -124,6 +124,16 @@ int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxcell, uint64
 int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha,
               const double *const *V, double dt, void *stream);
 
+/* advection! in two launches, for overlapping update_cell_halo! (src/CellArrays/ImplicitGlobalGrid.jl:36-41, called between
+ * advection! and move_particles! in scripts/temperature_advection3D_MPI.jl:83-91) with the bulk of the advection:
+ * JP_REGION_SHELL advects every brick of cells that holds one of the two outermost cell layers -- everything the exchange
+ * reads (layers 1, n-2) or rewrites (layers 0, n-1) --, JP_REGION_INTERIOR the remaining bricks; the pair equals one
+ * jp_advect (bit-identical results, same hand-off to jp_move).  The caller runs the exchange on another stream after the
+ * SHELL call and joins before jp_move.  JP_REGION_ALL = jp_advect. */
+typedef enum { JP_REGION_ALL = 0, JP_REGION_SHELL = 1, JP_REGION_INTERIOR = 2 } jp_region;
+int jp_advect_region(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt,
+                     int32_t region, void *stream);
+
 /* advection_LinP!(particles, method, V, dt) (src/Particles/Advection/advection_LinP.jl:12-391) and
  * advection_MQS!(particles, method, V, dt) (advection_MQS.jl:16-124, src/Interpolations/MQS.jl):
  * same integrators, velocity reconstructed with the LinP / MQS interpolant where the interpolation

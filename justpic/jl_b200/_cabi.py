@@ -16,6 +16,7 @@ LIB_PATH = Path(os.environ["JUSTPIC_LIB"]) if os.environ.get("JUSTPIC_LIB") else
 
 JP_MAX_ARGS = 16
 JP_MAX_SLOTS = 64          # occupancy-word kernels
+JP_REGION_ALL, JP_REGION_SHELL, JP_REGION_INTERIOR = 0, 1, 2
 JP_MAX_SLOTS_WIDE = 1024   # largest max_xcell accepted (chunked launches + literal move / inject above 64)
 JP_MAX_PHASES = 32
 JP_OPT_P2G_MODE = 1
@@ -63,6 +64,8 @@ SYMBOLS = {
     "jp_init_particles": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_uint64, C.c_void_p]),
     "jp_advect": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
                             C.POINTER(C.c_void_p), C.c_double, C.c_void_p]),
+    "jp_advect_region": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
+                                   C.POINTER(C.c_void_p), C.c_double, C.c_int32, C.c_void_p]),
     "jp_advect_interp": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
                                    C.POINTER(C.c_void_p), C.c_double, C.c_int32, C.c_void_p]),
     "jp_move": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),

@@ -331,14 +331,17 @@ def _args(args, p: Particles):
 
 # --------------------------------------------------------------------------- hot path
 def advection(particles: Particles, method, V, dt: float, affine: Optional[bool] = None,
-              classify: Optional[bool] = None) -> None:
+              classify: Optional[bool] = None, region: Optional[str] = None) -> None:
     """``advection!(particles, method, V, dt)`` (src/Particles/Advection/advection.jl:21-62).
     ``affine=False`` forces grid-coordinate table look-ups even when the grid vectors were verified
     to be exactly affine (identical results; the parity tests run both).
     ``classify=True`` switches on the advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY in
     include/justpic_c.h; sticky per ``Particles``): the kernel also classifies every new position for the
     following ``move_particles``, which then skips its own pass over the coordinates.  Results are
-    bit-identical; the caller must not write coordinates / index between the two calls by other means."""
+    bit-identical; the caller must not write coordinates / index between the two calls by other means.
+    ``region="shell"`` then ``region="interior"``: the same advection in two launches (jp_advect_region) -- first every
+    brick of cells holding one of the two outermost cell layers, then the rest -- so that ``update_cell_halo`` can run
+    on another stream while the interior is advected (``halo.advection_with_halo``)."""
     p = particles
     if classify is not None:
         _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_ADVECT_CLASSIFY, 1 if classify else 0), "jp_set_option")
@@ -352,8 +355,11 @@ def advection(particles: Particles, method, V, dt: float, affine: Optional[bool]
     lib = _cabi.load()
     pc = p._c()
     with torch.cuda.device(p.device):
-        _cabi.check(lib.jp_advect(C.c_void_p(p._ctx), C.byref(pc), method.scheme, float(method.alpha),
-                                  _ptr_array(V), float(dt), _stream()), "advection")
+        regions = {None: _cabi.JP_REGION_ALL, "all": _cabi.JP_REGION_ALL, "shell": _cabi.JP_REGION_SHELL, "interior": _cabi.JP_REGION_INTERIOR}
+        if region not in regions:
+            raise ValueError("advection: region must be None, 'shell' or 'interior'")
+        _cabi.check(lib.jp_advect_region(C.c_void_p(p._ctx), C.byref(pc), method.scheme, float(method.alpha),
+                                         _ptr_array(V), float(dt), regions[region], _stream()), "advection")
         _done()
 
 

@@ -183,6 +183,16 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
     // brick origin (cells) and first staged node (one below)
     const int b0[3] = {(int)blockIdx.x * T::TX, (int)blockIdx.y * T::TY, N == 3 ? (int)blockIdx.z * T::TZ : 0};
     const int c0[3] = {b0[0] - T::OX, b0[1] - 1, N == 3 ? b0[2] - 1 : 0};
+    if (g.region) {                         // CTA-uniform: shell bricks first, interior bricks while the halo planes travel
+        const int ext[3] = {T::TX, T::TY, T::TZ};
+        bool shell = false;
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            const int hi = min(b0[d] + ext[d], g.n[d]);           // brick covers cells [b0, hi)
+            shell = shell || b0[d] <= 1 || hi >= g.n[d] - 1;      // holds a cell of layers {0, 1, n-2, n-1}
+        }
+        if ((g.region == 1) != shell) return;
+    }
 
     // ---- 1. stage velocity stencils and grid-vector segments.
     // Components whose array meets the TMA constraints (16-byte aligned base and row pitch) are

@@ -50,6 +50,9 @@ struct JpGrid {
     // 1: range grid whose vertices were checked on the host to be affine within 1e-6 dx (and dx >> ulp of the
     //    coordinates): jp_classify_fast may decide particles that are clearly inside a cell (see there)
     int32_t cls_fast;
+    // advection! split for the halo overlap (jp_advect_region): 0 = every cell, 1 = only bricks that hold a cell of the two
+    // outermost cell layers (what update_cell_halo! reads and rewrites), 2 = the other bricks
+    int32_t region;
 };
 
 struct JpArgs {               // particle fields carried along by move/inject/clean

@@ -77,6 +77,7 @@ struct jp_ctx {
     const void *hint_key[4]; // coords[0..2], index the words belong to
     int hint_ndirty; int hint_dirty[8][2];   // (dim, plane) rewritten since the hand-off
     int last_classify;       // 0: coordinates (k_move_classify3), 1: hand-off bytes (diagnostics)
+    int adv_split;           // jp_advect_region: the shell part has run, the interior part is still to come
 };
 static inline void hint_invalidate(jp_ctx *ctx) { ctx->hint_valid = 0; ctx->hint_ndirty = 0; }
 
@@ -1277,8 +1278,25 @@ static cudaError_t launch_advect(const JpGrid &g, dim3 grd, dim3 blk, cudaStream
     return cudaSuccess;
 }
 
+static int advect_impl(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt, int region, void *stream);
 extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt, void *stream) {
+    return advect_impl(ctx, p, scheme, alpha, V, dt, JP_REGION_ALL, stream);
+}
+// advection! in two launches so that update_cell_halo! can overlap the bulk of it: JP_REGION_SHELL advects every
+// brick holding a cell of the two outermost cell layers (all the halo exchange reads or rewrites), JP_REGION_INTERIOR the rest.
+// The two calls together are one jp_advect (same kernel, same results, same hand-off); the caller runs the exchange
+// between them on another stream and joins before move_particles!.
+extern "C" int jp_advect_region(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt,
+                                int32_t region, void *stream) {
+    if (region != JP_REGION_ALL && region != JP_REGION_SHELL && region != JP_REGION_INTERIOR) return jp_fail(JP_ERR_INVALID, "jp_advect_region: unknown region");
+    return advect_impl(ctx, p, scheme, alpha, V, dt, region, stream);
+}
+static int advect_impl(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt, int region, void *stream) {
     PREP("jp_advect");
+    if (region == JP_REGION_INTERIOR && !ctx->adv_split) return jp_fail(JP_ERR_INVALID, "jp_advect_region: JP_REGION_INTERIOR without a preceding JP_REGION_SHELL call");
+    if (region != JP_REGION_INTERIOR && ctx->adv_split) { ctx->adv_split = 0; return jp_fail(JP_ERR_INVALID, "jp_advect_region: JP_REGION_SHELL must be followed by JP_REGION_INTERIOR"); }
+    const bool tiled = jp_standard_staggering(g);
+    if (region == JP_REGION_INTERIOR && !tiled) { ctx->adv_split = 0; return JP_OK; }      // the generic kernel did every cell in the shell call
     if (!V) return jp_fail(JP_ERR_INVALID, "jp_advect: null velocity tuple");
     CPtr3 v = {{nullptr, nullptr, nullptr}};
     for (int d = 0; d < g.ndim; d++) {
@@ -1287,18 +1305,19 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
     }
     if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect: Only 0 < alpha < 1 is supported");
     if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect: unknown integrator");
-    hint_invalidate(ctx);
+    if (region != JP_REGION_INTERIOR) hint_invalidate(ctx);          // the interior call completes the shell call's hand-off
     AdvHandoff hint;
     memset(&hint, 0, sizeof(hint));
-    if (ctx->hint_opt && jp_standard_staggering(g) && g.S <= JP_MAX_SLOTS) {
+    if (ctx->hint_opt && tiled && g.S <= JP_MAX_SLOTS) {
         int rc = move_plan_alloc(ctx);
         if (rc) return rc;
         hint.ws = ctx->mp; hint.flag = ctx->mp_flag;
-        JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
+        if (region != JP_REGION_INTERIOR) JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
     }
     bool hinted = false;
     for (int ch = 0; ch < jp_nchunks(g); ch++) {          // one launch unless max_xcell > 64
-        const SlotChunk k = jp_chunk(g, ch);
+        SlotChunk k = jp_chunk(g, ch);
+        k.g.region = tiled ? region : 0;
         const Ptr3 kc = jp_shift(co, k.off);
         const uint8_t *ki = p->index + k.off;
         cudaError_t le;
@@ -1314,7 +1333,9 @@ extern "C" int jp_advect(jp_ctx *ctx, const jp_particles *p, int32_t scheme, dou
         if (le != cudaSuccess) return jp_fail(JP_ERR_CUDA, "jp_advect: %s", cudaGetErrorString(le));
     }
     JP_CHECK_LAUNCH();
-    if (hinted) {
+    const bool hint_void = ctx->adv_split == 2;
+    ctx->adv_split = region == JP_REGION_SHELL;
+    if (hinted && region != JP_REGION_SHELL && !hint_void) {               // after a shell call the words are still incomplete
         ctx->hint_valid = 1;
         for (int d = 0; d < 3; d++) ctx->hint_key[d] = d < g.ndim ? (const void *)p->coords[d] : nullptr;
         ctx->hint_key[3] = p->index;
@@ -1936,12 +1957,12 @@ static int halo_common(jp_ctx *ctx, int dim, int plane, double *const *arrays, i
     if (pack) k_halo<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
     else {
         k_halo<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
-        if (ctx->hint_valid) {                     // the hand-off bytes of this plane are stale now
+        if (ctx->hint_valid || (ctx->adv_split && ctx->hint_opt)) {   // the hand-off bytes of this plane are stale now
             bool seen = false;
             for (int i = 0; i < ctx->hint_ndirty; i++) seen = seen || (ctx->hint_dirty[i][0] == dim && ctx->hint_dirty[i][1] == plane);
             if (!seen) {
                 if (ctx->hint_ndirty < 8) { ctx->hint_dirty[ctx->hint_ndirty][0] = dim; ctx->hint_dirty[ctx->hint_ndirty][1] = plane; ctx->hint_ndirty++; }
-                else hint_invalidate(ctx);
+                else { hint_invalidate(ctx); if (ctx->adv_split) ctx->adv_split = 2; }     // 2: this step's hand-off is void
             }
         }
     }

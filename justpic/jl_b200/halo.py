@@ -29,9 +29,9 @@ import torch
 import torch.distributed as dist
 
 from . import _cabi
-from .api import Particles, _ptr_array, _stream
+from .api import Particles, _ptr_array, _stream, advection
 
-__all__ = ["CartesianTopology", "update_cell_halo", "exchange_planes"]
+__all__ = ["CartesianTopology", "update_cell_halo", "exchange_planes", "advection_with_halo", "join_halo"]
 
 
 @dataclass(frozen=True)
@@ -187,3 +187,47 @@ def update_cell_halo(particles: Particles, args=(), topo: Optional[CartesianTopo
             lambda dim, plane, b: _cuda_pack(p, dim, plane, arrays, b),
             lambda dim, plane, b: _cuda_unpack(p, dim, plane, arrays, b),
             group=group, buffers=buffers)
+
+
+_SIDE_STREAMS: dict = {}
+_PENDING: dict = {}          # id(particles) -> event recorded on the side stream after the last unpack
+
+
+def join_halo(particles: Particles) -> None:
+    """Make the current stream wait for an exchange started by ``advection_with_halo(..., join=False)``."""
+    ev = _PENDING.pop(id(particles), None)
+    if ev is not None:
+        with torch.cuda.device(particles.device):
+            torch.cuda.current_stream().wait_event(ev)
+
+
+def advection_with_halo(particles: Particles, method, V, dt: float, args=(), topo: Optional[CartesianTopology] = None, group=None,
+                        buffers: Optional[dict] = None, classify: Optional[bool] = None, join: bool = True) -> int:
+    """``advection!(particles, method, V, dt)`` followed by ``update_cell_halo!(coords..., args..., index)``
+    (scripts/temperature_advection3D_MPI.jl:83-91) with the exchange hidden behind the advection: the bricks holding the two
+    outermost cell layers are advected first (``jp_advect_region`` SHELL), the planes are then packed, sent over NCCL and unpacked
+    on a high-priority side stream while the current stream advects the interior bricks; the current stream waits for the side
+    stream before returning control to the next call (``move_particles``).  Same results as the two calls in sequence."""
+    if topo is None or topo.size == 1 and not any(topo.periodic):
+        advection(particles, method, V, dt, classify=classify)
+        return 0
+    p = particles
+    with torch.cuda.device(p.device):
+        main = torch.cuda.current_stream()
+        side = _SIDE_STREAMS.get(p.device)
+        if side is None:
+            side = _SIDE_STREAMS[p.device] = torch.cuda.Stream(device=p.device, priority=-1)
+        advection(p, method, V, dt, classify=classify, region="shell")
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            sent = update_cell_halo(p, args, topo, group=group, buffers=buffers)
+            done = torch.cuda.Event()
+            done.record(side)
+        advection(p, method, V, dt, region="interior")
+        if join:
+            main.wait_event(done)
+        else:
+            _PENDING[id(p)] = done          # the caller joins with join_halo(p) (bench.py: to time what is left of the exchange)
+    return sent

@@ -85,3 +85,88 @@ def test_update_cell_halo_nccl_two_gpus(tmp_path):
         assert eq(r[1]["after"][a][..., 0], r[0]["before"][a][..., nx - 2])
         assert eq(r[0]["after"][a][..., : nx - 1], r[0]["before"][a][..., : nx - 1])
         assert eq(r[1]["after"][a][..., 1:], r[1]["before"][a][..., 1:])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# advection! split into shell + interior launches (jp_advect_region), the basis of the halo overlap
+@pytest.mark.parametrize("classify", [False, True])
+@pytest.mark.parametrize("g", [(2, (70, 19), True), (3, (40, 9, 7), True), (3, (33, 6, 5), False), (3, (70, 11, 6), True)],
+                         ids=lambda g: f"{g[0]}D-{g[1]}-{'range' if g[2] else 'vector'}")
+def test_advection_shell_plus_interior_equals_advection(g, classify):
+    """The two region launches together are one advection!: bit-identical coordinates for every integrator, and the
+    advection -> move hand-off they leave drives move_particles! to the oracle's result."""
+    import numpy as np
+    import justpic.jl_b200 as J
+    from tests.problems import cfl_dt, stream_velocity
+    from tests.test_gpu_parity import Twin, dev
+    ndim, n, uniform = g
+    t = Twin(ndim, n, uniform=uniform)
+    V = stream_velocity(t.gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(t.gr, V, 0.8)
+    pT, = J.init_cell_arrays(t.p, 1)
+    opT = np.zeros_like(t.co[0])
+    methods = [(J.RungeKutta2(), 1, 0.5), (J.RungeKutta4(), 2, 0.0), (J.Euler(), 0, 0.0), (J.RungeKutta2(2 / 3), 1, 2 / 3)]
+    for it, m in enumerate(methods):
+        J.advection(t.p, m[0], Vd, dt, classify=classify, region="shell")
+        J.advection(t.p, m[0], Vd, dt, region="interior")
+        t.o.advect(t.co, t.idx, m[1], m[2], V, dt)
+        t.check_state(f"step {it} advection (shell + interior)")
+        J.move_particles(t.p, (pT,)); st = t.o.move(t.co, t.idx, [opT])
+        t.check_state(f"step {it} move_particles", (pT,), (opT,))
+        assert J.move_stats(t.p) == st
+        if classify:
+            assert J.last_move_classify(t.p) == "handoff"
+    with pytest.raises(ValueError):                    # interior without shell (JP_ERR_INVALID)
+        J.advection(t.p, methods[0][0], Vd, dt, region="interior")
+    J.advection(t.p, methods[0][0], Vd, dt, region="shell")
+    with pytest.raises(ValueError):                    # shell not completed
+        J.advection(t.p, methods[0][0], Vd, dt)
+    J.advection(t.p, methods[0][0], Vd, dt)            # the failed call reset the split: a plain advection works again
+
+
+def _overlap_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import numpy as np
+        import justpic.jl_b200 as J
+        from justpic.jl_b200.halo import CartesianTopology, advection_with_halo, update_cell_halo
+        from tests.problems import cfl_dt, make_grids, stream_velocity
+        gr = make_grids((40, 9, 10), 3, True)
+        V = stream_velocity(gr); Vd = [torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in V]
+        dt = cfl_dt(gr, V, 0.7)
+        topo = CartesianTopology((2, 1, 1), rank)
+        res = []
+        for overlapped in (False, True):
+            p = J.init_particles(J.CUDABackend, 12, 24, 6, *gr.grid_vel, seed=10 + rank, device=f"cuda:{rank}")
+            pT, = J.init_cell_arrays(p, 1)
+            pT.copy_(p.coords[0] * 3.0)
+            bufs = {}
+            for it in range(4):
+                if overlapped:
+                    advection_with_halo(p, J.RungeKutta2(), Vd, dt, (pT,), topo, buffers=bufs, classify=True)
+                else:
+                    J.advection(p, J.RungeKutta2(), Vd, dt, classify=True)
+                    update_cell_halo(p, (pT,), topo, buffers=bufs)
+                J.move_particles(p, (pT,))
+                assert J.last_move_classify(p) == "handoff"
+            torch.cuda.synchronize()
+            res.append([c.cpu() for c in p.coords] + [pT.cpu(), p.index.cpu()])
+        torch.save(res, out + f".{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_advection_with_halo_overlap_two_gpus(tmp_path):
+    """advection_with_halo (shell launch, exchange on a side stream behind the interior launch) == advection! then
+    update_cell_halo!, bit for bit, over coupled steps with move_particles! and the hand-off."""
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "ovl")
+    mp.spawn(_overlap_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for k in range(2):
+        seq, ovl = torch.load(out + f".{k}")
+        for a, b in zip(seq, ovl):
+            assert torch.equal(torch.nan_to_num(a.double(), nan=-1.0), torch.nan_to_num(b.double(), nan=-1.0))

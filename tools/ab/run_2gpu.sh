@@ -1,6 +1,15 @@
-set -x
 mkdir -p gpurun_out
-nvidia-smi -L
-timeout 300 python -m pytest tests/test_gpu_halo.py -m gpu -x -q 2>&1 | tail -4
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/r01f_bench_2gpu.json 2> gpurun_out/r01f_bench_2gpu.err; tail -c 1500 gpurun_out/r01f_bench_2gpu.json; tail -5 gpurun_out/r01f_bench_2gpu.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 | tail -c 400
+timeout 600 python -m pytest tests/test_gpu_halo.py -m gpu -x -q 2>&1 | grep -v Warning | tail -40 | cut -c1-220
+run() { # $1 tag, $2 overlap, extra env already exported
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29530 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e --overlap $2 > gpurun_out/ovl_$1.json 2> gpurun_out/ovl_$1.err; tail -2 gpurun_out/ovl_$1.err | cut -c1-300
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/ovl_$1.json').read().strip().splitlines()[-1])
+print("$1 overlap", $2, round(d['value']/1e9,3), round(d['ms_per_step'],2), {k:round(v,2) for k,v in d['phase_ms'].items()})
+PY
+}
+run seq 0
+run ovl256 1
+NCCL_NTHREADS=512 run ovl512 1
+NCCL_NTHREADS=128 run ovl128 1
+NCCL_NTHREADS=256 NCCL_MAX_NCHANNELS=8 run ovl256c8 1
