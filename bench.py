@@ -402,6 +402,9 @@ def run_ours(args):
                        "migrant_fraction": round(f_mig, 4), "move_path": move_path, "dropped_per_step": dropped,
                        "advect_move_handoff": bool(args.handoff), "move_classify": move_classify,
                        "halo_overlap": bool(world > 1 and args.overlap),
+                       # rank 0's final state in three numbers (compare two runs, e.g. --overlap 0 / 1: must be identical)
+                       "state_checksum": [float(torch.nan_to_num(p.coords[0]).sum().item()), float(torch.nan_to_num(pT).sum().item()),
+                                          int(p.index.sum().item())],
                        "p2g_mode": J.api.P2G_MODE, "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
                        "topology": list(topo.dims)},
             # per step: advect 1; move (plan path) classify 1 (hand-off: 0, + 1 per halo plane rewritten) + plan 27 +

@@ -133,14 +133,25 @@ def _overlap_worker(rank, world, port, out):
         import numpy as np
         import justpic.jl_b200 as J
         from justpic.jl_b200.halo import CartesianTopology, advection_with_halo, update_cell_halo
-        from tests.problems import cfl_dt, make_grids, stream_velocity
-        gr = make_grids((40, 9, 10), 3, True)
-        V = stream_velocity(gr); Vd = [torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in V]
-        dt = cfl_dt(gr, V, 0.7)
+        from bench import stream_velocity_np
+        # a real block decomposition (2 x 1 x 1, overlap 2 as ImplicitGlobalGrid): the particles a rank receives in its halo
+        # cells lie in those cells, so move_particles! re-buckets over <= 1 cell (longer moves are racy in the reference itself)
         topo = CartesianTopology((2, 1, 1), rank)
+        n = (72, 9, 10)                                  # 72 cells in x: bricks 0 and 2 are shell, brick 1 is interior
+        xv, xc = [], []
+        for d in range(3):
+            nglob = topo.dims[d] * (n[d] - 2) + 2 if topo.dims[d] > 1 else n[d]
+            dx = 1.0 / nglob
+            i0 = topo.coords()[d] * (n[d] - 2) if topo.dims[d] > 1 else 0
+            xv.append(J.LinRange(i0 * dx, (i0 + n[d]) * dx, n[d] + 1))
+            xc.append(J.LinRange(i0 * dx + dx / 2, (i0 + n[d]) * dx - dx / 2, n[d]))
+        xg = [J.expand_range(c) for c in xc]
+        grid_vel = tuple(tuple(xv[d] if d == comp else xg[d] for d in range(3)) for comp in range(3))
+        Vd = [torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in stream_velocity_np(grid_vel)]
+        dt = 0.7 * min(float(xv[d][1] - xv[d][0]) for d in range(3)) / 250.0
         res = []
         for overlapped in (False, True):
-            p = J.init_particles(J.CUDABackend, 12, 24, 6, *gr.grid_vel, seed=10 + rank, device=f"cuda:{rank}")
+            p = J.init_particles(J.CUDABackend, 12, 24, 6, *grid_vel, seed=10 + rank, device=f"cuda:{rank}")
             pT, = J.init_cell_arrays(p, 1)
             pT.copy_(p.coords[0] * 3.0)
             bufs = {}
