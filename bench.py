@@ -84,6 +84,16 @@ def stream_velocity_np(grid_vel):
     return V
 
 
+def state_checksum(p, pT):
+    """Three finite numbers that pin rank 0's final particle state (NaN / Inf slots count as 0)."""
+    try:
+        import torch
+        fin = lambda t: float(torch.nan_to_num(t, nan=0.0, posinf=0.0, neginf=0.0).sum().item())
+        return [fin(p.coords[0]), fin(pT), int(p.index.sum().item())]
+    except Exception as e:           # never lose the bench line over a diagnostic
+        return [repr(e)]
+
+
 def algorithmic_bytes(f_mig):
     """SURVEY.md section 8(d), per live particle, N=3, S=48, ppc=24, F=3 fields."""
     adv = 16 * 3 + SLOTS / PPC + 8 * 3 / PPC
@@ -403,8 +413,7 @@ def run_ours(args):
                        "advect_move_handoff": bool(args.handoff), "move_classify": move_classify,
                        "halo_overlap": bool(world > 1 and args.overlap),
                        # rank 0's final state in three numbers (compare two runs, e.g. --overlap 0 / 1: must be identical)
-                       "state_checksum": [float(torch.nan_to_num(p.coords[0]).sum().item()), float(torch.nan_to_num(pT).sum().item()),
-                                          int(p.index.sum().item())],
+                       "state_checksum": state_checksum(p, pT),
                        "p2g_mode": J.api.P2G_MODE, "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
                        "topology": list(topo.dims)},
             # per step: advect 1; move (plan path) classify 1 (hand-off: 0, + 1 per halo plane rewritten) + plan 27 +
