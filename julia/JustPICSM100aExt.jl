@@ -94,6 +94,21 @@ function JustPIC.advection!(p::Particles{CUDABackend, N}, method::AbstractAdvect
     done()
 end
 
+# advection! split for the halo overlap (jp_advect_region): region 1 = bricks holding one of the two outermost cell layers,
+# region 2 = the rest.  A multi-GPU time loop (scripts/temperature_advection3D_MPI.jl:83-91) becomes
+#     advection_region!(p, method, V, dt, 1); ev = CUDA.CuEvent(); CUDA.record(ev)
+#     CUDA.stream!(side_stream) do; CUDA.wait(ev); update_cell_halo!(p.coords..., args..., p.index); CUDA.record(done_ev); end
+#     advection_region!(p, method, V, dt, 2); CUDA.wait(done_ev)
+#     move_particles!(p, args)
+function advection_region!(p::Particles{CUDABackend}, method::AbstractAdvectionIntegrator, V, dt, region::Integer)
+    s, α = scheme(method)
+    Vp = CuPtr{Float64}[pointer(v) for v in V]
+    check(ccall((:jp_advect_region, libjustpic), Cint,
+                (Ptr{Cvoid}, Ref{JpParticles}, Int32, Float64, Ptr{CuPtr{Float64}}, Float64, Int32, Ptr{Cvoid}),
+                context(p), jp(p), s, α, Vp, Float64(dt), Int32(region), stream()), "advection!")
+    done()
+end
+
 # move_particles!(particles, grid, args, dxi)           src/Particles/move_safe.jl:23-49
 function JustPIC.move_particles!(p::Particles{CUDABackend}, grid::NTuple{N}, args, dxi) where {N}
     a = argptrs(args)
