@@ -137,7 +137,7 @@ def _overlap_worker(rank, world, port, out):
         # a real block decomposition (2 x 1 x 1, overlap 2 as ImplicitGlobalGrid): the particles a rank receives in its halo
         # cells lie in those cells, so move_particles! re-buckets over <= 1 cell (longer moves are racy in the reference itself)
         topo = CartesianTopology((2, 1, 1), rank)
-        n = (72, 9, 10)                                  # 72 cells in x: bricks 0 and 2 are shell, brick 1 is interior
+        n = (72, 14, 10)                                 # bricks are 32 x 4 x 2 cells: x [32,64), y [4,12), z [2,8) are interior
         xv, xc = [], []
         for d in range(3):
             nglob = topo.dims[d] * (n[d] - 2) + 2 if topo.dims[d] > 1 else n[d]
