@@ -113,3 +113,12 @@ class Emul:
     def inject(self, coords, index, args, min_xcell, seed, step):
         return int(lib().jpe_inject(C.c_void_p(self.h), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args),
                                     int(min_xcell), C.c_uint64(int(seed)), C.c_uint32(int(step))))
+
+    def classify(self, ci, p):
+        """(fast pre-filter, exact classification, literal move_kernel! route) of one particle stored in cell ``ci``."""
+        ci3 = (C.c_int * 3)(*(list(ci) + [0] * (3 - len(ci))))
+        p3 = (C.c_double * 3)(*(list(p) + [0.0] * (3 - len(p))))
+        out = (C.c_int * 3)()
+        lib().jpe_classify.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        lib().jpe_classify(C.c_void_p(self.h), ci3, p3, out)
+        return int(out[0]), int(out[1]), int(out[2])

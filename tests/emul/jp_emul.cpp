@@ -168,3 +168,50 @@ extern "C" int64_t jpe_inject(Emul *e, double *const *co, uint8_t *index, double
     return e->g.ndim == 2 ? inject_t<2>(e, co, index, a, min_xcell, seed, step) : inject_t<3>(e, co, index, a, min_xcell, seed, step);
 }
 
+
+// ---- move_particles! classification of one particle, three ways (tests/test_classify_emul.py):
+// out[0] = jp_classify_fast (single-precision pre-filter; -2 when the grid does not qualify),
+// out[1] = jp_classify_particle with the four vertices around the storage cell as k_move_classify3 / the
+//          advection hand-off load them (NaN outside the grid),
+// out[2] = the literal route of move_kernel! (src/Particles/move_safe.jl:86-106): isincell -> indomain -> bisection,
+//          expressed in the same codes (JP_CLS_CPLX + r where the planner would hand over to the direct sweeps).
+template <int N> static void classify_t(Emul *e, const int *ci, const double *p, int *out) {
+    const JpGrid &g = e->g;
+    double am[3], a[3], b[3], bp[3], corner[3], dx[3];
+    for (int d = 0; d < N; d++) {
+        am[d] = ci[d] > 0 ? g.xv[d][ci[d] - 1] : NAN;
+        a[d] = g.xv[d][ci[d]];
+        b[d] = g.xv[d][ci[d] + 1];
+        bp[d] = ci[d] + 2 <= g.n[d] ? g.xv[d][ci[d] + 2] : NAN;
+        corner[d] = a[d]; dx[d] = jp_d_of(g.xv[d], g.uniform, ci[d]);
+    }
+    out[0] = g.cls_fast ? jp_classify_fast<N>(g, ci, a, p) : -2;
+    out[1] = jp_classify_particle<N>(g, am, a, b, bp, p);
+    int lit;
+    if (jp_isincell<N>(p, corner, dx)) lit = JP_CLS_STAY;
+    else {
+        bool indom = true;
+        for (int d = 0; d < N; d++) indom = indom && (g.xv[d][0] < p[d] && p[d] < g.xv[d][g.n[d]]);
+        if (!indom) lit = JP_CODE_DELETE;
+        else {
+            int dv[3] = {0, 0, 0}, nc[3] = {0, 0, 0};
+            bool far = false;
+            double c2[3], dx2[3];
+            for (int d = 0; d < N; d++) {
+                nc[d] = jp_bisect1(p[d], g.xv[d], g.n[d] + 1, ci[d] + 1) - 1;
+                dv[d] = nc[d] - ci[d];
+                far = far || dv[d] < -1 || dv[d] > 1;
+                c2[d] = g.xv[d][nc[d]]; dx2[d] = jp_d_of(g.xv[d], g.uniform, nc[d]);
+            }
+            if (far) lit = JP_CLS_CPLX + 1;
+            else if (dv[0] == 0 && dv[1] == 0 && dv[2] == 0) lit = JP_CLS_CPLX + 2;
+            else if (!jp_isincell<N>(p, c2, dx2)) lit = JP_CLS_CPLX + 3;
+            else lit = (dv[0] + 1) + 3 * (dv[1] + 1) + (N == 3 ? 9 * (dv[2] + 1) : 9);
+        }
+    }
+    out[2] = lit;
+}
+extern "C" int jpe_classify(Emul *e, const int *ci, const double *p, int *out) {
+    if (e->g.ndim == 2) classify_t<2>(e, ci, p, out); else classify_t<3>(e, ci, p, out);
+    return e->g.cls_fast;
+}
