@@ -14,7 +14,9 @@
  * (test/test_integrators.jl:11-78) and N-linear lerp
  * (test/test_interpolation_kernels.jl:47-60), plus the reference's property
  * tests (linear-field grid2particle == coordinate, phase ratios sum to 1, cell
- * bracket).  move_particles!/inject_particles!/particle2grid! slot-level
+ * bracket), and force_injection! by the exact expectations of its reference
+ * tests (test/test_2D.jl:301-384, test/test_3D.jl:279-333, transcribed in
+ * tests/test_force_injection.py).  move_particles!/inject_particles!/particle2grid! slot-level
  * results are NOT pinned by any reference test ("parity unpinned"): this
  * literal restatement is the only pin.  RNG streams are unpinned in the
  * reference (backend rand()); both this oracle and the CUDA library use
