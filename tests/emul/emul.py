@@ -122,3 +122,29 @@ class Emul:
         lib().jpe_classify.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
         lib().jpe_classify(C.c_void_p(self.h), ci3, p3, out)
         return int(out[0]), int(out[1]), int(out[2])
+
+    # ---- cell-local kernels (loops of justpic_sm100a.cu around the per-particle functions of jp_core.h)
+    def _h(self):
+        return C.c_void_p(self.h)
+
+    def grid2particle(self, coords, index, Fp, F):
+        lib().jpe_grid2particle(self._h(), _pp(coords), index.ctypes.data_as(C.c_void_p), _dp(Fp), _dp(F))
+
+    def centroid2particle(self, coords, Fp, Fc):
+        lib().jpe_centroid2particle(self._h(), _pp(coords), _dp(Fp), _dp(Fc))
+
+    def particle2grid(self, coords, index, F, Fp):
+        lib().jpe_particle2grid(self._h(), _pp(coords), index.ctypes.data_as(C.c_void_p), _dp(F), _dp(Fp))
+
+    def particle2centroid(self, coords, Fc, Fp):
+        lib().jpe_particle2centroid(self._h(), _pp(coords), _dp(Fc), _dp(Fp))
+
+    def phase_ratios_center(self, coords, ratios, phases, K):
+        lib().jpe_phase_ratios_center(self._h(), _pp(coords), _dp(ratios), _dp(phases), int(K))
+
+    def clean(self, coords, index, args):
+        lib().jpe_clean(self._h(), _pp(coords), index.ctypes.data_as(C.c_void_p), _pp(args), len(args))
+
+    def advect_interp(self, coords, index, scheme, alpha, V, dt, interp):
+        lib().jpe_advect_interp(self._h(), _pp(coords), index.ctypes.data_as(C.c_void_p), int(scheme), C.c_double(alpha), _pp(V),
+                                C.c_double(dt), int(interp))

@@ -215,3 +215,178 @@ extern "C" int jpe_classify(Emul *e, const int *ci, const double *p, int *out) {
     if (e->g.ndim == 2) classify_t<2>(e, ci, p, out); else classify_t<3>(e, ci, p, out);
     return e->g.cls_fast;
 }
+
+// ---- cell-local interpolation / cleanup kernels: the kernels' loops (k_g2p, k_c2p, k_p2g, k_p2c, k_phase, k_clean,
+// k_advect_hi in justpic_sm100a.cu) around the SAME per-particle functions of jp_core.h
+template <int N> static void g2p_t(Emul *e, double *const *co, const uint8_t *index, double *Fp, const double *F) {
+    const JpGrid &g = e->g;
+    for (int64_t c = 0; c < g.C; c++) {
+        int ci[3]; jp_cell_ijk<N>(g, c, ci);
+        double v[8], xcorner[3], idx[3];
+        const int64_t s1 = g.n[0] + 1, s2 = (int64_t)(g.n[0] + 1) * (g.n[1] + 1);
+        jp_corners<N>(F, ci[0] + s1 * ci[1] + (N == 3 ? s2 * ci[2] : 0), s1, s2, v);
+        for (int d = 0; d < N; d++) { xcorner[d] = g.xv[d][ci[d]]; idx[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            if (!index[el]) continue;
+            double p[3];
+            for (int d = 0; d < N; d++) p[d] = co[d][el];
+            Fp[el] = jp_g2p<N>(v, xcorner, idx, p);
+        }
+    }
+}
+extern "C" void jpe_grid2particle(Emul *e, double *const *co, const uint8_t *index, double *Fp, const double *F) {
+    if (e->g.ndim == 2) g2p_t<2>(e, co, index, Fp, F); else g2p_t<3>(e, co, index, Fp, F);
+}
+
+template <int N> static void c2p_t(Emul *e, double *const *co, double *Fp, const double *Fc) {
+    const JpGrid &g = e->g;
+    for (int64_t c = 0; c < g.C; c++) {
+        int ci[3]; jp_cell_ijk<N>(g, c, ci);
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            double p[3]; bool nan = false;
+            for (int d = 0; d < N; d++) { p[d] = co[d][el]; nan |= std::isnan(p[d]); }
+            if (nan) continue;
+            Fp[el] = jp_c2p<N>(g, Fc, ci, p);
+        }
+    }
+}
+extern "C" void jpe_centroid2particle(Emul *e, double *const *co, double *Fp, const double *Fc) {
+    if (e->g.ndim == 2) c2p_t<2>(e, co, Fp, Fc); else c2p_t<3>(e, co, Fp, Fc);
+}
+
+template <int N> static void p2g_t(Emul *e, double *const *co, const uint8_t *index, double *F, const double *Fp) {
+    const JpGrid &g = e->g;
+    const int nx = g.n[0], ny = g.n[1], nz = N == 3 ? g.n[2] : 1;
+    for (int kn = 0; kn <= (N == 3 ? nz : 0); kn++)
+        for (int jn = 0; jn <= ny; jn++)
+            for (int in = 0; in <= nx; in++) {
+                const double xn[3] = {g.xv[0][in], g.xv[1][jn], N == 3 ? g.xv[2][kn] : 0.0};
+                double w = 0.0, wF = 0.0;
+                for (int ko = (N == 3 ? -1 : 0); ko <= 0; ko++) {
+                    const int kc = kn + ko;
+                    if (N == 3 && (kc < 0 || kc >= nz)) continue;
+                    for (int jo = -1; jo <= 0; jo++) {
+                        const int jc = jn + jo;
+                        if (jc < 0 || jc >= ny) continue;
+                        for (int io = -1; io <= 0; io++) {
+                            const int ic = in + io;
+                            if (ic < 0 || ic >= nx) continue;
+                            const int64_t c = ic + (int64_t)nx * (jc + (int64_t)ny * kc);
+                            for (int s = 0; s < g.S; s++) {
+                                const int64_t el = c + (int64_t)s * g.C;
+                                if (!index[el]) continue;
+                                double p[3];
+                                for (int d = 0; d < N; d++) p[d] = co[d][el];
+                                const double wi = jp_p2g_weight<N>(xn, p);
+                                w += wi;
+                                wF = fma(wi, Fp[el], wF);
+                            }
+                        }
+                    }
+                }
+                const int64_t nd = in + (int64_t)(nx + 1) * (jn + (N == 3 ? (int64_t)(ny + 1) * kn : 0));
+                F[nd] = N == 2 ? wF / w : wF * (1.0 / w);
+            }
+}
+extern "C" void jpe_particle2grid(Emul *e, double *const *co, const uint8_t *index, double *F, const double *Fp) {
+    if (e->g.ndim == 2) p2g_t<2>(e, co, index, F, Fp); else p2g_t<3>(e, co, index, F, Fp);
+}
+
+template <int N> static void p2c_t(Emul *e, double *const *co, double *Fc, const double *Fp) {
+    const JpGrid &g = e->g;
+    for (int64_t c = 0; c < g.C; c++) {
+        int ci[3]; jp_cell_ijk<N>(g, c, ci);
+        double xcn[3], idi[3];
+        for (int d = 0; d < N; d++) { xcn[d] = g.xc[d][ci[d]]; idi[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
+        double w = 0.0, wF = 0.0;
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            double p[3];
+            for (int d = 0; d < N; d++) p[d] = co[d][el];
+            if (N == 2 ? (std::isnan(p[0]) || std::isnan(p[1])) : std::isnan(p[0])) continue;
+            const double wi = jp_bilinear_weight<N>(xcn, p, idi);
+            w += wi;
+            wF = fma(wi, Fp[el], wF);
+        }
+        Fc[c] = N == 2 ? wF / w : wF * (1.0 / w);
+    }
+}
+extern "C" void jpe_particle2centroid(Emul *e, double *const *co, double *Fc, const double *Fp) {
+    if (e->g.ndim == 2) p2c_t<2>(e, co, Fc, Fp); else p2c_t<3>(e, co, Fc, Fp);
+}
+
+template <int N> static void phase_t(Emul *e, double *const *co, double *ratios, const double *phases, int K) {
+    const JpGrid &g = e->g;
+    for (int64_t c = 0; c < g.C; c++) {
+        int ci[3]; jp_cell_ijk<N>(g, c, ci);
+        double xcn[3], idi[3], w[JP_MAX_PHASES];
+        for (int d = 0; d < N; d++) { xcn[d] = g.xc[d][ci[d]]; idi[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
+        for (int k = 0; k < K; k++) w[k] = 0.0;
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            if (std::isnan(co[0][el])) continue;
+            const double p[3] = {co[0][el], co[1][el], N == 3 ? co[2][el] : 0.0};
+            const double x = jp_bilinear_weight<N>(xcn, p, idi);
+            for (int k = 0; k < K; k++) w[k] = w[k] + (phases[el] == (double)(k + 1) ? x : copysign(0.0, x));
+        }
+        double sum = w[0];
+        for (int k = 1; k < K; k++) sum = sum + w[k];
+        const double inv = 1.0 / sum;
+        for (int k = 0; k < K; k++) ratios[c + (int64_t)k * g.C] = w[k] * inv;
+    }
+}
+extern "C" void jpe_phase_ratios_center(Emul *e, double *const *co, double *ratios, const double *phases, int K) {
+    if (e->g.ndim == 2) phase_t<2>(e, co, ratios, phases, K); else phase_t<3>(e, co, ratios, phases, K);
+}
+
+template <int N> static void clean_t(Emul *e, double *const *co, uint8_t *index, const JpArgs &args) {
+    const JpGrid &g = e->g;
+    for (int64_t c = 0; c < g.C; c++) {
+        int ci[3]; jp_cell_ijk<N>(g, c, ci);
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            if (!index[el]) continue;
+            double p[3];
+            for (int d = 0; d < N; d++) p[d] = co[d][el];
+            if (jp_clean_removes<N>(g, ci, p)) {
+                index[el] = 0;
+                for (int d = 0; d < N; d++) co[d][el] = NAN;
+                for (int a = 0; a < args.n; a++) args.a[a][el] = NAN;
+            }
+        }
+    }
+}
+extern "C" void jpe_clean(Emul *e, double *const *co, uint8_t *index, double *const *args, int nargs) {
+    JpArgs a; a.n = nargs;
+    for (int i = 0; i < nargs; i++) a.a[i] = args[i];
+    if (e->g.ndim == 2) clean_t<2>(e, co, index, a); else clean_t<3>(e, co, index, a);
+}
+
+template <int N, int SCHEME, int INTERP>
+static void advect_hi_t(Emul *e, double *const *co, const uint8_t *index, const double *const *V, double alpha, double dt) {
+    const JpGrid &g = e->g;
+    for (int64_t c = 0; c < g.C; c++) {
+        int ci[3]; jp_cell_ijk<N>(g, c, ci);
+        const int cell1[3] = {ci[0] + 1, ci[1] + 1, ci[2] + 1};
+        for (int s = 0; s < g.S; s++) {
+            const int64_t el = c + (int64_t)s * g.C;
+            if (!index[el]) continue;
+            double p0[3], p1[3];
+            for (int d = 0; d < N; d++) p0[d] = co[d][el];
+            jp_advect_particle_hi<N, SCHEME, INTERP>(g, alpha, V, dt, cell1, p0, p1);
+            for (int d = 0; d < N; d++) co[d][el] = p1[d];
+        }
+    }
+}
+template <int N, int INTERP>
+static void advect_hi_s(Emul *e, double *const *co, const uint8_t *index, int scheme, const double *const *V, double alpha, double dt) {
+    if (scheme == 0) advect_hi_t<N, 0, INTERP>(e, co, index, V, alpha, dt);
+    else if (scheme == 1) advect_hi_t<N, 1, INTERP>(e, co, index, V, alpha, dt);
+    else advect_hi_t<N, 2, INTERP>(e, co, index, V, alpha, dt);
+}
+extern "C" void jpe_advect_interp(Emul *e, double *const *co, const uint8_t *index, int scheme, double alpha, const double *const *V, double dt, int interp) {
+    if (e->g.ndim == 2) { if (interp == 1) advect_hi_s<2, 1>(e, co, index, scheme, V, alpha, dt); else advect_hi_s<2, 2>(e, co, index, scheme, V, alpha, dt); }
+    else                { if (interp == 1) advect_hi_s<3, 1>(e, co, index, scheme, V, alpha, dt); else advect_hi_s<3, 2>(e, co, index, scheme, V, alpha, dt); }
+}
