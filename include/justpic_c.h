@@ -73,8 +73,21 @@ typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_
  *   calls by other means -- the reference's time loops never do (advection! -> update_halo! ->
  *   move_particles!), but the library cannot see such writes, hence opt-in.
  * JP_OPT_LAST_CLASSIFY (jp_get_option only): 1 if the last planned jp_move used the hand-off bytes. */
+/* JP_OPT_MOVE_INTERP (0/1, default 0): move -> interpolation hand-off.  With 1, the last streaming pass of jp_move (which
+ *   already touches nearly every sector of every particle array) also accumulates, for each cell's FINAL content and in slot
+ *   order, (a) the per-cell partial sums of the two-pass particle2grid! of the particle field registered with
+ *   jp_move_interp_fields and (b) the centre phase ratios of the registered phase field -- the same arithmetic in the same
+ *   order as jp_particle2grid's cell pass / jp_phase_ratios_center, results bit-identical to option 0.  The next
+ *   jp_particle2grid(F, Fp) with that Fp then only runs its node pass and the next jp_phase_ratios_center(ratios, phases, K)
+ *   copies the ratios out; neither reads the particles again.  Dropped by every library call that changes particles or writes
+ *   a particle field (init, advect, inject, clean, force_injection, halo unpack, grid2particle, ...); the caller must not
+ *   modify the particle arrays or the two fields between jp_move and the consumers by other means -- the reference's time
+ *   loops never do (move_particles! -> particle2grid! -> phase ratios) -- hence opt-in.  Needs max_xcell <= 64, a two-pass
+ *   particle2grid mode, <= 4 phases, and containers whose dead slots hold NaN coordinates (everything init_particles /
+ *   move_particles! / inject_particles! produce): liveness is the occupancy word, not phase_ratios_center!'s isnan(px) probe.
+ * JP_OPT_LAST_INTERP (jp_get_option only): bit 0 / bit 1 = the last jp_particle2grid / jp_phase_ratios_center used the hand-off. */
 typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3, JP_OPT_MOVE_POLICY = 4,
-               JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6 } jp_option;
+               JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6, JP_OPT_MOVE_INTERP = 7, JP_OPT_LAST_INTERP = 8 } jp_option;
 typedef enum { JP_MOVE_POLICY_REFERENCE = 0, JP_MOVE_POLICY_COMPACT = 1 } jp_move_policy;
 typedef enum { JP_MOVE_AUTO = 0, JP_MOVE_DIRECT = 1 } jp_move_mode;
 typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;
@@ -146,12 +159,18 @@ int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double 
  * <= 1 cell; larger ones are racy in the reference itself).  JP_MOVE_AUTO plans the
  * sweeps on per-cell occupancy words and moves payloads in two streaming passes, and
  * falls back to JP_MOVE_DIRECT (literal sweeps on the particle arrays) when a particle
- * sits exactly on a cell face.  Synchronises `stream` internally (two 4-byte read-backs). */
+ * sits exactly on a cell face.  Asynchronous on `stream`: the fallback is decided on the device (the kernels of
+ * the path not taken return at once); only the very first planned call on a context blocks, once, to size its staging buffer. */
 int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream);
+/* JP_OPT_MOVE_INTERP: which particle field the following particle2grid!(F, Fp, particles) will interpolate and which field /
+ * how many phases the following phase_ratios_center!(phase_ratios, particles, phases) will use (either may be NULL).  Both must
+ * be among the `args` of jp_move to take effect.  Sticky until changed. */
+int jp_move_interp_fields(jp_ctx *ctx, const double *Fp, const double *phases, int32_t K);
 /* Counters of the last jp_move on this context: {moved, dropped (destination
  * full), deleted (left the domain)}.  Synchronises `stream`. */
 int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream);
-/* 0 = the last jp_move took the plan/gather/scatter path, 1 = direct sweeps. */
+/* bits 0-7: 0 = the last jp_move took the plan/gather/scatter path, 1 = direct sweeps; bits 8+: why (1 move of more than one
+ * cell, 2 / 4 particle on a face of its own / destination cell, 8 staging buffer too small).  Synchronises that jp_move's stream. */
 int jp_last_move_path(const jp_ctx *ctx);
 
 /* inject_particles!(particles, args) (src/Particles/injection.jl:19-131).

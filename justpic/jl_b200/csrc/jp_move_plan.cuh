@@ -5,7 +5,7 @@
 // lands in.  That decision needs only per-cell occupancy bit-masks and the
 // destination of each leaving particle -- not the particle payload.  So:
 //
-//  A. k_move_classify2 (one coalesced pass over coords + mask): per cell the
+//  A. k_move_classify3 (one coalesced pass over coords + mask): per cell the
 //     occupancy word, the leave word and a packed list of 5-bit destination
 //     codes (one of the 3^N neighbours, or "left the domain").  Anything the
 //     planner cannot express exactly -- a particle that fails isincell but
@@ -43,139 +43,12 @@ __device__ __forceinline__ void jp_code_dir(int code, int *dv) {
     dv[0] = code % 3 - 1; dv[1] = (code / 3) % 3 - 1; dv[2] = code / 9 - 1;
 }
 
-// ---- A. classify
-// Phase 1 (thread = cell, slot-synchronous, coalesced): strict isincell test of every live
-// particle -> leave word.  Phase 2: the warp's leavers (~40 % of the particles) are compacted
-// through a shared-memory ring and classified 32 at a time at full lane occupancy:
-// destination by comparisons against the four vertices around the storage cell -- a particle
-// strictly inside (xv[j], xv[j+1]) for j in {i-1, i, i+1} is exactly where the reference's
-// seeded bisection puts it; anything else (on a vertex, further away) is left to the direct
-// sweeps.  Codes are staged as bytes in shared memory ([cell][k], k = rank of the slot among
-// the cell's leavers) and written out as packed 8-byte words.
-struct ClsGeom { double am, a, b, bp, dx, lo, hi; };
-__device__ __forceinline__ ClsGeom jp_cls_geom(const JpGrid &g, int d, int i) {
-    const double *xv = g.xv[d];
-    ClsGeom q;
-    q.a = xv[i]; q.b = xv[i + 1];
-    q.am = i > 0 ? xv[i - 1] : NAN;
-    q.bp = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
-    q.dx = jp_d_of(xv, g.uniform, i);
-    q.lo = xv[0]; q.hi = xv[g.n[d]];
-    return q;
-}
-// one dimension of the destination search; returns false when the planner cannot express it
-__device__ __forceinline__ bool jp_cls_dim(const ClsGeom &q, int uniform, double pd, int &dv, bool &dest_ok) {
-    double lower, dxd;
-    if (q.a < pd && pd < q.b) { dv = 0; lower = q.a; dxd = uniform ? q.dx : q.b - q.a; }
-    else if (q.am < pd && pd < q.a) { dv = -1; lower = q.am; dxd = uniform ? q.dx : q.a - q.am; }
-    else if (q.b < pd && pd < q.bp) { dv = 1; lower = q.b; dxd = uniform ? q.dx : q.bp - q.b; }
-    else { dv = 0; return false; }                   // on a vertex or more than one cell away
-    dest_ok = dest_ok && (lower < pd) && (pd < lower + dxd);
-    return true;
-}
-
-template <int N>
-__global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify2(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
-                                                        unsigned int *complex_flag) {
-    __shared__ uint64_t lv_sm[JP_BY][32];
-    __shared__ __align__(8) uint8_t code_sm[JP_BY][32][JP_MAX_SLOTS];
-    __shared__ uint16_t ring_sm[JP_BY][128];
-    int ci[3]; int64_t c;
-    const bool ok = tile_cell<N>(g, ci, c);
-    const int lane = threadIdx.x, w = threadIdx.y;
-    const uint64_t m = load_mask(index, c, g.C, g.S, ok);
-    // ---- phase 1: leave word
-    uint64_t lv = 0;
-    {
-        double a[3], ub[3];
-        if (ok)
-            for (int d = 0; d < N; d++) { a[d] = g.xv[d][ci[d]]; ub[d] = a[d] + jp_d_of(g.xv[d], g.uniform, ci[d]); }
-        for (int s0 = 0; s0 < g.S; s0 += 4) {
-            const unsigned bits = (unsigned)(m >> s0) & 15u;
-            if (!__any_sync(0xffffffffu, bits != 0)) continue;
-            double p[4][3];
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-#pragma unroll
-                for (int d = 0; d < N; d++) p[u][d] = ((bits >> u) & 1u) ? co.p[d][c + (int64_t)(s0 + u) * g.C] : 0.0;
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                bool in = true;
-#pragma unroll
-                for (int d = 0; d < N; d++) in = in & (a[d] < p[u][d]) & (p[u][d] < ub[d]);
-                if (((bits >> u) & 1u) && !in) lv |= 1ull << (s0 + u);
-            }
-        }
-    }
-    lv_sm[w][lane] = lv;
-    if (ok) { ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv; }
-    __syncwarp();
-    if (!__any_sync(0xffffffffu, lv != 0)) return;
-    // ---- phase 2: compacted leavers
-    const int x0 = blockIdx.x * JP_BX;
-    ClsGeom gy = jp_cls_geom(g, 1, min(ci[1], g.n[1] - 1)), gz;
-    if (N == 3) gz = jp_cls_geom(g, 2, ci[2]);
-    const int64_t crow = (int64_t)g.n[0] * (ci[1] + (N == 3 ? (int64_t)g.n[1] * ci[2] : 0));
-    unsigned cplx = 0;     // reason bits: 1 far / on a vertex, 2 same cell (ulp gap), 4 fails isincell in destination
-    const unsigned lt = (1u << lane) - 1u;
-    int head = 0, tail = 0;
-    for (int s = 0; s <= g.S; s++) {
-        if (s < g.S) {
-            const bool l = (lv >> s) & 1ull;
-            const unsigned bal = __ballot_sync(0xffffffffu, l);
-            if (l) ring_sm[w][(tail + __popc(bal & lt)) & 127] = (uint16_t)((s << 5) | lane);
-            tail += __popc(bal);
-            __syncwarp();
-        }
-        while (tail - head >= 32 || (s == g.S && tail > head)) {
-            const int k = head + lane;
-            if (k < tail) {
-                const int ent = ring_sm[w][k & 127];
-                const int sl = ent >> 5, l = ent & 31;
-                const int cx = x0 + l;
-                const int64_t e = crow + cx + (int64_t)sl * g.C;
-                double p[3];
-#pragma unroll
-                for (int d = 0; d < N; d++) p[d] = co.p[d][e];
-                const ClsGeom gx = jp_cls_geom(g, 0, cx);
-                bool indom = (gx.lo < p[0] && p[0] < gx.hi) && (gy.lo < p[1] && p[1] < gy.hi);
-                if (N == 3) indom = indom && (gz.lo < p[2] && p[2] < gz.hi);
-                int code = JP_CODE_DELETE;
-                if (indom) {
-                    int dv[3] = {0, 0, 0};
-                    bool dest_ok = true;
-                    bool near = jp_cls_dim(gx, g.uniform, p[0], dv[0], dest_ok);
-                    near = jp_cls_dim(gy, g.uniform, p[1], dv[1], dest_ok) && near;
-                    if (N == 3) near = jp_cls_dim(gz, g.uniform, p[2], dv[2], dest_ok) && near;
-                    const bool same = dv[0] == 0 && dv[1] == 0 && dv[2] == 0;
-                    if (!near) cplx |= 1u;
-                    else if (same) cplx |= 2u;
-                    else if (!dest_ok) cplx |= 4u;
-                    else code = jp_dir_code(dv, N);
-                }
-                const int kk = __popcll(lv_sm[w][l] & ((1ull << sl) - 1));
-                code_sm[w][l][kk] = (uint8_t)code;
-            }
-            head += 32;
-            __syncwarp();
-        }
-    }
-    // ---- packed code words (8 byte-codes per word), one plane per 8 leavers
-    if (lv) {
-        const int nl = __popcll(lv);
-        const uint64_t *cw = reinterpret_cast<const uint64_t *>(&code_sm[w][lane][0]);
-        for (int q = 0; q * 8 < nl; q++) ws.code[(int64_t)q * g.C + c] = cw[q];
-    }
-    const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
-    if (wc && lane == 0) atomicOr(complex_flag, wc);
-}
-
-// ---- A'. single-pass classify: every live particle is classified where it is loaded (no second
+// ---- A. single-pass classify: every live particle is classified where it is loaded (no second
 // look at the leavers, no shared memory): the strict isincell test, the domain test and the
 // destination search share their comparisons, and since thread = cell walks its slots in order the
-// k-th leaver's code byte is simply shifted into the thread's own code word.  k_move_classify2
-// re-read the coordinates of the ~38 % leavers; with 4 CTAs/SM resident that second look missed the
-// L2 and cost 40 % extra DRAM traffic at 256^3 (27.7 GB read for 19.3 GB of coordinates).
+// k-th leaver's code byte is simply shifted into the thread's own code word.  (A first version compacted
+// the ~38 % leavers through a shared-memory ring and re-read their coordinates; with 4 CTAs/SM resident
+// that second look missed the L2 and cost 40 % extra DRAM traffic at 256^3.)
 struct JpBox { int o[3], e[3]; };      // sub-box of cells (origin, extent) for the BOX instantiation
 template <int N, bool BOX>
 __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, MovePlanWs ws,
@@ -261,7 +134,8 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
 // words; the slot given to the k-th leaver goes to res (one byte: slot | placed << 6).
 template <int N>
 __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
-                                                   long long *stats, int compact) {
+                                                   long long *stats, int compact, const unsigned int *__restrict__ skip_flag) {
+    if (*skip_flag) return;                                   // the call takes the direct sweeps (decided on the device)
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncol) return;
     int ci[3];
@@ -307,9 +181,10 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
 // ---- C. arrival mask + count per cell: every slot occupied at the end that is not a
 // non-leaving original occupant holds an arrival.
 template <int N>
-__global__ void __launch_bounds__(256) k_move_finalize(JpGrid g, MovePlanWs ws) {
+__global__ void __launch_bounds__(256) k_move_finalize(JpGrid g, MovePlanWs ws, const unsigned int *__restrict__ skip_flag) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= g.C) return;
+    if (*skip_flag) { ws.cnt[c] = 0; return; }
     const uint64_t am = ws.occ[c] & (~ws.occ0[c] | ws.leave[c]);
     ws.arrmask[c] = am;
     ws.cnt[c] = (uint32_t)__popcll(am);
@@ -325,7 +200,9 @@ struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 #endif
 #define JP_MV_A 4      // arrays handled per register batch (coords + fields); more arrays loop again
 template <int N>
-__global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage, int64_t M /* unused */) {
+__global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage,
+                                                                   const unsigned int *__restrict__ skip_flag) {
+    if (*skip_flag) return;
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t lv = ok ? ws.leave[c] : 0;
@@ -383,7 +260,9 @@ __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, M
 // 32-byte sector -- is 3x SLOWER; the slot-synchronous order stays.  prefetch.global.L2 of the cell's
 // staging records ahead of the sweep: +4 % time; of the leavers' sectors in the gather: +80 %.)
 template <int N>
-__global__ void __launch_bounds__(256, JP_MINB_SCATTER) k_move_scatter(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index, const double *__restrict__ stage, int64_t M) {
+__global__ void __launch_bounds__(256, JP_MINB_SCATTER) k_move_scatter(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index, const double *__restrict__ stage,
+                                                                     const unsigned int *__restrict__ skip_flag) {
+    if (*skip_flag) return;
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t amask = ok ? ws.arrmask[c] : 0, lmask = ok ? ws.leave[c] : 0;
@@ -422,4 +301,18 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER) k_move_scatter(JpGrid g,
     }
 }
 
-__global__ void k_move_set_moved(long long *stats, const uint32_t *total) { stats[0] = (long long)*total; }
+// after the scan: total number of arrivals -> stats / read-back word; a staging buffer that is too small sends the call
+// to the direct sweeps (flag bit 8) -- the host learns the count asynchronously and grows the buffer for the next call
+#define JP_CPLX_STAGING 8u
+__global__ void k_move_after_scan(long long *stats, const uint32_t *total, uint64_t cap_rows, unsigned int *flag, unsigned int *m_out) {
+    const unsigned int f = *flag;
+    if (f) return;
+    const uint32_t M = *total;
+    *m_out = M;
+    if ((uint64_t)M > cap_rows) {
+        *flag = JP_CPLX_STAGING;
+        stats[0] = 0; stats[1] = 0; stats[2] = 0;       // the plan kernels counted drops / deletions: the direct sweeps count again
+        return;
+    }
+    stats[0] = (long long)M;
+}

@@ -78,8 +78,24 @@ struct jp_ctx {
     int hint_ndirty; int hint_dirty[8][2];   // (dim, plane) rewritten since the hand-off
     int last_classify;       // 0: coordinates (k_move_classify3), 1: hand-off bytes (diagnostics)
     int adv_split;           // jp_advect_region: the shell part has run, the interior part is still to come
+    int mp_ready;            // every buffer of the plan workspace is allocated
+    void *last_stream;       // stream of the last jp_move (jp_last_move_path reads the device flag on it)
+    cudaEvent_t m_event; int m_pending, m_probed;   // asynchronous read-back of the last arrival count (sizes the staging buffer)
+    // move -> interpolation hand-off (JP_OPT_MOVE_INTERP, csrc/jp_move_interp.cuh): the scatter pass of jp_move also leaves the
+    // two-pass particle2grid! partial sums of field mi_fp and the centre phase ratios of field mi_ph; valid for the arrays in
+    // mi_key until the next library call that changes particles or those fields
+    int mi_opt;
+    const double *mi_fp, *mi_ph; int mi_K;          // registered by jp_move_interp_fields
+    int mi_valid_p2g, mi_valid_ph, mi_p2g_mode;
+    int last_p2g_handoff, last_phase_handoff;       // diagnostics: the last particle2grid! / phase_ratios_center! used the hand-off
+    const void *mi_key[4];
+    double *mi_rc; size_t mi_rc_elems;              // [K][C] centre ratios left by the scatter
 };
 static inline void hint_invalidate(jp_ctx *ctx) { ctx->hint_valid = 0; ctx->hint_ndirty = 0; }
+static void move_plan_free(jp_ctx *ctx);
+static inline void mi_invalidate(jp_ctx *ctx) { ctx->mi_valid_p2g = 0; ctx->mi_valid_ph = 0; }
+// every entry point that changes particles (or may change particle fields) drops both hand-offs
+static inline void handoffs_invalidate(jp_ctx *ctx) { hint_invalidate(ctx); mi_invalidate(ctx); }
 
 struct Ptr3 { double *p[3]; };
 struct CPtr3 { const double *p[3]; };
@@ -183,7 +199,9 @@ __global__ void __launch_bounds__(256) k_advect_hi(JpGrid g, Ptr3 co, const uint
 
 // move_particles! pass A: occupancy + leave words (order-free, coalesced)
 template <int N>
-__global__ void __launch_bounds__(256) k_move_classify(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, uint64_t *occ, uint64_t *leave) {
+__global__ void __launch_bounds__(256) k_move_classify(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, uint64_t *occ, uint64_t *leave,
+                                                       const unsigned int *__restrict__ run_flag) {
+    if (run_flag && !*run_flag) return;                       // JP_MOVE_AUTO: only when the planned path declined (device-side decision)
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
@@ -222,7 +240,9 @@ __device__ __forceinline__ int nth_set_bit64(uint64_t m, int i) {
 
 template <int N>
 __global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ, uint64_t *leave,
-                                                    int ox, int oy, int oz, int ncx, int ncy, int64_t ncol, long long *stats, int compact) {
+                                                    int ox, int oy, int oz, int ncx, int ncy, int64_t ncol, long long *stats, int compact,
+                                                    const unsigned int *__restrict__ run_flag) {
+    if (run_flag && !*run_flag) return;
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= ncol) return;                                   // warp-uniform
@@ -922,9 +942,10 @@ __device__ __forceinline__ double jp_rcp_fast(double x) {
 
 template <int N, bool FASTW>
 __global__ void __launch_bounds__(256, JP_MINB_P2G) k_p2g_cell(JpGrid g, CPtr3 co, const uint8_t *__restrict__ index, const double *__restrict__ Fp,
-                                                  double *__restrict__ PW, double *__restrict__ PWF) {
+                                                  double *__restrict__ PW, double *__restrict__ PWF, const unsigned int *__restrict__ run_flag) {
     constexpr int NQ = N == 2 ? 4 : 8;
     constexpr int U = 4;                       // slots per batch: loads of a batch are issued together
+    if (run_flag && !*run_flag) return;        // move -> interpolation hand-off: the partial sums are already there
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const uint64_t m = load_mask(index, c, g.C, g.S, ok);
@@ -1024,8 +1045,10 @@ __global__ void __launch_bounds__(256) k_p2c(JpGrid g, CPtr3 co, double *__restr
 // phase_ratios_center!  Liveness is the reference's isnan(px) test, so px of EVERY slot
 // is read; slots are processed in batches of U with the loads of a batch in flight together.
 template <int N, int KMAX>
-__global__ void __launch_bounds__(256, KMAX <= 8 ? 3 : 1) k_phase(JpGrid g, CPtr3 co, double *__restrict__ ratios, const double *__restrict__ phases, int K) {
+__global__ void __launch_bounds__(256, KMAX <= 8 ? 3 : 1) k_phase(JpGrid g, CPtr3 co, double *__restrict__ ratios, const double *__restrict__ phases, int K,
+                                                                  const unsigned int *__restrict__ run_flag) {
     constexpr int U = 4;
+    if (run_flag && !*run_flag) return;        // move -> interpolation hand-off: the ratios are copied from the workspace instead
     int ci[3]; int64_t c;
     if (!tile_cell<N>(g, ci, c)) return;
     double xcn[3], idi[3], w[KMAX];
@@ -1063,6 +1086,13 @@ __global__ void __launch_bounds__(256, KMAX <= 8 ? 3 : 1) k_phase(JpGrid g, CPtr
 }
 
 #include "jp_phase_ratios.cuh"
+#include "jp_move_interp.cuh"
+
+// move -> interpolation hand-off: centre ratios left by k_move_scatter_interp -> the caller's array (unless the move took the direct sweeps)
+__global__ void __launch_bounds__(256) k_copy_unless(double *__restrict__ dst, const double *__restrict__ src, int64_t n, const unsigned int *__restrict__ skip_flag) {
+    if (*skip_flag) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
 
 // update_cell_halo! pack / unpack of one cell-plane
 struct HaloArrs { double *a[JP_MAX_ARGS + 3]; int n; };
@@ -1131,9 +1161,8 @@ extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->inj_list); cudaFree(ctx->inj_count); cudaFree(ctx->inbox); cudaFree(ctx->stats);
     cudaFree(ctx->p2g_ws);
-    cudaFree(ctx->mp.code); cudaFree(ctx->mp.res); cudaFree(ctx->mp.occ0); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
-    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp); cudaFree(ctx->stage); cudaFree(ctx->pr_ws);
-    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    move_plan_free(ctx);
+    cudaFree(ctx->stage); cudaFree(ctx->pr_ws); cudaFree(ctx->mi_rc);
     free(ctx);
 }
 
@@ -1184,7 +1213,7 @@ static inline JpArgs jp_shift(JpArgs a, int64_t off) { for (int i = 0; i < a.n; 
 
 extern "C" int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxcell, uint64_t seed, void *stream) {
     PREP("jp_init_particles");
-    hint_invalidate(ctx);
+    handoffs_invalidate(ctx);
     const int NQ = g.ndim == 2 ? 4 : 8;
     if (nxcell < 0) return jp_fail(JP_ERR_INVALID, "jp_init_particles: nxcell < 0");     // 0: empty container (test/test_2D.jl:302)
     const int npq = (nxcell + NQ - 1) / NQ;
@@ -1306,6 +1335,7 @@ static int advect_impl(jp_ctx *ctx, const jp_particles *p, int32_t scheme, doubl
     if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect: Only 0 < alpha < 1 is supported");
     if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect: unknown integrator");
     if (region != JP_REGION_INTERIOR) hint_invalidate(ctx);          // the interior call completes the shell call's hand-off
+    mi_invalidate(ctx);
     AdvHandoff hint;
     memset(&hint, 0, sizeof(hint));
     if (ctx->hint_opt && tiled && g.S <= JP_MAX_SLOTS) {
@@ -1354,7 +1384,7 @@ extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t sche
                                 int32_t interp, void *stream) {
     if (interp == JP_INTERP_LINEAR) return jp_advect(ctx, p, scheme, alpha, V, dt, stream);
     PREP("jp_advect_interp");
-    hint_invalidate(ctx);
+    handoffs_invalidate(ctx);
     if (interp != JP_INTERP_LINP && interp != JP_INTERP_MQS) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: unknown interpolant");
     if (!V) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: null velocity tuple");
     CPtr3 v = {{nullptr, nullptr, nullptr}};
@@ -1380,27 +1410,76 @@ extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t sche
     return JP_OK;
 }
 
+static void move_plan_free(jp_ctx *ctx) {
+    cudaFree(ctx->mp.code); cudaFree(ctx->mp.res); cudaFree(ctx->mp.occ0); cudaFree(ctx->mp.arrmask); cudaFree(ctx->mp.cnt); cudaFree(ctx->mp.off);
+    cudaFree(ctx->mp_flag); cudaFree(ctx->cub_tmp);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->m_event) cudaEventDestroy(ctx->m_event);
+    memset(&ctx->mp, 0, sizeof(ctx->mp));
+    ctx->mp_flag = nullptr; ctx->cub_tmp = nullptr; ctx->cub_tmp_bytes = 0; ctx->h_pinned = nullptr; ctx->m_event = nullptr;
+    ctx->mp_ready = 0;
+}
+// the plan workspace (~11 GB at 256^3): all or nothing -- a failed allocation frees what it got, so that the next call
+// retries cleanly instead of launching kernels on a half-built workspace
 static int move_plan_alloc(jp_ctx *ctx) {
     const JpGrid &g = ctx->g;
-    if (ctx->mp.code) return JP_OK;
-    JP_CUDA(cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * (size_t)((g.S + 7) / 8) * g.C));
-    JP_CUDA(cudaMalloc(&ctx->mp.res, sizeof(uint64_t) * (size_t)((g.S + 7) / 8) * g.C));
-    JP_CUDA(cudaMalloc(&ctx->mp.occ0, sizeof(uint64_t) * g.C));
-    JP_CUDA(cudaMalloc(&ctx->mp.arrmask, sizeof(uint64_t) * g.C));
-    JP_CUDA(cudaMalloc(&ctx->mp.cnt, sizeof(uint32_t) * (g.C + 1)));
-    JP_CUDA(cudaMalloc(&ctx->mp.off, sizeof(uint32_t) * (g.C + 1)));
-    JP_CUDA(cudaMemset(ctx->mp.cnt, 0, sizeof(uint32_t) * (g.C + 1)));
-    JP_CUDA(cudaMalloc(&ctx->mp_flag, sizeof(unsigned int)));
-    JP_CUDA(cudaMallocHost(&ctx->h_pinned, 4 * sizeof(unsigned int)));
-    ctx->mp.occ = ctx->occ; ctx->mp.leave = ctx->leave;
+    if (ctx->mp_ready) return JP_OK;
+    cudaError_t e = cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * (size_t)((g.S + 7) / 8) * g.C);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->mp.res, sizeof(uint64_t) * (size_t)((g.S + 7) / 8) * g.C);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->mp.occ0, sizeof(uint64_t) * g.C);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->mp.arrmask, sizeof(uint64_t) * g.C);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->mp.cnt, sizeof(uint32_t) * (g.C + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->mp.off, sizeof(uint32_t) * (g.C + 1));
+    if (e == cudaSuccess) e = cudaMemset(ctx->mp.cnt, 0, sizeof(uint32_t) * (g.C + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->mp_flag, 2 * sizeof(unsigned int));          // [0] complex flag, [1] arrival count of the last call
+    if (e == cudaSuccess) e = cudaMemset(ctx->mp_flag, 0, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_pinned, 4 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->m_event, cudaEventDisableTiming);
     size_t tmp = 0;
-    JP_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->mp.cnt, ctx->mp.off, (int)(g.C + 1)));
-    JP_CUDA(cudaMalloc(&ctx->cub_tmp, tmp));
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->mp.cnt, ctx->mp.off, (int)(g.C + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->cub_tmp, tmp);
+    if (e != cudaSuccess) {
+        move_plan_free(ctx);
+        cudaGetLastError();
+        return jp_fail(JP_ERR_CUDA, "move_particles!: plan workspace: %s", cudaGetErrorString(e));
+    }
     ctx->cub_tmp_bytes = tmp;
+    ctx->mp.occ = ctx->occ; ctx->mp.leave = ctx->leave;
+    ctx->mp_ready = 1;
     return JP_OK;
 }
 
-// plan / gather / scatter path; returns 1 when the call must take the direct sweeps instead
+static int stage_reserve(jp_ctx *ctx, size_t elems) {
+    if (elems <= ctx->stage_elems) return JP_OK;
+    if (ctx->stage) JP_CUDA(cudaFree(ctx->stage));
+    ctx->stage = nullptr; ctx->stage_elems = 0;
+    JP_CUDA(cudaMalloc(&ctx->stage, elems * sizeof(double)));
+    ctx->stage_elems = elems;
+    return JP_OK;
+}
+
+static int p2g_ws_reserve(jp_ctx *ctx) {
+    const int NQ = ctx->g.ndim == 2 ? 4 : 8;
+    if (!ctx->p2g_ws) JP_CUDA(cudaMalloc(&ctx->p2g_ws, sizeof(double) * 2 * NQ * ctx->g.C));
+    return JP_OK;
+}
+
+template <int N>
+static void launch_scatter_interp(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, const MovePlanWs &ws, const MoveArrays &arrs, uint8_t *index,
+                                  const double *stage, const MoveInterp &mi, bool fastw, const unsigned int *flag) {
+    if (mi.K <= 2) {
+        if (fastw) k_move_scatter_interp<N, 2, true><<<grd, blk, 0, st>>>(g, ws, arrs, index, stage, mi, flag);
+        else       k_move_scatter_interp<N, 2, false><<<grd, blk, 0, st>>>(g, ws, arrs, index, stage, mi, flag);
+    } else {
+        if (fastw) k_move_scatter_interp<N, 4, true><<<grd, blk, 0, st>>>(g, ws, arrs, index, stage, mi, flag);
+        else       k_move_scatter_interp<N, 4, false><<<grd, blk, 0, st>>>(g, ws, arrs, index, stage, mi, flag);
+    }
+}
+
+// plan / gather / scatter path.  Everything is enqueued without waiting for the device: whether the call has to take the
+// direct sweeps instead (a particle on a cell face, a move of more than one cell, a staging buffer that turned out too
+// small) is decided ON THE DEVICE -- every kernel of this path returns at once when the flag is set, and the direct-sweep
+// kernels enqueued behind it (jp_move) run only then.
 template <int N>
 static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cudaStream_t st) {
     const JpGrid &g = ctx->g;
@@ -1414,7 +1493,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     int nev = 0;
     auto mark = [&]() { if (timing) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); nev++; } };
     mark();
-    static const bool cls2 = getenv("JP_MOVE_CLASSIFY2") != nullptr;       // developer A/B switch
+    unsigned int *flag = ctx->mp_flag;
     const JpBox whole = {{0, 0, 0}, {g.n[0], g.n[1], g.n[2]}};
     bool use_hint = ctx->hint_valid && ctx->hint_key[3] == (const void *)p->index;
     for (int d = 0; d < N; d++) use_hint = use_hint && ctx->hint_key[d] == (const void *)p->coords[d];
@@ -1425,69 +1504,97 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
             JpBox bx = whole;
             bx.o[ctx->hint_dirty[i][0]] = ctx->hint_dirty[i][1];
             bx.e[ctx->hint_dirty[i][0]] = 1;
-            k_move_classify3<N, true><<<tile_grid(bx.e[0], bx.e[1], N == 3 ? bx.e[2] : 1), blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag, bx);
+            k_move_classify3<N, true><<<tile_grid(bx.e[0], bx.e[1], N == 3 ? bx.e[2] : 1), blk, 0, st>>>(g, cco, p->index, ctx->mp, flag, bx);
         }
     } else {
-        JP_CUDA(cudaMemsetAsync(ctx->mp_flag, 0, sizeof(unsigned int), st));
-        if (cls2) k_move_classify2<N><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag);
-        else      k_move_classify3<N, false><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, ctx->mp_flag, whole);
+        JP_CUDA(cudaMemsetAsync(flag, 0, sizeof(unsigned int), st));
+        k_move_classify3<N, false><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->mp, flag, whole);
     }
     hint_invalidate(ctx);
     JP_CHECK_LAUNCH();
-    JP_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->mp_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    JP_CUDA(cudaStreamSynchronize(st));
-    ctx->last_complex = (int)ctx->h_pinned[0];
     mark();
-    if (ctx->h_pinned[0]) return 1;                       // ties / far moves / overfull leave list: direct sweeps
+    MoveArrays arrs; arrs.n = 0;
+    for (int d = 0; d < N; d++) arrs.a[arrs.n++] = p->coords[d];
+    for (int i = 0; i < a.n; i++) arrs.a[arrs.n++] = a.a[i];
+    const size_t AS = (size_t)((arrs.n + 3) & ~3);              // array-of-structs staging, stride padded to 4 doubles
+    // staging capacity: the arrival count of the previous call comes back asynchronously (pinned word + event); grow when it is
+    // known and calls for it.  Never blocks except to reallocate.
+    if (ctx->m_pending && cudaEventQuery(ctx->m_event) == cudaSuccess) {
+        ctx->m_pending = 0;
+        const size_t lastM = ctx->h_pinned[1];
+        if (lastM * AS > ctx->stage_elems || (lastM + lastM / 8) * AS > ctx->stage_elems) {
+            rc = stage_reserve(ctx, (lastM + lastM / 4) * AS);
+            if (rc) return rc;
+        }
+    }
     const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = N == 3 ? (g.n[2] + 2) / 3 : 1;
     const int64_t ncol = (int64_t)ncx * ncy * ncz;
     const unsigned nblk = (unsigned)((ncol + 255) / 256);
     for (int ox = 0; ox < 3; ox++)
         for (int oy = 0; oy < 3; oy++)
             for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
-                k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
+                k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy, flag);
     const unsigned cblk = (unsigned)((g.C + 255) / 256);
     mark();
-    k_move_finalize<N><<<cblk, 256, 0, st>>>(g, ctx->mp);
+    k_move_finalize<N><<<cblk, 256, 0, st>>>(g, ctx->mp, flag);
     JP_CHECK_LAUNCH();
     JP_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, ctx->cub_tmp_bytes, ctx->mp.cnt, ctx->mp.off, (int)(g.C + 1), st));
-    k_move_set_moved<<<1, 1, 0, st>>>(ctx->stats, ctx->mp.off + g.C);
-    JP_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->mp.off + g.C, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-    JP_CUDA(cudaStreamSynchronize(st));
-    const size_t M = ctx->h_pinned[1];
-    mark();
-    if (M == 0) {                                        // nothing arrives; still vacate deleted / dropped slots
-        MoveArrays arrs; arrs.n = 0;
-        for (int d = 0; d < N; d++) arrs.a[arrs.n++] = p->coords[d];
-        for (int i = 0; i < a.n; i++) arrs.a[arrs.n++] = a.a[i];
-        k_move_scatter<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, p->index, ctx->stage, 0);
-        JP_CHECK_LAUNCH();
-        return JP_OK;
+    if (!ctx->m_probed) {
+        // very first planned call on this context: learn the arrival count now (the only blocking read-back there is)
+        ctx->m_probed = 1;
+        JP_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->mp.off + g.C, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        JP_CUDA(cudaStreamSynchronize(st));
+        const size_t M0 = ctx->h_pinned[1];
+        if (M0) { rc = stage_reserve(ctx, (M0 + M0 / 4) * AS); if (rc) return rc; }
     }
-    MoveArrays arrs; arrs.n = 0;
-    for (int d = 0; d < N; d++) arrs.a[arrs.n++] = p->coords[d];
-    for (int i = 0; i < a.n; i++) arrs.a[arrs.n++] = a.a[i];
-    const size_t need = M * (size_t)((arrs.n + 3) & ~3);        // array-of-structs staging, stride padded to 4 doubles
-    if (need > ctx->stage_elems) {
-        if (ctx->stage) JP_CUDA(cudaFree(ctx->stage));
-        ctx->stage = nullptr; ctx->stage_elems = 0;
-        const size_t want = need + need / 4;
-        JP_CUDA(cudaMalloc(&ctx->stage, want * sizeof(double)));
-        ctx->stage_elems = want;
+    k_move_after_scan<<<1, 1, 0, st>>>(ctx->stats, ctx->mp.off + g.C, (uint64_t)(ctx->stage_elems / AS), flag, flag + 1);
+    if (!ctx->m_pending) {
+        JP_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, flag + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        JP_CUDA(cudaEventRecord(ctx->m_event, st));
+        ctx->m_pending = 1;
     }
-    const int64_t stride = (int64_t)(ctx->stage_elems / arrs.n);
     mark();
-    k_move_gather<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, ctx->stage, stride);
+    k_move_gather<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, ctx->stage, flag);
     mark();
-    k_move_scatter<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, p->index, ctx->stage, stride);
+    // move -> interpolation hand-off: the scatter also leaves particle2grid!'s cell sums / the centre phase ratios
+    MoveInterp mi; mi.iT = mi.iP = -1; mi.K = 0; mi.PW = mi.PWF = mi.RC = nullptr;
+    if (ctx->mi_opt) {
+        const bool twopass = ctx->p2g_mode == JP_P2G_TWOPASS || ctx->p2g_mode == JP_P2G_TWOPASS_FASTW;
+        for (int i = 0; i < a.n; i++) {
+            if (twopass && ctx->mi_fp && a.a[i] == ctx->mi_fp) mi.iT = N + i;
+            if (ctx->mi_ph && a.a[i] == ctx->mi_ph && ctx->mi_K >= 1 && ctx->mi_K <= 4) mi.iP = N + i;
+        }
+        if (mi.iT >= 0) {
+            rc = p2g_ws_reserve(ctx); if (rc) return rc;
+            mi.PW = ctx->p2g_ws; mi.PWF = ctx->p2g_ws + (int64_t)(N == 2 ? 4 : 8) * g.C;
+        }
+        if (mi.iP >= 0) {
+            mi.K = ctx->mi_K;
+            const size_t need = (size_t)mi.K * g.C;
+            if (need > ctx->mi_rc_elems) {
+                if (ctx->mi_rc) JP_CUDA(cudaFree(ctx->mi_rc));
+                ctx->mi_rc = nullptr; ctx->mi_rc_elems = 0;
+                JP_CUDA(cudaMalloc(&ctx->mi_rc, need * sizeof(double)));
+                ctx->mi_rc_elems = need;
+            }
+            mi.RC = ctx->mi_rc;
+        }
+    }
+    if (mi.iT >= 0 || mi.iP >= 0) {
+        launch_scatter_interp<N>(g, grd, blk, st, ctx->mp, arrs, p->index, ctx->stage, mi, ctx->p2g_mode == JP_P2G_TWOPASS_FASTW, flag);
+        ctx->mi_valid_p2g = mi.iT >= 0; ctx->mi_valid_ph = mi.iP >= 0; ctx->mi_p2g_mode = ctx->p2g_mode;
+        for (int d = 0; d < 3; d++) ctx->mi_key[d] = d < N ? (const void *)p->coords[d] : nullptr;
+        ctx->mi_key[3] = p->index;
+    } else
+        k_move_scatter<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, p->index, ctx->stage, flag);
     mark();
     JP_CHECK_LAUNCH();
     if (timing) {
         cudaStreamSynchronize(st);
-        const char *names[] = {"classify+flag", "plan", "finalize+scan+M", "alloc", "gather", "scatter"};
+        const char *names[] = {"classify", "plan", "finalize+scan", "gather", "scatter"};
         fprintf(stderr, "[jp_move]");
         for (int i = 0; i + 1 < nev; i++) { float ms; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, " %s %.3f", names[i], ms); }
-        fprintf(stderr, " M=%zu\n", M);
+        fprintf(stderr, "\n");
         for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
     }
     return JP_OK;
@@ -1498,6 +1605,8 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_move");
     if (rc) return rc;
+    mi_invalidate(ctx);
+    ctx->last_stream = stream;
     JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
     if (g.S > JP_MAX_SLOTS) {                                // wide cells: literal per-cell sweeps on the index bytes
         ctx->last_move_path = 1;
@@ -1514,15 +1623,16 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
         JP_CHECK_LAUNCH();
         return JP_OK;
     }
+    const unsigned int *run_flag = nullptr;                  // JP_MOVE_DIRECT: the sweeps always run
     if (ctx->move_mode == JP_MOVE_AUTO) {
         rc = g.ndim == 2 ? move_planned<2>(ctx, p, a, st) : move_planned<3>(ctx, p, a, st);
-        if (rc <= 0) { ctx->last_move_path = 0; return rc; }
-        JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
-    }
-    ctx->last_move_path = 1;
+        if (rc) return rc;
+        ctx->last_move_path = -1;                            // decided on the device: jp_last_move_path reads the flag
+        run_flag = ctx->mp_flag;                             // the sweeps below run only if the planned path declined
+    } else ctx->last_move_path = 1;
     hint_invalidate(ctx);
-    if (g.ndim == 2) k_move_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
-    else             k_move_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave);
+    if (g.ndim == 2) k_move_classify<2><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave, run_flag);
+    else             k_move_classify<3><<<grd, blk, 0, st>>>(g, cco, p->index, ctx->occ, ctx->leave, run_flag);
     JP_CHECK_LAUNCH();
     const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = g.ndim == 3 ? (g.n[2] + 2) / 3 : 1;
     const int64_t ncol = (int64_t)ncx * ncy * ncz;          // source cells per colour (upper bound)
@@ -1530,14 +1640,27 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     for (int ox = 0; ox < 3; ox++)
         for (int oy = 0; oy < 3; oy++)
             for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {
-                if (g.ndim == 2) k_move_sweep<2><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
-                else             k_move_sweep<3><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
+                if (g.ndim == 2) k_move_sweep<2><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy, run_flag);
+                else             k_move_sweep<3><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy, run_flag);
             }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
 
-extern "C" int jp_last_move_path(const jp_ctx *ctx) { return ctx ? (ctx->last_move_path | (ctx->last_complex << 8)) : -1; }
+// bits 0-7: 0 = the last jp_move took the plan / gather / scatter path, 1 = direct sweeps; bits 8+: why (1 far move, 2 particle
+// on a face of its own cell, 4 on a face of its destination, 8 staging buffer too small).  In JP_MOVE_AUTO the choice was made
+// on the device, so this reads the flag back (synchronises the stream of that jp_move).
+extern "C" int jp_last_move_path(const jp_ctx *cctx) {
+    jp_ctx *ctx = const_cast<jp_ctx *>(cctx);
+    if (!ctx) return -1;
+    if (ctx->last_move_path >= 0) return ctx->last_move_path;
+    unsigned int f = 0;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&f, ctx->mp_flag, sizeof(f), cudaMemcpyDeviceToHost, (cudaStream_t)ctx->last_stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize((cudaStream_t)ctx->last_stream) != cudaSuccess) return -1;
+    ctx->last_complex = (int)f;
+    return (f ? 1 : 0) | ((int)f << 8);
+}
 
 extern "C" int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream) {
     if (!ctx || !out) return jp_fail(JP_ERR_INVALID, "jp_move_stats: null argument");
@@ -1566,7 +1689,7 @@ static void launch_inject_wide(const JpGrid &g, cudaStream_t st, Ptr3 co, uint8_
 
 extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream) {
     PREP("jp_inject");
-    hint_invalidate(ctx);
+    handoffs_invalidate(ctx);
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_inject");
     if (rc) return rc;
@@ -1597,7 +1720,7 @@ extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args
 extern "C" int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phases, double *const *args, const double *const *fields,
                                const int32_t *field_kind, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream) {
     PREP("jp_inject_phase");
-    hint_invalidate(ctx);
+    handoffs_invalidate(ctx);
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_inject_phase");
     if (rc) return rc;
@@ -1646,7 +1769,7 @@ extern "C" int jp_inject_stats(jp_ctx *ctx, int64_t *out, void *stream) {
 extern "C" int jp_force_injection(jp_ctx *ctx, const jp_particles *p, const double *const *pnew, double *const *fields, const double *values,
                                   int32_t nfields, void *stream) {
     PREP("jp_force_injection");
-    hint_invalidate(ctx);
+    handoffs_invalidate(ctx);
     JpArgs f;
     int rc = pack_args(fields, nfields, f, "jp_force_injection");
     if (rc) return rc;
@@ -1667,7 +1790,7 @@ extern "C" int jp_force_injection(jp_ctx *ctx, const jp_particles *p, const doub
 
 extern "C" int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream) {
     PREP("jp_clean");
-    hint_invalidate(ctx);
+    handoffs_invalidate(ctx);
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_clean");
     if (rc) return rc;
@@ -1682,6 +1805,7 @@ extern "C" int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args,
 
 extern "C" int jp_grid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *F, void *stream) {
     PREP("jp_grid2particle");
+    mi_invalidate(ctx);                                  // a particle field is rewritten
     if (!Fp || !F) return jp_fail(JP_ERR_INVALID, "jp_grid2particle: null field");
     for (int ch = 0; ch < jp_nchunks(g); ch++) {
         const SlotChunk k = jp_chunk(g, ch);
@@ -1694,6 +1818,7 @@ extern "C" int jp_grid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, 
 
 extern "C" int jp_grid2particle_flip(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *F, const double *F0, double alpha, void *stream) {
     PREP("jp_grid2particle_flip");
+    mi_invalidate(ctx);                                  // a particle field is rewritten
     if (!Fp || !F || !F0) return jp_fail(JP_ERR_INVALID, "jp_grid2particle_flip: null field");
     for (int ch = 0; ch < jp_nchunks(g); ch++) {
         const SlotChunk k = jp_chunk(g, ch);
@@ -1709,6 +1834,7 @@ extern "C" int jp_subgrid_diffusion(jp_ctx *ctx, const jp_particles *p, double *
                                     const int32_t *dT_extents, double *pT0, double *pdT, const double *dt0, double *dT_subgrid,
                                     double dt, double d, int32_t centroid, void *stream) {
     PREP("jp_subgrid_diffusion");
+    mi_invalidate(ctx);                                  // a particle field is rewritten
     if (!pT || !T_grid || !dT_grid || !dT_extents || !pT0 || !pdT || !dt0 || !dT_subgrid) return jp_fail(JP_ERR_INVALID, "jp_subgrid_diffusion: null argument");
     const int plus = centroid ? 0 : 1;
     const int n0 = g.n[0] + plus, n1 = g.n[1] + plus, n2 = g.ndim == 3 ? g.n[2] + plus : 1;
@@ -1740,6 +1866,7 @@ extern "C" int jp_subgrid_diffusion(jp_ctx *ctx, const jp_particles *p, double *
 
 extern "C" int jp_centroid2particle(jp_ctx *ctx, const jp_particles *p, double *Fp, const double *Fc, void *stream) {
     PREP("jp_centroid2particle");
+    mi_invalidate(ctx);                                  // a particle field is rewritten
     if (!Fp || !Fc) return jp_fail(JP_ERR_INVALID, "jp_centroid2particle: null field");
     if (g.ndim == 2) k_c2p<2><<<grd, blk, 0, st>>>(g, cco, Fp, Fc);
     else             k_c2p<3><<<grd, blk, 0, st>>>(g, cco, Fp, Fc);
@@ -1754,7 +1881,16 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (option == JP_OPT_MOVE_POLICY && (value == JP_MOVE_POLICY_REFERENCE || value == JP_MOVE_POLICY_COMPACT)) { ctx->move_policy = value; return JP_OK; }
     if (option == JP_OPT_ADVECT_AFFINE && (value == 0 || value == 1)) { ctx->g.affine = value ? ctx->affine_detected : 0; return JP_OK; }
     if (option == JP_OPT_ADVECT_CLASSIFY && (value == 0 || value == 1)) { ctx->hint_opt = value; hint_invalidate(ctx); return JP_OK; }
+    if (option == JP_OPT_MOVE_INTERP && (value == 0 || value == 1)) { ctx->mi_opt = value; mi_invalidate(ctx); return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
+}
+
+extern "C" int jp_move_interp_fields(jp_ctx *ctx, const double *Fp, const double *phases, int32_t K) {
+    if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_move_interp_fields: null context");
+    if (phases && (K < 1 || K > JP_MAX_PHASES)) return jp_fail(JP_ERR_UNSUPPORTED, "jp_move_interp_fields: 1 <= nphases <= 32 required");
+    ctx->mi_fp = Fp; ctx->mi_ph = phases; ctx->mi_K = phases ? K : 0;
+    mi_invalidate(ctx);
+    return JP_OK;
 }
 
 extern "C" int jp_get_option(const jp_ctx *ctx, int32_t option, int32_t *value) {
@@ -1765,7 +1901,15 @@ extern "C" int jp_get_option(const jp_ctx *ctx, int32_t option, int32_t *value) 
     if (option == JP_OPT_MOVE_POLICY) { *value = ctx->move_policy; return JP_OK; }
     if (option == JP_OPT_ADVECT_CLASSIFY) { *value = ctx->hint_opt; return JP_OK; }
     if (option == JP_OPT_LAST_CLASSIFY) { *value = ctx->last_classify; return JP_OK; }
+    if (option == JP_OPT_MOVE_INTERP) { *value = ctx->mi_opt; return JP_OK; }
+    if (option == JP_OPT_LAST_INTERP) { *value = (ctx->last_p2g_handoff ? 1 : 0) | (ctx->last_phase_handoff ? 2 : 0); return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_get_option: unknown option");
+}
+
+static bool mi_matches(const jp_ctx *ctx, const jp_particles *p) {
+    if (ctx->mi_key[3] != (const void *)p->index) return false;
+    for (int d = 0; d < ctx->g.ndim; d++) if (ctx->mi_key[d] != (const void *)p->coords[d]) return false;
+    return true;
 }
 
 extern "C" int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, const double *Fp, void *stream) {
@@ -1777,16 +1921,23 @@ extern "C" int jp_particle2grid(jp_ctx *ctx, const jp_particles *p, double *F, c
         else             k_p2g<3><<<ng, blk, 0, st>>>(g, cco, p->index, F, Fp);
     } else {
         const int NQ = g.ndim == 2 ? 4 : 8;
-        if (!ctx->p2g_ws) JP_CUDA(cudaMalloc(&ctx->p2g_ws, sizeof(double) * 2 * NQ * g.C));
+        int rc = p2g_ws_reserve(ctx);
+        if (rc) return rc;
         double *PW = ctx->p2g_ws, *PWF = ctx->p2g_ws + (int64_t)NQ * g.C;
         const bool fw = ctx->p2g_mode == JP_P2G_TWOPASS_FASTW;
+        // move -> interpolation hand-off: the cell sums of this field were left by the last jp_move's scatter pass; the cell pass
+        // then runs only if that move took the direct sweeps after all (device-side flag)
+        const unsigned int *run_flag = nullptr;
+        if (ctx->mi_valid_p2g && Fp == ctx->mi_fp && ctx->mi_p2g_mode == ctx->p2g_mode && mi_matches(ctx, p)) run_flag = ctx->mp_flag;
+        else ctx->mi_valid_p2g = 0;                                 // the workspace is overwritten with another field's sums
+        ctx->last_p2g_handoff = run_flag != nullptr;
         if (g.ndim == 2) {
-            if (fw) k_p2g_cell<2, true><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
-            else    k_p2g_cell<2, false><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
+            if (fw) k_p2g_cell<2, true><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF, run_flag);
+            else    k_p2g_cell<2, false><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF, run_flag);
             k_p2g_node<2><<<ng, blk, 0, st>>>(g, PW, PWF, F);
         } else {
-            if (fw) k_p2g_cell<3, true><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
-            else    k_p2g_cell<3, false><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF);
+            if (fw) k_p2g_cell<3, true><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF, run_flag);
+            else    k_p2g_cell<3, false><<<grd, blk, 0, st>>>(g, cco, p->index, Fp, PW, PWF, run_flag);
             k_p2g_node<3><<<ng, blk, 0, st>>>(g, PW, PWF, F);
         }
     }
@@ -1804,20 +1955,27 @@ extern "C" int jp_particle2centroid(jp_ctx *ctx, const jp_particles *p, double *
 }
 
 template <int N>
-static void launch_phase(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, CPtr3 cco, double *ratios, const double *phases, int K) {
-    if (K <= 2) k_phase<N, 2><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
-    else if (K <= 4) k_phase<N, 4><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
-    else if (K <= 8) k_phase<N, 8><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
-    else if (K <= 16) k_phase<N, 16><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
-    else k_phase<N, 32><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K);
+static void launch_phase(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, CPtr3 cco, double *ratios, const double *phases, int K,
+                         const unsigned int *run_flag) {
+    if (K <= 2) k_phase<N, 2><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K, run_flag);
+    else if (K <= 4) k_phase<N, 4><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K, run_flag);
+    else if (K <= 8) k_phase<N, 8><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K, run_flag);
+    else if (K <= 16) k_phase<N, 16><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K, run_flag);
+    else k_phase<N, 32><<<grd, blk, 0, st>>>(g, cco, ratios, phases, K, run_flag);
 }
 
 extern "C" int jp_phase_ratios_center(jp_ctx *ctx, const jp_particles *p, double *ratios, const double *phases, int32_t K, void *stream) {
     PREP("jp_phase_ratios_center");
     if (!ratios || !phases) return jp_fail(JP_ERR_INVALID, "jp_phase_ratios_center: null field");
     if (K < 1 || K > JP_MAX_PHASES) return jp_fail(JP_ERR_UNSUPPORTED, "jp_phase_ratios_center: 1 <= nphases <= 32 required");
-    if (g.ndim == 2) launch_phase<2>(g, grd, blk, st, cco, ratios, phases, K);
-    else             launch_phase<3>(g, grd, blk, st, cco, ratios, phases, K);
+    // move -> interpolation hand-off: the ratios were left by the last jp_move's scatter pass (k_phase runs only if that move
+    // took the direct sweeps after all)
+    const unsigned int *run_flag = nullptr;
+    if (ctx->mi_valid_ph && phases == ctx->mi_ph && K == ctx->mi_K && mi_matches(ctx, p)) run_flag = ctx->mp_flag;
+    ctx->last_phase_handoff = run_flag != nullptr;
+    if (g.ndim == 2) launch_phase<2>(g, grd, blk, st, cco, ratios, phases, K, run_flag);
+    else             launch_phase<3>(g, grd, blk, st, cco, ratios, phases, K, run_flag);
+    if (run_flag) k_copy_unless<<<148 * 8, 256, 0, st>>>(ratios, ctx->mi_rc, (int64_t)K * g.C, run_flag);
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1956,6 +2114,7 @@ static int halo_common(jp_ctx *ctx, int dim, int plane, double *const *arrays, i
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     if (pack) k_halo<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
     else {
+        mi_invalidate(ctx);
         k_halo<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
         if (ctx->hint_valid || (ctx->adv_split && ctx->hint_opt)) {   // the hand-off bytes of this plane are stale now
             bool seen = false;
