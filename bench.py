@@ -11,6 +11,14 @@ the halo exchange of configs[4] between advection! and move_particles!.
 
 Prints ONE JSON line (see DESIGN.md "Measurement" for every key).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells CELLS]
+                    [--config cfg1|cfg2|cfg3|cfg4] [--scaling weak|strong --global-cells G]
+
+--config selects one of BASELINE.json's single-GPU configurations (default cfg4 = configs[3], the headline):
+    cfg1  2-D 256^2, RK2(2/3), CFL 0.75: advection! + move_particles! + inject_particles! + particle2grid! + grid2particle!
+          (the reference's own timing harness, scripts/temperature_advection_timer.jl:64-68)
+    cfg2  2-D 512^2, solid rotation, RK4: advection! + move_particles! + inject_particles! + particle2grid!  (scripts/rotating_circle.jl)
+    cfg3  3-D 128^3, RK2, CFL 0.5: advection! + move_particles! + inject_particles! + particle2grid! + grid2particle!
+    cfg4  3-D 256^3, RK2, 3 fields, 2 phases: advection! + move_particles! + particle2grid! + phase_ratios_center!
 """
 from __future__ import annotations
 
@@ -45,6 +53,16 @@ def parse():
     ap.add_argument("--handoff", type=int, default=1, choices=[0, 1],
                     help="1 (default): advection! also leaves move_particles!' classification words (JP_OPT_ADVECT_CLASSIFY, "
                          "bit-identical results, see include/justpic_c.h); 0: move_particles! classifies the coordinates itself")
+    ap.add_argument("--interp-handoff", type=int, default=1, choices=[0, 1],
+                    help="1 (default): move_particles!' last pass also leaves particle2grid!'s cell sums and the centre phase ratios "
+                         "(JP_OPT_MOVE_INTERP, bit-identical results); 0: the two calls stream the particles again")
+    ap.add_argument("--config", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one --cells^3 block per GPU (same dx, dt and flow pattern on every rank); strong = a fixed "
+                         "--global-cells^3 grid split over the GPUs (BASELINE configs[4]: 512)")
+    ap.add_argument("--global-cells", type=int, default=512)
+    ap.add_argument("--topology", default="auto", choices=["auto", "mpi"],
+                    help="auto: never split x (its planes are strided in the CellArray layout): 8 -> 1x2x4; mpi: MPI_Dims_create order, 8 -> 2x2x2")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="N > 1 only. 1 (default): advection! runs as shell + interior launches and update_cell_halo! travels on a side "
                          "stream behind the interior launch (halo.advection_with_halo, bit-identical results); 0: advection!, then the exchange")
@@ -52,17 +70,27 @@ def parse():
 
 
 # ----------------------------------------------------------------------------- workload
-def local_grids(n, topo_dims=(1, 1, 1), coords=(0, 0, 0)):
-    """Unit cube split into blocks of n cells with a 1-cell halo ring (overlap 2,
-    as ImplicitGlobalGrid does); returns LinRange staggered grids of this block."""
+def block_cells(n, gpus_dims, scaling, global_cells):
+    """cells per dimension of one rank's block (incl. its halo ring where the dimension is decomposed)"""
+    if scaling == "weak":
+        return (n, n, n)
+    return tuple(global_cells if gpus_dims[d] == 1 else -(-(global_cells - 2) // gpus_dims[d]) + 2 for d in range(3))
+
+
+def local_grids(nloc, topo_dims=(1, 1, 1), coords=(0, 0, 0), dx0=None):
+    """Blocks of nloc cells with a 1-cell halo ring where a dimension is decomposed (overlap 2, as ImplicitGlobalGrid does),
+    cell size dx0 in every dimension on every rank (default 1 / nloc[0]: the unit cube at N = 1); returns the LinRange
+    staggered grids of this block.  Weak scaling therefore keeps dx, dt and the flow pattern per rank fixed as N grows
+    (the stream-function field below is periodic in x and z with period 2)."""
     from justpic.jl_b200 import LinRange, expand_range
+    if isinstance(nloc, int):
+        nloc = (nloc,) * 3
+    dx = dx0 if dx0 is not None else 1.0 / nloc[0]
     xv, xc = [], []
     for d in range(3):
-        nglob = topo_dims[d] * (n - 2) + 2 if topo_dims[d] > 1 else n
-        dx = 1.0 / nglob
+        n = nloc[d]
         i0 = coords[d] * (n - 2) if topo_dims[d] > 1 else 0
-        v = LinRange(i0 * dx, (i0 + n) * dx, n + 1)
-        xv.append(v)
+        xv.append(LinRange(i0 * dx, (i0 + n) * dx, n + 1))
         xc.append(LinRange(i0 * dx + dx / 2, (i0 + n) * dx - dx / 2, n))
     xg = [expand_range(c) for c in xc]
     return tuple(tuple(xv[d] if d == comp else xg[d] for d in range(3)) for comp in range(3))
@@ -185,25 +213,37 @@ def run_reference(args):
         "impl": "reference", "metric": "particle-updates/s per step (advect+move+p2g)", "value": v, "unit": "particle-updates/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.n, args.gpus), "note": "JustPIC.CPU cannot run here (no Julia); CPU restatement (oracle/, OpenMP over same-colour cells) timed on a bounded sample"},
+        "config": {"workload": workload_name(args.n, args.gpus, args.scaling, args.global_cells), "note": "JustPIC.CPU cannot run here (no Julia); CPU restatement (oracle/, OpenMP over same-colour cells) timed on a bounded sample"},
         "cpu_baseline": {"value": v, "unit": "particle-updates/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name(n, gpus):
-    return (f"3D {n}^3 cells/GPU x {gpus} GPU, {PPC} ppc ({SLOTS} slots), RK2(0.5) advection! + "
+def workload_name(n, gpus, scaling="weak", global_cells=None):
+    size = f"3D {n}^3 cells/GPU x {gpus} GPU" if scaling == "weak" or gpus == 1 else f"3D ~{global_cells}^3 cells split over {gpus} GPU"
+    return (f"{size}, {PPC} ppc ({SLOTS} slots), RK2(0.5) advection! + "
             f"{'update_cell_halo! + ' if gpus > 1 else ''}move_particles!({NFIELDS} fields) + particle2grid!(T) + "
             f"phase_ratios_center!({NPHASES} phases), stream-function velocity, CFL {CFL}")
 
 
-# ----------------------------------------------------------------------------- GPU arm
+def measured_peak():
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------- GPU arm (headline configuration, 1..N GPUs)
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import justpic.jl_b200 as J
-    from justpic.jl_b200.halo import CartesianTopology, update_cell_halo, advection_with_halo, join_halo
+    from justpic.jl_b200.halo import (CartesianTopology, update_cell_halo, advection_with_halo, join_halo, create_comm,
+                                      allreduce_max)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -212,38 +252,45 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device -- the JustPIC hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
-        opts = None
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keeps stdout to the one JSON line unless the caller asks for more
         if args.overlap:
-            # the exchange runs behind the interior advection launch: NCCL's copy kernels must win SM slots as advection
-            # CTAs retire (high-priority stream) and fit into one such slot (256 threads per channel instead of 640)
+            # the exchange runs behind the interior advection launch: NCCL's copy kernels must fit into the slot a retiring
+            # advection CTA frees (256 threads per channel instead of 640); the exchange itself runs on a high-priority stream
             os.environ.setdefault("NCCL_NTHREADS", "256")
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.is_high_priority_stream = True
-        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-    topo = CartesianTopology.create(world, 3, rank)
-    n = args.n
-    gv = local_grids(n, topo.dims, topo.coords())
+        dist.init_process_group("nccl", device_id=dev)    # plumbing only: barrier, the final reductions, the NCCL id of jp_comm_init
+        comm = create_comm(device=dev)                    # the communicator jp_halo_exchange sends / receives on
+    topo = CartesianTopology.create(world, 3, rank, split_x_last=(args.topology == "auto"))
+    nloc = block_cells(args.n, topo.dims, args.scaling if world > 1 else "weak", args.global_cells)
+    dx0 = 1.0 / (args.global_cells if (world > 1 and args.scaling == "strong") else args.n)
+    gv = local_grids(nloc, topo.dims, topo.coords(), dx0)
     p = J.init_particles(J.CUDABackend, PPC, SLOTS, MIN_XCELL, *gv, seed=42 + rank, device=dev)
     V_host = [torch.from_numpy(v).pin_memory() for v in stream_velocity_np(gv)]
     V = [v.to(dev, non_blocking=True) for v in V_host]
     vmax = torch.tensor([float(np.abs(V_host[0].numpy()).max()), float(np.abs(V_host[2].numpy()).max())], device=dev)
     if world > 1:
-        dist.all_reduce(vmax, op=dist.ReduceOp.MAX)     # dt = MPI.Allreduce(max) in the reference script
-    dx = p.di.vertex[0]
-    dt = CFL * min(dx / float(vmax[0]), p.di.vertex[2] / float(vmax[1]))
+        allreduce_max(comm, vmax)                         # dt = MPI.Allreduce(max) in the reference script (:71)
+    dt = CFL * min(p.di.vertex[0] / float(vmax[0]), p.di.vertex[2] / float(vmax[1]))
     zv = torch.from_numpy(np.asarray(p.xvi[2])).to(dev)
-    T = zv[:, None, None].expand(n + 1, n + 1, n + 1).contiguous()
+    T = zv[:, None, None].expand(nloc[2] + 1, nloc[1] + 1, nloc[0] + 1).contiguous()
     T_host = torch.empty(T.shape, dtype=T.dtype).pin_memory()
     pT, ph, strain = J.init_cell_arrays(p, NFIELDS)
     J.grid2particle(pT, T, p)
     ph.copy_(torch.where(p.index > 0, 1.0 + (p.coords[0] < p.coords[2]).double(), torch.zeros_like(pT)))
-    pr = J.PhaseRatios(J.CUDABackend, NPHASES, (n, n, n), device=dev)
+    pr = J.PhaseRatios(J.CUDABackend, NPHASES, nloc, device=dev)
     fields = (pT, ph, strain)
     rk2 = J.RungeKutta2()
-    halo_buffers = {}
+    if args.interp_handoff:
+        J.move_interp_handoff(p, Fp=pT, phases=ph, nphases=NPHASES)
+    J.profile_move(p, True)          # CUDA events between the stages of move_particles! on the launching stream (no synchronisation)
     phases = ["advect", "halo", "move", "p2g", "phase_ratios"]
+    # cells this rank OWNS (a decomposed dimension's outer planes are copies of the neighbours' cells)
+    own = tuple(slice(1 if topo.neighbor(d, -1) is not None else 0, nloc[d] - 1 if topo.neighbor(d, +1) is not None else nloc[d])
+                for d in (2, 1, 0))
+
+    def live_counts():
+        return int(p.index.sum().item()), int(p.index[(slice(None),) + own].sum().item())
 
     def step(ev=None):
         def mark(i):
@@ -251,16 +298,16 @@ def run_ours(args):
                 ev[i].record()
         mark(0)
         if world > 1 and args.overlap:
-            # shell bricks -> [side stream: pack / NCCL / unpack] || interior bricks -> join: the "halo" phase below is what is
+            # shell bricks -> [side stream: jp_halo_exchange] || interior bricks -> join: the "halo" phase below is what is
             # left of the exchange after the interior launch has finished (the "advect" phase holds both launches)
-            advection_with_halo(p, rk2, V, dt, fields, topo, buffers=halo_buffers, classify=bool(args.handoff), join=False)
+            advection_with_halo(p, rk2, V, dt, fields, topo, classify=bool(args.handoff), join=False, comm=comm)
             mark(1)
             join_halo(p)
         else:
             J.advection(p, rk2, V, dt, classify=bool(args.handoff))
             mark(1)
             if world > 1:
-                update_cell_halo(p, fields, topo, buffers=halo_buffers)
+                update_cell_halo(p, fields, topo, comm=comm)
         mark(2)
         J.move_particles(p, fields)
         mark(3)
@@ -278,12 +325,12 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    live0 = int(p.index.sum().item())
+    J.read_move_profile(p)           # drop the warm-up calls
+    live0, uniq0 = live_counts()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
-    lives, migr = [], []
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record()
@@ -293,22 +340,26 @@ def run_ours(args):
     barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
     clocks = sampler.stop() if sampler else None
+    move_prof = J.read_move_profile(p)      # mean ms per stage of move_particles! over the timed steps (at most the last 32)
+    J.profile_move(p, False)
     # particle count / migrant fraction are read AFTER the timed region (one extra step, untimed)
-    live = int(p.index.sum().item())
+    live, uniq = live_counts()
     step()
     moved, dropped, deleted = J.move_stats(p)
     move_path = J.last_move_path(p)
     move_classify = J.last_move_classify(p)
+    interp_used = J.last_interp_handoff(p)
     f_mig = (moved + dropped + deleted) / max(live, 1)
-    # particles processed per step ~ live count (changes by drops only); use mean of start/end
-    updates = 0.5 * (live0 + live) * args.steps
+    # updates = live particles in OWNED cells (changes by drops only: mean of start / end); the particles in halo cells are
+    # the neighbours' and are processed twice -- they are work, not throughput
     tmax = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-    tot_updates = torch.tensor([updates], device=dev, dtype=torch.float64)
+    tot = torch.tensor([0.5 * (uniq0 + uniq) * args.steps, 0.5 * (live0 + live) * args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot_updates, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     elapsed_ms = float(tmax.item())
-    value = float(tot_updates.item()) / (elapsed_ms * 1e-3)
+    value = float(tot[0].item()) / (elapsed_ms * 1e-3)
+    value_incl_halo = float(tot[1].item()) / (elapsed_ms * 1e-3)
     per_phase = {ph_: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)])) for i, ph_ in enumerate(phases)}
 
     # ---- e2e: same step through the public API with HOST buffers.  Every step the velocity field
@@ -333,7 +384,7 @@ def run_ours(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         esteps = max(2, args.steps)          # same step count as the device-timed region: the un-overlapped first upload / last download amortise alike
-        live_a = int(p.index.sum().item())
+        _, uniq_a = live_counts()
 
         def upload(k):
             with torch.cuda.stream(copy_stream):
@@ -374,9 +425,9 @@ def run_ours(args):
         e1.record()
         barrier()
         V, T = Vbuf[0], Tbuf[0]
-        live_b = int(p.index.sum().item())
+        _, uniq_b = live_counts()
         ems = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        eupd = torch.tensor([0.5 * (live_a + live_b) * esteps], device=dev, dtype=torch.float64)
+        eupd = torch.tensor([0.5 * (uniq_a + uniq_b) * esteps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
             dist.all_reduce(eupd, op=dist.ReduceOp.SUM)
@@ -386,54 +437,83 @@ def run_ours(args):
                        "grid field T + live count D2H; copies double-buffered on a side stream"}
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        peak, peak_src = measured_peak()
         ab = algorithmic_bytes(f_mig)
         nlive_mean = 0.5 * (live0 + live)
-        kernel_gbs = {k: ab[k] * nlive_mean / (per_phase[k] * 1e-3) / 1e9 for k in ab}
+        kernel_gbs = {k: ab[k] * nlive_mean / (per_phase[k] * 1e-3) / 1e9 if per_phase[k] > 0 else None for k in ab}
         step_bytes = sum(ab.values()) * nlive_mean
         step_ms = elapsed_ms / args.steps
+        # The dominant kernel.  With the move -> interpolation hand-off it is k_move_scatter_interp: the scatter pass of
+        # move_particles! that also does particle2grid!'s cell pass and phase_ratios_center! (their phases shrink to a node
+        # pass / a copy); its duration is not separable by CUDA events on the stream (it is one of ~60 launches of the move
+        # phase), so the roofline line is reported for the PHASE GROUP it dominates: move + p2g + phase_ratios, with the
+        # algorithmic bytes of those three API calls.  Without the hand-off: k_advect_tile, whose phase is exactly one launch.
+        # Candidates, each ONE launch per step timed with CUDA events on its stream: k_advect_tile (the advect phase is exactly that
+        # launch) and the scatter pass of move_particles! (events recorded inside the library, JP_OPT_PROFILE).  Algorithmic bytes of the
+        # scatter pass: the part of move's migrant term that is not the gather's read (f * (8N + 2*8F + 2): write the destination,
+        # NaN-vacate the source fields, two mask bytes) and, with the move -> interpolation hand-off, all of particle2grid!'s and
+        # phase_ratios_center!'s bytes, whose work it does.
+        f_sc = f_mig * (8 * 3 + 2 * 8 * NFIELDS + 2)
+        sc_fused = bool(args.interp_handoff and all(interp_used))
+        sc_bytes = (f_sc + (ab["p2g"] + ab["phase_ratios"] if sc_fused else 0.0)) * nlive_mean
+        cands = [{"kernel": "k_advect_tile<3,RK2,uniform,hand-off>" if args.handoff else "k_advect_tile<3,RK2,uniform>",
+                  "achieved": kernel_gbs["advect"], "duration_ms": per_phase["advect"], "bytes_per_particle": ab["advect"],
+                  "traffic_key": "k_advect_tile_hint" if args.handoff else "k_advect_tile"}]
+        if move_prof["calls"] > 0 and move_prof["scatter"] > 0:
+            cands.append({"kernel": "k_move_scatter_interp<3,2,fastw> (move_particles! scatter + particle2grid! cell pass + phase_ratios_center!)"
+                                    if sc_fused else "k_move_scatter<3>",
+                          "achieved": sc_bytes / (move_prof["scatter"] * 1e-3) / 1e9, "duration_ms": move_prof["scatter"],
+                          "bytes_per_particle": sc_bytes / nlive_mean,
+                          "traffic_key": "k_move_scatter_interp" if sc_fused else "k_move_scatter"})
+        dom = max(cands, key=lambda c_: c_["duration_ms"])
         traffic = None
-        try:   # dram__bytes_read+write per launch of the same kernel/config from the committed ncu --set full capture
+        try:   # dram__bytes_read+write per launch from the committed ncu --set full capture of the same kernel variant / size
             tj = json.loads((ROOT / "profiles" / "traffic.json").read_text())
-            traffic = tj.get(f"k_advect_tile@{n}")
+            traffic = tj.get(f"{dom['traffic_key']}@{args.n}")
         except Exception:
             pass
+        ndec = sum(1 for d in topo.dims if d > 1)
+        nfaces = sum(1 for d in range(3) for s_ in (-1, 1) if topo.neighbor(d, s_) is not None)
         line = {
             "metric": "particle-updates/s per step (advect+move+p2g)", "value": value, "unit": "particle-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n, world), "cells_per_gpu": n ** 3, "live_particles_per_gpu": int(nlive_mean),
+            "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.n, world, args.scaling, args.global_cells), "cells_per_gpu": int(np.prod(nloc)),
+                       "block_cells": list(nloc), "live_particles_per_gpu": int(nlive_mean),
+                       "value_counts": "live particles in cells the rank owns (halo-ring copies excluded)",
+                       "updates_per_s_incl_halo_copies": value_incl_halo,
                        "migrant_fraction": round(f_mig, 4), "move_path": move_path, "dropped_per_step": dropped,
                        "advect_move_handoff": bool(args.handoff), "move_classify": move_classify,
-                       "halo_overlap": bool(world > 1 and args.overlap),
+                       "move_interp_handoff": bool(args.interp_handoff), "p2g_phase_used_handoff": list(interp_used),
+                       "halo_overlap": bool(world > 1 and args.overlap), "halo_transport": "jp_halo_exchange (C, ncclSend/ncclRecv)" if world > 1 else None,
                        # rank 0's final state in three numbers (compare two runs, e.g. --overlap 0 / 1: must be identical)
                        "state_checksum": state_checksum(p, pT),
                        "p2g_mode": J.api.P2G_MODE, "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
-                       "topology": list(topo.dims)},
-            # per step: advect 1; move (plan path) classify 1 (hand-off: 0, + 1 per halo plane rewritten) + plan 27 +
-            # finalize 1 + scan 2 + set 1 + gather 1 + scatter 1; p2g 2 (cell + node); phase ratios 1;
-            # halo: 2 pack + 2 unpack per decomposed dimension
-            "gpu_launches": args.steps * ((2 if world > 1 and args.overlap else 1) + 33 + (0 if args.handoff else 1) + 2 + 1
-                                          + ((4 + (2 if args.handoff else 0)) * sum(1 for d in topo.dims if d > 1) if world > 1 else 0)),
+                       "topology": list(topo.dims), "dt": dt},
+            # launches per step (every kernel is this library's except cub::DeviceScan's two): advect 1 (2 with the overlap);
+            # move: classify 1 (hand-off: 0, + 1 per halo plane rewritten) + plan 27 + finalize 1 + scan 2 + after-scan 1 +
+            # gather 1 + scatter 1 + the direct-sweep fallback, enqueued behind a device-side flag: 1 + 27 (they return at once);
+            # p2g 2 (cell [skipped on the device with the hand-off] + node); phase ratios 1 (+ 1 copy with the hand-off);
+            # halo: one pack + one unpack per face
+            "gpu_launches": args.steps * ((2 if world > 1 and args.overlap else 1) + 61 + (0 if args.handoff else 1) + 2 + 1
+                                          + (1 if args.interp_handoff else 0)
+                                          + ((2 * nfaces + (nfaces if args.handoff else 0)) if world > 1 else 0)),
             "phase_ms": per_phase,
-            # dominant single kernel: k_advect_tile (the advect phase is exactly one launch, so its
-            # CUDA-event time is the kernel's duration); the move phase is longer but spans 34 launches
-            "roofline": {"bound": "hbm", "kernel": "k_advect_tile<3,RK2,uniform>",
-                         "achieved": kernel_gbs["advect"], "peak": peak, "unit": "GB/s", "frac": kernel_gbs["advect"] / peak,
+            "move_stage_ms": move_prof,
+            "roofline": {"bound": "hbm", "kernel": dom["kernel"],
+                         "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["achieved"] / peak,
+                         "duration_ms": dom["duration_ms"], "algorithmic_bytes_per_particle_of_kernel": dom["bytes_per_particle"],
                          "traffic": traffic, "peak_source": peak_src,
+                         "single_launch_kernels": [{k_: c_[k_] for k_ in ("kernel", "duration_ms", "achieved", "bytes_per_particle")} | {"frac": c_["achieved"] / peak} for c_ in cands],
                          "algorithmic_bytes_per_particle": ab, "per_phase_GBps": kernel_gbs,
-                         "per_phase_frac": {k: v / peak for k, v in kernel_gbs.items()},
+                         "per_phase_frac": {k: (v / peak if v else None) for k, v in kernel_gbs.items()},
                          "step_GBps": step_bytes / (step_ms * 1e-3) / 1e9,
                          "step_frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                         "note": "advect is bound by instruction issue and shared-memory (LDS) latency, not HBM; with the hand-off it also "
-                                 "does move_particles!' classification (its 26 B/particle scan is no longer read) but is still "
-                                 "credited with the 51 B/particle of advection! only; see DESIGN.md 4.1-4.2"},
+                         "note": "algorithmic bytes: SURVEY section 8(d) per live particle x live particles (halo copies included: "
+                                 "they are processed).  advect is bound by instruction issue and shared memory, not HBM; with the "
+                                 "advection -> move hand-off it also does move_particles!' classification but is credited with "
+                                 "advection!'s 51 B only; with the move -> interpolation hand-off p2g / phase_ratios are a node pass / a "
+                                 "copy, their per-phase numbers mean nothing on their own -- see the group line; DESIGN.md 4-5"},
             "clocks": clocks,
         }
         if e2e:
@@ -445,14 +525,174 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": threads, "kind": "port", "sample": sample,
                                     "ms_per_step": ms}
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.destroy()
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- BASELINE configs[0..2] (single GPU)
+CONFIGS = {
+    # name: ndim, n, integrator (scheme id, alpha), velocity, CFL, calls of one step
+    "cfg1": dict(ndim=2, n=256, scheme=(1, 2 / 3), rot=False, cfl=0.75, calls=("advect", "move", "inject", "p2g", "g2p"),
+                 what="2D 256^2 cells, 24 ppc (min 12 / max 48), RK2(2/3) advection! + move_particles! + inject_particles! + particle2grid!(T) + "
+                      "grid2particle!(T): the reference's timing harness (scripts/temperature_advection_timer.jl:64-68), CFL 0.75"),
+    "cfg2": dict(ndim=2, n=512, scheme=(2, 0.0), rot=True, cfl=None, calls=("advect", "move", "inject", "p2g"),
+                 what="2D 512^2 cells, 24 ppc, solid rotation, RK4 advection! + move_particles! + inject_particles! + particle2grid! "
+                      "(scripts/rotating_circle.jl at its Courant number 0.63)"),
+    "cfg3": dict(ndim=3, n=128, scheme=(1, 0.5), rot=False, cfl=0.5, calls=("advect", "move", "inject", "p2g", "g2p"),
+                 what="3D 128^3 cells, 24 ppc, RK2 advection! + move_particles! + inject_particles! + trilinear particle2grid! / grid2particle! "
+                      "(scripts/temperature_advection3D.jl), CFL 0.5"),
+}
+
+
+def config_problem(name, n=None):
+    from tests.problems import cfl_dt, make_grids, rotation_velocity, stream_velocity, vertex_field_linear
+    cfg = CONFIGS[name]
+    n = n or cfg["n"]
+    gr = make_grids(n, cfg["ndim"], True)
+    if cfg["rot"]:
+        V = rotation_velocity(gr); dt = 200.0 * 200 / n
+    else:
+        V = stream_velocity(gr); dt = cfl_dt(gr, V, cfg["cfl"])
+    return cfg, gr, V, dt, vertex_field_linear(gr)
+
+
+def config_cpu_run(name, n, steps, warmup, threads):
+    """the same configuration in the oracle (reference semantics on the host cores)"""
+    from oracle.oracle import Oracle
+    cfg, gr, V, dt, T = config_problem(name, n)
+    o = Oracle(gr.xvi, gr.xci, gr.xi_vel, SLOTS, True)
+    Oracle.set_threads(threads)
+    co, idx = o.init_particles(PPC, 42)
+    pT = np.zeros_like(co[0]); o.grid2particle(co, idx, pT, T)
+    F = np.empty_like(T)
+    total, updates = 0.0, 0
+    for it in range(warmup + steps):
+        live = int(idx.sum())
+        t0 = time.perf_counter()
+        for call in cfg["calls"]:
+            if call == "advect": o.advect(co, idx, cfg["scheme"][0], cfg["scheme"][1], V, dt)
+            elif call == "move": o.move(co, idx, [pT])
+            elif call == "inject": o.inject(co, idx, [pT], MIN_XCELL, 42, it)
+            elif call == "p2g": o.particle2grid(co, idx, F, pT)
+            elif call == "g2p": o.grid2particle(co, idx, pT, F)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            total += t1 - t0; updates += live
+    Oracle.set_threads(1)
+    return updates / total, total / steps * 1e3
+
+
+def run_config(args):
+    import torch
+    import justpic.jl_b200 as J
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the JustPIC hot path has no CPU fallback")
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("bench.py: --config cfg1..cfg3 are single-GPU configurations")
+    name = args.config
+    cfg, gr, Vnp, dt, Tnp = config_problem(name)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    p = J.init_particles(J.CUDABackend, PPC, SLOTS, MIN_XCELL, *gr.grid_vel, seed=42, device=dev)
+    V_host = [torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for v in Vnp]
+    V = [v.to(dev) for v in V_host]
+    T = torch.from_numpy(Tnp).to(dev)
+    T_host = torch.empty(T.shape, dtype=T.dtype).pin_memory()
+    pT, = J.init_cell_arrays(p, 1)
+    J.grid2particle(pT, T, p)
+    method = {0: J.Euler(), 1: J.RungeKutta2(cfg["scheme"][1] or 0.5), 2: J.RungeKutta4()}[cfg["scheme"][0]]
+    if args.interp_handoff and "inject" not in cfg["calls"]:
+        J.move_interp_handoff(p, Fp=pT)
+    calls = cfg["calls"]
+    counter = {"it": 0}
+
+    def step(ev=None):
+        for i, call in enumerate(calls):
+            if ev is not None:
+                ev[i].record()
+            if call == "advect": J.advection(p, method, V, dt, classify=bool(args.handoff))
+            elif call == "move": J.move_particles(p, (pT,))
+            elif call == "inject": J.inject_particles(p, (pT,), step=counter["it"])
+            elif call == "p2g": J.particle2grid(T, pT, p)
+            elif call == "g2p": J.grid2particle(pT, T, p)
+        if ev is not None:
+            ev[len(calls)].record()
+        counter["it"] += 1
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB): written between timed steps, these inputs fit the L2
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    live0 = int(p.index.sum().item())
+    sampler = ClockSampler(0); sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(calls) + 1)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 255)
+        step(evs[k])
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    live = int(p.index.sum().item())
+    step_ms = float(np.mean([evs[k][0].elapsed_time(evs[k][len(calls)]) for k in range(args.steps)]))
+    per_phase = {c: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)])) for i, c in enumerate(calls)}
+    moved, dropped, deleted = J.move_stats(p)
+    f_mig = (moved + dropped + deleted) / max(live, 1)
+    nlive = 0.5 * (live0 + live)
+    value = nlive / (step_ms * 1e-3)
+    # e2e: V from pinned host memory and T back to the host every step, synchronously, inside the timed region
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(args.steps):
+        for vd, vh in zip(V, V_host):
+            vd.copy_(vh, non_blocking=True)
+        step()
+        T_host.copy_(T, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _ = float(T_host.view(-1)[0])
+    e1.record(); torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    N = cfg["ndim"]
+    ab = {"advect": 16 * N + SLOTS / PPC + 8 * N / PPC, "move": 8 * N + SLOTS / PPC + f_mig * (2 * 8 * N + 3 * 8 + 2),
+          "inject": 8 * N + SLOTS / PPC, "p2g": 8 * N + SLOTS / PPC + 8 + 8 / PPC, "g2p": 8 * N + SLOTS / PPC + 8 + 8 / PPC}
+    peak, peak_src = measured_peak()
+    gbs = {c: ab[c] * nlive / (per_phase[c] * 1e-3) / 1e9 for c in calls}
+    dom = max(calls, key=lambda c: per_phase[c])
+    step_bytes = sum(ab[c] for c in calls) * nlive
+    from oracle.oracle import Oracle
+    threads = Oracle.max_threads()
+    cpu_n = cfg["n"] if N == 2 else args.cpu_n
+    cv, cms = config_cpu_run(name, cpu_n, 2, 1, threads)
+    line = {"metric": "particle-updates/s per step (advect+move+p2g)", "value": value, "unit": "particle-updates/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["what"], "name": name, "cells": int(np.prod(gr.n)), "live_particles": int(nlive),
+                       "migrant_fraction": round(f_mig, 4), "move_path": J.last_move_path(p), "advect_move_handoff": bool(args.handoff),
+                       "l2": "particle state fits the 126 MB L2 (2-D) / is 10x larger (3-D 128^3): a 256 MB buffer is written between timed steps",
+                       "dt": dt},
+            "gpu_launches": args.steps * (1 + 62 + (0 if args.handoff else 1) + (1 + 2 ** N if "inject" in calls else 0) + 2 + (1 if "g2p" in calls else 0)),
+            "phase_ms": per_phase,
+            "roofline": {"bound": "hbm", "kernel": f"{dom} phase", "achieved": gbs[dom], "peak": peak, "unit": "GB/s", "frac": gbs[dom] / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": {c: ab[c] for c in calls},
+                         "per_phase_GBps": gbs, "per_phase_frac": {c: gbs[c] / peak for c in calls},
+                         "step_GBps": step_bytes / (step_ms * 1e-3) / 1e9, "step_frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
+                         "note": "small grids are launch-latency bound, not HBM bound: ~70 launches per step"},
+            "clocks": clocks,
+            "e2e": {"value": nlive / (e2e_ms * 1e-3), "unit": "particle-updates/s", "h2d_bytes_per_step": sum(v.numel() * 8 for v in V_host),
+                    "d2h_bytes_per_step": T_host.numel() * 8, "ms_per_step": e2e_ms},
+            "cpu_baseline": {"value": cv, "unit": "particle-updates/s", "cores": threads, "kind": "port", "ms_per_step": cms,
+                             "sample": f"the same configuration at {cpu_n}^{N} cells, 2 steps" + ("" if cpu_n == cfg["n"] else " (bounded sample)")}}
+    print(json.dumps(line), flush=True)
 
 
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "cfg4":
+        run_config(args)
     else:
         run_ours(args)
 

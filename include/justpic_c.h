@@ -87,7 +87,7 @@ typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_
  *   move_particles! / inject_particles! produce): liveness is the occupancy word, not phase_ratios_center!'s isnan(px) probe.
  * JP_OPT_LAST_INTERP (jp_get_option only): bit 0 / bit 1 = the last jp_particle2grid / jp_phase_ratios_center used the hand-off. */
 typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3, JP_OPT_MOVE_POLICY = 4,
-               JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6, JP_OPT_MOVE_INTERP = 7, JP_OPT_LAST_INTERP = 8 } jp_option;
+               JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6, JP_OPT_MOVE_INTERP = 7, JP_OPT_LAST_INTERP = 8, JP_OPT_PROFILE = 9 } jp_option;
 typedef enum { JP_MOVE_POLICY_REFERENCE = 0, JP_MOVE_POLICY_COMPACT = 1 } jp_move_policy;
 typedef enum { JP_MOVE_AUTO = 0, JP_MOVE_DIRECT = 1 } jp_move_mode;
 typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;
@@ -166,6 +166,11 @@ int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nar
  * how many phases the following phase_ratios_center!(phase_ratios, particles, phases) will use (either may be NULL).  Both must
  * be among the `args` of jp_move to take effect.  Sticky until changed. */
 int jp_move_interp_fields(jp_ctx *ctx, const double *Fp, const double *phases, int32_t K);
+/* JP_OPT_PROFILE = 1: jp_move (planned path) records CUDA events between its stages on the caller's stream (no
+ * synchronisation); jp_profile_read returns the mean duration in ms of {classify, plan (3^N launches), finalize + scan,
+ * gather, scatter (+ interpolation hand-off)} over the calls since the last read (at most the last 32) and synchronises the
+ * device.  This is how bench.py times the dominant kernel inside the move phase. */
+int jp_profile_read(jp_ctx *ctx, double out_ms[5], int32_t *ncalls);
 /* Counters of the last jp_move on this context: {moved, dropped (destination
  * full), deleted (left the domain)}.  Synchronises `stream`. */
 int jp_move_stats(jp_ctx *ctx, int64_t out[3], void *stream);
@@ -284,6 +289,29 @@ int jp_halo_pack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays,
                  const uint8_t *index, void *buf, void *stream);
 int jp_halo_unpack(jp_ctx *ctx, int32_t dim, int32_t plane, double *const *arrays, int32_t narrays,
                    uint8_t *index, const void *buf, void *stream);
+
+/* update_cell_halo!(particles.coords..., args..., particles.index) (src/CellArrays/ImplicitGlobalGrid.jl:36-41 =
+ * ImplicitGlobalGrid.update_halo! on every CellArray; scripts/temperature_advection3D_MPI.jl:86) as ONE library call: for each
+ * dimension x -> y -> z the planes 2 / n-1 (1-based; overlap 2, halo width 1) of all listed CellArrays and the index mask are
+ * packed into one message per face, exchanged with ncclSend / ncclRecv inside one ncclGroup and unpacked into the neighbours'
+ * planes n / 1, so edges and corners propagate through the sequential dimensions.  comm: an ncclComm_t (from jp_comm_init, or
+ * the host's own NCCL binding -- NCCL.jl's communicator handle); nbr[2*d], nbr[2*d+1]: rank of the left / right neighbour
+ * along dimension d in that communicator, -1 at a non-periodic boundary; a rank that is its own neighbour (periodic, one
+ * rank along d) wraps around locally and needs no communicator.  Asynchronous on `stream`. */
+int jp_halo_exchange(jp_ctx *ctx, void *comm, const int32_t *nbr, double *const *arrays, int32_t narrays, uint8_t *index,
+                     void *stream);
+/* update_halo!(A) for a plain grid array A (a staggered velocity component, a vertex field ...) with extents ext[0..ndim) on
+ * the same decomposition: overlap = 2 + ext[d] - n[d] as ImplicitGlobalGrid computes it for staggered arrays.  This is the
+ * velocity-ghost-layer exchange when V comes from a solver rather than a formula. */
+int jp_halo_exchange_grid(jp_ctx *ctx, void *comm, const int32_t *nbr, double *A, const int32_t *ext, void *stream);
+/* NCCL plumbing for hosts without their own binding.  libnccl.so.2 is dlopen'ed on first use (override: JP_NCCL_LIB);
+ * jp_comm_unique_id on one rank -> broadcast the 128 bytes by any means -> jp_comm_init on every rank (collective). */
+int jp_comm_unique_id(void *id128);
+int jp_comm_init(const void *id128, int32_t nranks, int32_t rank, int32_t device, void **comm_out);
+int jp_comm_destroy(void *comm);
+/* dt = min(dx / MPI.Allreduce(maximum(abs(V)), MPI.MAX)) of the reference's MPI scripts (temperature_advection3D_MPI.jl:71):
+ * in-place max over the ranks of n device doubles. */
+int jp_allreduce_max(void *comm, double *buf, int32_t n, void *stream);
 
 /* Array(CA) / Array(T, CA) and CuArray(CA) / CuArray(T, CA) for a CellArray
  * (src/CellArrays/conversion.jl:19-43, ext/JustPICCUDAExt.jl:166-179; checkpoints, test/test_save_load.jl:120-173):

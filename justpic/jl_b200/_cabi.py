@@ -25,6 +25,9 @@ JP_OPT_ADVECT_AFFINE = 3
 JP_OPT_MOVE_POLICY = 4
 JP_OPT_ADVECT_CLASSIFY = 5
 JP_OPT_LAST_CLASSIFY = 6
+JP_OPT_MOVE_INTERP = 7
+JP_OPT_LAST_INTERP = 8
+JP_OPT_PROFILE = 9
 JP_F64, JP_F32, JP_BOOL = 0, 1, 2
 JP_LAYOUT_TO_HOST, JP_LAYOUT_TO_DEVICE = 0, 1
 JP_MOVE_POLICY_REFERENCE, JP_MOVE_POLICY_COMPACT = 0, 1
@@ -69,6 +72,8 @@ SYMBOLS = {
     "jp_advect_interp": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.c_int32, C.c_double,
                                    C.POINTER(C.c_void_p), C.c_double, C.c_int32, C.c_void_p]),
     "jp_move": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "jp_move_interp_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "jp_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "jp_move_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "jp_last_move_path": (C.c_int, [C.c_void_p]),
     "jp_inject": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_int32,
@@ -100,6 +105,13 @@ SYMBOLS = {
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "jp_cellarray_permute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                        C.c_void_p]),
+    "jp_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
+                                   C.c_void_p]),
+    "jp_halo_exchange_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
+    "jp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "jp_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "jp_comm_destroy": (C.c_int, [C.c_void_p]),
+    "jp_allreduce_max": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "jp_halo_plane_bytes": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32]),
     "jp_halo_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
                                C.c_void_p, C.c_void_p]),

@@ -45,6 +45,7 @@ __all__ = [
     "phase_ratios_center", "phase_ratios_vertex", "phase_ratios_face", "phase_ratios_midpoint",
     "update_phase_ratios", "set_synchronous",
     "Array", "CuArray", "HostParticles", "HostPhaseRatios", "last_move_classify",
+    "move_interp_handoff", "last_interp_handoff", "profile_move", "read_move_profile",
 ]
 
 
@@ -442,6 +443,45 @@ def last_move_classify(particles: Particles) -> str:
     v = C.c_int32(0)
     _cabi.check(_cabi.load().jp_get_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_LAST_CLASSIFY, C.byref(v)), "jp_get_option")
     return "handoff" if v.value else "coords"
+
+
+def move_interp_handoff(particles: Particles, Fp: Optional[torch.Tensor] = None, phases: Optional[torch.Tensor] = None,
+                        nphases: int = 0, enable: bool = True) -> None:
+    """Move -> interpolation hand-off (JP_OPT_MOVE_INTERP in include/justpic_c.h; sticky per ``Particles``, opt-in).
+    Tell the library which particle field the ``particle2grid(F, Fp, particles)`` after the next ``move_particles`` will
+    interpolate and which field / how many phases ``phase_ratios_center(phase_ratios, particles, phases)`` will use: the last
+    streaming pass of ``move_particles`` then also accumulates that call's per-cell sums / the centre ratios (same arithmetic,
+    same order: bit-identical results), and the two calls do not read the particles again.  Both fields must be among the
+    ``args`` of ``move_particles``; the caller must not write the particle arrays or the two fields between ``move_particles``
+    and the consumers other than through this API (which drops the hand-off where needed)."""
+    p = particles
+    lib = _cabi.load()
+    fp = _pfield(Fp, p, "Fp").data_ptr() if Fp is not None else None
+    ph = _pfield(phases, p, "phases").data_ptr() if phases is not None else None
+    _cabi.check(lib.jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_MOVE_INTERP, 1 if enable else 0), "jp_set_option")
+    _cabi.check(lib.jp_move_interp_fields(C.c_void_p(p._ctx), C.c_void_p(fp), C.c_void_p(ph), int(nphases) if ph else 0),
+                "move_interp_handoff")
+
+
+def last_interp_handoff(particles: Particles) -> Tuple[bool, bool]:
+    """(particle2grid, phase_ratios_center): whether the last call of each used the sums left by ``move_particles``."""
+    v = C.c_int32(0)
+    _cabi.check(_cabi.load().jp_get_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_LAST_INTERP, C.byref(v)), "jp_get_option")
+    return bool(v.value & 1), bool(v.value & 2)
+
+
+def profile_move(particles: Particles, enable: bool = True) -> None:
+    """JP_OPT_PROFILE: record CUDA events between the stages of the planned ``move_particles`` (no synchronisation)."""
+    _cabi.check(_cabi.load().jp_set_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_PROFILE, 1 if enable else 0), "jp_set_option")
+
+
+def read_move_profile(particles: Particles) -> dict:
+    """Mean ms per stage of the planned ``move_particles`` over the calls since the last read (synchronises the device)."""
+    out = (C.c_double * 5)()
+    n = C.c_int32(0)
+    with torch.cuda.device(particles.device):
+        _cabi.check(_cabi.load().jp_profile_read(C.c_void_p(particles._ctx), out, C.byref(n)), "jp_profile_read")
+    return {"calls": int(n.value), "classify": out[0], "plan": out[1], "finalize_scan": out[2], "gather": out[3], "scatter": out[4]}
 
 
 def last_move_reasons(particles: Particles) -> int:

@@ -17,6 +17,7 @@
 // phase_ratios_center! -- identical for every container this library (or the reference) produces, where dead slots
 // hold NaN.
 #pragma once
+#include <type_traits>
 
 // one particle into the 2^N corner sums of its cell (the body of k_p2g_cell)
 template <int N, bool FASTW>
@@ -105,7 +106,9 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
         for (int u = 0; u < U; u++)
 #pragma unroll
             for (int q = 0; q < 5; q++) cap[u][q] = 0.0;
-        for (int a0 = 0; a0 < arrs.n; a0 += JP_MV_A) {
+        // arrays in register batches of JP_MV_A; the first batch (coordinates + the first field) has compile-time indices
+        auto batch = [&](const int a0, auto first) {
+            constexpr bool FIRST = decltype(first)::value;
             double v[U][JP_MV_A];
 #pragma unroll
             for (int u = 0; u < U; u++)
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
                     v[u][a] = NAN;
                     if (ia < arrs.n) {
                         if ((chb >> u) & 1u) { if ((arb >> u) & 1u) v[u][a] = stage[pos[u] + ia]; }
-                        else if (((fb >> u) & 1u) && (ia < N || ia == mi.iT || ia == mi.iP))
+                        else if (((fb >> u) & 1u) && ((FIRST && a < N) || ia == mi.iT || ia == mi.iP))
                             v[u][a] = arrs.a[ia][c + (int64_t)(s0 + u) * g.C];
                     }
                 }
@@ -125,11 +128,13 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
                 for (int a = 0; a < JP_MV_A; a++) {
                     const int ia = a0 + a;
                     if (ia < arrs.n && ((chb >> u) & 1u)) arrs.a[ia][c + (int64_t)(s0 + u) * g.C] = v[u][a];
-                    if (ia < N) cap[u][ia] = v[u][a];
+                    if (FIRST && a < N) cap[u][a] = v[u][a];
                     if (ia == mi.iT) cap[u][3] = v[u][a];
                     if (ia == mi.iP) cap[u][4] = v[u][a];
                 }
-        }
+        };
+        batch(0, std::true_type());
+        for (int a0 = JP_MV_A; a0 < arrs.n; a0 += JP_MV_A) batch(a0, std::false_type());
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int s = s0 + u;

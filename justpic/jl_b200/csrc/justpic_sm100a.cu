@@ -90,9 +90,14 @@ struct jp_ctx {
     int last_p2g_handoff, last_phase_handoff;       // diagnostics: the last particle2grid! / phase_ratios_center! used the hand-off
     const void *mi_key[4];
     double *mi_rc; size_t mi_rc_elems;              // [K][C] centre ratios left by the scatter
+    void *halo_buf; size_t halo_buf_bytes;          // jp_halo_exchange: 4 face buffers (send / receive, left / right), grow-only
+    // JP_OPT_PROFILE: CUDA events around the stages of the planned jp_move (ring of the last JP_PROF_RING calls), read by jp_profile_read
+    int prof_opt; cudaEvent_t *prof_ev; int prof_calls;
 };
 static inline void hint_invalidate(jp_ctx *ctx) { ctx->hint_valid = 0; ctx->hint_ndirty = 0; }
 static void move_plan_free(jp_ctx *ctx);
+#define JP_PROF_RING 32
+#define JP_PROF_MARKS 6      // classify | plan | finalize + scan | gather | scatter | end
 static inline void mi_invalidate(jp_ctx *ctx) { ctx->mi_valid_p2g = 0; ctx->mi_valid_ph = 0; }
 // every entry point that changes particles (or may change particle fields) drops both hand-offs
 static inline void handoffs_invalidate(jp_ctx *ctx) { hint_invalidate(ctx); mi_invalidate(ctx); }
@@ -1094,30 +1099,8 @@ __global__ void __launch_bounds__(256) k_copy_unless(double *__restrict__ dst, c
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
-// update_cell_halo! pack / unpack of one cell-plane
+// update_cell_halo!: arrays of one exchange (kernels in jp_halo_nccl.cuh)
 struct HaloArrs { double *a[JP_MAX_ARGS + 3]; int n; };
-template <bool PACK>
-__global__ void __launch_bounds__(256) k_halo(JpGrid g, int dim, int plane, HaloArrs arrs, uint8_t *index, unsigned char *buf, int64_t M) {
-    const int64_t total = (int64_t)(arrs.n + 1) * g.S * M;
-    const int nx = g.n[0], ny = g.n[1];
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t m = t % M;
-        const int s = (int)((t / M) % g.S);
-        const int a = (int)(t / (M * g.S));
-        int i, j, k;
-        if (dim == 0) { i = plane; j = (int)(m % ny); k = (int)(m / ny); }
-        else if (dim == 1) { i = (int)(m % nx); j = plane; k = (int)(m / nx); }
-        else { i = (int)(m % nx); j = (int)(m / nx); k = plane; }
-        const int64_t e = i + (int64_t)nx * (j + (int64_t)ny * k) + (int64_t)s * g.C;
-        if (a < arrs.n) {
-            double *b = (double *)buf + ((int64_t)a * g.S + s) * M + m;
-            if (PACK) *b = arrs.a[a][e]; else arrs.a[a][e] = *b;
-        } else {
-            unsigned char *b = buf + (int64_t)arrs.n * g.S * M * 8 + (int64_t)s * M + m;
-            if (PACK) *b = index[e]; else index[e] = *b;
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------
 // host side
@@ -1162,7 +1145,8 @@ extern "C" void jp_ctx_destroy(jp_ctx *ctx) {
     cudaFree(ctx->gridmem); cudaFree(ctx->occ); cudaFree(ctx->leave); cudaFree(ctx->inj_list); cudaFree(ctx->inj_count); cudaFree(ctx->inbox); cudaFree(ctx->stats);
     cudaFree(ctx->p2g_ws);
     move_plan_free(ctx);
-    cudaFree(ctx->stage); cudaFree(ctx->pr_ws); cudaFree(ctx->mi_rc);
+    cudaFree(ctx->stage); cudaFree(ctx->pr_ws); cudaFree(ctx->mi_rc); cudaFree(ctx->halo_buf);
+    if (ctx->prof_ev) { for (int i = 0; i < JP_PROF_RING * JP_PROF_MARKS; i++) cudaEventDestroy(ctx->prof_ev[i]); free(ctx->prof_ev); }
     free(ctx);
 }
 
@@ -1488,10 +1472,18 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     const dim3 blk(JP_BX, JP_BY, 1);
     const dim3 grd = tile_grid(g.n[0], g.n[1], g.n[2]);
     CPtr3 cco = {{p->coords[0], p->coords[1], p->coords[2]}};
-    static const bool timing = getenv("JP_MOVE_TIMING") != nullptr;
-    cudaEvent_t ev[8];
+    // JP_OPT_PROFILE: events between the stages (no synchronisation; jp_profile_read turns them into milliseconds later)
+    cudaEvent_t *pev = nullptr;
+    if (ctx->prof_opt) {
+        if (!ctx->prof_ev) {
+            ctx->prof_ev = (cudaEvent_t *)calloc(JP_PROF_RING * JP_PROF_MARKS, sizeof(cudaEvent_t));
+            for (int i = 0; i < JP_PROF_RING * JP_PROF_MARKS; i++) JP_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+        }
+        pev = ctx->prof_ev + (size_t)(ctx->prof_calls % JP_PROF_RING) * JP_PROF_MARKS;
+        ctx->prof_calls++;
+    }
     int nev = 0;
-    auto mark = [&]() { if (timing) { cudaEventCreate(&ev[nev]); cudaEventRecord(ev[nev], st); nev++; } };
+    auto mark = [&]() { if (pev && nev < JP_PROF_MARKS) cudaEventRecord(pev[nev++], st); };
     mark();
     unsigned int *flag = ctx->mp_flag;
     const JpBox whole = {{0, 0, 0}, {g.n[0], g.n[1], g.n[2]}};
@@ -1589,14 +1581,26 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
         k_move_scatter<N><<<grd, blk, 0, st>>>(g, ctx->mp, arrs, p->index, ctx->stage, flag);
     mark();
     JP_CHECK_LAUNCH();
-    if (timing) {
-        cudaStreamSynchronize(st);
-        const char *names[] = {"classify", "plan", "finalize+scan", "gather", "scatter"};
-        fprintf(stderr, "[jp_move]");
-        for (int i = 0; i + 1 < nev; i++) { float ms; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); fprintf(stderr, " %s %.3f", names[i], ms); }
-        fprintf(stderr, "\n");
-        for (int i = 0; i < nev; i++) cudaEventDestroy(ev[i]);
-    }
+    return JP_OK;
+}
+
+// mean duration (ms) of each stage of the planned jp_move over the calls recorded since the last read:
+// out[0..4] = classify, plan (3^N launches), finalize + scan, gather, scatter(+interp).  Synchronises the device.
+extern "C" int jp_profile_read(jp_ctx *ctx, double *out_ms, int32_t *ncalls) {
+    if (!ctx || !out_ms) return jp_fail(JP_ERR_INVALID, "jp_profile_read: null argument");
+    JP_CUDA(cudaSetDevice(ctx->device));
+    JP_CUDA(cudaDeviceSynchronize());
+    const int n = ctx->prof_calls < JP_PROF_RING ? ctx->prof_calls : JP_PROF_RING;
+    for (int k = 0; k < JP_PROF_MARKS - 1; k++) out_ms[k] = 0.0;
+    for (int c = 0; c < n; c++)
+        for (int k = 0; k < JP_PROF_MARKS - 1; k++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->prof_ev[c * JP_PROF_MARKS + k], ctx->prof_ev[c * JP_PROF_MARKS + k + 1]);
+            out_ms[k] += ms / n;
+        }
+    if (ncalls) *ncalls = n;
+    ctx->prof_calls = 0;
+    cudaGetLastError();
     return JP_OK;
 }
 
@@ -1882,6 +1886,7 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (option == JP_OPT_ADVECT_AFFINE && (value == 0 || value == 1)) { ctx->g.affine = value ? ctx->affine_detected : 0; return JP_OK; }
     if (option == JP_OPT_ADVECT_CLASSIFY && (value == 0 || value == 1)) { ctx->hint_opt = value; hint_invalidate(ctx); return JP_OK; }
     if (option == JP_OPT_MOVE_INTERP && (value == 0 || value == 1)) { ctx->mi_opt = value; mi_invalidate(ctx); return JP_OK; }
+    if (option == JP_OPT_PROFILE && (value == 0 || value == 1)) { ctx->prof_opt = value; ctx->prof_calls = 0; return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
 }
 
@@ -2098,6 +2103,17 @@ extern "C" int64_t jp_halo_plane_bytes(const jp_ctx *ctx, int32_t dim, int32_t n
     if (!ctx || dim < 0 || dim >= ctx->g.ndim || narrays < 0) return -1;
     return plane_cells(ctx->g, dim) * ctx->g.S * (8 * (int64_t)narrays + 1);
 }
+// a plane was rewritten after the advection -> move hand-off was left: its classification words are stale
+static void halo_mark_dirty(jp_ctx *ctx, int dim, int plane) {
+    if (!(ctx->hint_valid || (ctx->adv_split && ctx->hint_opt))) return;
+    for (int i = 0; i < ctx->hint_ndirty; i++)
+        if (ctx->hint_dirty[i][0] == dim && ctx->hint_dirty[i][1] == plane) return;
+    if (ctx->hint_ndirty < 8) { ctx->hint_dirty[ctx->hint_ndirty][0] = dim; ctx->hint_dirty[ctx->hint_ndirty][1] = plane; ctx->hint_ndirty++; }
+    else { hint_invalidate(ctx); if (ctx->adv_split) ctx->adv_split = 2; }     // 2: this step's hand-off is void
+}
+
+#include "jp_halo_nccl.cuh"
+
 static int halo_common(jp_ctx *ctx, int dim, int plane, double *const *arrays, int narrays, uint8_t *index, void *buf, void *stream, bool pack) {
     if (!ctx || !buf || !index) return jp_fail(JP_ERR_INVALID, "jp_halo: null argument");
     const JpGrid &g = ctx->g;
@@ -2110,20 +2126,12 @@ static int halo_common(jp_ctx *ctx, int dim, int plane, double *const *arrays, i
     }
     JP_CUDA(cudaSetDevice(ctx->device));
     const int64_t M = plane_cells(g, dim);
-    const int64_t total = (int64_t)(narrays + 1) * g.S * M;
-    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    if (pack) k_halo<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
+    const dim3 grd((unsigned)((M + 255) / 256 < 64 ? (M + 255) / 256 : 64), (unsigned)((narrays + 1) * g.S));
+    if (pack) k_halo_plane<true><<<grd, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, (int)M);
     else {
         mi_invalidate(ctx);
-        k_halo<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, M);
-        if (ctx->hint_valid || (ctx->adv_split && ctx->hint_opt)) {   // the hand-off bytes of this plane are stale now
-            bool seen = false;
-            for (int i = 0; i < ctx->hint_ndirty; i++) seen = seen || (ctx->hint_dirty[i][0] == dim && ctx->hint_dirty[i][1] == plane);
-            if (!seen) {
-                if (ctx->hint_ndirty < 8) { ctx->hint_dirty[ctx->hint_ndirty][0] = dim; ctx->hint_dirty[ctx->hint_ndirty][1] = plane; ctx->hint_ndirty++; }
-                else { hint_invalidate(ctx); if (ctx->adv_split) ctx->adv_split = 2; }     // 2: this step's hand-off is void
-            }
-        }
+        k_halo_plane<false><<<grd, 256, 0, (cudaStream_t)stream>>>(g, dim, plane, h, index, (unsigned char *)buf, (int)M);
+        halo_mark_dirty(ctx, dim, plane);
     }
     JP_CHECK_LAUNCH();
     return JP_OK;

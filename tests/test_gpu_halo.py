@@ -49,7 +49,7 @@ def _free_port():
     return port
 
 
-def _nccl_worker(rank, world, port, out):
+def _nccl_worker(rank, world, port, out, use_comm=True):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -64,8 +64,12 @@ def _nccl_worker(rank, world, port, out):
         pT.fill_(float(rank) + 0.5)
         before = [c.clone().cpu() for c in p.coords] + [pT.clone().cpu(), p.index.clone().cpu()]
         topo = CartesianTopology((2, 1, 1), rank)
-        sent = update_cell_halo(p, (pT,), topo)
+        from justpic.jl_b200.halo import create_comm
+        comm = create_comm(device=f"cuda:{rank}") if use_comm else None      # jp_halo_exchange (C, NCCL) / torch.distributed transport
+        sent = update_cell_halo(p, (pT,), topo, comm=comm)
         torch.cuda.synchronize()
+        if comm is not None:
+            comm.destroy()
         after = [c.cpu() for c in p.coords] + [pT.cpu(), p.index.cpu()]
         torch.save({"before": before, "after": after, "sent": sent}, out + f".{rank}")
     finally:
@@ -73,10 +77,11 @@ def _nccl_worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_update_cell_halo_nccl_two_gpus(tmp_path):
+@pytest.mark.parametrize("use_comm", [True, False], ids=["jp_halo_exchange", "torch.distributed"])
+def test_update_cell_halo_nccl_two_gpus(tmp_path, use_comm):
     import torch.multiprocessing as mp
     out = str(tmp_path / "halo")
-    mp.spawn(_nccl_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, _free_port(), out, use_comm), nprocs=2, join=True)
     r = [torch.load(out + f".{k}") for k in range(2)]
     nx = 6
     eq = lambda a, b: torch.equal(torch.nan_to_num(a.double(), nan=-1.0), torch.nan_to_num(b.double(), nan=-1.0))
@@ -132,8 +137,9 @@ def _overlap_worker(rank, world, port, out):
     try:
         import numpy as np
         import justpic.jl_b200 as J
-        from justpic.jl_b200.halo import CartesianTopology, advection_with_halo, update_cell_halo
+        from justpic.jl_b200.halo import CartesianTopology, advection_with_halo, update_cell_halo, create_comm
         from bench import stream_velocity_np
+        comm = create_comm(device=f"cuda:{rank}")
         # a real block decomposition (2 x 1 x 1, overlap 2 as ImplicitGlobalGrid): the particles a rank receives in its halo
         # cells lie in those cells, so move_particles! re-buckets over <= 1 cell (longer moves are racy in the reference itself)
         topo = CartesianTopology((2, 1, 1), rank)
@@ -157,10 +163,10 @@ def _overlap_worker(rank, world, port, out):
             bufs = {}
             for it in range(4):
                 if overlapped:
-                    advection_with_halo(p, J.RungeKutta2(), Vd, dt, (pT,), topo, buffers=bufs, classify=True)
+                    advection_with_halo(p, J.RungeKutta2(), Vd, dt, (pT,), topo, buffers=bufs, classify=True, comm=comm)
                 else:
                     J.advection(p, J.RungeKutta2(), Vd, dt, classify=True)
-                    update_cell_halo(p, (pT,), topo, buffers=bufs)
+                    update_cell_halo(p, (pT,), topo, buffers=bufs, comm=comm)
                 J.move_particles(p, (pT,))
                 assert J.last_move_classify(p) == "handoff"
             torch.cuda.synchronize()
@@ -181,3 +187,42 @@ def test_advection_with_halo_overlap_two_gpus(tmp_path):
         seq, ovl = torch.load(out + f".{k}")
         for a, b in zip(seq, ovl):
             assert torch.equal(torch.nan_to_num(a.double(), nan=-1.0), torch.nan_to_num(b.double(), nan=-1.0))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# jp_halo_exchange / jp_halo_exchange_grid on ONE GPU: a rank that is its own neighbour (periodic, one rank along the dimension)
+# wraps around locally -- the library's pack kernels, plane numbers and x -> y -> z order without a second GPU
+@pytest.mark.parametrize("ndim,n,periodic", [(2, (9, 7), (True, True)), (3, (6, 5, 7), (True, False, True)), (3, (8, 6, 5), (False, True, False))])
+def test_halo_exchange_periodic_self_wrap(ndim, n, periodic):
+    from justpic.jl_b200.halo import CartesianTopology, update_cell_halo, update_halo
+    J, gr, p = _particles(ndim, n)
+    pT, = J.init_cell_arrays(p, 1)
+    pT.copy_(torch.rand_like(pT))
+    topo = CartesianTopology((1,) * ndim, 0, periodic)
+    arrays = list(p.coords) + [pT, p.index]
+    want = [a.clone() for a in arrays]
+    for dim in range(ndim):                       # update_halo! semantics, dimensions in sequence
+        if not periodic[dim]:
+            continue
+        ax, nn = ndim - dim, n[dim]
+        for w in want:
+            src_lo, src_hi = w.select(ax, nn - 2).clone(), w.select(ax, 1).clone()
+            w.select(ax, 0).copy_(src_lo)
+            w.select(ax, nn - 1).copy_(src_hi)
+    update_cell_halo(p, (pT,), topo)
+    for a, w in zip(arrays, want):
+        assert torch.equal(torch.nan_to_num(a.double(), nan=-1.0), torch.nan_to_num(w.double(), nan=-1.0))
+    # a staggered grid array (overlap 2 + extent - cells): planes ol-1 / ext-ol -> planes ext-1 / 0 (0-based)
+    for plus in ((1, 2, 2), (2, 1, 2), (1, 1, 1), (0, 0, 0)):
+        ext = tuple(n[d] + plus[d] for d in range(ndim))
+        A = torch.rand(tuple(reversed(ext)), dtype=torch.float64, device="cuda")
+        W = A.clone()
+        for dim in range(ndim):
+            if not periodic[dim]:
+                continue
+            ax, ol = ndim - 1 - dim, 2 + plus[dim]
+            lo, hi = W.select(ax, ext[dim] - ol).clone(), W.select(ax, ol - 1).clone()
+            W.select(ax, 0).copy_(lo)
+            W.select(ax, ext[dim] - 1).copy_(hi)
+        update_halo(p, A, topo)
+        assert torch.equal(A, W)

@@ -1,0 +1,171 @@
+"""Move -> interpolation hand-off (JP_OPT_MOVE_INTERP, csrc/jp_move_interp.cuh): the scatter pass of move_particles! also
+leaves particle2grid!'s per-cell sums and phase_ratios_center!'s ratios.  Results must be BIT-IDENTICAL to the stand-alone
+kernels (same arithmetic, same order) -- hence bit-exact centre ratios and exact-to-1e-12 grid fields against the oracle --
+on every path: plan path, device-side fallback to the direct sweeps (a particle on a cell face), invalidation by any call
+that changes particles or the fields, other particle2grid modes, more phases than the hand-off serves."""
+import numpy as np
+import pytest
+import torch
+
+from tests.problems import cfl_dt, stream_velocity, vertex_field_linear
+from tests.test_gpu_parity import Twin, assert_close, assert_same, dev, jp
+
+pytestmark = pytest.mark.gpu
+
+GRIDS = [(2, (40, 21), True), (3, (34, 9, 7), True), (3, (12, 10, 11), False), (2, (19, 33), False)]
+ids = lambda g: f"{g[0]}D-{g[1]}-{'range' if g[2] else 'vector'}"
+
+
+def _setup(g, K=2):
+    J = jp()
+    t = Twin(*g, nxcell=12, max_xcell=24, min_xcell=6)
+    gr = t.gr
+    V = stream_velocity(gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(gr, V, 0.7)
+    T = vertex_field_linear(gr) + 0.3 * np.cos(5 * vertex_field_linear(gr, 0))
+    pT, ph, pS = J.init_cell_arrays(t.p, 3)
+    opT = np.zeros_like(t.co[0])
+    J.grid2particle(pT, dev(T), t.p); t.o.grid2particle(t.co, t.idx, opT, T)
+    oph = np.where(t.idx > 0, 1.0 + np.floor(np.nan_to_num(t.co[0]) * K).clip(0, K - 1), 0.0)
+    ph.copy_(dev(oph))
+    oS = np.where(t.idx > 0, t.co[1] * 2.0, 0.0); pS.copy_(dev(oS))
+    return J, t, V, Vd, dt, T, (pT, ph, pS), [opT, oph, oS]
+
+
+@pytest.mark.parametrize("g", GRIDS, ids=ids)
+@pytest.mark.parametrize("K", [2, 3])
+@pytest.mark.parametrize("p2g_mode", ["twopass_fastw", "twopass"])
+def test_handoff_equals_standalone_kernels_and_oracle(g, K, p2g_mode):
+    J, t, V, Vd, dt, T, gargs, oargs = _setup(g, K)
+    pT, ph, pS = gargs
+    pr = J.PhaseRatios(J.CUDABackend, K, t.gr.n)
+    pr2 = J.PhaseRatios(J.CUDABackend, K, t.gr.n)
+    F = dev(np.zeros_like(T)); F2 = torch.empty_like(F)
+    J.particle2grid(F, pT, t.p, mode=p2g_mode)                     # sets the context's mode before the first move
+    J.move_interp_handoff(t.p, Fp=pT, phases=ph, nphases=K)
+    for it in range(4):
+        J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=(it % 2 == 1)); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+        J.move_particles(t.p, gargs); st = t.o.move(t.co, t.idx, oargs)
+        assert J.last_move_path(t.p) == "plan"
+        t.check_state(f"step {it} move_particles", gargs, oargs)
+        assert J.move_stats(t.p) == st
+        J.particle2grid(F, pT, t.p, mode=p2g_mode)
+        J.phase_ratios_center(pr, t.p, ph)
+        assert J.last_interp_handoff(t.p) == (True, True)
+        # the same calls again: the hand-off is still valid (nothing changed) -- and once more with the option off
+        J.particle2grid(F2, pT, t.p, mode=p2g_mode)
+        assert torch.equal(F, F2)
+        J.move_interp_handoff(t.p, Fp=pT, phases=ph, nphases=K, enable=False)
+        J.particle2grid(F2, pT, t.p, mode=p2g_mode); J.phase_ratios_center(pr2, t.p, ph)
+        assert J.last_interp_handoff(t.p) == (False, False)
+        assert torch.equal(F.view(torch.int64), F2.view(torch.int64)), "hand-off particle2grid differs from the stand-alone kernels"
+        assert torch.equal(pr.center.view(torch.int64), pr2.center.view(torch.int64)), "hand-off phase ratios differ from k_phase"
+        J.move_interp_handoff(t.p, Fp=pT, phases=ph, nphases=K)
+        oF = np.empty_like(T); t.o.particle2grid(t.co, t.idx, oF, oargs[0])
+        assert_close(F, oF, f"step {it} particle2grid via hand-off vs oracle")
+        ratios = np.zeros(t.o.cell_shape(K)); t.o.phase_ratios_center(t.co, ratios, oargs[1], K)
+        assert_same(pr.center, ratios, f"step {it} phase_ratios_center via hand-off vs oracle")
+
+
+def test_handoff_invalidation_and_partial_registration():
+    g = (3, (34, 9, 7), True)
+    J, t, V, Vd, dt, T, gargs, oargs = _setup(g, 2)
+    pT, ph, pS = gargs
+    K = 2
+    pr = J.PhaseRatios(J.CUDABackend, K, t.gr.n)
+    F = dev(np.zeros_like(T)); oF = np.empty_like(T); ratios = np.zeros(t.o.cell_shape(K))
+    J.particle2grid(F, pT, t.p)
+    J.move_interp_handoff(t.p, Fp=pT, phases=ph, nphases=K)
+
+    def step(it):
+        J.advection(t.p, J.RungeKutta2(), Vd, dt); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+        J.move_particles(t.p, gargs); t.o.move(t.co, t.idx, oargs)
+
+    def check(what, expect):
+        J.particle2grid(F, pT, t.p); J.phase_ratios_center(pr, t.p, ph)
+        assert J.last_interp_handoff(t.p) == expect, what
+        t.o.particle2grid(t.co, t.idx, oF, oargs[0]); t.o.phase_ratios_center(t.co, ratios, oargs[1], K)
+        assert_close(F, oF, what); assert_same(pr.center, ratios, what)
+
+    step(0); check("plain", (True, True))
+    # inject_particles! between move and the consumers drops the hand-off
+    step(1)
+    J.inject_particles(t.p, gargs, step=1); t.o.inject(t.co, t.idx, oargs, 6, t.seed, 1)
+    check("after inject", (False, False))
+    # grid2particle! rewrites the field: both parts dropped (conservative)
+    step(2)
+    J.grid2particle(pT, F, t.p); t.o.grid2particle(t.co, t.idx, oargs[0], F.cpu().numpy())
+    check("after grid2particle", (False, False))
+    # particle2grid of ANOTHER field overwrites the workspace: only the phase part survives
+    step(3)
+    F3 = torch.empty_like(F); J.particle2grid(F3, pS, t.p)
+    oF3 = np.empty_like(T); t.o.particle2grid(t.co, t.idx, oF3, oargs[2]); assert_close(F3, oF3, "other field")
+    check("after p2g of another field", (False, True))
+    # exact mode at move time: no particle2grid part
+    J.particle2grid(F3, pT, t.p, mode="exact")
+    step(4)
+    J.phase_ratios_center(pr, t.p, ph); assert J.last_interp_handoff(t.p)[1]
+    J.particle2grid(F, pT, t.p); assert not J.last_interp_handoff(t.p)[0]
+    t.o.particle2grid(t.co, t.idx, oF, oargs[0]); assert_close(F, oF, "default mode after an exact-mode move")
+    # only a phase field registered; field not among the args of the move -> nothing handed off
+    J.move_interp_handoff(t.p, Fp=None, phases=ph, nphases=K)
+    step(5); check("phase only", (False, True))
+    step(6)
+    J.advection(t.p, J.RungeKutta2(), Vd, dt); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+    J.move_particles(t.p, (pT, pS)); t.o.move(t.co, t.idx, [oargs[0], oargs[2]])
+    J.phase_ratios_center(pr, t.p, ph); assert J.last_interp_handoff(t.p) == (False, False)
+    # 5 phases: beyond what the hand-off serves -> stand-alone kernel
+    J.move_interp_handoff(t.p, Fp=pT, phases=ph, nphases=5)
+    pr5 = J.PhaseRatios(J.CUDABackend, 5, t.gr.n)
+    J.advection(t.p, J.RungeKutta2(), Vd, dt); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+    oargs[1][...] = np.where(t.idx > 0, oargs[1], 0.0)
+    J.move_particles(t.p, gargs)
+    # (the oracle state was advanced without ph above; only the GPU-side consistency of the K = 5 path is checked here)
+    J.phase_ratios_center(pr5, t.p, ph); assert J.last_interp_handoff(t.p)[1] is False
+    s = pr5.center.sum(dim=0)
+    assert bool(torch.allclose(s[~torch.isnan(s)], torch.ones_like(s[~torch.isnan(s)]), rtol=1e-13))
+
+
+@pytest.mark.parametrize("g", [(2, (24, 13), True), (3, (33, 6, 5), True)], ids=ids)
+def test_handoff_with_device_side_fallback_to_direct_sweeps(g):
+    """A particle exactly on a cell face sends the whole call to the direct sweeps -- decided on the device, after the
+    consumers' launch configuration was fixed on the host: they must then run their own cell passes."""
+    J, t, V, Vd, dt, T, gargs, oargs = _setup(g, 2)
+    pT, ph, pS = gargs
+    K = 2
+    pr = J.PhaseRatios(J.CUDABackend, K, t.gr.n)
+    F = dev(np.zeros_like(T)); oF = np.empty_like(T); ratios = np.zeros(t.o.cell_shape(K))
+    J.particle2grid(F, pT, t.p)
+    J.move_interp_handoff(t.p, Fp=pT, phases=ph, nphases=K)
+    for it in range(3):
+        J.advection(t.p, J.RungeKutta2(), Vd, dt); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+        if it == 1:                                   # put one live particle exactly on the upper x face of its cell
+            live = np.argwhere(t.idx > 0)[37]
+            i = live[-1]
+            t.co[0][tuple(live)] = t.gr.xvi[0][i + 1]
+            t.p.coords[0].copy_(dev(t.co[0]))
+        J.move_particles(t.p, gargs); st = t.o.move(t.co, t.idx, oargs)
+        assert J.last_move_path(t.p) == ("direct" if it == 1 else "plan")
+        t.check_state(f"step {it} move_particles", gargs, oargs)
+        assert J.move_stats(t.p) == st
+        J.particle2grid(F, pT, t.p); J.phase_ratios_center(pr, t.p, ph)
+        t.o.particle2grid(t.co, t.idx, oF, oargs[0]); t.o.phase_ratios_center(t.co, ratios, oargs[1], K)
+        assert_close(F, oF, f"step {it} particle2grid"); assert_same(pr.center, ratios, f"step {it} phase ratios")
+
+
+@pytest.mark.parametrize("g", [(2, (40, 21), True), (3, (34, 9, 7), True)], ids=ids)
+def test_staging_buffer_too_small_falls_back_on_device_then_grows(g):
+    """jp_move never waits for the device to learn how many particles migrate: the staging buffer is sized from the previous
+    call's count (read back asynchronously).  A step with far more migrants than the last one finds it too small -- decided
+    on the device, the call takes the direct sweeps -- and the next call has grown it.  Results equal the oracle throughout."""
+    J, t, V, Vd, dt, T, gargs, oargs = _setup(g, 2)
+    paths = []
+    for it, scale in enumerate([0.02, 1.0, 1.0, 1.0]):
+        J.advection(t.p, J.RungeKutta2(), Vd, dt * scale); t.o.advect(t.co, t.idx, 1, 0.5, V, dt * scale)
+        J.move_particles(t.p, gargs); st = t.o.move(t.co, t.idx, oargs)
+        t.check_state(f"step {it} move_particles", gargs, oargs)
+        assert J.move_stats(t.p) == st
+        paths.append((J.last_move_path(t.p), J.last_move_reasons(t.p)))
+    assert paths[0] == ("plan", 0)
+    assert paths[1] == ("direct", 8), paths          # staging sized for step 0's handful of migrants
+    assert paths[2] == ("plan", 0) and paths[3] == ("plan", 0), paths

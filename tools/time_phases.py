@@ -17,6 +17,7 @@ ap.add_argument("--exact", action="store_true", help="Julia range() grids (exact
 ap.add_argument("--affine", type=int, default=1)
 ap.add_argument("--policy", default="reference", help="move slot policy: reference | compact")
 ap.add_argument("--classify", type=int, default=0, help="1: advection -> move hand-off (JP_OPT_ADVECT_CLASSIFY)")
+ap.add_argument("--interp", type=int, default=0, help="1: move -> interpolation hand-off (JP_OPT_MOVE_INTERP)")
 a = ap.parse_args()
 gr = make_grids(a.cells, a.ndim, True, exact=a.exact)
 p = J.init_particles(J.CUDABackend, 24, 48, 12, *gr.grid_vel, seed=42)
@@ -30,6 +31,9 @@ if a.fields > 1:
     fields[1].copy_(torch.where(p.index > 0, 1.0 + (p.coords[0] < p.coords[-1]).double(), torch.zeros_like(fields[0])))
 pr = J.PhaseRatios(J.CUDABackend, 2, gr.n)
 m = {"rk2": J.RungeKutta2(), "rk4": J.RungeKutta4(), "euler": J.Euler()}[a.method]
+if a.interp:
+    J.move_interp_handoff(p, Fp=fields[0], phases=fields[1] if a.fields > 1 else None, nphases=2)
+J.profile_move(p, True)
 names = ["advect", "move", "p2g", "phase"]
 rows = []
 for it in range(a.steps):
@@ -42,6 +46,7 @@ for it in range(a.steps):
     ev[4].record(); torch.cuda.synchronize()
     rows.append([ev[i].elapsed_time(ev[i + 1]) for i in range(4)])
 r = np.array(rows)
+print("move stages (mean ms over all steps)", {k: round(v, 3) for k, v in J.read_move_profile(p).items()}, "interp hand-off used", J.last_interp_handoff(p))
 print("classify", a.classify, J.last_move_classify(p) if a.classify else "-", "policy", a.policy, "lib", os.environ.get("JUSTPIC_LIB", "default"), "affine", J.advect_affine_level(p) if hasattr(J, "advect_affine_level") else None, "cells", a.cells, "live", int(p.index.sum()))
 for i, n in enumerate(names):
     print(f"{n:8s}", " ".join(f"{x:7.3f}" for x in r[:, i]), f"| mean(last half) {r[len(r)//2:, i].mean():7.3f}")
