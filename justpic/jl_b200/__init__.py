@@ -8,6 +8,6 @@ any compute call without the built library or a CUDA device raises.
 """
 from . import _cabi
 from .api import *  # noqa: F401,F403
-from .api import move_stats, inject_stats, last_move_path, advect_affine_level  # noqa: F401
+from .api import move_stats, inject_stats, last_move_path, last_move_reasons, advect_affine_level  # noqa: F401
 
 __version__ = "0.1.0"

@@ -156,7 +156,8 @@ static int halo_exchange_dim(JpNccl *nc, ncclComm_t comm, int me, int left, int 
     unsigned char *sl = buf, *sr = buf + pitch, *rl = buf + 2 * pitch, *rr = buf + 3 * pitch;
     if (left >= 0) pack(send_lo, sl);
     if (right >= 0) pack(send_hi, sr);
-    if (left == me || right == me) {
+    const bool self = me == -2 ? true : (left == me || right == me);     // no communicator: the only possible neighbour is the rank itself
+    if (self) {
         if (left != right) return jp_fail(JP_ERR_INVALID, "jp_halo_exchange: a rank can only be its own neighbour on both sides (periodic, one rank along the dimension)");
         unpack(recv_hi, sl);
         unpack(recv_lo, sr);
@@ -175,7 +176,7 @@ static int halo_exchange_dim(JpNccl *nc, ncclComm_t comm, int me, int left, int 
 }
 
 static int halo_comm_rank(JpNccl *nc, void *comm, int *me) {
-    *me = -2;                                             // no communicator: only self-neighbours (single-rank periodic) are possible
+    *me = -2;                                             // no communicator: every neighbour listed is the rank itself (periodic, undecomposed)
     if (comm) {
         if (!nc) return jp_fail(JP_ERR_UNSUPPORTED, "jp_halo_exchange: libnccl.so.2 could not be loaded");
         JP_NCCL(nc->CommUserRank((ncclComm_t)comm, me));

@@ -163,3 +163,191 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
         }
     }
 }
+
+
+// ---- the same pass for the usual argument order -- move_particles!(particles, (Fp, phases, ...)): the particle2grid! field is
+// the first particle field and the phase field (if registered) the second -- with 4-slot load batches like k_move_scatter:
+// coordinates + Fp (3-D) / coordinates + Fp + phases (2-D) are exactly the first register batch of JP_MV_A = 4 arrays, so what
+// the scatter has in registers is what the accumulation needs, with compile-time indices throughout.
+// Measured at 256^3 (B200, profiles/r02c_ab_scatter.log; the separate kernels take 11.9 + 5.7 + 3.9 = 21.5 ms):
+//   generic kernel above (run-time indices, 2-slot batches)            20.0 ms
+//   this kernel, 2-slot batches, sums in registers (128 regs, 2 CTA/SM) 14.9 ms   <- shipped
+//   2-slot batches, sums in shared memory                              15.2 ms
+//   4-slot batches (spills at 128 registers), sums in smem / registers 16.8 / 16.9 ms
+//   cell constants in shared memory as well                            19.6 ms;  3 CTAs/SM at 80 registers (spills): 37 ms
+#ifndef JP_SCI_FAST_U
+#define JP_SCI_FAST_U 2
+#endif
+#ifndef JP_SCI_ACC_SMEM
+#define JP_SCI_ACC_SMEM 0
+#endif
+#ifndef JP_SCI_CONST_SMEM
+#define JP_SCI_CONST_SMEM 0
+#endif
+template <int N> constexpr size_t jp_sci_fast_smem() {
+    return sizeof(double) * 256 * ((JP_SCI_ACC_SMEM ? 2 * (N == 2 ? 4 : 8) : 0) + (JP_SCI_CONST_SMEM ? 12 : 0));
+}
+template <int N, int KMAX, bool FASTW, bool HAS_PH>
+__global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_interp_fast(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index,
+                                                                                          const double *__restrict__ stage, MoveInterp mi,
+                                                                                          const unsigned int *__restrict__ skip_flag) {
+    constexpr int NQ = N == 2 ? 4 : 8;
+    constexpr int U = JP_SCI_FAST_U;
+    constexpr int IT = N;                                     // arrays: x, y[, z], Fp, phases, others...
+    constexpr int IP = N + 1;
+    constexpr int NG = HAS_PH ? N + 2 : N + 1;                // arrays the accumulation reads
+    extern __shared__ double sci_smem[];                      // dynamic: [2 * 2^N sums][256] (+ [12 cell constants][256])
+#if JP_SCI_ACC_SMEM
+    double (*acc_sm)[256] = reinterpret_cast<double (*)[256]>(sci_smem);
+#endif
+#if JP_SCI_CONST_SMEM
+    double (*cst_sm)[256] = reinterpret_cast<double (*)[256]>(sci_smem + (JP_SCI_ACC_SMEM ? 2 * NQ * 256 : 0));   // node / centre coordinates, reciprocal spacings
+#endif
+    if (*skip_flag) return;
+    int ci[3]; int64_t c;
+    const bool ok = tile_cell<N>(g, ci, c);
+    const int tid = threadIdx.y * JP_BX + threadIdx.x;
+    const uint64_t amask = ok ? ws.arrmask[c] : 0, lmask = ok ? ws.leave[c] : 0, occf = ok ? ws.occ[c] : 0;
+    const uint64_t changed = amask | lmask;
+    const uint64_t visit = changed | occf;
+    const unsigned base = ok ? ws.off[c] : 0;
+#if JP_SCI_CONST_SMEM
+    if (ok) {
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            cst_sm[2 * d][tid] = g.xv[d][ci[d]]; cst_sm[2 * d + 1][tid] = g.xv[d][ci[d] + 1];
+            if (HAS_PH) { cst_sm[6 + d][tid] = g.xc[d][ci[d]]; cst_sm[9 + d][tid] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
+        }
+    }
+#else
+    double xn[3][2], xcn[3], idi[3];
+    if (ok) {
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            xn[d][0] = g.xv[d][ci[d]]; xn[d][1] = g.xv[d][ci[d] + 1];
+            if (HAS_PH) { xcn[d] = g.xc[d][ci[d]]; idi[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
+        }
+    }
+#endif
+#if JP_SCI_ACC_SMEM
+#pragma unroll
+    for (int q = 0; q < 2 * NQ; q++) acc_sm[q][tid] = 0.0;
+#else
+    double aw[NQ], awf[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) { aw[q] = 0.0; awf[q] = 0.0; }
+#endif
+    double w[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) w[k] = 0.0;
+    const int AS = (arrs.n + 3) & ~3;
+    const double *a0p = arrs.a[0], *a1p = arrs.a[1], *a2p = arrs.a[2], *a3p = arrs.a[3];
+    for (int s0 = 0; s0 < g.S; s0 += U) {
+        const unsigned vb = (unsigned)(visit >> s0) & ((1u << U) - 1u);
+        if (!__any_sync(0xffffffffu, vb != 0)) continue;
+        const unsigned chb = (unsigned)(changed >> s0) & ((1u << U) - 1u);
+        const unsigned arb = (unsigned)(amask >> s0) & ((1u << U) - 1u);
+        const unsigned fb = (unsigned)(occf >> s0) & ((1u << U) - 1u);
+        const double *sp[U];                                   // staging record of the slot's arrival
+#pragma unroll
+        for (int u = 0; u < U; u++) sp[u] = stage + (size_t)(base + (unsigned)__popcll(amask & ((1ull << (s0 + u)) - 1))) * AS;
+        double v[U][JP_MV_A], phv[U];
+        // ---- loads: arrivals from staging, unchanged occupants from the arrays (only what the accumulation reads)
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int64_t e = c + (int64_t)(s0 + u) * g.C;
+            const bool ch = (chb >> u) & 1u, ar = (arb >> u) & 1u, keep = !ch && ((fb >> u) & 1u);
+#pragma unroll
+            for (int a = 0; a < JP_MV_A; a++) {
+                v[u][a] = NAN;
+                if (a < arrs.n) {
+                    if (ar) v[u][a] = sp[u][a];
+                    else if (keep && a < NG) v[u][a] = (a == 0 ? a0p : a == 1 ? a1p : a == 2 ? a2p : a3p)[e];
+                }
+            }
+            phv[u] = NAN;
+            if (HAS_PH && N == 3) {
+                if (ar) phv[u] = sp[u][IP];
+                else if (keep) phv[u] = arrs.a[IP][e];
+            }
+        }
+        // ---- stores of the changed slots
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!((chb >> u) & 1u)) continue;
+            const int64_t e = c + (int64_t)(s0 + u) * g.C;
+#pragma unroll
+            for (int a = 0; a < JP_MV_A; a++) if (a < arrs.n) arrs.a[a][e] = v[u][a];
+            if (HAS_PH && N == 3) arrs.a[IP][e] = phv[u];
+        }
+        // ---- the other particle fields: scatter only
+        for (int a0 = (HAS_PH && N == 3) ? JP_MV_A + 1 : JP_MV_A; a0 < arrs.n; a0++) {
+            double o[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) o[u] = (((chb & arb) >> u) & 1u) ? sp[u][a0] : NAN;
+#pragma unroll
+            for (int u = 0; u < U; u++) if ((chb >> u) & 1u) arrs.a[a0][c + (int64_t)(s0 + u) * g.C] = o[u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s = s0 + u;
+            if ((chb >> u) & 1u) {
+                if ((arb >> u) & 1u) { if (!((lmask >> s) & 1ull)) index[c + (int64_t)s * g.C] = 1; }
+                else index[c + (int64_t)s * g.C] = 0;
+            }
+            if ((fb >> u) & 1u) {                              // slot order = the reference's summation order
+                const double p[3] = {v[u][0], v[u][1], N == 3 ? v[u][2] : 0.0};
+                const double f = v[u][IT];
+#if JP_SCI_CONST_SMEM
+                double xn[3][2], xcn[3], idi[3];
+#pragma unroll
+                for (int d = 0; d < N; d++) {
+                    xn[d][0] = cst_sm[2 * d][tid]; xn[d][1] = cst_sm[2 * d + 1][tid];
+                    if (HAS_PH) { xcn[d] = cst_sm[6 + d][tid]; idi[d] = cst_sm[9 + d][tid]; }
+                }
+#endif
+#if JP_SCI_ACC_SMEM
+                {
+                    double d2[3][2];
+#pragma unroll
+                    for (int d = 0; d < N; d++) {
+                        const double b0 = xn[d][0] - p[d], b1 = xn[d][1] - p[d];
+                        d2[d][0] = b0 * b0; d2[d][1] = b1 * b1;
+                    }
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        double ss = d2[0][q & 1] + d2[1][(q >> 1) & 1];
+                        if (N == 3) ss = ss + d2[2][(q >> 2) & 1];
+                        double wi;
+                        if (FASTW) wi = jp_rcp_fast(ss);
+                        else { const double dist = sqrt(ss); wi = 1.0 / (dist * dist); }
+                        acc_sm[q][tid] += wi;
+                        acc_sm[NQ + q][tid] = fma(wi, f, acc_sm[NQ + q][tid]);
+                    }
+                }
+#else
+                jp_p2g_cell_accum<N, FASTW>(xn, p, f, aw, awf);
+#endif
+                if (HAS_PH) jp_phase_accum<N, KMAX>(xcn, idi, p, N == 3 ? phv[u] : v[u][IP], mi.K, w);
+            }
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+#if JP_SCI_ACC_SMEM
+            mi.PW[(int64_t)q * g.C + c] = acc_sm[q][tid]; mi.PWF[(int64_t)q * g.C + c] = acc_sm[NQ + q][tid];
+#else
+            mi.PW[(int64_t)q * g.C + c] = aw[q]; mi.PWF[(int64_t)q * g.C + c] = awf[q];
+#endif
+        }
+        if (HAS_PH) {
+            double sum = w[0];
+#pragma unroll
+            for (int k = 1; k < KMAX; k++) if (k < mi.K) sum = sum + w[k];
+            const double inv = 1.0 / sum;
+#pragma unroll
+            for (int k = 0; k < KMAX; k++) if (k < mi.K) mi.RC[c + (int64_t)k * g.C] = w[k] * inv;
+        }
+    }
+}
