@@ -268,7 +268,7 @@ def run_ours(args):
     p = J.init_particles(J.CUDABackend, PPC, SLOTS, MIN_XCELL, *gv, seed=42 + rank, device=dev)
     V_host = [torch.from_numpy(v).pin_memory() for v in stream_velocity_np(gv)]
     V = [v.to(dev, non_blocking=True) for v in V_host]
-    vmax = torch.tensor([float(np.abs(V_host[0].numpy()).max()), float(np.abs(V_host[2].numpy()).max())], device=dev)
+    vmax = torch.tensor([float(np.abs(V_host[0].numpy()).max()), float(np.abs(V_host[2].numpy()).max())], device=dev, dtype=torch.float64)
     if world > 1:
         allreduce_max(comm, vmax)                         # dt = MPI.Allreduce(max) in the reference script (:71)
     dt = CFL * min(p.di.vertex[0] / float(vmax[0]), p.di.vertex[2] / float(vmax[1]))

@@ -239,7 +239,8 @@ def create_comm(device=None, group=None) -> Comm:
 
 def allreduce_max(comm: Comm, t: torch.Tensor) -> torch.Tensor:
     """In-place max over the ranks of a float64 device tensor (the reference scripts' ``MPI.Allreduce(..., MPI.MAX)`` for dt)."""
-    assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+    if not (isinstance(t, torch.Tensor) and t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()):
+        raise ValueError("allreduce_max: expected a contiguous float64 device tensor")
     with torch.cuda.device(t.device):
         _cabi.check(_cabi.load().jp_allreduce_max(C.c_void_p(comm.handle), C.c_void_p(t.data_ptr()), t.numel(), _stream()), "allreduce_max")
     return t

@@ -218,7 +218,7 @@ def _worker(rank, world, port, dims, nloc, overlap, out):
         comm = halo.create_comm(device=f"cuda:{rank}")
         p, args, Vd, i0 = pb.make_rank(topo, torch.device("cuda", rank))
         F = torch.empty(tuple(n + 1 for n in reversed(nloc)), dtype=torch.float64, device=f"cuda:{rank}")
-        vmax = torch.tensor([float(np.abs(v.cpu().numpy()).max()) for v in Vd], device=f"cuda:{rank}")
+        vmax = torch.tensor([float(np.abs(v.cpu().numpy()).max()) for v in Vd], device=f"cuda:{rank}", dtype=torch.float64)
         halo.allreduce_max(comm, vmax)                                    # the reference's dt reduction (:71)
         assert float(vmax.max()) <= 250.0
         snaps = []
