@@ -18,6 +18,7 @@
 module JustPICSM100aExt
 
 using CUDA, JustPIC, CellArrays
+import MPI
 using CUDA: CUDABackend
 import JustPIC: Particles, Euler, RungeKutta2, RungeKutta4, AbstractAdvectionIntegrator
 
@@ -290,10 +291,54 @@ function fill_coords_index!(p::Particles{CUDABackend}; seed::UInt64 = UInt64(42)
     done()
 end
 
-# update_cell_halo!: jp_halo_pack / jp_halo_unpack replace the per-array
-# ImplicitGlobalGrid.update_halo! calls (src/CellArrays/ImplicitGlobalGrid.jl:36-41);
-# the transport between ranks stays with the host (MPI.Isend/Irecv of ONE packed
-# buffer per face, or NCCL as in justpic/jl_b200/halo.py).
+# update_cell_halo!(particles.coords..., args..., particles.index)      src/CellArrays/ImplicitGlobalGrid.jl:36-41
+# ONE library call replaces the per-CellArray ImplicitGlobalGrid.update_halo! calls: pack kernels, the x -> y -> z schedule and
+# the NCCL transport (ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd) are inside jp_halo_exchange.  The host supplies an
+# NCCL communicator -- NCCL.jl's `comm.handle`, or one made by jp_comm_init from an id broadcast over MPI -- and the neighbour
+# ranks of ImplicitGlobalGrid's Cartesian topology (MPI.Cart_shift on IGG's communicator; -1 = no neighbour).
+const HALO = Ref{Any}(nothing)          # (comm::Ptr{Cvoid}, nbr::Vector{Int32} of length 6: left / right per dimension)
+
+function init_halo!(mpicomm, cart_comm; device = CUDA.deviceid(CUDA.device()))
+    id = zeros(UInt8, 128)
+    MPI.Comm_rank(mpicomm) == 0 && check(ccall((:jp_comm_unique_id, libjustpic), Cint, (Ptr{UInt8},), id), "jp_comm_unique_id")
+    MPI.Bcast!(id, 0, mpicomm)
+    comm = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jp_comm_init, libjustpic), Cint, (Ptr{UInt8}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+                id, Int32(MPI.Comm_size(mpicomm)), Int32(MPI.Comm_rank(mpicomm)), Int32(device), comm), "jp_comm_init")
+    nbr = fill(Int32(-1), 6)
+    for d in 0:(MPI.Cartdim_get(cart_comm) - 1)
+        l, r = MPI.Cart_shift(cart_comm, d, 1)
+        nbr[2d + 1] = l == MPI.PROC_NULL ? Int32(-1) : Int32(l)
+        nbr[2d + 2] = r == MPI.PROC_NULL ? Int32(-1) : Int32(r)
+    end
+    HALO[] = (comm[], nbr)
+end
+
+# the reference's signature takes bare CellArrays; the Particles object (for the context) is found through its index array
+function update_cell_halo!(p::Particles{CUDABackend}, args::Vararg{CellArray})
+    comm, nbr = HALO[]
+    arrays = CuPtr{Float64}[cptr(a) for a in (p.coords..., args...)]
+    check(ccall((:jp_halo_exchange, libjustpic), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, Ptr{CuPtr{Float64}}, Int32, CuPtr{UInt8}, Ptr{Cvoid}),
+                context(p), comm, nbr, arrays, Int32(length(arrays)), cptr(p.index), stream()), "update_cell_halo!")
+    done()
+end
+
+# update_halo!(A) of a plain (staggered) grid array on the same decomposition -- the velocity ghost layers when V comes from a solver
+function update_halo!(p::Particles{CUDABackend}, A::CuArray{Float64})
+    comm, nbr = HALO[]
+    ext = Int32[size(A)...]
+    check(ccall((:jp_halo_exchange_grid, libjustpic), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int32}, CuPtr{Float64}, Ptr{Int32}, Ptr{Cvoid}),
+                context(p), comm, nbr, pointer(A), ext, stream()), "update_halo!")
+    done()
+end
+
+# dt = min(dx / MPI.Allreduce(maximum(abs.(V)), MPI.MAX, comm)) (scripts/temperature_advection3D_MPI.jl:71) without leaving the GPU
+function allreduce_max!(buf::CuArray{Float64})
+    check(ccall((:jp_allreduce_max, libjustpic), Cint, (Ptr{Cvoid}, CuPtr{Float64}, Int32, Ptr{Cvoid}),
+                HALO[][1], pointer(buf), Int32(length(buf)), stream()), "jp_allreduce_max")
+    done(); buf
+end
 
 # Array(CA) / Array(T, CA) for a device CellArray                  src/CellArrays/conversion.jl:19-43
 # CuArray(CA) / CuArray(T, CA) for a host CellArray                ext/JustPICCUDAExt.jl:166-179
@@ -331,5 +376,16 @@ end
 const ADVECT_CLASSIFY = Ref{Int32}(parse(Int32, get(ENV, "JUSTPIC_ADVECT_CLASSIFY", "0")))
 set_handoff!(p::Particles{CUDABackend}, on::Bool = ADVECT_CLASSIFY[] != 0) =
     check(ccall((:jp_set_option, libjustpic), Cint, (Ptr{Cvoid}, Int32, Int32), context(p), Int32(5), Int32(on)), "jp_set_option")
+
+# move -> interpolation hand-off (JP_OPT_MOVE_INTERP = 7): the last pass of move_particles! also leaves particle2grid!'s cell sums
+# of `Fp` and the centre phase ratios of `phases` (both must be among the args of move_particles!); the following
+# particle2grid!(F, Fp, particles) / phase_ratios_center!(ratios, particles, phases) then do not read the particles again.
+# Bit-identical results; opt-in for the same reason as above.
+function set_interp_handoff!(p::Particles{CUDABackend}, Fp::Union{CellArray, Nothing}, phases::Union{CellArray, Nothing}, nphases::Integer = 0; on::Bool = true)
+    check(ccall((:jp_set_option, libjustpic), Cint, (Ptr{Cvoid}, Int32, Int32), context(p), Int32(7), Int32(on)), "jp_set_option")
+    check(ccall((:jp_move_interp_fields, libjustpic), Cint, (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Int32),
+                context(p), Fp === nothing ? CuPtr{Float64}(0) : cptr(Fp), phases === nothing ? CuPtr{Float64}(0) : cptr(phases), Int32(nphases)),
+          "jp_move_interp_fields")
+end
 
 end # module

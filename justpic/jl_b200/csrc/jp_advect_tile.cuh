@@ -163,9 +163,12 @@ __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__rest
 // HINT (JP_OPT_ADVECT_CLASSIFY, the advection -> move hand-off): every new position is also classified
 // for the following move_particles! -- jp_classify_fast / jp_classify_particle on the value being stored,
 // i.e. exactly what k_move_classify3 would compute from memory -- into a per-warp byte table in shared
-// memory ([slot][cell of the x-run]); when the warp has finished its x-run, lane = cell packs its leavers'
-// codes in slot order and writes the occupancy / leave / code words of the move plan itself.  jp_move then
-// starts at the plan kernels: no pass over the coordinates, no intermediate plane in HBM.
+// memory ([cell of the x-run][slot], rows of ADV_HINT_ROW bytes preset to "stays").  The move plan's code words
+// are indexed by slot (byte s & 7 of word s >> 3), so when the warp has finished its x-run, lane = cell
+// copies its row out as 64-bit words, derives the leave word from them with byte-parallel bit tricks and
+// writes the occupancy / leave words: ~12 instructions per word instead of a 48-iteration byte loop.
+// jp_move then starts at the plan kernels: no pass over the coordinates, no intermediate plane in HBM.
+#define ADV_HINT_ROW 72          // bytes per cell row: JP_MAX_SLOTS + 8 (18 words: 64-bit row loads of a half-warp hit 32 distinct banks)
 template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
 __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 768) / (AdvTile<N>::NW * 32)) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
                                                                      double alpha, double dt,
@@ -228,6 +231,10 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
                 val = F[gx + (int64_t)n0 * (gy + (int64_t)n1 * gz)];
             sm[L::V_OFF + c * T::VOL + t] = val;
         }
+    }
+    if (HINT) {                                                   // this warp's rows of the byte table: every slot "stays" until a lane says otherwise
+        uint64_t *rows = reinterpret_cast<uint64_t *>(code_all + (size_t)warp * 32 * ADV_HINT_ROW);
+        for (int t = lane; t < 32 * ADV_HINT_ROW / 8; t += 32) rows[t] = 0x0101010101010101ull * JP_CLS_STAY;
     }
     if (tid < 3 * L::VEC) {
         const int d = tid / L::VEC, j = tid % L::VEC;
@@ -372,7 +379,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
                         }
                         code = jp_classify_particle<N>(g, vm, va, vb, vp, pn);
                     }
-                    code_all[(warp * g.S + (cur_l >> 5)) * 32 + l] = (uint8_t)code;
+                    code_all[(warp * 32 + l) * ADV_HINT_ROW + (cur_l >> 5)] = (uint8_t)code;
                 }
             }
         }
@@ -383,27 +390,31 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
         __syncwarp();
     }
     if (HINT) {
-        // ---- 4. lane = cell: the words k_move_classify3 would have produced (same packing, same order)
+        // ---- 4. lane = cell: the words k_move_classify3 would have produced (code bytes by slot, eight slots per word)
         __syncwarp();
         const int64_t c = crow + cx;
-        const uint8_t *cs = code_all + (warp * g.S) * 32 + lane;
-        uint64_t lv = 0, codew = 0;
-        int k = 0;
+        const uint64_t *row = reinterpret_cast<const uint64_t *>(code_all + (size_t)(warp * 32 + lane) * ADV_HINT_ROW);
+        const uint64_t STAYS = 0x0101010101010101ull * JP_CLS_STAY;
+        uint64_t lv = 0;
         unsigned cplx = 0;
-        for (int s = 0; s < g.S; s++) {
-            int code = cs[s * 32];
-            const bool leaver = ((m >> s) & 1ull) && code != JP_CLS_STAY;
-            if (leaver) {
-                lv |= 1ull << s;
-                if (code > JP_CLS_CPLX) { cplx |= 1u << ((code - JP_CLS_CPLX - 1) & 3); code = JP_CODE_DELETE; }
-                codew |= (uint64_t)code << (8 * (k & 7));
-                if ((++k & 7) == 0) { ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
+        for (int q = 0; q * 8 < g.S; q++) {
+            uint64_t w = row[q];
+            if ((w + 0x0101010101010101ull * (127 - JP_CLS_STAY)) & 0x8080808080808080ull) {      // a byte above JP_CLS_STAY: "the planner cannot express it" (rare)
+                for (int i = 0; i < 8; i++) {
+                    const int code = (int)((w >> (8 * i)) & 255);
+                    if (code > JP_CLS_CPLX) {
+                        cplx |= 1u << ((code - JP_CLS_CPLX - 1) & 3);
+                        w = (w & ~(0xffull << (8 * i))) | ((uint64_t)JP_CODE_DELETE << (8 * i));
+                    }
+                }
             }
+            const uint64_t x = w ^ STAYS;                                                          // non-zero bytes = leavers
+            const uint64_t t = (((x & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | x) & 0x8080808080808080ull;
+            const uint64_t bits = ((t >> 7) * 0x0102040810204080ull) >> 56;                        // bit i = byte i is non-zero
+            lv |= bits << (8 * q);
+            if (ok && bits) ws.code[(int64_t)q * g.C + c] = w;
         }
-        if (ok) {
-            ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
-            if (k & 7) ws.code[(int64_t)(k >> 3) * g.C + c] = codew;
-        }
+        if (ok) { ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv; }
         const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
         if (wc && lane == 0) atomicOr(complex_flag, wc);
     }

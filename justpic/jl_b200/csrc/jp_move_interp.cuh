@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
     const int tid = threadIdx.y * JP_BX + threadIdx.x;
+    (void)tid;
     const uint64_t amask = ok ? ws.arrmask[c] : 0, lmask = ok ? ws.leave[c] : 0, occf = ok ? ws.occ[c] : 0;
     const uint64_t changed = amask | lmask;
     const uint64_t visit = changed | occf;

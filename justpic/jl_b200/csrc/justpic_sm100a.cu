@@ -244,13 +244,9 @@ __device__ __forceinline__ int nth_set_bit64(uint64_t m, int i) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ, uint64_t *leave,
-                                                    int ox, int oy, int oz, int ncx, int ncy, int64_t ncol, long long *stats, int compact,
-                                                    const unsigned int *__restrict__ run_flag) {
-    if (run_flag && !*run_flag) return;
+__device__ __forceinline__ void jp_move_sweep_cell(const JpGrid &g, Ptr3 co, uint8_t *index, const JpArgs &args, uint64_t *occ, uint64_t *leave,
+                                                   int ox, int oy, int oz, int ncx, int ncy, int64_t t, long long *stats, int compact) {
     const int lane = threadIdx.x & 31;
-    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= ncol) return;                                   // warp-uniform
     int ci[3];
     ci[0] = 3 * (int)(t % ncx) + ox;
     ci[1] = 3 * (int)((t / ncx) % ncy) + oy;
@@ -358,6 +354,21 @@ __global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *
         if (n_moved) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)n_moved);
         if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
         if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);
+    }
+}
+
+// The launch: one warp per source cell of the colour, grid-stride over the cells with a capped grid -- in JP_MOVE_AUTO these 3^N
+// launches sit behind the planned path and return at once unless it declined (device-side flag); a full-size grid of ~80 000
+// blocks costs ~40 us just to start and retire, 27 times per call.
+template <int N>
+__global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ, uint64_t *leave,
+                                                    int ox, int oy, int oz, int ncx, int ncy, int64_t ncol, long long *stats, int compact,
+                                                    const unsigned int *__restrict__ run_flag) {
+    if (run_flag && !*run_flag) return;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ncol; t += nwarps) {     // warp-uniform
+        jp_move_sweep_cell<N>(g, co, index, args, occ, leave, ox, oy, oz, ncx, ncy, t, stats, compact);
+        __syncwarp();
     }
 }
 
@@ -1252,11 +1263,11 @@ struct AdvHandoff { MovePlanWs ws; unsigned int *flag; };        // flag == null
 template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
 static cudaError_t launch_advect_tile_h(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, const AdvHandoff &ho) {
     using T = AdvTile<N>;
-    const size_t smem = AdvSmem<N, UNIFORM>::BYTES + (HINT ? (size_t)T::NW * g.S * 32 : 0);     // + the per-warp classification bytes
+    const size_t smem = AdvSmem<N, UNIFORM>::BYTES + (HINT ? (size_t)T::NW * 32 * ADV_HINT_ROW : 0);     // + the per-warp classification bytes
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(AdvSmem<N, UNIFORM>::BYTES + (HINT ? T::NW * JP_MAX_SLOTS * 32 : 0)));
+                                             (int)(AdvSmem<N, UNIFORM>::BYTES + (HINT ? T::NW * 32 * ADV_HINT_ROW : 0)));
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -1532,8 +1543,8 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     if (ctx->m_pending && cudaEventQuery(ctx->m_event) == cudaSuccess) {
         ctx->m_pending = 0;
         const size_t lastM = ctx->h_pinned[1];
-        if (lastM * AS > ctx->stage_elems || (lastM + lastM / 8) * AS > ctx->stage_elems) {
-            rc = stage_reserve(ctx, (lastM + lastM / 4) * AS);
+        if ((lastM + lastM / 4 + 2048) * AS > ctx->stage_elems) {           // keep >= 25 % + 2048 rows of head room over the last count ...
+            rc = stage_reserve(ctx, (lastM + lastM / 2 + 4096) * AS);      // ... by growing to 50 % + 4096 (grow-only)
             if (rc) return rc;
         }
     }
@@ -1555,7 +1566,8 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
         JP_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, ctx->mp.off + g.C, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         JP_CUDA(cudaStreamSynchronize(st));
         const size_t M0 = ctx->h_pinned[1];
-        if (M0) { rc = stage_reserve(ctx, (M0 + M0 / 4) * AS); if (rc) return rc; }
+        rc = stage_reserve(ctx, (M0 + M0 / 2 + 4096) * AS);
+        if (rc) return rc;
     }
     k_move_after_scan<<<1, 1, 0, st>>>(ctx->stats, ctx->mp.off + g.C, (uint64_t)(ctx->stage_elems / AS), flag, flag + 1);
     if (!ctx->m_pending) {
@@ -1658,7 +1670,8 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     JP_CHECK_LAUNCH();
     const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = g.ndim == 3 ? (g.n[2] + 2) / 3 : 1;
     const int64_t ncol = (int64_t)ncx * ncy * ncz;          // source cells per colour (upper bound)
-    const unsigned nblk = (unsigned)((ncol + 7) / 8);        // one warp per source cell, 8 warps per block
+    const int64_t want_blk = (ncol + 7) / 8;                 // one warp per source cell, 8 warps per block, grid-stride beyond 148 x 16 blocks
+    const unsigned nblk = (unsigned)(want_blk < 148 * 16 ? want_blk : 148 * 16);
     for (int ox = 0; ox < 3; ox++)
         for (int oy = 0; oy < 3; oy++)
             for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {

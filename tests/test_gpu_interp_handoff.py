@@ -153,7 +153,7 @@ def test_handoff_with_device_side_fallback_to_direct_sweeps(g):
         assert_close(F, oF, f"step {it} particle2grid"); assert_same(pr.center, ratios, f"step {it} phase ratios")
 
 
-@pytest.mark.parametrize("g", [(2, (40, 21), True), (3, (34, 9, 7), True)], ids=ids)
+@pytest.mark.parametrize("g", [(2, (160, 96), True), (3, (34, 24, 20), True)], ids=ids)
 def test_staging_buffer_too_small_falls_back_on_device_then_grows(g):
     """jp_move never waits for the device to learn how many particles migrate: the staging buffer is sized from the previous
     call's count (read back asynchronously).  A step with far more migrants than the last one finds it too small -- decided
