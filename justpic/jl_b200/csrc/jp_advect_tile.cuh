@@ -163,10 +163,10 @@ __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__rest
 // HINT (JP_OPT_ADVECT_CLASSIFY, the advection -> move hand-off): every new position is also classified
 // for the following move_particles! -- jp_classify_fast / jp_classify_particle on the value being stored,
 // i.e. exactly what k_move_classify3 would compute from memory -- into a per-warp byte table in shared
-// memory ([cell of the x-run][slot], rows of ADV_HINT_ROW bytes preset to "stays").  The move plan's code words
-// are indexed by slot (byte s & 7 of word s >> 3), so when the warp has finished its x-run, lane = cell
-// copies its row out as 64-bit words, derives the leave word from them with byte-parallel bit tricks and
-// writes the occupancy / leave words: ~12 instructions per word instead of a 48-iteration byte loop.
+// memory ([cell of the x-run][slot], rows of ADV_HINT_ROW bytes preset to "stays").  When the warp has finished its
+// x-run, lane = cell reads its row as 64-bit words, finds the leavers of each word with byte-parallel bit tricks
+// (~12 instructions per 8 slots) and appends their codes -- the leavers only, ~9 of 48 slots -- to the packed code
+// words of the move plan, in slot order, exactly as k_move_classify3 packs them; then the occupancy / leave words.
 // jp_move then starts at the plan kernels: no pass over the coordinates, no intermediate plane in HBM.
 #define ADV_HINT_ROW 72          // bytes per cell row: JP_MAX_SLOTS + 8 (18 words: 64-bit row loads of a half-warp hit 32 distinct banks)
 template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
@@ -397,23 +397,24 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
         const uint64_t STAYS = 0x0101010101010101ull * JP_CLS_STAY;
         uint64_t lv = 0;
         unsigned cplx = 0;
+        uint64_t codew = 0;
+        int k = 0;
         for (int q = 0; q * 8 < g.S; q++) {
-            uint64_t w = row[q];
-            if ((w + 0x0101010101010101ull * (127 - JP_CLS_STAY)) & 0x8080808080808080ull) {      // a byte above JP_CLS_STAY: "the planner cannot express it" (rare)
-                for (int i = 0; i < 8; i++) {
-                    const int code = (int)((w >> (8 * i)) & 255);
-                    if (code > JP_CLS_CPLX) {
-                        cplx |= 1u << ((code - JP_CLS_CPLX - 1) & 3);
-                        w = (w & ~(0xffull << (8 * i))) | ((uint64_t)JP_CODE_DELETE << (8 * i));
-                    }
-                }
-            }
+            const uint64_t w = row[q];
             const uint64_t x = w ^ STAYS;                                                          // non-zero bytes = leavers
             const uint64_t t = (((x & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | x) & 0x8080808080808080ull;
-            const uint64_t bits = ((t >> 7) * 0x0102040810204080ull) >> 56;                        // bit i = byte i is non-zero
-            lv |= bits << (8 * q);
-            if (ok && bits) ws.code[(int64_t)q * g.C + c] = w;
+            unsigned bits = (unsigned)(((t >> 7) * 0x0102040810204080ull) >> 56);                  // bit i = byte i is non-zero
+            lv |= (uint64_t)bits << (8 * q);
+            while (bits) {                                                                         // this word's leavers, in slot order
+                const int i = __ffs((int)bits) - 1;
+                bits &= bits - 1;
+                int code = (int)((w >> (8 * i)) & 255);
+                if (code > JP_CLS_CPLX) { cplx |= 1u << ((code - JP_CLS_CPLX - 1) & 3); code = JP_CODE_DELETE; }
+                codew |= (uint64_t)code << (8 * (k & 7));
+                if ((++k & 7) == 0) { if (ok) ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
+            }
         }
+        if (ok && (k & 7)) ws.code[(int64_t)(k >> 3) * g.C + c] = codew;
         if (ok) { ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv; }
         const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
         if (wc && lane == 0) atomicOr(complex_flag, wc);

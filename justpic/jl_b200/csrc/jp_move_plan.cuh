@@ -6,9 +6,8 @@
 // destination of each leaving particle -- not the particle payload.  So:
 //
 //  A. k_move_classify3 (one coalesced pass over coords + mask): per cell the
-//     occupancy word, the leave word and the destination code of every slot
-//     (one byte per slot, eight slots per word: one of the 3^N neighbours, "left
-//     the domain", or "stays").  Anything the
+//     occupancy word, the leave word and a packed list of 5-bit destination
+//     codes (one of the 3^N neighbours, or "left the domain").  Anything the
 //     planner cannot express exactly -- a particle that fails isincell but
 //     bisects back into its own cell or fails isincell in its destination (on a
 //     face / in the fl(x+dx) ulp gap) or a displacement of more than one cell --
@@ -69,73 +68,70 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
         for (int d = 0; d < N; d++) a[d] = g.xv[d][ci[d]];
     }
     uint64_t lv = 0, codew = 0;
+    int k = 0;
     unsigned cplx = 0;     // reason bits: 1 far / on a vertex, 2 same cell (ulp gap), 4 fails isincell in destination
 #ifndef JP_CLS_U
 #define JP_CLS_U 4
 #endif
     constexpr int U = JP_CLS_U;
-    static_assert(U == 4, "a batch must not straddle a code word (8 slots) and the all-stay filler below assumes 4 slots");
     for (int s0 = 0; s0 < g.S; s0 += U) {
         const unsigned bits = (unsigned)(m >> s0) & ((1u << U) - 1u);
-        if (__any_sync(0xffffffffu, bits != 0)) {
-            double p[U][3];
+        if (!__any_sync(0xffffffffu, bits != 0)) continue;
+        double p[U][3];
 #pragma unroll
-            for (int u = 0; u < U; u++)
+        for (int u = 0; u < U; u++)
 #pragma unroll
-                for (int d = 0; d < N; d++) p[u][d] = ((bits >> u) & 1u) ? co.p[d][c + (int64_t)(s0 + u) * g.C] : 0.0;
-            // range grids: single-precision pre-filter (jp_classify_fast), branch-free; the exact comparisons
-            // (isincell with upper edge fl(a + dx), domain test, destination among the four vertices) run only
-            // for batches holding a particle within 1e-4 dx of a vertex -- and always on vector grids
-            int codes[U];
-            bool unsure = false;
+            for (int d = 0; d < N; d++) p[u][d] = ((bits >> u) & 1u) ? co.p[d][c + (int64_t)(s0 + u) * g.C] : 0.0;
+        // range grids: single-precision pre-filter (jp_classify_fast), branch-free; the exact comparisons
+        // (isincell with upper edge fl(a + dx), domain test, destination among the four vertices) run only
+        // for batches holding a particle within 1e-4 dx of a vertex -- and always on vector grids
+        int codes[U];
+        bool unsure = false;
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const bool live = (bits >> u) & 1u;
-                const int cf = g.cls_fast ? jp_classify_fast<N>(g, ci, a, p[u]) : -1;
-                codes[u] = live ? cf : JP_CLS_STAY;
-                unsure = unsure || codes[u] < 0;
-            }
-            if (__any_sync(0xffffffffu, unsure)) {
-                if (unsure) {
-                    // the four vertices around the cell per dimension (NaN outside the grid: comparisons fail)
-                    double am[3], b[3], bp[3];
+        for (int u = 0; u < U; u++) {
+            const bool live = (bits >> u) & 1u;
+            const int cf = g.cls_fast ? jp_classify_fast<N>(g, ci, a, p[u]) : -1;
+            codes[u] = live ? cf : JP_CLS_STAY;
+            unsure = unsure || codes[u] < 0;
+        }
+        if (__any_sync(0xffffffffu, unsure)) {
+            if (unsure) {
+                // the four vertices around the cell per dimension (NaN outside the grid: comparisons fail)
+                double am[3], b[3], bp[3];
 #pragma unroll
-                    for (int d = 0; d < N; d++) {
-                        const double *xv = g.xv[d];
-                        const int i = ci[d];
-                        b[d] = xv[i + 1];
-                        am[d] = i > 0 ? xv[i - 1] : NAN;
-                        bp[d] = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; u++)
-                        if (codes[u] < 0) codes[u] = jp_classify_particle<N>(g, am, a, b, bp, p[u]);
+                for (int d = 0; d < N; d++) {
+                    const double *xv = g.xv[d];
+                    const int i = ci[d];
+                    b[d] = xv[i + 1];
+                    am[d] = i > 0 ? xv[i - 1] : NAN;
+                    bp[d] = i + 2 <= g.n[d] ? xv[i + 2] : NAN;
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                int code = codes[u];
-                if (code != JP_CLS_STAY) {
-                    lv |= 1ull << (s0 + u);
-                    if (code > JP_CLS_CPLX) { cplx |= 1u << (code - JP_CLS_CPLX - 1); code = JP_CODE_DELETE; }
-                }
-                codew |= (uint64_t)code << (8 * ((s0 + u) & 7));
+                for (int u = 0; u < U; u++)
+                    if (codes[u] < 0) codes[u] = jp_classify_particle<N>(g, am, a, b, bp, p[u]);
             }
-        } else codew |= (uint64_t)(0x01010101u * JP_CLS_STAY) << (8 * (s0 & 7));   // a batch without a live particle in the whole warp
-        // code words are indexed BY SLOT (byte s & 7 of word s >> 3 = the code of slot s, JP_CLS_STAY if it does not leave)
-        if (((s0 + U) & 7) == 0 || s0 + U >= g.S) {
-            if (ok && (lv >> (s0 & ~7)) & 0xffull) ws.code[(int64_t)(s0 >> 3) * g.C + c] = codew;     // only words that hold a leaver are ever read
-            codew = 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int code = codes[u];
+            if (code == JP_CLS_STAY) continue;
+            lv |= 1ull << (s0 + u);
+            if (code > JP_CLS_CPLX) { cplx |= 1u << (code - JP_CLS_CPLX - 1); code = JP_CODE_DELETE; }
+            codew |= (uint64_t)code << (8 * (k & 7));
+            if ((++k & 7) == 0) { ws.code[(int64_t)((k >> 3) - 1) * g.C + c] = codew; codew = 0; }
         }
     }
-    if (ok) { ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv; }
+    if (ok) {
+        ws.occ[c] = m; ws.occ0[c] = m; ws.leave[c] = lv;
+        if (k & 7) ws.code[(int64_t)(k >> 3) * g.C + c] = codew;
+    }
     const unsigned wc = __reduce_or_sync(0xffffffffu, cplx);
     if (wc && threadIdx.x == 0) atomicOr(complex_flag, wc);
 }
 
 // ---- B. one colour of the plan (thread = source cell; 8-byte words only).
 // Literal slot logic of move_kernel! (src/Particles/move_safe.jl:72-125) on the occupancy
-// words; the slot given to the leaver of slot ip goes to byte ip & 7 of res word ip >> 3 (slot | placed << 6).
+// words; the slot given to the k-th leaver goes to res (one byte: slot | placed << 6).
 template <int N>
 __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
                                                    long long *stats, int compact, const unsigned int *__restrict__ skip_flag) {
@@ -153,16 +149,16 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
     const uint64_t smask = g.S == 64 ? ~0ull : ((1ull << g.S) - 1);
     uint64_t occ_c = ws.occ[c];
     uint64_t codew = 0, resw = 0;
-    int cursor = 0, curw = -1, n_dropped = 0, n_deleted = 0;
+    int cursor = 0, k = 0, n_dropped = 0, n_deleted = 0;
     while (lv) {
         const int ip = __ffsll((long long)lv) - 1;
         lv &= lv - 1;
-        if ((ip >> 3) != curw) {                                 // code / result words are indexed by slot: word ip >> 3, byte ip & 7
-            if (curw >= 0) ws.res[(int64_t)curw * g.C + c] = resw;
-            curw = ip >> 3; resw = 0;
-            codew = ws.code[(int64_t)curw * g.C + c];
+        if ((k & 7) == 0) {
+            codew = ws.code[(int64_t)(k >> 3) * g.C + c];
+            if (k > 0) { ws.res[(int64_t)((k >> 3) - 1) * g.C + c] = resw; resw = 0; }
         }
-        const int code = (int)((codew >> (8 * (ip & 7))) & 255);
+        const int code = (int)((codew >> (8 * (k & 7))) & 255);
+        const int kk = k++;
         occ_c &= ~(1ull << ip);
         if (code == JP_CODE_DELETE) { n_deleted++; continue; }
         int dv[3];
@@ -174,10 +170,10 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
         const int fs = __ffsll((long long)freebits) - 1;
         if (!compact) cursor = fs;            // JP_MOVE_POLICY_COMPACT: every search starts at slot 0
         ws.occ[c2] = o2 | (1ull << fs);
-        resw |= (uint64_t)(fs | 64) << (8 * (ip & 7));
+        resw |= (uint64_t)(fs | 64) << (8 * (kk & 7));
     }
     ws.occ[c] = occ_c;
-    ws.res[(int64_t)curw * g.C + c] = resw;
+    ws.res[(int64_t)((k - 1) >> 3) * g.C + c] = resw;
     if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
     if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);
 }
@@ -218,16 +214,17 @@ __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, M
         if (!__any_sync(0xffffffffu, bits != 0)) continue;
         int64_t pos[JP_MV_U], e[JP_MV_U];
         bool act[JP_MV_U];
-        if (bits && (s0 >> 3) != respl) { respl = s0 >> 3; resw = ws.res[(int64_t)respl * g.C + c]; codew = ws.code[(int64_t)respl * g.C + c]; }
 #pragma unroll
         for (int u = 0; u < JP_MV_U; u++) {
             const int s = s0 + u;
             act[u] = false; pos[u] = 0; e[u] = c + (int64_t)s * g.C;
             if ((bits >> u) & 1u) {
-                const int r = (int)((resw >> (8 * (s & 7))) & 255);
+                const int k = __popcll(lv & ((1ull << s) - 1));
+                if ((k >> 3) != respl) { respl = k >> 3; resw = ws.res[(int64_t)respl * g.C + c]; codew = ws.code[(int64_t)respl * g.C + c]; }
+                const int r = (int)((resw >> (8 * (k & 7))) & 255);
                 if (r & 64) {
                     const int fs = r & 63;
-                    const int code = (int)((codew >> (8 * (s & 7))) & 255);
+                    const int code = (int)((codew >> (8 * (k & 7))) & 255);
                     int dv[3];
                     jp_code_dir(code, dv);
                     const int64_t c2 = c + dv[0] + (int64_t)g.n[0] * (dv[1] + (N == 3 ? (int64_t)g.n[1] * dv[2] : 0));
