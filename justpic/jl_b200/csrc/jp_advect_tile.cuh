@@ -53,7 +53,7 @@ __device__ __forceinline__ void adv_tma_load_2d(void *smem_dst, const CUtensorMa
 template <int N> struct AdvTile {
     static constexpr int TX = 32;
 #ifndef JP_ADV_TPSM
-#define JP_ADV_TPSM 768      // resident threads per SM the register budget is sized for
+#define JP_ADV_TPSM 512      // resident threads per SM the register budget is sized for (r02: 2 CTAs of 256 at <= 128 registers beat 3 at 80)
 #endif
 #ifndef JP_ADV_TY
 #define JP_ADV_TY 4
@@ -93,7 +93,21 @@ template <int N, bool UNIFORM> struct AdvSmem {
 // bit -- instead of being loaded from shared memory:
 // the kernel is bound by LDS return bandwidth (128 B/clk/SM) and 30 of its 78 loads per particle
 // were grid-vector entries.
-template <int N, bool UNIFORM, int AFFINE>
+// JP_ADV_STAGE1: the first interpolation of a particle (at its own position) skips the warp vote / re-centring block -- after
+// move_particles! every particle lies strictly inside its storage cell; one that does not is flagged and takes the literal routine
+// (same result).  JP_ADV_NOVOTE: the later stages run the re-centring arithmetic unconditionally -- at CFL 0.5 nearly every warp holds
+// a lane whose stage position left its seed cell, so the vote only cost a divergent-branch frame.  Measured at 256^3 (r02l, all
+// bit-identical): 14.44 -> 13.44 (stage 1) -> 13.32 (no vote) -> 13.09 ms (2 CTAs / SM at <= 128 registers instead of 3 at 80).
+// Dropped: stencil loads as ld.shared.f64 on a 32-bit address held in one opaque register (the compiler re-derives the shared
+// window base at every group of loads: S2R CgaCtaId, MOV, VIADD, LEA) -- 13.09 -> 13.32 ms; bricks of 32 x 8 x 2 / 32 x 4 x 4 cells
+// (16 warps): 15.0 / 14.4 ms; 4 CTAs / SM at 64 registers: 17.5 ms.
+#ifndef JP_ADV_STAGE1
+#define JP_ADV_STAGE1 1
+#endif
+#ifndef JP_ADV_NOVOTE
+#define JP_ADV_NOVOTE 1
+#endif
+template <int N, bool UNIFORM, int AFFINE, bool FIRST = false>
 __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *__restrict__ sm, const int *c0, const int *r0,
                                                 const double *gd0, const double *p, double *vout, unsigned amask) {
     using T = AdvTile<N>;
@@ -116,7 +130,11 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
         if (AFFINE) { a = fma(gd, g.aff_dv[d], g.aff_v0[d]); b = fma(gd + 1.0, g.aff_dv[d], g.aff_v0[d]); }
         else { a = xv[r]; b = xv[r + 1]; }
         const bool up = pd > b, dn = pd < a;
-        if (__any_sync(amask, up || dn)) {          // warp-uniform: stage positions that left the seed cell
+#if JP_ADV_NOVOTE
+        if (!(JP_ADV_STAGE1 && FIRST)) {            // later stages: nearly every warp holds a lane that left its seed cell -- no vote, no branch
+#else
+        if (!(JP_ADV_STAGE1 && FIRST) && __any_sync(amask, up || dn)) {          // warp-uniform: stage positions that left the seed cell
+#endif
             r += (up ? 1 : 0) - (dn ? 1 : 0);
             if (AFFINE) {
                 gd += (up ? 1.0 : 0.0) - (dn ? 1.0 : 0.0);
@@ -141,8 +159,8 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
         const int iy = c == 1 ? iv[1] : ig[1];
         const int iz = N == 3 ? (c == 2 ? iv[2] : ig[2]) : 0;
         const double t[3] = {c == 0 ? tv[0] : tg[0], c == 1 ? tv[1] : tg[1], N == 3 ? (c == 2 ? tv[2] : tg[2]) : 0.0};
-        const double *F = sm + L::V_OFF + c * T::VOL + ix + T::EX * (iy + T::EY * iz);
         double v[8];
+        const double *F = sm + L::V_OFF + c * T::VOL + ix + T::EX * (iy + T::EY * iz);
         v[0] = F[0]; v[1] = F[1]; v[2] = F[T::EX]; v[3] = F[T::EX + 1];
         if (N == 3) {
             v[4] = F[T::EX * T::EY]; v[5] = F[T::EX * T::EY + 1];
@@ -153,10 +171,10 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
     return !bad;
 }
 
-template <int N, bool UNIFORM, int AFFINE>
+template <int N, bool UNIFORM, int AFFINE, bool FIRST = false>
 __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__restrict__ sm, const double *const *V, const int *c0,
                                            const int *r0, const double *gd0, const int *cell1, const double *p, double *vout, unsigned amask) {
-    if (adv_interp_tile<N, UNIFORM, AFFINE>(g, sm, c0, r0, gd0, p, vout, amask)) return;
+    if (adv_interp_tile<N, UNIFORM, AFFINE, FIRST>(g, sm, c0, r0, gd0, p, vout, amask)) return;
     jp_interp_velocity_literal<N>(g, V, p, cell1, vout);
 }
 
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
                 double p0[3], k1[3], k2[3], qq[3], pn[3];
 #pragma unroll
                 for (int d = 0; d < N; d++) p0[d] = cur_p[d];
-                adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, p0, k1, amask);
+                adv_interp<N, UNIFORM, AFFINE, true>(g, sm, Vp, c0, r0, gd0, cell1, p0, k1, amask);
                 if (SCHEME == 0) {
                     const double cdt = 1.0 * dt;
 #pragma unroll
