@@ -166,6 +166,10 @@ int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nar
  * how many phases the following phase_ratios_center!(phase_ratios, particles, phases) will use (either may be NULL).  Both must
  * be among the `args` of jp_move to take effect.  Sticky until changed. */
 int jp_move_interp_fields(jp_ctx *ctx, const double *Fp, const double *phases, int32_t K);
+/* Both hand-offs are keyed on the coordinate / index (and field) POINTERS: a write to those arrays that does not go through a jp_*
+ * entry point (a host-side boundary fix-up, a torch / CUDA.jl kernel of the caller) between the producing and the consuming call is
+ * invisible to the library.  Call this after such a write: the consumers then work from the arrays again. */
+int jp_invalidate_handoffs(jp_ctx *ctx);
 /* JP_OPT_PROFILE = 1: jp_move (planned path) records CUDA events between its stages on the caller's stream (no
  * synchronisation); jp_profile_read returns the mean duration in ms of {classify, plan (3^N launches), finalize + scan,
  * gather, scatter (+ interpolation hand-off)} over the calls since the last read (at most the last 32) and synchronises the

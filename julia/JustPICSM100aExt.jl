@@ -388,4 +388,7 @@ function set_interp_handoff!(p::Particles{CUDABackend}, Fp::Union{CellArray, Not
           "jp_move_interp_fields")
 end
 
+# after a write to coords / index / a registered field that did not go through this extension
+invalidate_handoffs!(p::Particles{CUDABackend}) = check(ccall((:jp_invalidate_handoffs, libjustpic), Cint, (Ptr{Cvoid},), context(p)), "jp_invalidate_handoffs")
+
 end # module

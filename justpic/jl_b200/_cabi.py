@@ -73,6 +73,7 @@ SYMBOLS = {
                                    C.POINTER(C.c_void_p), C.c_double, C.c_int32, C.c_void_p]),
     "jp_move": (C.c_int, [C.c_void_p, C.POINTER(ParticlesC), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "jp_move_interp_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "jp_invalidate_handoffs": (C.c_int, [C.c_void_p]),
     "jp_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "jp_move_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
     "jp_last_move_path": (C.c_int, [C.c_void_p]),

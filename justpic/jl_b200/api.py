@@ -45,7 +45,7 @@ __all__ = [
     "phase_ratios_center", "phase_ratios_vertex", "phase_ratios_face", "phase_ratios_midpoint",
     "update_phase_ratios", "set_synchronous",
     "Array", "CuArray", "HostParticles", "HostPhaseRatios", "last_move_classify",
-    "move_interp_handoff", "last_interp_handoff", "profile_move", "read_move_profile",
+    "move_interp_handoff", "last_interp_handoff", "invalidate_handoffs", "profile_move", "read_move_profile",
 ]
 
 
@@ -461,6 +461,12 @@ def move_interp_handoff(particles: Particles, Fp: Optional[torch.Tensor] = None,
     _cabi.check(lib.jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_MOVE_INTERP, 1 if enable else 0), "jp_set_option")
     _cabi.check(lib.jp_move_interp_fields(C.c_void_p(p._ctx), C.c_void_p(fp), C.c_void_p(ph), int(nphases) if ph else 0),
                 "move_interp_handoff")
+
+
+def invalidate_handoffs(particles: Particles) -> None:
+    """Call after writing ``particles.coords`` / ``particles.index`` / a registered particle field by other means than this API
+    between ``advection`` and ``move_particles`` (or ``move_particles`` and its consumers): drops what the hand-offs left."""
+    _cabi.check(_cabi.load().jp_invalidate_handoffs(C.c_void_p(particles._ctx)), "jp_invalidate_handoffs")
 
 
 def last_interp_handoff(particles: Particles) -> Tuple[bool, bool]:

@@ -67,7 +67,10 @@ template <int N> struct AdvTile {
     // The x extent (needed: TX + 5) is padded to 48 so that the row pitch is a multiple of 16 doubles:
     // every stencil row then starts on bank 0 and a lane's bank depends on its x index only.
     static constexpr int OX = 2;
-    static constexpr int EX = N == 3 ? JP_ADV_EX : 40, EY = TY + 4, EZ = N == 3 ? TZ + 4 : 1;
+#ifndef JP_ADV_EYPAD
+#define JP_ADV_EYPAD 0       // extra (unused) stencil rows per z-plane: shifts the banks of consecutive z-planes (the plane pitch EX * EY is 0 mod 32 banks otherwise)
+#endif
+    static constexpr int EX = N == 3 ? JP_ADV_EX : 40, EY = TY + 4 + (N == 3 ? JP_ADV_EYPAD : 0), EZ = N == 3 ? TZ + 4 : 1;
     static constexpr int VOL = ((EX * EY * EZ + 15) / 16) * 16;                 // tile pitch: multiple of 128 bytes
     static constexpr int NW = TY * TZ;                                          // warps per CTA
 };

@@ -1921,6 +1921,14 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
 }
 
+// The caller changed coordinates, the index mask or a registered particle field by other means than this library: drop what the
+// hand-offs left (the next jp_move classifies from the coordinates, the next particle2grid! / phase_ratios_center! stream the particles).
+extern "C" int jp_invalidate_handoffs(jp_ctx *ctx) {
+    if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_invalidate_handoffs: null context");
+    handoffs_invalidate(ctx);
+    return JP_OK;
+}
+
 extern "C" int jp_move_interp_fields(jp_ctx *ctx, const double *Fp, const double *phases, int32_t K) {
     if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_move_interp_fields: null context");
     if (phases && (K < 1 || K > JP_MAX_PHASES)) return jp_fail(JP_ERR_UNSUPPORTED, "jp_move_interp_fields: 1 <= nphases <= 32 required");

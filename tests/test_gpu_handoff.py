@@ -152,3 +152,27 @@ def test_handoff_ties_fall_back_to_direct_sweeps(ndim):
     assert J.last_move_classify(t.p) == "handoff" and J.last_move_path(t.p) == "direct"
     t.check_state("move from tie positions", (pT,), (opT,))
     assert J.move_stats(t.p) == st
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_invalidate_handoffs_after_a_foreign_write(ndim):
+    """A write to the coordinates that does not go through the library (here: a host-side shift of some particles by a cell)
+    between advection! and move_particles! is invisible to the hand-off; jp_invalidate_handoffs tells the library, and
+    move_particles! then classifies from the arrays as without the option."""
+    J = jp()
+    t = Twin(ndim, 14 if ndim == 2 else 9, True)
+    V = stream_velocity(t.gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(t.gr, V, 0.6)
+    pT, ph, opT, oph = _fields(J, t)
+    for it in range(3):
+        J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=True); t.o.advect(t.co, t.idx, 1, 0.5, V, dt)
+        live = t.idx > 0
+        sel = live & (np.arange(t.idx.size).reshape(t.idx.shape) % 11 == it)
+        dx = float(t.gr.xvi[0][1] - t.gr.xvi[0][0])
+        t.co[0][sel] += 0.7 * dx                         # the "boundary fix-up" of some host code
+        t.p.coords[0].copy_(dev(t.co[0]))
+        J.invalidate_handoffs(t.p)
+        J.move_particles(t.p, (pT, ph)); st = t.o.move(t.co, t.idx, [opT, oph])
+        assert J.last_move_classify(t.p) == "coords"
+        t.check_state(f"step {it} move after a foreign write", (pT, ph), (opT, oph))
+        assert J.move_stats(t.p) == st
