@@ -156,7 +156,7 @@ def test_handoff_ties_fall_back_to_direct_sweeps(ndim):
 
 @pytest.mark.parametrize("ndim", [2, 3])
 def test_invalidate_handoffs_after_a_foreign_write(ndim):
-    """A write to the coordinates that does not go through the library (here: a host-side shift of some particles by a cell)
+    """A write to the coordinates that does not go through the library (here: a host-side shift of some particles by a third of a cell)
     between advection! and move_particles! is invisible to the hand-off; jp_invalidate_handoffs tells the library, and
     move_particles! then classifies from the arrays as without the option."""
     J = jp()
@@ -169,7 +169,7 @@ def test_invalidate_handoffs_after_a_foreign_write(ndim):
         live = t.idx > 0
         sel = live & (np.arange(t.idx.size).reshape(t.idx.shape) % 11 == it)
         dx = float(t.gr.xvi[0][1] - t.gr.xvi[0][0])
-        t.co[0][sel] += 0.7 * dx                         # the "boundary fix-up" of some host code
+        t.co[0][sel] += 0.35 * dx                        # the "boundary fix-up" of some host code (total displacement stays below one cell)
         t.p.coords[0].copy_(dev(t.co[0]))
         J.invalidate_handoffs(t.p)
         J.move_particles(t.p, (pT, ph)); st = t.o.move(t.co, t.idx, [opT, oph])
