@@ -198,6 +198,9 @@ struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 #ifndef JP_MV_U
 #define JP_MV_U 4
 #endif
+#ifndef JP_GATHER_PREFETCH
+#define JP_GATHER_PREFETCH 0
+#endif
 #define JP_MV_A 4      // arrays handled per register batch (coords + fields); more arrays loop again
 template <int N>
 __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage,
@@ -233,6 +236,18 @@ __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, M
                 }
             }
         }
+#if JP_GATHER_PREFETCH
+        {   // the leavers' sectors of the batch JP_GATHER_PREFETCH batches ahead: requested now, no register held
+            const int sn = s0 + JP_GATHER_PREFETCH * JP_MV_U;
+            const unsigned nb = sn < 64 ? (unsigned)(lv >> sn) & ((1u << JP_MV_U) - 1u) : 0u;
+#pragma unroll
+            for (int u = 0; u < JP_MV_U; u++)
+                if ((nb >> u) & 1u) {
+                    const int64_t en = c + (int64_t)(sn + u) * g.C;
+                    for (int a = 0; a < arrs.n; a++) asm volatile("prefetch.global.L1 [%0];" ::"l"(arrs.a[a] + en));
+                }
+        }
+#endif
         // staging is array-of-structs: one migrant = AS consecutive doubles (AS = n rounded up to 4,
         // padding written too), so every touched 32-byte sector is written completely (no fill read)
         const int AS = (arrs.n + 3) & ~3;
