@@ -67,10 +67,7 @@ template <int N> struct AdvTile {
     // The x extent (needed: TX + 5) is padded to 48 so that the row pitch is a multiple of 16 doubles:
     // every stencil row then starts on bank 0 and a lane's bank depends on its x index only.
     static constexpr int OX = 2;
-#ifndef JP_ADV_EYPAD
-#define JP_ADV_EYPAD 0       // extra (unused) stencil rows per z-plane: shifts the banks of consecutive z-planes (the plane pitch EX * EY is 0 mod 32 banks otherwise)
-#endif
-    static constexpr int EX = N == 3 ? JP_ADV_EX : 40, EY = TY + 4 + (N == 3 ? JP_ADV_EYPAD : 0), EZ = N == 3 ? TZ + 4 : 1;
+    static constexpr int EX = N == 3 ? JP_ADV_EX : 40, EY = TY + 4, EZ = N == 3 ? TZ + 4 : 1;
     static constexpr int VOL = ((EX * EY * EZ + 15) / 16) * 16;                 // tile pitch: multiple of 128 bytes
     static constexpr int NW = TY * TZ;                                          // warps per CTA
 };
@@ -103,7 +100,9 @@ template <int N, bool UNIFORM> struct AdvSmem {
 // bit-identical): 14.44 -> 13.44 (stage 1) -> 13.32 (no vote) -> 13.09 ms (2 CTAs / SM at <= 128 registers instead of 3 at 80).
 // Dropped: stencil loads as ld.shared.f64 on a 32-bit address held in one opaque register (the compiler re-derives the shared
 // window base at every group of loads: S2R CgaCtaId, MOV, VIADD, LEA) -- 13.09 -> 13.32 ms; bricks of 32 x 8 x 2 / 32 x 4 x 4 cells
-// (16 warps): 15.0 / 14.4 ms; 4 CTAs / SM at 64 registers: 17.5 ms.
+// (16 warps): 15.0 / 14.4 ms; 4 CTAs / SM at 64 registers: 17.5 ms; an extra stencil row per z-plane so that consecutive planes fall
+// into different banks (the plane pitch is 0 mod 32 banks): 13.08 -> 13.32 ms; a second, one-node-shifted copy of every tile so that
+// the two x-adjacent corners are one 16-byte LDS.128 (24 instead of 48 stencil loads per particle): 13.07 -> 13.67 ms.
 #ifndef JP_ADV_STAGE1
 #define JP_ADV_STAGE1 1
 #endif
