@@ -50,7 +50,8 @@ __device__ __forceinline__ void adv_tma_load_2d(void *smem_dst, const CUtensorMa
                    "r"(x), "r"(y) : "memory");
 }
 
-template <int N> struct AdvTile {
+// H = 1: one more staged node below and two more above in y / z, for the LinP / MQS stencils (interpolation cell -1 .. +2)
+template <int N, int H = 0> struct AdvTile {
     static constexpr int TX = 32;
 #ifndef JP_ADV_TPSM
 #define JP_ADV_TPSM 512      // resident threads per SM the register budget is sized for (r02: 2 CTAs of 256 at <= 128 registers beat 3 at 80)
@@ -67,14 +68,14 @@ template <int N> struct AdvTile {
     // The x extent (needed: TX + 5) is padded to 48 so that the row pitch is a multiple of 16 doubles:
     // every stencil row then starts on bank 0 and a lane's bank depends on its x index only.
     static constexpr int OX = 2;
-    static constexpr int EX = N == 3 ? JP_ADV_EX : 40, EY = TY + 4, EZ = N == 3 ? TZ + 4 : 1;
+    static constexpr int EX = N == 3 ? JP_ADV_EX : 40, EY = TY + 4 + 2 * H, EZ = N == 3 ? TZ + 4 + 2 * H : 1;
     static constexpr int VOL = ((EX * EY * EZ + 15) / 16) * 16;                 // tile pitch: multiple of 128 bytes
     static constexpr int NW = TY * TZ;                                          // warps per CTA
 };
 
 // shared-memory layout (doubles first, then the uint16 work lists)
-template <int N, bool UNIFORM> struct AdvSmem {
-    using T = AdvTile<N>;
+template <int N, bool UNIFORM, int H = 0> struct AdvSmem {
+    using T = AdvTile<N, H>;
     static constexpr int V_OFF = 0;                       // N tiles of VOL doubles
     static constexpr int VEC = 40;                        // grid-vector segment per dim (needed: TX + 6)
     static constexpr int XV_OFF = N * T::VOL;
@@ -109,11 +110,18 @@ template <int N, bool UNIFORM> struct AdvSmem {
 #ifndef JP_ADV_NOVOTE
 #define JP_ADV_NOVOTE 1
 #endif
-template <int N, bool UNIFORM, int AFFINE, bool FIRST = false>
+// stencil values of the LinP / MQS interpolants from the staged tile: A(i1, j1, k1) with 1-based GLOBAL node indices (jp_core.h)
+template <int N, class T> struct AdvTileAcc {
+    const double *tile; int c0x, c0y, c0z;
+    __device__ __forceinline__ double operator()(int i1, int j1, int k1) const {
+        return tile[(i1 - 1 - c0x) + T::EX * ((j1 - 1 - c0y) + (N == 3 ? T::EY * (k1 - 1 - c0z) : 0))];
+    }
+};
+template <int N, bool UNIFORM, int AFFINE, bool FIRST = false, int INTERP = 0>
 __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *__restrict__ sm, const int *c0, const int *r0,
                                                 const double *gd0, const double *p, double *vout, unsigned amask) {
-    using T = AdvTile<N>;
-    using L = AdvSmem<N, UNIFORM>;
+    using T = AdvTile<N, INTERP ? 1 : 0>;
+    using L = AdvSmem<N, UNIFORM, INTERP ? 1 : 0>;
     // Straight-line code: a lane that cannot be served from the tile (tie with a grid node, NaN, more
     // than one cell from its seed, outside the domain) only raises `bad` and is redone by the literal
     // routine afterwards.  Divergent early exits made the compiler run the rest of the stage once per
@@ -121,6 +129,7 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
     bool bad = false;
     int iv[3], ig[3];
     double tv[3], tg[3];
+    double xav[3], xag[3], dxv[3], dxg[3];        // INTERP > 0: lower coordinate / spacing of the interpolation cell per grid kind
 #pragma unroll
     for (int d = 0; d < N; d++) {
         const double *xv = sm + L::XV_OFF + d * L::VEC;
@@ -148,12 +157,14 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
         bad = bad || !(a < pd && pd < b);                     // also catches ties and NaN
         iv[d] = r;
         tv[d] = (pd - a) * (UNIFORM ? g.inv_dv[d] : sm[L::IXV_OFF + d * L::VEC + r]);
+        if (INTERP) { xav[d] = a; dxv[d] = UNIFORM ? g.dxv0[d] : b - a; }
         const double m = AFFINE == 2 ? fma(gd + 1.0, g.aff_dg[d], g.aff_g0[d]) : xg[r + 1];
         bad = bad || pd == m;
         const bool lower = pd < m;
         ig[d] = lower ? r : r + 1;
         const double gl = AFFINE == 2 ? fma(gd, g.aff_dg[d], g.aff_g0[d]) : xg[r];
         tg[d] = (pd - (lower ? gl : m)) * (UNIFORM ? g.inv_dg[d] : sm[L::IXG_OFF + d * L::VEC + ig[d]]);
+        if (INTERP) { xag[d] = lower ? gl : m; dxg[d] = UNIFORM ? g.dxg0[d] : (lower ? m - gl : xg[r + 2] - m); }
     }
 #pragma unroll
     for (int c = 0; c < N; c++) {
@@ -168,16 +179,43 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
             v[4] = F[T::EX * T::EY]; v[5] = F[T::EX * T::EY + 1];
             v[6] = F[T::EX * T::EY + T::EX]; v[7] = F[T::EX * T::EY + T::EX + 1];
         }
-        vout[c] = jp_lerp<N>(v, t);
+        const double VL = jp_lerp<N>(v, t);
+        if (INTERP == 0) vout[c] = VL;
+        else {
+            // advection_LinP! / advection_MQS!: the linear value plus a correction when the interpolation cell is interior
+            // (1 < idx < size(F) - 1 in every direction, jp_interp_velocity_hi); the stencil idx - 1 .. idx + 2 must lie in the tile
+            const int ti[3] = {ix, iy, iz};
+            const int ext[3] = {T::EX, T::EY, T::EZ};
+            int idx1[3] = {1, 1, 1};
+            bool interior = true, intile = true;
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                idx1[d] = c0[d] + ti[d] + 1;
+                interior = interior && 1 < idx1[d] && idx1[d] < g.nvel[c][d] - 1;
+                intile = intile && ti[d] >= 1 && ti[d] + 2 < ext[d];
+            }
+            vout[c] = VL;
+            if (interior && !intile) bad = true;
+            else if (interior) {
+                const AdvTileAcc<N, T> acc = {sm + L::V_OFF + c * T::VOL, c0[0], c0[1], N == 3 ? c0[2] : 0};
+                if (INTERP == 2) vout[c] = jp_mqs<N>(acc, g.nvel[c], c, idx1, v, t);
+                else {
+                    const double xcn[3] = {c == 0 ? xav[0] : xag[0], c == 1 ? xav[1] : xag[1], N == 3 ? (c == 2 ? xav[2] : xag[2]) : 0.0};
+                    const double dxi[3] = {c == 0 ? dxv[0] : dxg[0], c == 1 ? dxv[1] : dxg[1], N == 3 ? (c == 2 ? dxv[2] : dxg[2]) : 1.0};
+                    vout[c] = jp_linp<N>(acc, g.nvel[c], c, idx1, xcn, dxi, p, VL);
+                }
+            }
+        }
     }
     return !bad;
 }
 
-template <int N, bool UNIFORM, int AFFINE, bool FIRST = false>
+template <int N, bool UNIFORM, int AFFINE, bool FIRST = false, int INTERP = 0>
 __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__restrict__ sm, const double *const *V, const int *c0,
                                            const int *r0, const double *gd0, const int *cell1, const double *p, double *vout, unsigned amask) {
-    if (adv_interp_tile<N, UNIFORM, AFFINE, FIRST>(g, sm, c0, r0, gd0, p, vout, amask)) return;
-    jp_interp_velocity_literal<N>(g, V, p, cell1, vout);
+    if (adv_interp_tile<N, UNIFORM, AFFINE, FIRST, INTERP>(g, sm, c0, r0, gd0, p, vout, amask)) return;
+    if (INTERP == 0) jp_interp_velocity_literal<N>(g, V, p, cell1, vout);
+    else jp_interp_velocity_hi<N, INTERP>(g, V, p, cell1, vout);
 }
 
 // HINT (JP_OPT_ADVECT_CLASSIFY, the advection -> move hand-off): every new position is also classified
@@ -189,14 +227,15 @@ __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__rest
 // words of the move plan, in slot order, exactly as k_move_classify3 packs them; then the occupancy / leave words.
 // jp_move then starts at the plan kernels: no pass over the coordinates, no intermediate plane in HBM.
 #define ADV_HINT_ROW 72          // bytes per cell row: JP_MAX_SLOTS + 8 (18 words: 64-bit row loads of a half-warp hit 32 distinct banks)
-template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
+template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT, int INTERP = 0>
 __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 768) / (AdvTile<N>::NW * 32)) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
                                                                      double alpha, double dt,
                                                                      const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                                                                      const __grid_constant__ CUtensorMap tm2, int tma_mask, MovePlanWs ws,
                                                                      unsigned int *complex_flag) {
-    using T = AdvTile<N>;
-    using L = AdvSmem<N, UNIFORM>;
+    constexpr int H = INTERP ? 1 : 0;
+    using T = AdvTile<N, H>;
+    using L = AdvSmem<N, UNIFORM, H>;
     extern __shared__ __align__(128) unsigned char smem_raw[];   // TMA destinations: 128-byte aligned (VOL*8 is a multiple of 128)
     double *sm = reinterpret_cast<double *>(smem_raw);
     uint16_t *wl_all = reinterpret_cast<uint16_t *>(smem_raw + sizeof(double) * L::NDOUBLES);
@@ -205,7 +244,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // brick origin (cells) and first staged node (one below)
     const int b0[3] = {(int)blockIdx.x * T::TX, (int)blockIdx.y * T::TY, N == 3 ? (int)blockIdx.z * T::TZ : 0};
-    const int c0[3] = {b0[0] - T::OX, b0[1] - 1, N == 3 ? b0[2] - 1 : 0};
+    const int c0[3] = {b0[0] - T::OX, b0[1] - 1 - H, N == 3 ? b0[2] - 1 - H : 0};
     if (g.region) {                         // CTA-uniform: shell bricks first, interior bricks while the halo planes travel
         const int ext[3] = {T::TX, T::TY, T::TZ};
         bool shell = false;
@@ -341,13 +380,13 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
             if (cur_valid) {
                 const int l = cur_l & 31;
                 const int64_t e = cur_e;
-                const int r0[3] = {l + T::OX, wy + 1, wz + 1};
+                const int r0[3] = {l + T::OX, wy + 1 + H, wz + 1 + H};
                 const int cell1[3] = {b0[0] + l + 1, cy + 1, cz + 1};
                 const double gd0[3] = {(double)(b0[0] + l), (double)cy, (double)cz};     // global index of the seed cell's lower node
                 double p0[3], k1[3], k2[3], qq[3], pn[3];
 #pragma unroll
                 for (int d = 0; d < N; d++) p0[d] = cur_p[d];
-                adv_interp<N, UNIFORM, AFFINE, true>(g, sm, Vp, c0, r0, gd0, cell1, p0, k1, amask);
+                adv_interp<N, UNIFORM, AFFINE, true, INTERP>(g, sm, Vp, c0, r0, gd0, cell1, p0, k1, amask);
                 if (SCHEME == 0) {
                     const double cdt = 1.0 * dt;
 #pragma unroll
@@ -356,7 +395,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
                     const double cdt = (1.0 * alpha) * dt;
 #pragma unroll
                     for (int d = 0; d < N; d++) qq[d] = fma(cdt, k1[d], p0[d]);
-                    adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, qq, k2, amask);
+                    adv_interp<N, UNIFORM, AFFINE, false, INTERP>(g, sm, Vp, c0, r0, gd0, cell1, qq, k2, amask);
                     if (alpha == 0.5) {
 #pragma unroll
                         for (int d = 0; d < N; d++) pn[d] = fma(1.0 * dt, k2[d], p0[d]);
@@ -369,13 +408,13 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
                     double k3[3], k4[3];
 #pragma unroll
                     for (int d = 0; d < N; d++) qq[d] = p0[d] + dt * k1[d] / 2;
-                    adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, qq, k2, amask);
+                    adv_interp<N, UNIFORM, AFFINE, false, INTERP>(g, sm, Vp, c0, r0, gd0, cell1, qq, k2, amask);
 #pragma unroll
                     for (int d = 0; d < N; d++) qq[d] = p0[d] + dt * k2[d] / 2;
-                    adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, qq, k3, amask);
+                    adv_interp<N, UNIFORM, AFFINE, false, INTERP>(g, sm, Vp, c0, r0, gd0, cell1, qq, k3, amask);
 #pragma unroll
                     for (int d = 0; d < N; d++) qq[d] = p0[d] + dt * k3[d];
-                    adv_interp<N, UNIFORM, AFFINE>(g, sm, Vp, c0, r0, gd0, cell1, qq, k4, amask);
+                    adv_interp<N, UNIFORM, AFFINE, false, INTERP>(g, sm, Vp, c0, r0, gd0, cell1, qq, k4, amask);
 #pragma unroll
                     for (int d = 0; d < N; d++) pn[d] = p0[d] + dt * (((k1[d] + 2 * k2[d]) + 2 * k3[d]) + k4[d]) / 6;
                 }

@@ -46,6 +46,7 @@ struct JpGrid {
     double aff_v0[3], aff_dv[3], aff_g0[3], aff_dg[3];
     double dom_lo[3], dom_hi[3];   // xv[d][0], xv[d][n]  (kernel-parameter constants instead of per-thread loads)
     double dxv0[3];                // xv[d][1] - xv[d][0]  (the scalar spacing of range grids)
+    double dxg0[3];                // xg[d][1] - xg[d][0]  (the same for the ghosted-centre vectors)
     double inv_dmin_v[3];          // inv(grid_size(xvi)) = 1 / abs(minimum(diff(xv)))  (grid2particle_flip!)
     // 1: range grid whose vertices were checked on the host to be affine within 1e-6 dx (and dx >> ulp of the
     //    coordinates): jp_classify_fast may decide particles that are clearly inside a cell (see there)
@@ -132,9 +133,15 @@ JP_HD void jp_interp_velocity_literal(const JpGrid &g, const double *const *V, c
 // src/Particles/Advection/advection_LinP.jl:96-391, advection_MQS.jl:96-124): the linear
 // interpolant of interp_velocity2particle plus a correction when the interpolation cell is interior
 // (1 < idx < size(F) - 1 in every direction).  Literal, quirks included (listed in DESIGN.md).
-template <int N> JP_HD double jp_Fat(const double *F, const int32_t *nF, int i1, int j1, int k1) {   // 1-based
-    return F[(i1 - 1) + (int64_t)nF[0] * ((j1 - 1) + (N == 3 ? (int64_t)nF[1] * (k1 - 1) : 0))];
-}
+// The stencil values are read through an accessor A(i1, j1, k1) (1-based GLOBAL node indices of the velocity array): the global array
+// itself (JpGlobalAcc) or the shared-memory tile of the tiled advection kernel (jp_advect_tile.cuh) -- same arithmetic either way.
+template <int N> struct JpGlobalAcc {
+    const double *F; const int32_t *nF;
+    JP_HD double operator()(int i1, int j1, int k1) const {
+        return F[(i1 - 1) + (int64_t)nF[0] * ((j1 - 1) + (N == 3 ? (int64_t)nF[1] * (k1 - 1) : 0))];
+    }
+};
+template <int N, class Acc> JP_HD double jp_Fat(const Acc &F, const int32_t *nF, int i1, int j1, int k1) { (void)nF; return F(i1, j1, k1); }
 // quadratic correction of one edge (v0e, v1e) at tq with the outer nodes on either side
 JP_HD double jp_mqs_edge(double v0e, double v1e, double tq, double outer_lo, double outer_hi) {
     const double l = jp_lerp1(tq, v0e, v1e);
@@ -142,7 +149,7 @@ JP_HD double jp_mqs_edge(double v0e, double v1e, double tq, double outer_lo, dou
     const double a = low ? outer_lo : v0e, b = low ? v0e : v1e, c = low ? v1e : outer_hi;
     return l + (0.5 * ((tq - 0.5) * (tq - 0.5))) * (fma(-2.0, b, a) + c);
 }
-template <int N> JP_HD double jp_mqs(const double *F, const int32_t *nF, int comp, const int *idx1, const double *v, const double *t) {
+template <int N, class Acc> JP_HD double jp_mqs(const Acc &F, const int32_t *nF, int comp, const int *idx1, const double *v, const double *t) {
     const int i = idx1[0], j = idx1[1], k = N == 3 ? idx1[2] : 1;
     if (N == 2) {
         if (comp == 0)
@@ -170,8 +177,8 @@ template <int N> JP_HD double jp_mqs(const double *F, const int32_t *nF, int com
     return comp == 2 ? jp_lerp1(t[1], f[0], f[1]) : jp_lerp1(t[2], f[0], f[1]);
 }
 JP_HD int jp_clampi(int x, int lo, int hi) { return x > hi ? hi : (x < lo ? lo : x); }
-template <int N> JP_HD double jp_linp(const double *F, const int32_t *nF, int comp, const int *idx1, const double *xc, const double *dxi,
-                                      const double *p, double VL) {
+template <int N, class Acc> JP_HD double jp_linp(const Acc &F, const int32_t *nF, int comp, const int *idx1, const double *xc, const double *dxi,
+                                               const double *p, double VL) {
     int ijk[3] = {idx1[0], idx1[1], N == 3 ? idx1[2] : 1};
     ijk[comp] += p[comp] > xc[comp] + dxi[comp] / 2 ? 1 : 0;                  // offset_LinP (advection_LinP.jl:345-347)
     // augment_offset (:364-391): three offsets (-1, 0, 1) along `comp`; the two transverse directions take
@@ -238,8 +245,11 @@ JP_HD void jp_interp_velocity_hi(const JpGrid &g, const double *const *V, const 
         jp_corners<N>(V[c], (idx[0] - 1) + s1 * (idx[1] - 1) + (N == 3 ? s2 * (idx[2] - 1) : 0), s1, s2, v);
         const double VL = jp_lerp<N>(v, t);
         if (INTERP == 0 || !interior) vout[c] = VL;
-        else if (INTERP == 2) vout[c] = jp_mqs<N>(V[c], g.nvel[c], c, idx, v, t);
-        else vout[c] = jp_linp<N>(V[c], g.nvel[c], c, idx, xcn, dxi, p, VL);
+        else {
+            const JpGlobalAcc<N> acc = {V[c], g.nvel[c]};
+            if (INTERP == 2) vout[c] = jp_mqs<N>(acc, g.nvel[c], c, idx, v, t);
+            else vout[c] = jp_linp<N>(acc, g.nvel[c], c, idx, xcn, dxi, p, VL);
+        }
     }
 }
 

@@ -103,6 +103,7 @@ static inline const char *jp_grid_build(const jp_grid_desc *d, JpGrid &g, std::v
             for (int i = 0; i <= d->n[dim]; i++) ig[i] = 1.0 / (hxg[dim][i + 1] - hxg[dim][i]);
             o.ixg[dim] = push(ig.data(), d->n[dim] + 1);
             g.inv_dg[dim] = 1.0 / (hxg[dim][1] - hxg[dim][0]);
+            g.dxg0[dim] = hxg[dim][1] - hxg[dim][0];
         }
     }
     return nullptr;

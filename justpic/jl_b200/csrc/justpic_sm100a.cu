@@ -1238,9 +1238,9 @@ static jp_encode_tiled_fn jp_get_encode_tiled() {
 }
 
 // Tensor maps for the velocity components that satisfy the TMA constraints; returns the component mask.
-template <int N>
+template <int N, int H = 0>
 static int build_advect_tma(const JpGrid &g, CPtr3 V, AdvTmaMaps &maps) {
-    using T = AdvTile<N>;
+    using T = AdvTile<N, H>;
     memset(&maps, 0, sizeof(maps));
     jp_encode_tiled_fn enc = jp_get_encode_tiled();
     if (!enc) return 0;
@@ -1260,21 +1260,21 @@ static int build_advect_tma(const JpGrid &g, CPtr3 V, AdvTmaMaps &maps) {
 
 static int move_plan_alloc(jp_ctx *ctx);
 struct AdvHandoff { MovePlanWs ws; unsigned int *flag; };        // flag == nullptr: no hand-off
-template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT>
+template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT, int INTERP = 0>
 static cudaError_t launch_advect_tile_h(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, const AdvHandoff &ho) {
-    using T = AdvTile<N>;
-    const size_t smem = AdvSmem<N, UNIFORM>::BYTES + (HINT ? (size_t)T::NW * 32 * ADV_HINT_ROW : 0);     // + the per-warp classification bytes
+    constexpr int H = INTERP ? 1 : 0;
+    using T = AdvTile<N, H>;
+    const size_t smem = AdvSmem<N, UNIFORM, H>::BYTES + (HINT ? (size_t)T::NW * 32 * ADV_HINT_ROW : 0);     // + the per-warp classification bytes
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(AdvSmem<N, UNIFORM>::BYTES + (HINT ? T::NW * 32 * ADV_HINT_ROW : 0)));
+        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT, INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     AdvTmaMaps maps;
-    const int tma_mask = build_advect_tma<N>(g, V, maps);
+    const int tma_mask = build_advect_tma<N, H>(g, V, maps);
     const dim3 grd((g.n[0] + T::TX - 1) / T::TX, (g.n[1] + T::TY - 1) / T::TY, N == 3 ? (g.n[2] + T::TZ - 1) / T::TZ : 1);
-    k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask, ho.ws, ho.flag);
+    k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT, INTERP><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask, ho.ws, ho.flag);
     return cudaSuccess;
 }
 template <int N, int SCHEME, bool UNIFORM, int AFFINE>
@@ -1368,11 +1368,27 @@ static int advect_impl(jp_ctx *ctx, const jp_particles *p, int32_t scheme, doubl
     return JP_OK;
 }
 
+// advection_LinP! / advection_MQS!: the tiled kernel (stencils idx - 1 .. idx + 2 served from a tile with one more halo node) on the
+// standard staggering, the thread-per-cell kernel on global memory otherwise.  Same results either way (tests/test_advection_interpolants.py).
 template <int N, int INTERP>
-static void launch_advect_hi(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, int scheme, double alpha, double dt) {
+static cudaError_t launch_advect_hi(const JpGrid &g, dim3 grd, dim3 blk, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, int scheme, double alpha, double dt) {
+    static const bool no_tile = getenv("JP_ADVECT_HI_GLOBAL") != nullptr;          // developer A/B switch
+    if (!no_tile && jp_standard_staggering(g)) {
+        const AdvHandoff none = {};
+        JpGrid gt = g; gt.region = 0;
+        if (g.uniform) {
+            if (scheme == 0) return launch_advect_tile_h<N, 0, true, 0, false, INTERP>(gt, st, co, index, V, alpha, dt, none);
+            if (scheme == 1) return launch_advect_tile_h<N, 1, true, 0, false, INTERP>(gt, st, co, index, V, alpha, dt, none);
+            return launch_advect_tile_h<N, 2, true, 0, false, INTERP>(gt, st, co, index, V, alpha, dt, none);
+        }
+        if (scheme == 0) return launch_advect_tile_h<N, 0, false, 0, false, INTERP>(gt, st, co, index, V, alpha, dt, none);
+        if (scheme == 1) return launch_advect_tile_h<N, 1, false, 0, false, INTERP>(gt, st, co, index, V, alpha, dt, none);
+        return launch_advect_tile_h<N, 2, false, 0, false, INTERP>(gt, st, co, index, V, alpha, dt, none);
+    }
     if (scheme == 0) k_advect_hi<N, 0, INTERP><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
     else if (scheme == 1) k_advect_hi<N, 1, INTERP><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
     else k_advect_hi<N, 2, INTERP><<<grd, blk, 0, st>>>(g, co, index, V, alpha, dt);
+    return cudaSuccess;
 }
 
 extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t scheme, double alpha, const double *const *V, double dt,
@@ -1393,13 +1409,15 @@ extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t sche
         const SlotChunk k = jp_chunk(g, ch);
         const Ptr3 kc = jp_shift(co, k.off);
         const uint8_t *ki = p->index + k.off;
+        cudaError_t le;
         if (g.ndim == 2) {
-            if (interp == JP_INTERP_LINP) launch_advect_hi<2, 1>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
-            else                          launch_advect_hi<2, 2>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
+            if (interp == JP_INTERP_LINP) le = launch_advect_hi<2, 1>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
+            else                          le = launch_advect_hi<2, 2>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
         } else {
-            if (interp == JP_INTERP_LINP) launch_advect_hi<3, 1>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
-            else                          launch_advect_hi<3, 2>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
+            if (interp == JP_INTERP_LINP) le = launch_advect_hi<3, 1>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
+            else                          le = launch_advect_hi<3, 2>(k.g, grd, blk, st, kc, ki, v, scheme, alpha, dt);
         }
+        if (le != cudaSuccess) return jp_fail(JP_ERR_CUDA, "jp_advect_interp: %s", cudaGetErrorString(le));
     }
     JP_CHECK_LAUNCH();
     return JP_OK;
