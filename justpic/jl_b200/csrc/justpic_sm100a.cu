@@ -520,8 +520,11 @@ __device__ __forceinline__ double jp_inject_field(const JpGrid &g, const double 
     return tmp > hi ? hi : (tmp < lo ? lo : tmp);
 }
 
+#ifndef JP_MINB_INJECT
+#define JP_MINB_INJECT 2
+#endif
 template <int N, bool PHASE>
-__global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ,
+__global__ void __launch_bounds__(256, JP_MINB_INJECT) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ,
                                                       uint8_t *inbox, const int *__restrict__ list, const unsigned int *__restrict__ count,
                                                       int min_xcell, uint64_t seed, uint32_t step, long long *stats, InjPhase ph) {
     const int lane = threadIdx.x & 31;
@@ -548,6 +551,21 @@ __global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t
         double xvc[3], dq[3];
 #pragma unroll
         for (int d = 0; d < N; d++) { xvc[d] = g.xv[d][ci[d]]; dq[d] = jp_d_of(g.xv[d], g.uniform, ci[d]) / 2; }
+        // the 3^N neighbourhood, one neighbour per lane (fetched once per cell, broadcast by shuffle in the donor search below;
+        // the neighbours have other colours, so their occupancy / pruning flag do not change during this launch)
+        long long nb_c2 = -1;
+        unsigned long long nb_occ = 0;
+        int nb_inbox = 0;
+        double nb_lo[3] = {0, 0, 0}, nb_hi[3] = {0, 0, 0};           // the neighbour's closed box (pruning)
+        if (lane < (N == 3 ? 27 : 9)) {
+            const int cc[3] = {ci[0] + lane % 3 - 1, ci[1] + (lane / 3) % 3 - 1, N == 3 ? ci[2] + lane / 9 - 1 : 0};
+            if (cc[0] >= 0 && cc[1] >= 0 && cc[2] >= 0 && cc[0] < nx && cc[1] < ny && cc[2] < nz) {
+                nb_c2 = cc[0] + (int64_t)nx * (cc[1] + (int64_t)ny * cc[2]);
+                if (nb_c2 != c) { nb_occ = occ[nb_c2]; nb_inbox = inbox[nb_c2]; }
+#pragma unroll
+                for (int d = 0; d < N; d++) { nb_lo[d] = g.xv[d][cc[d]]; nb_hi[d] = g.xv[d][cc[d] + 1]; }
+            }
+        }
         int injected = 0;
 #pragma unroll 1
         for (int iq = 0; iq < NQ; iq++) {
@@ -594,46 +612,71 @@ __global__ void __launch_bounds__(256) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t
                 // holds is known to lie in its closed box (inbox) and the box is farther than the
                 // best distance so far (all IEEE operations involved are monotonic, so the computed
                 // box distance never exceeds the computed distance of a particle inside the box).
+                // Every lane keeps its own best candidate (key: distance, then the reference's visiting order); ONE full
+                // reduction at the end.  The pruning bound is the warp-wide minimum distance, refreshed (distance only) after each
+                // visited cell.
                 double best_d = INFINITY;
                 int best_ord = 0x7fffffff;
                 long long best_e = -1;
-#pragma unroll 1
-                for (int it = 0; it < (N == 3 ? 27 : 9); it++) {
-                    const int self = N == 3 ? 13 : 4;
-                    const int nidx = it == 0 ? self : (it <= self ? it - 1 : it);      // own cell first
-                    const int ii = ci[0] + nidx % 3 - 1, jj = ci[1] + (nidx / 3) % 3 - 1, kk = N == 3 ? ci[2] + nidx / 9 - 1 : 0;
-                    if (ii < 0 || jj < 0 || kk < 0 || ii >= nx || jj >= ny || kk >= nz) continue;
-                    const int64_t c2 = ii + (int64_t)nx * (jj + (int64_t)ny * kk);
-                    if (c2 != c && inbox[c2]) {
-                        const int cc[3] = {ii, jj, kk};
+                const int self = N == 3 ? 13 : 4;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {                       // own cell first, from registers
+                    const int s = lane + 32 * h;
+                    if (live[h] && s != i) {
+                        const double dist = jp_distance<N>(p[h], pn);
+                        const int ord = self * 64 + s;
+                        if (dist < best_d || (dist == best_d && ord < best_ord)) { best_d = dist; best_ord = ord; best_e = c + (int64_t)s * g.C; }
+                    }
+                }
+                double bound = best_d;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) { const double od = __shfl_xor_sync(0xffffffffu, bound, off); bound = od < bound ? od : bound; }
+                // which neighbours can hold a closer particle: decided by all lanes at once (lane = neighbour): a cell whose particles
+                // all lie in its closed box (inbox) is skipped when the box is farther than the bound (all IEEE operations involved are
+                // monotonic, so the computed box distance never exceeds the computed distance of a particle inside the box)
+                double bd = INFINITY;
+                if (nb_c2 >= 0 && nb_c2 != c && nb_occ != 0) {
+                    bd = 0.0;
+                    if (nb_inbox) {
                         double bx[3];
 #pragma unroll
-                        for (int d = 0; d < N; d++) {
-                            const double lo = g.xv[d][cc[d]], hi = g.xv[d][cc[d] + 1];
-                            bx[d] = pn[d] < lo ? lo : (pn[d] > hi ? hi : pn[d]);      // nearest point of the box
-                        }
-                        if (jp_distance<N>(bx, pn) > best_d) continue;
+                        for (int d = 0; d < N; d++) bx[d] = pn[d] < nb_lo[d] ? nb_lo[d] : (pn[d] > nb_hi[d] ? nb_hi[d] : pn[d]);      // nearest point of the box
+                        bd = jp_distance<N>(bx, pn);
                     }
-                    const uint64_t o2 = c2 == c ? occ_c : occ[c2];
+                }
+                unsigned vis = __ballot_sync(0xffffffffu, !(bd > bound));
+#pragma unroll 1
+                while (vis) {
+                    const int nidx = __ffs((int)vis) - 1;
+                    vis &= vis - 1;
+                    if (__shfl_sync(0xffffffffu, bd, nidx) > bound) continue;          // the bound has tightened since the ballot
+                    const long long c2 = __shfl_sync(0xffffffffu, nb_c2, nidx);
+                    const unsigned long long o2 = __shfl_sync(0xffffffffu, nb_occ, nidx);
+                    double dmin = INFINITY;
 #pragma unroll
                     for (int h = 0; h < 2; h++) {
                         const int s = lane + 32 * h;
-                        if (s < S && ((o2 >> s) & 1ull) && !(c2 == c && s == i)) {
+                        if (s < S && ((o2 >> s) & 1ull)) {
                             double q[3];
-                            if (c2 == c) { for (int d = 0; d < N; d++) q[d] = p[h][d]; }
-                            else { for (int d = 0; d < N; d++) q[d] = co.p[d][c2 + (int64_t)s * g.C]; }
+#pragma unroll
+                            for (int d = 0; d < N; d++) q[d] = co.p[d][c2 + (int64_t)s * g.C];
                             const double dist = jp_distance<N>(q, pn);
                             const int ord = nidx * 64 + s;
                             if (dist < best_d || (dist == best_d && ord < best_ord)) { best_d = dist; best_ord = ord; best_e = c2 + (int64_t)s * g.C; }
+                            dmin = dist < dmin ? dist : dmin;
                         }
                     }
+                    dmin = dmin < bound ? dmin : bound;
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        const double od = __shfl_xor_sync(0xffffffffu, best_d, off);
-                        const int oo = __shfl_xor_sync(0xffffffffu, best_ord, off);
-                        const long long oe = __shfl_xor_sync(0xffffffffu, best_e, off);
-                        if (od < best_d || (od == best_d && oo < best_ord)) { best_d = od; best_ord = oo; best_e = oe; }
-                    }
+                    for (int off = 16; off > 0; off >>= 1) { const double od = __shfl_xor_sync(0xffffffffu, dmin, off); dmin = od < dmin ? od : dmin; }
+                    bound = dmin;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const double od = __shfl_xor_sync(0xffffffffu, best_d, off);
+                    const int oo = __shfl_xor_sync(0xffffffffu, best_ord, off);
+                    const long long oe = __shfl_xor_sync(0xffffffffu, best_e, off);
+                    if (od < best_d || (od == best_d && oo < best_ord)) { best_d = od; best_ord = oo; best_e = oe; }
                 }
                 if (PHASE) {
                     if (best_e >= 0 && lane == 0) ph.phases[e] = ph.phases[best_e];
@@ -1763,8 +1806,8 @@ extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args
     // colour order of the reference: offset_i outermost (src/Particles/injection.jl:30-49)
     const int ncol = g.ndim == 3 ? 8 : 4;
     for (int col = 0; col < ncol; col++) {
-        if (g.ndim == 2) k_inject_sweep<2, false><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, InjPhase());
-        else             k_inject_sweep<3, false><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, InjPhase());
+        if (g.ndim == 2) k_inject_sweep<2, false><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, InjPhase());
+        else             k_inject_sweep<3, false><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, InjPhase());
     }
     JP_CHECK_LAUNCH();
     return JP_OK;
@@ -1802,8 +1845,8 @@ extern "C" int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phase
     JP_CHECK_LAUNCH();
     const int ncol = g.ndim == 3 ? 8 : 4;
     for (int col = 0; col < ncol; col++) {
-        if (g.ndim == 2) k_inject_sweep<2, true><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
-        else             k_inject_sweep<3, true><<<148 * 4, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
+        if (g.ndim == 2) k_inject_sweep<2, true><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
+        else             k_inject_sweep<3, true><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
     }
     JP_CHECK_LAUNCH();
     return JP_OK;
