@@ -40,12 +40,24 @@ J.move_particles(p, fields)
 J.particle2grid(T, pT, p)                             # two-pass (default)
 J.phase_ratios_center(pr, p, ph)
 J.inject_particles(p, fields, step=10)
-# --- headline step with the hand-off
+# --- headline step with the advection -> move hand-off
 J.advection(p, rk2, V, dt, classify=True)
 J.move_particles(p, fields)
 J.particle2grid(T, pT, p, mode="exact")
 J.particle2grid(T, pT, p, mode="twopass_fastw")
 J.inject_particles_phase(p, ph, (pT,), (T,), step=11)
+# --- headline step the way bench.py runs it: both hand-offs (k_move_scatter_interp_fast, node pass, ratio copy)
+J.move_interp_handoff(p, Fp=pT, phases=ph, nphases=2)
+J.advection(p, rk2, V, dt, classify=True)
+J.move_particles(p, fields)
+J.particle2grid(T, pT, p)
+J.phase_ratios_center(pr, p, ph)
+# ... and with an argument order the fast path does not serve (generic fused scatter)
+J.move_interp_handoff(p, Fp=pT, phases=ph, nphases=2)
+J.advection(p, rk2, V, 0.5 * dt, classify=True)
+J.move_particles(p, (strain, ph, pT))
+J.particle2grid(T, pT, p)
+J.move_interp_handoff(p, enable=False)
 # --- other integrators / interpolants
 J.advection(p, J.Euler(), V, 0.1 * dt, classify=False)
 J.advection(p, J.RungeKutta4(), V, 0.1 * dt)
@@ -71,6 +83,10 @@ J.update_phase_ratios(pr, p, ph, mode="fused")
 arrays = [*p.coords, *fields]
 buf = torch.empty(H.plane_bytes(p.ncells, p.max_xcell, 0, len(arrays)), dtype=torch.uint8, device="cuda")
 H._cuda_pack(p, 0, 1, arrays, buf); H._cuda_unpack(p, 0, 0, arrays, buf)
+# jp_halo_exchange / jp_halo_exchange_grid: a rank that is its own neighbour (periodic) runs the library's schedule without NCCL
+topo = H.CartesianTopology((1,) * a.ndim, 0, (True,) * a.ndim)
+H.update_cell_halo(p, fields, topo)
+H.update_halo(p, V[0], topo)
 h = J.Array(pT); J.CuArray(h)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
