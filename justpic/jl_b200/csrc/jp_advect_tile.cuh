@@ -94,9 +94,10 @@ template <int N, bool UNIFORM, int H = 0> struct AdvSmem {
 // bit -- instead of being loaded from shared memory:
 // the kernel is bound by LDS return bandwidth (128 B/clk/SM) and 30 of its 78 loads per particle
 // were grid-vector entries.
-// JP_ADV_STAGE1: the first interpolation of a particle (at its own position) skips the warp vote / re-centring block -- after
-// move_particles! every particle lies strictly inside its storage cell; one that does not is flagged and takes the literal routine
-// (same result).  JP_ADV_NOVOTE: the later stages run the re-centring arithmetic unconditionally -- at CFL 0.5 nearly every warp holds
+// JP_ADV_STAGE1: the first interpolation of a particle (at its own position) skips the re-centring block when the library knows
+// that every particle lies strictly inside its storage cell (g.bucketed: the last call that touched the particles was
+// move_particles!, init, inject or clean -- not another advection!, a halo unpack or a foreign write); a particle that is not is
+// flagged and takes the literal routine (same result).  JP_ADV_NOVOTE: the later stages run the re-centring arithmetic unconditionally -- at CFL 0.5 nearly every warp holds
 // a lane whose stage position left its seed cell, so the vote only cost a divergent-branch frame.  Measured at 256^3 (r02l, all
 // bit-identical): 14.44 -> 13.44 (stage 1) -> 13.32 (no vote) -> 13.09 ms (2 CTAs / SM at <= 128 registers instead of 3 at 80).
 // Dropped: stencil loads as ld.shared.f64 on a 32-bit address held in one opaque register (the compiler re-derives the shared
@@ -142,9 +143,9 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
         else { a = xv[r]; b = xv[r + 1]; }
         const bool up = pd > b, dn = pd < a;
 #if JP_ADV_NOVOTE
-        if (!(JP_ADV_STAGE1 && FIRST)) {            // later stages: nearly every warp holds a lane that left its seed cell -- no vote, no branch
+        if (!(JP_ADV_STAGE1 && FIRST && g.bucketed)) {   // later stages: nearly every warp holds a lane that left its seed cell -- no vote, no divergent branch
 #else
-        if (!(JP_ADV_STAGE1 && FIRST) && __any_sync(amask, up || dn)) {          // warp-uniform: stage positions that left the seed cell
+        if (!(JP_ADV_STAGE1 && FIRST && g.bucketed) && __any_sync(amask, up || dn)) {          // warp-uniform: stage positions that left the seed cell
 #endif
             r += (up ? 1 : 0) - (dn ? 1 : 0);
             if (AFFINE) {

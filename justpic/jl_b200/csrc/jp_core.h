@@ -54,6 +54,9 @@ struct JpGrid {
     // advection! split for the halo overlap (jp_advect_region): 0 = every cell, 1 = only bricks that hold a cell of the two
     // outermost cell layers (what update_cell_halo! reads and rewrites), 2 = the other bricks
     int32_t region;
+    // 1: every live particle lies strictly inside its storage cell (the state move_particles! / init / inject / clean leave);
+    // the tiled advection kernel then skips the re-centring of its first interpolation.  Set per launch from the context's state.
+    int32_t bucketed;
 };
 
 struct JpArgs {               // particle fields carried along by move/inject/clean

@@ -78,6 +78,7 @@ struct jp_ctx {
     int hint_ndirty; int hint_dirty[8][2];   // (dim, plane) rewritten since the hand-off
     int last_classify;       // 0: coordinates (k_move_classify3), 1: hand-off bytes (diagnostics)
     int adv_split;           // jp_advect_region: the shell part has run, the interior part is still to come
+    int bucketed;            // every live particle lies strictly inside its storage cell (set by move / init / inject / clean, cleared by advect, halo unpack, foreign writes)
     int mp_ready;            // every buffer of the plan workspace is allocated
     void *last_stream;       // stream of the last jp_move (jp_last_move_path reads the device flag on it)
     cudaEvent_t m_event; int m_pending, m_probed;   // asynchronous read-back of the last arrival count (sizes the staging buffer)
@@ -1252,6 +1253,7 @@ static inline JpArgs jp_shift(JpArgs a, int64_t off) { for (int i = 0; i < a.n; 
 extern "C" int jp_init_particles(jp_ctx *ctx, const jp_particles *p, int32_t nxcell, uint64_t seed, void *stream) {
     PREP("jp_init_particles");
     handoffs_invalidate(ctx);
+    ctx->bucketed = 1;
     const int NQ = g.ndim == 2 ? 4 : 8;
     if (nxcell < 0) return jp_fail(JP_ERR_INVALID, "jp_init_particles: nxcell < 0");     // 0: empty container (test/test_2D.jl:302)
     const int npq = (nxcell + NQ - 1) / NQ;
@@ -1386,6 +1388,7 @@ static int advect_impl(jp_ctx *ctx, const jp_particles *p, int32_t scheme, doubl
     for (int ch = 0; ch < jp_nchunks(g); ch++) {          // one launch unless max_xcell > 64
         SlotChunk k = jp_chunk(g, ch);
         k.g.region = tiled ? region : 0;
+        k.g.bucketed = ctx->bucketed;
         const Ptr3 kc = jp_shift(co, k.off);
         const uint8_t *ki = p->index + k.off;
         cudaError_t le;
@@ -1403,6 +1406,7 @@ static int advect_impl(jp_ctx *ctx, const jp_particles *p, int32_t scheme, doubl
     JP_CHECK_LAUNCH();
     const bool hint_void = ctx->adv_split == 2;
     ctx->adv_split = region == JP_REGION_SHELL;
+    if (region != JP_REGION_SHELL) ctx->bucketed = 0;             // (the interior launch of a split advection still sees the shell call's state)
     if (hinted && region != JP_REGION_SHELL && !hint_void) {               // after a shell call the words are still incomplete
         ctx->hint_valid = 1;
         for (int d = 0; d < 3; d++) ctx->hint_key[d] = d < g.ndim ? (const void *)p->coords[d] : nullptr;
@@ -1418,7 +1422,7 @@ static cudaError_t launch_advect_hi(const JpGrid &g, dim3 grd, dim3 blk, cudaStr
     static const bool no_tile = getenv("JP_ADVECT_HI_GLOBAL") != nullptr;          // developer A/B switch
     if (!no_tile && jp_standard_staggering(g)) {
         const AdvHandoff none = {};
-        JpGrid gt = g; gt.region = 0;
+        JpGrid gt = g; gt.region = 0;        // (gt.bucketed comes with g)
         if (g.uniform) {
             if (scheme == 0) return launch_advect_tile_h<N, 0, true, 0, false, INTERP>(gt, st, co, index, V, alpha, dt, none);
             if (scheme == 1) return launch_advect_tile_h<N, 1, true, 0, false, INTERP>(gt, st, co, index, V, alpha, dt, none);
@@ -1449,7 +1453,8 @@ extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t sche
     if (scheme == JP_RK2 && !(0 < alpha && alpha < 1)) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: Only 0 < alpha < 1 is supported");
     if (scheme < 0 || scheme > 2) return jp_fail(JP_ERR_INVALID, "jp_advect_interp: unknown integrator");
     for (int ch = 0; ch < jp_nchunks(g); ch++) {
-        const SlotChunk k = jp_chunk(g, ch);
+        SlotChunk k = jp_chunk(g, ch);
+        k.g.bucketed = ctx->bucketed;
         const Ptr3 kc = jp_shift(co, k.off);
         const uint8_t *ki = p->index + k.off;
         cudaError_t le;
@@ -1462,6 +1467,7 @@ extern "C" int jp_advect_interp(jp_ctx *ctx, const jp_particles *p, int32_t sche
         }
         if (le != cudaSuccess) return jp_fail(JP_ERR_CUDA, "jp_advect_interp: %s", cudaGetErrorString(le));
     }
+    ctx->bucketed = 0;
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1701,6 +1707,7 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     int rc = pack_args(args, nargs, a, "jp_move");
     if (rc) return rc;
     mi_invalidate(ctx);
+    ctx->bucketed = 1;                                       // whatever path the call takes, it leaves every particle inside its cell
     ctx->last_stream = stream;
     JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
     if (g.S > JP_MAX_SLOTS) {                                // wide cells: literal per-cell sweeps on the index bytes
@@ -1866,6 +1873,7 @@ extern "C" int jp_force_injection(jp_ctx *ctx, const jp_particles *p, const doub
                                   int32_t nfields, void *stream) {
     PREP("jp_force_injection");
     handoffs_invalidate(ctx);
+    ctx->bucketed = 0;                                       // the caller's points go where the caller says
     JpArgs f;
     int rc = pack_args(fields, nfields, f, "jp_force_injection");
     if (rc) return rc;
@@ -1887,6 +1895,7 @@ extern "C" int jp_force_injection(jp_ctx *ctx, const jp_particles *p, const doub
 extern "C" int jp_clean(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, void *stream) {
     PREP("jp_clean");
     handoffs_invalidate(ctx);
+    ctx->bucketed = 1;
     JpArgs a;
     int rc = pack_args(args, nargs, a, "jp_clean");
     if (rc) return rc;
@@ -1987,6 +1996,7 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
 extern "C" int jp_invalidate_handoffs(jp_ctx *ctx) {
     if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_invalidate_handoffs: null context");
     handoffs_invalidate(ctx);
+    ctx->bucketed = 0;
     return JP_OK;
 }
 
@@ -2205,6 +2215,7 @@ extern "C" int64_t jp_halo_plane_bytes(const jp_ctx *ctx, int32_t dim, int32_t n
 }
 // a plane was rewritten after the advection -> move hand-off was left: its classification words are stale
 static void halo_mark_dirty(jp_ctx *ctx, int dim, int plane) {
+    ctx->bucketed = 0;                                       // a plane of the neighbour's advected particles
     if (!(ctx->hint_valid || (ctx->adv_split && ctx->hint_opt))) return;
     for (int i = 0; i < ctx->hint_ndirty; i++)
         if (ctx->hint_dirty[i][0] == dim && ctx->hint_dirty[i][1] == plane) return;

@@ -18,5 +18,9 @@ for name, fn in (("linear", J.advection), ("LinP", J.advection_LinP), ("MQS", J.
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(p, J.RungeKutta2(), V, dt); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1)); J.move_particles(p)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn(p, J.RungeKutta2(), V, 0.1 * dt); e0.record(); fn(p, J.RungeKutta2(), V, 0.1 * dt); e1.record(); torch.cuda.synchronize()
+    J.move_particles(p)
+    print(f"{name:7s} RK2 second advection! in a row (no move_particles! between: first interpolation re-centres): {e0.elapsed_time(e1):7.3f} ms")
     print(f"{name:7s} RK2 {a.cells}^3: " + " ".join(f"{t:7.3f}" for t in ts) + " ms", "(global-memory kernel)" if os.environ.get("JP_ADVECT_HI_GLOBAL") and name != "linear" else "")
 print("checksum", float(torch.nan_to_num(p.coords[0]).sum()), int(p.index.sum()))
