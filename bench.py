@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--interp-handoff", type=int, default=1, choices=[0, 1],
                     help="1 (default): move_particles!' last pass also leaves particle2grid!'s cell sums and the centre phase ratios "
                          "(JP_OPT_MOVE_INTERP, bit-identical results); 0: the two calls stream the particles again")
+    ap.add_argument("--move-policy", default="reference", choices=["reference", "compact", "dense"],
+                    help="slot policy of move_particles! (JP_OPT_MOVE_POLICY): 'reference' is the reference's rule and the credited number; "
+                         "'compact' / 'dense' are the library's opt-in deviations, reported side by side in DESIGN.md")
     ap.add_argument("--config", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one --cells^3 block per GPU (same dx, dt and flow pattern on every rank); strong = a fixed "
@@ -292,6 +295,17 @@ def run_ours(args):
     def live_counts():
         return int(p.index.sum().item()), int(p.index[(slice(None),) + own].sum().item())
 
+    def slot_fill():
+        """how full the slot planes are at the end of the run (what every streaming kernel pays for): live fraction of planes
+        0, 8, 16, ... and the dead slots below the highest live one, per cell"""
+        S = p.index.shape[0]
+        fill = [round(float(p.index[s].float().mean().item()), 3) for s in range(0, S, 8)]
+        top = torch.zeros(p.index.shape[1:], dtype=torch.uint8, device=p.index.device)
+        for s in range(S):
+            top = torch.maximum(top, p.index[s] * (s + 1))
+        holes = float(top.float().mean().item()) - float(p.index.float().sum(0).mean().item())
+        return {"live_fraction_of_planes_0_8_16_etc": fill, "dead_slots_below_top_per_cell": round(holes, 2), "mean_top_slot": round(float(top.float().mean().item()), 2)}
+
     def step(ev=None):
         def mark(i):
             if ev is not None:
@@ -309,7 +323,7 @@ def run_ours(args):
             if world > 1:
                 update_cell_halo(p, fields, topo, comm=comm)
         mark(2)
-        J.move_particles(p, fields)
+        J.move_particles(p, fields, policy=args.move_policy)
         mark(3)
         J.particle2grid(T, pT, p)
         mark(4)
@@ -482,7 +496,7 @@ def run_ours(args):
                        "block_cells": list(nloc), "live_particles_per_gpu": int(nlive_mean),
                        "value_counts": "live particles in cells the rank owns (halo-ring copies excluded)",
                        "updates_per_s_incl_halo_copies": value_incl_halo,
-                       "migrant_fraction": round(f_mig, 4), "move_path": move_path, "dropped_per_step": dropped,
+                       "migrant_fraction": round(f_mig, 4), "move_path": move_path, "move_policy": args.move_policy, "slot_fill": slot_fill(), "dropped_per_step": dropped,
                        "advect_move_handoff": bool(args.handoff), "move_classify": move_classify,
                        "move_interp_handoff": bool(args.interp_handoff), "p2g_phase_used_handoff": list(interp_used),
                        "halo_overlap": bool(world > 1 and args.overlap), "halo_transport": "jp_halo_exchange (C, ncclSend/ncclRecv)" if world > 1 else None,

@@ -61,7 +61,14 @@ typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_
  *     line `starting_point = free_idx` dropped).  Same particles in the same cells (up to fewer drops in
  *     over-full cells), but in the lowest free slots: slot planes stay dense, so every streaming kernel
  *     moves fewer dead-slot sectors.  Slot positions -- hence masks and summation order -- differ from the
- *     reference's; checked against the oracle run with the same rule. */
+ *     reference's; checked against the oracle run with the same rule.
+ *   DENSE: NOT reference behaviour, opt-in -- "vacate everything, then place": all cells give up their leavers' slots
+ *     first; then the migrants are placed in the reference's order (3^N colours, source cells, slot order), each in the
+ *     LOWEST free slot of its destination; dropped when the destination is full.  A migrant thus finds the slots its
+ *     destination vacates in the same call (under the other two rules only when the destination's colour came first),
+ *     so the cells stay packed towards slot 0.  Planned path only (JP_MOVE_AUTO, max_xcell <= 64: jp_move refuses
+ *     otherwise); a call the planner declines (a particle exactly on a cell face, a move of more than one cell --
+ *     jp_last_move_path says so) runs the in-place sweeps with the REFERENCE rule.  Oracle twin: jpo_set_move_policy(2). */
 /* JP_OPT_ADVECT_CLASSIFY (0/1, default 0): advection -> move hand-off.  With 1, jp_advect (tiled kernel:
  *   standard staggering) also classifies every new position for the following move_particles! -- the
  *   same comparisons jp_move makes, on the value being stored -- and writes the move plan's per-cell
@@ -88,7 +95,7 @@ typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_
  * JP_OPT_LAST_INTERP (jp_get_option only): bit 0 / bit 1 = the last jp_particle2grid / jp_phase_ratios_center used the hand-off. */
 typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3, JP_OPT_MOVE_POLICY = 4,
                JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6, JP_OPT_MOVE_INTERP = 7, JP_OPT_LAST_INTERP = 8, JP_OPT_PROFILE = 9 } jp_option;
-typedef enum { JP_MOVE_POLICY_REFERENCE = 0, JP_MOVE_POLICY_COMPACT = 1 } jp_move_policy;
+typedef enum { JP_MOVE_POLICY_REFERENCE = 0, JP_MOVE_POLICY_COMPACT = 1, JP_MOVE_POLICY_DENSE = 2 } jp_move_policy;
 typedef enum { JP_MOVE_AUTO = 0, JP_MOVE_DIRECT = 1 } jp_move_mode;
 typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;
 

@@ -388,6 +388,11 @@ function set_interp_handoff!(p::Particles{CUDABackend}, Fp::Union{CellArray, Not
           "jp_move_interp_fields")
 end
 
+# slot policy of move_particles! (JP_OPT_MOVE_POLICY = 4): 0 = the reference's rule (default), 1 = "compact", 2 = "dense" -- the two
+# opt-in deviations keep the same particles in the same cells but pack them into lower slots (include/justpic_c.h); JUSTPIC_MOVE_POLICY=0|1|2
+set_move_policy!(p::Particles{CUDABackend}, policy::Integer = parse(Int32, get(ENV, "JUSTPIC_MOVE_POLICY", "0"))) =
+    check(ccall((:jp_set_option, libjustpic), Cint, (Ptr{Cvoid}, Int32, Int32), context(p), Int32(4), Int32(policy)), "jp_set_option")
+
 # after a write to coords / index / a registered field that did not go through this extension
 invalidate_handoffs!(p::Particles{CUDABackend}) = check(ccall((:jp_invalidate_handoffs, libjustpic), Cint, (Ptr{Cvoid},), context(p)), "jp_invalidate_handoffs")
 

@@ -8,8 +8,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 SRC = HERE / "csrc" / "justpic_sm100a.cu"
-DEPS = [SRC, HERE / "csrc" / "jp_core.h", HERE / "csrc" / "jp_host_grid.h", HERE / "csrc" / "jp_advect_tile.cuh", HERE / "csrc" / "jp_move_plan.cuh", HERE / "csrc" / "jp_phase_ratios.cuh", HERE / "csrc" / "jp_convert.cuh",
-        HERE.parent.parent / "include" / "justpic_c.h"]
+DEPS = sorted((HERE / "csrc").glob("*.cu*")) + sorted((HERE / "csrc").glob("*.h")) + [HERE.parent.parent / "include" / "justpic_c.h"]
 LIB = HERE / "libjustpic_sm100a.so"
 
 NVCC_FLAGS = [

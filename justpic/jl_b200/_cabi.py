@@ -30,7 +30,7 @@ JP_OPT_LAST_INTERP = 8
 JP_OPT_PROFILE = 9
 JP_F64, JP_F32, JP_BOOL = 0, 1, 2
 JP_LAYOUT_TO_HOST, JP_LAYOUT_TO_DEVICE = 0, 1
-JP_MOVE_POLICY_REFERENCE, JP_MOVE_POLICY_COMPACT = 0, 1
+JP_MOVE_POLICY_REFERENCE, JP_MOVE_POLICY_COMPACT, JP_MOVE_POLICY_DENSE = 0, 1, 2
 JP_MOVE_AUTO, JP_MOVE_DIRECT = 0, 1
 JP_P2G_EXACT, JP_P2G_TWOPASS, JP_P2G_TWOPASS_FASTW = 0, 1, 2
 

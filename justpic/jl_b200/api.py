@@ -397,11 +397,15 @@ def advect_affine_level(particles: Particles) -> int:
     return int(v.value)
 
 
+_MOVE_POLICIES = {"reference": _cabi.JP_MOVE_POLICY_REFERENCE, "compact": _cabi.JP_MOVE_POLICY_COMPACT, "dense": _cabi.JP_MOVE_POLICY_DENSE}
+
+
 def move_particles(particles: Particles, args=(), mode: Optional[str] = None, policy: Optional[str] = None) -> None:
     """``move_particles!(particles, args)`` (src/Particles/move_safe.jl:21-49).
     ``policy``: "reference" (default: the reference's free-slot rule, bit for bit) or "compact" (opt-in, NOT
     reference behaviour: every migrant takes the lowest free slot of its destination, which keeps slot planes
-    dense; see JP_OPT_MOVE_POLICY in include/justpic_c.h).
+    dense) or "dense" (opt-in, NOT reference behaviour: all leavers vacate first, then every migrant takes the lowest
+    free slot; planned path only); see JP_OPT_MOVE_POLICY in include/justpic_c.h.
     ``mode``: "auto" (default: sweeps planned on occupancy words + streaming payload passes,
     direct sweeps when a particle sits exactly on a face) or "direct" (always the literal
     sweeps on the particle arrays).  Both give the reference's slot assignment bit for bit."""
@@ -412,11 +416,11 @@ def move_particles(particles: Particles, args=(), mode: Optional[str] = None, po
     if m not in ("auto", "direct"):
         raise ValueError("move_particles mode must be 'auto' or 'direct'")
     pol = (policy or MOVE_POLICY).lower()
-    if pol not in ("reference", "compact"):
-        raise ValueError("move_particles policy must be 'reference' or 'compact'")
+    if pol not in _MOVE_POLICIES:
+        raise ValueError("move_particles policy must be 'reference', 'compact' or 'dense'")
     with torch.cuda.device(p.device):
         _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_MOVE_POLICY,
-                                               _cabi.JP_MOVE_POLICY_COMPACT if pol == "compact" else _cabi.JP_MOVE_POLICY_REFERENCE), "jp_set_option")
+                                               _MOVE_POLICIES[pol]), "jp_set_option")
         _cabi.check(_cabi.load().jp_set_option(C.c_void_p(p._ctx), _cabi.JP_OPT_MOVE_MODE,
                                                _cabi.JP_MOVE_AUTO if m == "auto" else _cabi.JP_MOVE_DIRECT), "jp_set_option")
         _cabi.check(_cabi.load().jp_move(C.c_void_p(p._ctx), C.byref(pc), _ptr_array(args), len(args), _stream()),

@@ -129,12 +129,20 @@ __global__ void __launch_bounds__(256, JP_MINB_CLASSIFY) k_move_classify3(JpGrid
     if (wc && threadIdx.x == 0) atomicOr(complex_flag, wc);
 }
 
+// ---- JP_MOVE_POLICY_DENSE ("vacate everything, then place"; opt-in, not reference behaviour): every cell gives up its leavers'
+// slots before the first migrant is placed, so a migrant finds the slots its destination vacates in the same call.
+__global__ void __launch_bounds__(256) k_move_prevacate(int64_t C, MovePlanWs ws, const unsigned int *__restrict__ skip_flag) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C || *skip_flag) return;
+    ws.occ[c] = ws.occ0[c] & ~ws.leave[c];
+}
+
 // ---- B. one colour of the plan (thread = source cell; 8-byte words only).
 // Literal slot logic of move_kernel! (src/Particles/move_safe.jl:72-125) on the occupancy
 // words; the slot given to the k-th leaver goes to res (one byte: slot | placed << 6).
 template <int N>
 __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
-                                                   long long *stats, int compact, const unsigned int *__restrict__ skip_flag) {
+                                                   long long *stats, int policy, const unsigned int *__restrict__ skip_flag) {
     if (*skip_flag) return;                                   // the call takes the direct sweeps (decided on the device)
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncol) return;
@@ -150,6 +158,7 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
     uint64_t occ_c = ws.occ[c];
     uint64_t codew = 0, resw = 0;
     int cursor = 0, k = 0, n_dropped = 0, n_deleted = 0;
+    const bool compact = policy != JP_MOVE_POLICY_REFERENCE, dense = policy == JP_MOVE_POLICY_DENSE;
     while (lv) {
         const int ip = __ffsll((long long)lv) - 1;
         lv &= lv - 1;
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
         }
         const int code = (int)((codew >> (8 * (k & 7))) & 255);
         const int kk = k++;
-        occ_c &= ~(1ull << ip);
+        if (!dense) occ_c &= ~(1ull << ip);   // (DENSE: k_move_prevacate cleared it, and an earlier colour's migrant may sit there by now)
         if (code == JP_CODE_DELETE) { n_deleted++; continue; }
         int dv[3];
         jp_code_dir(code, dv);
@@ -168,11 +177,11 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
         const uint64_t freebits = ~o2 & smask & (~0ull << cursor);
         if (freebits == 0) { n_dropped++; continue; }
         const int fs = __ffsll((long long)freebits) - 1;
-        if (!compact) cursor = fs;            // JP_MOVE_POLICY_COMPACT: every search starts at slot 0
+        if (!compact) cursor = fs;            // JP_MOVE_POLICY_COMPACT / _DENSE: every search starts at slot 0
         ws.occ[c2] = o2 | (1ull << fs);
         resw |= (uint64_t)(fs | 64) << (8 * (kk & 7));
     }
-    ws.occ[c] = occ_c;
+    if (!dense) ws.occ[c] = occ_c;
     ws.res[(int64_t)((k - 1) >> 3) * g.C + c] = resw;
     if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
     if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);

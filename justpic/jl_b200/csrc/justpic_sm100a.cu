@@ -57,7 +57,7 @@ struct jp_ctx {
     long long *stats;     // device counters: [0..2] move, [3] inject
     double *p2g_ws;       // [2 * 2^N * C] per-cell partial sums of the two-pass particle2grid (lazy)
     int p2g_mode;         // JP_P2G_EXACT / JP_P2G_TWOPASS / JP_P2G_TWOPASS_FASTW
-    int move_policy;      // JP_MOVE_POLICY_REFERENCE (carried-over free-slot cursor) / JP_MOVE_POLICY_COMPACT
+    int move_policy;      // JP_MOVE_POLICY_REFERENCE (carried-over free-slot cursor) / JP_MOVE_POLICY_COMPACT / JP_MOVE_POLICY_DENSE
     int move_mode;        // JP_MOVE_AUTO (plan/gather/scatter, direct sweeps on ties) / JP_MOVE_DIRECT
     int affine_detected;  // grid vectors are exactly affine (jp_grid_build); g.affine = detected && option
     int last_move_path;   // 0 = plan, 1 = direct (diagnostics)
@@ -1618,11 +1618,12 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = N == 3 ? (g.n[2] + 2) / 3 : 1;
     const int64_t ncol = (int64_t)ncx * ncy * ncz;
     const unsigned nblk = (unsigned)((ncol + 255) / 256);
+    const unsigned cblk = (unsigned)((g.C + 255) / 256);
+    if (ctx->move_policy == JP_MOVE_POLICY_DENSE) k_move_prevacate<<<cblk, 256, 0, st>>>(g.C, ctx->mp, flag);
     for (int ox = 0; ox < 3; ox++)
         for (int oy = 0; oy < 3; oy++)
             for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
                 k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy, flag);
-    const unsigned cblk = (unsigned)((g.C + 255) / 256);
     mark();
     k_move_finalize<N><<<cblk, 256, 0, st>>>(g, ctx->mp, flag);
     JP_CHECK_LAUNCH();
@@ -1710,6 +1711,11 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     ctx->bucketed = 1;                                       // whatever path the call takes, it leaves every particle inside its cell
     ctx->last_stream = stream;
     JP_CUDA(cudaMemsetAsync(ctx->stats, 0, 3 * sizeof(long long), st));
+    if (ctx->move_policy == JP_MOVE_POLICY_DENSE && (g.S > JP_MAX_SLOTS || ctx->move_mode != JP_MOVE_AUTO))
+        return jp_fail(JP_ERR_INVALID, "jp_move: JP_MOVE_POLICY_DENSE needs the planned path (%s)", "JP_MOVE_AUTO, max_xcell <= 64");
+    // the in-place sweeps cannot vacate first (the slots still hold the leavers' payload): a DENSE call the planner declines
+    // (a particle on a face, a far move) runs them with the reference's rule -- jp_last_move_path tells
+    const int sweep_policy = ctx->move_policy == JP_MOVE_POLICY_COMPACT;
     if (g.S > JP_MAX_SLOTS) {                                // wide cells: literal per-cell sweeps on the index bytes
         ctx->last_move_path = 1;
         hint_invalidate(ctx);
@@ -1719,8 +1725,8 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
         for (int ox = 0; ox < 3; ox++)
             for (int oy = 0; oy < 3; oy++)
                 for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {
-                    if (g.ndim == 2) k_move_sweep_wide<2><<<nblk, 128, 0, st>>>(g, co, p->index, a, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
-                    else             k_move_sweep_wide<3><<<nblk, 128, 0, st>>>(g, co, p->index, a, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy);
+                    if (g.ndim == 2) k_move_sweep_wide<2><<<nblk, 128, 0, st>>>(g, co, p->index, a, ox, oy, oz, ncx, ncy, ncol, ctx->stats, sweep_policy);
+                    else             k_move_sweep_wide<3><<<nblk, 128, 0, st>>>(g, co, p->index, a, ox, oy, oz, ncx, ncy, ncol, ctx->stats, sweep_policy);
                 }
         JP_CHECK_LAUNCH();
         return JP_OK;
@@ -1743,8 +1749,8 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     for (int ox = 0; ox < 3; ox++)
         for (int oy = 0; oy < 3; oy++)
             for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {
-                if (g.ndim == 2) k_move_sweep<2><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy, run_flag);
-                else             k_move_sweep<3><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy, run_flag);
+                if (g.ndim == 2) k_move_sweep<2><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, sweep_policy, run_flag);
+                else             k_move_sweep<3><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, sweep_policy, run_flag);
             }
     JP_CHECK_LAUNCH();
     return JP_OK;
@@ -1983,7 +1989,7 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (!ctx) return jp_fail(JP_ERR_INVALID, "jp_set_option: null context");
     if (option == JP_OPT_MOVE_MODE && (value == JP_MOVE_AUTO || value == JP_MOVE_DIRECT)) { ctx->move_mode = value; return JP_OK; }
     if (option == JP_OPT_P2G_MODE && (value == JP_P2G_EXACT || value == JP_P2G_TWOPASS || value == JP_P2G_TWOPASS_FASTW)) { ctx->p2g_mode = value; return JP_OK; }
-    if (option == JP_OPT_MOVE_POLICY && (value == JP_MOVE_POLICY_REFERENCE || value == JP_MOVE_POLICY_COMPACT)) { ctx->move_policy = value; return JP_OK; }
+    if (option == JP_OPT_MOVE_POLICY && (value == JP_MOVE_POLICY_REFERENCE || value == JP_MOVE_POLICY_COMPACT || value == JP_MOVE_POLICY_DENSE)) { ctx->move_policy = value; return JP_OK; }
     if (option == JP_OPT_ADVECT_AFFINE && (value == 0 || value == 1)) { ctx->g.affine = value ? ctx->affine_detected : 0; return JP_OK; }
     if (option == JP_OPT_ADVECT_CLASSIFY && (value == 0 || value == 1)) { ctx->hint_opt = value; hint_invalidate(ctx); return JP_OK; }
     if (option == JP_OPT_MOVE_INTERP && (value == 0 || value == 1)) { ctx->mi_opt = value; mi_invalidate(ctx); return JP_OK; }

@@ -402,9 +402,10 @@ int jpo_init_particles(const jpo_grid *g, double *const *coords, uint8_t *index,
  * over from one migrant of the source cell to the next even when they go to DIFFERENT destination cells
  * (move_safe.jl:114-118).  1 = "compact" (an OPTION of the library, not reference behaviour): the search
  * starts at slot 0 for every migrant, i.e. the line `starting_point = free_idx` is dropped.  Everything
- * else (sweep order, strict tests, drop when no slot is found) is unchanged. */
-static int g_move_compact = 0;
-void jpo_set_move_policy(int compact) { g_move_compact = compact ? 1 : 0; }
+ * else (sweep order, strict tests, drop when no slot is found) is unchanged.
+ * 2 = "dense" (also an option of the library): vacate everything, then place -- jpo_move_dense below. */
+static int g_move_compact = 0, g_move_dense = 0;
+void jpo_set_move_policy(int policy) { g_move_compact = policy == 1; g_move_dense = policy == 2; }
 
 static void move_cell(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs,
                       const int *ci /*0-based*/, int64_t *n_moved, int64_t *n_dropped, int64_t *n_deleted) {
@@ -458,10 +459,76 @@ static void move_cell(const jpo_grid *g, double *const *coords, uint8_t *index, 
     }
 }
 
+/* The "dense" policy (library option, not in the reference).  Pass 0: every live particle that fails the strict isincell test
+ * of its cell leaves: its slot is vacated (mask 0, NaN) and its payload kept aside.  Pass 1: the leavers are visited in the
+ * reference's order (3^N colours; within a colour the source cells never share a destination; slot order within a cell); one
+ * outside the domain is deleted, any other goes to the LOWEST free slot of its destination cell (same bisection as the
+ * reference) or is dropped when there is none. */
+static int jpo_move_dense(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs, int64_t *stats) {
+    const int N = g->ndim, S = g->S, NA = N + nargs;
+    const int64_t C = NCELLS(g), E = C * S;
+    const int nx = g->n[0], ny = g->n[1];
+    double *arr[3 + 64];
+    for (int d = 0; d < N; d++) arr[d] = coords[d];
+    for (int a = 0; a < nargs; a++) arr[N + a] = args[a];
+    uint8_t *leaves = (uint8_t *)calloc((size_t)E, 1);
+    double *keep = (double *)malloc((size_t)E * NA * sizeof(double));      /* payload of the leavers, by element */
+    if (!leaves || !keep) { free(leaves); free(keep); return -2; }
+    for (int64_t c = 0; c < C; c++) {
+        const int ci[3] = {(int)(c % nx), (int)((c / nx) % ny), (int)(c / ((int64_t)nx * ny))};
+        for (int ip = 0; ip < S; ip++) {
+            const int64_t e = c + (int64_t)ip * C;
+            if (!index[e]) continue;
+            int incell = 1;
+            for (int d = 0; d < N; d++) {
+                const double corner = g->xv[d][ci[d]], p = coords[d][e];
+                incell &= (corner < p) & (p < corner + d_of(g->xv[d], g->uniform, ci[d]));
+            }
+            if (incell) continue;
+            leaves[e] = 1;
+            for (int a = 0; a < NA; a++) { keep[(size_t)e * NA + a] = arr[a][e]; arr[a][e] = NAN; }
+            index[e] = 0;
+        }
+    }
+    int64_t moved = 0, dropped = 0, deleted = 0;
+    const int ncol[3] = {(nx + 2) / 3, (ny + 2) / 3, N == 3 ? (g->n[2] + 2) / 3 : 1};
+    for (int ox = 0; ox < 3; ox++)
+        for (int oy = 0; oy < 3; oy++)
+            for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
+                for (int K = 0; K < ncol[2]; K++)
+                    for (int J = 0; J < ncol[1]; J++)
+                        for (int I = 0; I < ncol[0]; I++) {
+                            const int ci[3] = {3 * I + ox, 3 * J + oy, N == 3 ? 3 * K + oz : 0};
+                            if (ci[0] >= nx || ci[1] >= ny || (N == 3 && ci[2] >= g->n[2])) continue;
+                            const int64_t c = ci[0] + (int64_t)nx * (ci[1] + (int64_t)ny * ci[2]);
+                            for (int ip = 0; ip < S; ip++) {
+                                const int64_t e = c + (int64_t)ip * C;
+                                if (!leaves[e]) continue;
+                                const double *p = keep + (size_t)e * NA;
+                                int indom = 1, nc[3] = {0, 0, 0};
+                                for (int d = 0; d < N; d++) if (!(g->xv[d][0] < p[d] && p[d] < g->xv[d][g->n[d]])) { indom = 0; break; }
+                                if (!indom) { deleted++; continue; }
+                                for (int d = 0; d < N; d++) nc[d] = bisect1(p[d], g->xv[d], g->n[d] + 1, ci[d] + 1) - 1;
+                                const int64_t c2 = nc[0] + (int64_t)nx * (nc[1] + (int64_t)ny * nc[2]);
+                                int free_idx = -1;
+                                for (int i = 0; i < S; i++) if (!index[c2 + (int64_t)i * C]) { free_idx = i; break; }
+                                if (free_idx < 0) { dropped++; continue; }
+                                const int64_t e2 = c2 + (int64_t)free_idx * C;
+                                index[e2] = 1;
+                                for (int a = 0; a < NA; a++) arr[a][e2] = p[a];
+                                moved++;
+                            }
+                        }
+    free(leaves); free(keep);
+    if (stats) { stats[0] = moved; stats[1] = dropped; stats[2] = deleted; }
+    return 0;
+}
+
 int jpo_move(const jpo_grid *g, double *const *coords, uint8_t *index, double *const *args, int nargs,
              int64_t *stats /* moved, dropped, deleted */) {
     const int N = g->ndim;
     if (nargs > 64) return -1;
+    if (g_move_dense) return jpo_move_dense(g, coords, index, args, nargs, stats);
     int ncol[3] = {(g->n[0] + 2) / 3, (g->n[1] + 2) / 3, N == 3 ? (g->n[2] + 2) / 3 : 1};
     int64_t moved = 0, dropped = 0, deleted = 0;
     const int oz_max = N == 3 ? 3 : 1;

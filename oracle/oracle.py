@@ -122,9 +122,10 @@ class Oracle:
         return out
 
     @staticmethod
-    def set_move_policy(compact: bool):
-        """False: the reference's carried-over free-slot cursor; True: the library's optional "compact" policy."""
-        lib().jpo_set_move_policy(1 if compact else 0)
+    def set_move_policy(policy):
+        """False / "reference": the reference's carried-over free-slot cursor; True / "compact" and "dense": the library's two
+        optional policies (JP_OPT_MOVE_POLICY in include/justpic_c.h)."""
+        lib().jpo_set_move_policy({False: 0, True: 1, "reference": 0, "compact": 1, "dense": 2}[policy])
 
     def move(self, coords, index, args):
         st = (C.c_int64 * 3)()

@@ -208,6 +208,50 @@ def test_move_policy_compact(g, move_mode):
         Oracle.set_move_policy(False)
 
 
+@pytest.mark.parametrize("handoffs", [False, True], ids=["plain", "handoffs"])
+@pytest.mark.parametrize("g", [(2, 24, True), (2, (19, 33), False), (3, 10, True), (3, (9, 7, 12), False), (3, (34, 9, 8), True)], ids=ids)
+def test_move_policy_dense(g, handoffs):
+    """JP_MOVE_POLICY_DENSE (opt-in, not reference behaviour; "vacate everything, then place"): bit-exact against the oracle's twin
+    (jpo_move_dense), with and without the two hand-offs; same particles in the same cells as the reference policy whenever nothing
+    was dropped; and the cells end up packed at least as low as under the reference rule."""
+    J = jp()
+    t = Twin(*g, nxcell=12, max_xcell=24, min_xcell=8)
+    ref = Twin(*g, nxcell=12, max_xcell=24, min_xcell=8)
+    V = stream_velocity(t.gr); Vd = [dev(v) for v in V]
+    dt = cfl_dt(t.gr, V, 0.9)
+    pT, = J.init_cell_arrays(t.p, 1); J.grid2particle(pT, dev(vertex_field_linear(t.gr)), t.p)
+    opT = host(pT).copy(); rpT = host(pT).copy()
+    T = vertex_field_linear(t.gr)
+    F = dev(np.zeros_like(T))
+    if handoffs:
+        J.move_interp_handoff(t.p, Fp=pT)
+    try:
+        for it in range(6):
+            J.advection(t.p, J.RungeKutta2(), Vd, dt, classify=handoffs)
+            t.o.advect(t.co, t.idx, 1, 0.5, V, dt); ref.o.advect(ref.co, ref.idx, 1, 0.5, V, dt)
+            J.move_particles(t.p, (pT,), policy="dense")
+            assert J.last_move_path(t.p) == "plan"
+            Oracle.set_move_policy("dense"); st = t.o.move(t.co, t.idx, [opT]); Oracle.set_move_policy(False)
+            rst = ref.o.move(ref.co, ref.idx, [rpT])
+            t.check_state(f"step {it} move_particles[dense]", (pT,), (opT,))
+            assert J.move_stats(t.p) == st
+            J.particle2grid(F, pT, t.p)                                   # (uses the hand-off's cell sums when enabled)
+            assert J.last_interp_handoff(t.p)[0] == handoffs
+            oF = np.empty_like(T); t.o.particle2grid(t.co, t.idx, oF, opT)
+            assert_close(F, oF, f"step {it} particle2grid after a dense move")
+            if st[1] == 0 and rst[1] == 0:
+                for d in range(t.gr.ndim):
+                    a = np.sort(np.nan_to_num(t.co[d], nan=np.inf), axis=0); b = np.sort(np.nan_to_num(ref.co[d], nan=np.inf), axis=0)
+                    assert np.array_equal(a, b), f"step {it}: cell contents differ between the policies (coords[{d}])"
+                top = lambda idx: (idx * (np.arange(idx.shape[0]) + 1).reshape((-1,) + (1,) * (idx.ndim - 1))).max(axis=0)
+                assert top(t.idx).sum() <= top(ref.idx).sum(), "dense policy: cells are packed at least as low as under the reference rule"
+        with pytest.raises(Exception):
+            J.move_particles(t.p, (pT,), mode="direct", policy="dense")    # planned path only
+    finally:
+        Oracle.set_move_policy(False)
+        J.move_particles(t.p, (pT,), policy="reference")
+
+
 @pytest.mark.parametrize("move_mode", ["auto", "direct"])
 @pytest.mark.parametrize("g", GRIDS + [(2, 17, True), (3, (7, 5, 6), True), (2, (40, 9), True)], ids=ids)
 def test_trajectory_advect_move_inject(g, move_mode):
