@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--move-policy", default="reference", choices=["reference", "compact", "dense"],
                     help="slot policy of move_particles! (JP_OPT_MOVE_POLICY): 'reference' is the reference's rule and the credited number; "
                          "'compact' / 'dense' are the library's opt-in deviations, reported side by side in DESIGN.md")
+    ap.add_argument("--graph", type=int, default=0, choices=[0, 1],
+                    help="cfg1..cfg3: also capture the step into a CUDA graph (api.capture_step) and report the replayed step; the eager "
+                         "per-phase times stay in phase_ms")
     ap.add_argument("--config", default="cfg4", choices=["cfg1", "cfg2", "cfg3", "cfg4"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one --cells^3 block per GPU (same dx, dt and flow pattern on every rank); strong = a fixed "
@@ -505,11 +508,13 @@ def run_ours(args):
                        "p2g_mode": J.api.P2G_MODE, "l2": "inputs (39 GB/GPU) far larger than L2, no flush needed",
                        "topology": list(topo.dims), "dt": dt},
             # launches per step (every kernel is this library's except cub::DeviceScan's two): advect 1 (2 with the overlap);
-            # move: classify 1 (hand-off: 0, + 1 per halo plane rewritten) + plan 27 + finalize 1 + scan 2 + after-scan 1 +
-            # gather 1 + scatter 1 + the direct-sweep fallback, enqueued behind a device-side flag: 1 + 27 (they return at once);
+            # move: classify 1 (hand-off: 0, + 1 per halo plane rewritten) + plan 27 (1 cooperative launch when a colour fits the
+            # device at once) + finalize 1 + scan 2 + after-scan 1 + gather 1 + scatter 1 + the direct-sweep fallback, enqueued
+            # behind a device-side flag: classify 1 + one cooperative sweep launch (they return at once);
             # p2g 2 (cell [skipped on the device with the hand-off] + node); phase ratios 1 (+ 1 copy with the hand-off);
             # halo: one pack + one unpack per face
-            "gpu_launches": args.steps * ((2 if world > 1 and args.overlap else 1) + 61 + (0 if args.handoff else 1) + 2 + 1
+            "gpu_launches": args.steps * ((2 if world > 1 and args.overlap else 1) + plan_launches(nloc) + 8 + (1 if args.move_policy == "dense" else 0)
+                                          + (0 if args.handoff else 1) + 2 + 1
                                           + (1 if args.interp_handoff else 0)
                                           + ((2 * nfaces + (nfaces if args.handoff else 0)) if world > 1 else 0)),
             "phase_ms": per_phase,
@@ -599,6 +604,13 @@ def config_cpu_run(name, n, steps, warmup, threads):
     return updates / total, total / steps * 1e3
 
 
+def plan_launches(n):
+    """launches of the move plan: its 3^N ordered colours are ONE cooperative launch when a colour (every third cell per dimension,
+    one thread each) fits the device at once -- 148 SMs x 8 blocks of 256 threads -- else one launch per colour"""
+    ncol = int(np.prod([(int(v) + 2) // 3 for v in n]))
+    return 1 if (ncol + 255) // 256 <= 148 * 8 else 3 ** len(n)
+
+
 def run_config(args):
     import torch
     import justpic.jl_b200 as J
@@ -654,6 +666,22 @@ def run_config(args):
     moved, dropped, deleted = J.move_stats(p)
     f_mig = (moved + dropped + deleted) / max(live, 1)
     nlive = 0.5 * (live0 + live)
+    eager_ms, graph = step_ms, None
+    if args.graph:
+        # the same step as ONE graph launch: the launch-bound small grids are limited by ~70 host-side launches per step
+        graph = J.capture_step(p, step, warmup=1)
+        for _ in range(args.warmup):
+            graph.replay()
+        torch.cuda.synchronize()
+        live0 = int(p.index.sum().item())
+        gev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush.fill_(k & 255)
+            gev[k][0].record(); graph.replay(); gev[k][1].record()
+        torch.cuda.synchronize()
+        step_ms = float(np.mean([a.elapsed_time(b) for a, b in gev]))
+        nlive = 0.5 * (live0 + int(p.index.sum().item()))
+    run_step = graph.replay if graph is not None else step
     value = nlive / (step_ms * 1e-3)
     # e2e: V from pinned host memory and T back to the host every step, synchronously, inside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -662,7 +690,7 @@ def run_config(args):
     for k in range(args.steps):
         for vd, vh in zip(V, V_host):
             vd.copy_(vh, non_blocking=True)
-        step()
+        run_step()
         T_host.copy_(T, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         _ = float(T_host.view(-1)[0])
@@ -684,15 +712,16 @@ def run_config(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["what"], "name": name, "cells": int(np.prod(gr.n)), "live_particles": int(nlive),
                        "migrant_fraction": round(f_mig, 4), "move_path": J.last_move_path(p), "advect_move_handoff": bool(args.handoff),
+                       "cuda_graph": bool(args.graph), "eager_ms_per_step": eager_ms,
                        "l2": "particle state fits the 126 MB L2 (2-D) / is 10x larger (3-D 128^3): a 256 MB buffer is written between timed steps",
                        "dt": dt},
-            "gpu_launches": args.steps * (1 + 62 + (0 if args.handoff else 1) + (1 + 2 ** N if "inject" in calls else 0) + 2 + (1 if "g2p" in calls else 0)),
+            "gpu_launches": args.steps * (1 + plan_launches(gr.n) + 8 + (0 if args.handoff else 1) + (1 + 2 ** N if "inject" in calls else 0) + 2 + (1 if "g2p" in calls else 0)),
             "phase_ms": per_phase,
             "roofline": {"bound": "hbm", "kernel": f"{dom} phase", "achieved": gbs[dom], "peak": peak, "unit": "GB/s", "frac": gbs[dom] / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": {c: ab[c] for c in calls},
                          "per_phase_GBps": gbs, "per_phase_frac": {c: gbs[c] / peak for c in calls},
                          "step_GBps": step_bytes / (step_ms * 1e-3) / 1e9, "step_frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                         "note": "small grids are launch-latency bound, not HBM bound: ~70 launches per step"},
+                         "note": "small grids are launch-latency bound, not HBM bound: ~25 (2-D) / ~30 (3-D) kernels per step; --graph 1 replays them as one CUDA graph"},
             "clocks": clocks,
             "e2e": {"value": nlive / (e2e_ms * 1e-3), "unit": "particle-updates/s", "h2d_bytes_per_step": sum(v.numel() * 8 for v in V_host),
                     "d2h_bytes_per_step": T_host.numel() * 8, "ms_per_step": e2e_ms},

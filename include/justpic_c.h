@@ -92,9 +92,16 @@ typedef enum { JP_INTERP_LINEAR = 0, JP_INTERP_LINP = 1, JP_INTERP_MQS = 2 } jp_
  *   loops never do (move_particles! -> particle2grid! -> phase ratios) -- hence opt-in.  Needs max_xcell <= 64, a two-pass
  *   particle2grid mode, <= 4 phases, and containers whose dead slots hold NaN coordinates (everything init_particles /
  *   move_particles! / inject_particles! produce): liveness is the occupancy word, not phase_ratios_center!'s isnan(px) probe.
+ * JP_OPT_GRAPH_STEP_OFFSET (value >= 0; default 0): CUDA graphs.  Every entry point may be called on a stream that is being captured
+ *   (cudaStreamBeginCapture, CUDA.jl's @captured, torch.cuda.graph): nothing on the hot path reads the device back, jp_move skips its
+ *   asynchronous staging-size feedback, and what cannot be captured -- (re)allocating a workspace, the very first jp_move of a context --
+ *   returns JP_ERR_INVALID saying so (run the same calls once eagerly first).  Replays run with the arguments of the captured call; the
+ *   one argument that must change from call to call, the `step` of jp_inject / jp_inject_phase, is offset on the device by this word:
+ *   a captured inject call increments it when it has run, so replay i injects with step + i, like the eager loop.  Set it back to 0
+ *   (synchronous) when going back to eager calls or capturing a new graph; jp_get_option reads it.
  * JP_OPT_LAST_INTERP (jp_get_option only): bit 0 / bit 1 = the last jp_particle2grid / jp_phase_ratios_center used the hand-off. */
 typedef enum { JP_OPT_P2G_MODE = 1, JP_OPT_MOVE_MODE = 2, JP_OPT_ADVECT_AFFINE = 3, JP_OPT_MOVE_POLICY = 4,
-               JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6, JP_OPT_MOVE_INTERP = 7, JP_OPT_LAST_INTERP = 8, JP_OPT_PROFILE = 9 } jp_option;
+               JP_OPT_ADVECT_CLASSIFY = 5, JP_OPT_LAST_CLASSIFY = 6, JP_OPT_MOVE_INTERP = 7, JP_OPT_LAST_INTERP = 8, JP_OPT_PROFILE = 9, JP_OPT_GRAPH_STEP_OFFSET = 10 } jp_option;
 typedef enum { JP_MOVE_POLICY_REFERENCE = 0, JP_MOVE_POLICY_COMPACT = 1, JP_MOVE_POLICY_DENSE = 2 } jp_move_policy;
 typedef enum { JP_MOVE_AUTO = 0, JP_MOVE_DIRECT = 1 } jp_move_mode;
 typedef enum { JP_P2G_EXACT = 0, JP_P2G_TWOPASS = 1, JP_P2G_TWOPASS_FASTW = 2 } jp_p2g_mode;

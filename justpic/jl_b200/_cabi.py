@@ -28,6 +28,7 @@ JP_OPT_LAST_CLASSIFY = 6
 JP_OPT_MOVE_INTERP = 7
 JP_OPT_LAST_INTERP = 8
 JP_OPT_PROFILE = 9
+JP_OPT_GRAPH_STEP_OFFSET = 10
 JP_F64, JP_F32, JP_BOOL = 0, 1, 2
 JP_LAYOUT_TO_HOST, JP_LAYOUT_TO_DEVICE = 0, 1
 JP_MOVE_POLICY_REFERENCE, JP_MOVE_POLICY_COMPACT, JP_MOVE_POLICY_DENSE = 0, 1, 2

@@ -46,6 +46,7 @@ __all__ = [
     "update_phase_ratios", "set_synchronous",
     "Array", "CuArray", "HostParticles", "HostPhaseRatios", "last_move_classify",
     "move_interp_handoff", "last_interp_handoff", "invalidate_handoffs", "profile_move", "read_move_profile",
+    "capture_step", "graph_step_offset",
 ]
 
 
@@ -478,6 +479,34 @@ def last_interp_handoff(particles: Particles) -> Tuple[bool, bool]:
     v = C.c_int32(0)
     _cabi.check(_cabi.load().jp_get_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_LAST_INTERP, C.byref(v)), "jp_get_option")
     return bool(v.value & 1), bool(v.value & 2)
+
+
+def graph_step_offset(particles: Particles, value: Optional[int] = None) -> int:
+    """JP_OPT_GRAPH_STEP_OFFSET: the device word a captured ``inject_particles`` advances on every replay (replay i injects with
+    ``step + i``).  ``value`` sets it (0 when going back to eager calls or capturing anew); returns the current value."""
+    with torch.cuda.device(particles.device):
+        if value is not None:
+            _cabi.check(_cabi.load().jp_set_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_GRAPH_STEP_OFFSET, int(value)), "jp_set_option")
+        v = C.c_int32(0)
+        _cabi.check(_cabi.load().jp_get_option(C.c_void_p(particles._ctx), _cabi.JP_OPT_GRAPH_STEP_OFFSET, C.byref(v)), "jp_get_option")
+    return int(v.value)
+
+
+def capture_step(particles: Particles, step_fn, warmup: int = 1) -> "torch.cuda.CUDAGraph":
+    """Capture one call of ``step_fn()`` -- any sequence of this module's calls on ``particles`` with fixed tensors and scalars, e.g.
+    advection + move_particles + inject_particles + particle2grid -- into a CUDA graph; ``graph.replay()`` then runs the step with
+    one launch (what a launch-bound small grid wants; include/justpic_c.h, JP_OPT_GRAPH_STEP_OFFSET).  ``step_fn`` runs ``warmup``
+    times eagerly first (that sizes every workspace; the library refuses to allocate while capturing).  Replay i of the graph is
+    what the (warmup + 1 + i)-th eager call would have been: the arguments are frozen, tensors are read where they live (write new
+    velocities into the same tensors), and ``inject_particles``' step counter advances on the device."""
+    for _ in range(max(1, int(warmup))):
+        step_fn()
+    torch.cuda.synchronize(particles.device)
+    graph_step_offset(particles, 0)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.device(particles.device), torch.cuda.graph(g):
+        step_fn()
+    return g
 
 
 def profile_move(particles: Particles, enable: bool = True) -> None:

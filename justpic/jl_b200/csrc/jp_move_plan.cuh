@@ -12,8 +12,9 @@
 //     bisects back into its own cell or fails isincell in its destination (on a
 //     face / in the fl(x+dx) ulp gap) or a displacement of more than one cell --
 //     raises a flag and the whole call takes the direct sweep kernels
-//     (k_move_sweep), which handle every case.
-//  B. k_move_plan x 3^N (ordered, same colour order as the reference; touches
+//     (k_move_sweep_all), which handle every case.
+//  B. k_move_plan_all: the 3^N ordered colours (same order as the reference) in one cooperative launch (k_move_plan x 3^N
+//     when a colour is larger than what is co-resident); touches
 //     8-byte words only): literal slot logic -- vacate in slot order, first free
 //     slot >= cursor, cursor shared across destinations, drop when full -- on the
 //     occupancy words; the slot given to each leaver is recorded (7 bits each).
@@ -31,6 +32,7 @@
 // bit-identical to the direct sweeps by construction.
 #pragma once
 #include "jp_core.h"
+#include <cooperative_groups.h>
 
 // JP_CODE_DELETE / JP_CLS_STAY / JP_CLS_CPLX and jp_classify_particle live in jp_core.h
 
@@ -141,11 +143,8 @@ __global__ void __launch_bounds__(256) k_move_prevacate(int64_t C, MovePlanWs ws
 // Literal slot logic of move_kernel! (src/Particles/move_safe.jl:72-125) on the occupancy
 // words; the slot given to the k-th leaver goes to res (one byte: slot | placed << 6).
 template <int N>
-__global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
-                                                   long long *stats, int policy, const unsigned int *__restrict__ skip_flag) {
-    if (*skip_flag) return;                                   // the call takes the direct sweeps (decided on the device)
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ncol) return;
+__device__ __forceinline__ void jp_move_plan_cell(const JpGrid &g, const MovePlanWs &ws, int ox, int oy, int oz, int ncx, int ncy, int64_t t,
+                                                  long long *stats, int policy) {
     int ci[3];
     ci[0] = 3 * (int)(t % ncx) + ox;
     ci[1] = 3 * (int)((t / ncx) % ncy) + oy;
@@ -185,6 +184,35 @@ __global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int 
     ws.res[(int64_t)((k - 1) >> 3) * g.C + c] = resw;
     if (n_dropped) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)n_dropped);
     if (n_deleted) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)n_deleted);
+}
+
+// One colour per launch: grids whose colours are larger than what is co-resident (a grid-stride loop would serialise the dependent
+// loads of two cells per thread: 1.43 -> 1.93 ms at 256^3).
+template <int N>
+__global__ void __launch_bounds__(256) k_move_plan(JpGrid g, MovePlanWs ws, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
+                                                   long long *stats, int policy, const unsigned int *__restrict__ skip_flag) {
+    if (*skip_flag) return;                                   // the call takes the direct sweeps (decided on the device)
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ncol) jp_move_plan_cell<N>(g, ws, ox, oy, oz, ncx, ncy, t, stats, policy);
+}
+
+// All 3^N colours in ONE cooperative launch (grid-wide barrier between colours, grid-stride within a colour) instead of 3^N launches:
+// on a small grid a colour is a few microseconds of work behind a launch, and on any grid the 3^N - 1 launch gaps go away.
+// The flag is not written while this kernel runs, so the early return is taken by every thread or by none.
+template <int N>
+__global__ void __launch_bounds__(256) k_move_plan_all(JpGrid g, MovePlanWs ws, int ncx, int ncy, int64_t ncol,
+                                                       long long *stats, int policy, const unsigned int *__restrict__ skip_flag) {
+    if (*skip_flag) return;                                   // the call takes the direct sweeps (decided on the device)
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool first = true;
+    for (int ox = 0; ox < 3; ox++)
+        for (int oy = 0; oy < 3; oy++)
+            for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++) {
+                if (!first) grid.sync();
+                first = false;
+                for (int64_t t = tid; t < ncol; t += nthr) jp_move_plan_cell<N>(g, ws, ox, oy, oz, ncx, ncy, t, stats, policy);
+            }
 }
 
 // ---- C. arrival mask + count per cell: every slot occupied at the end that is not a

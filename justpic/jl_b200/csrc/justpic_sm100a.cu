@@ -78,6 +78,8 @@ struct jp_ctx {
     int hint_ndirty; int hint_dirty[8][2];   // (dim, plane) rewritten since the hand-off
     int last_classify;       // 0: coordinates (k_move_classify3), 1: hand-off bytes (diagnostics)
     int adv_split;           // jp_advect_region: the shell part has run, the interior part is still to come
+    int coop_plan_max, coop_sweep_max;   // co-resident blocks of the two cooperative move kernels (lazy)
+    int capturing;           // the stream of the current call is being captured into a CUDA graph (set by PREP): no allocation, no event query, no host read
     int bucketed;            // every live particle lies strictly inside its storage cell (set by move / init / inject / clean, cleared by advect, halo unpack, foreign writes)
     int mp_ready;            // every buffer of the plan workspace is allocated
     void *last_stream;       // stream of the last jp_move (jp_last_move_path reads the device flag on it)
@@ -358,19 +360,27 @@ __device__ __forceinline__ void jp_move_sweep_cell(const JpGrid &g, Ptr3 co, uin
     }
 }
 
-// The launch: one warp per source cell of the colour, grid-stride over the cells with a capped grid -- in JP_MOVE_AUTO these 3^N
-// launches sit behind the planned path and return at once unless it declined (device-side flag); a full-size grid of ~80 000
-// blocks costs ~40 us just to start and retire, 27 times per call.
+// The launch: one warp per source cell, all 3^N colours in ONE cooperative launch (grid-wide barrier between colours, grid-stride
+// within a colour).  In JP_MOVE_AUTO it sits behind the planned path and returns at once unless that declined (device-side flag;
+// run_flag is not written while the kernel runs, so every thread takes the early return or none does).
 template <int N>
-__global__ void __launch_bounds__(256) k_move_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ, uint64_t *leave,
-                                                    int ox, int oy, int oz, int ncx, int ncy, int64_t ncol, long long *stats, int compact,
-                                                    const unsigned int *__restrict__ run_flag) {
+__global__ void __launch_bounds__(256) k_move_sweep_all(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ, uint64_t *leave,
+                                                        int ncx, int ncy, int64_t ncol, long long *stats, int compact,
+                                                        const unsigned int *__restrict__ run_flag) {
     if (run_flag && !*run_flag) return;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ncol; t += nwarps) {     // warp-uniform
-        jp_move_sweep_cell<N>(g, co, index, args, occ, leave, ox, oy, oz, ncx, ncy, t, stats, compact);
-        __syncwarp();
-    }
+    bool first = true;
+    for (int ox = 0; ox < 3; ox++)
+        for (int oy = 0; oy < 3; oy++)
+            for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++) {
+                if (!first) grid.sync();
+                first = false;
+                for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < ncol; t += nwarps) {     // warp-uniform
+                    jp_move_sweep_cell<N>(g, co, index, args, occ, leave, ox, oy, oz, ncx, ncy, t, stats, compact);
+                    __syncwarp();
+                }
+            }
 }
 
 // force_injection! (src/Particles/forced_injection.jl:32-79): thread = cell; entry ip of p_new goes to slot ip if it is free
@@ -521,16 +531,22 @@ __device__ __forceinline__ double jp_inject_field(const JpGrid &g, const double 
     return tmp > hi ? hi : (tmp < lo ? lo : tmp);
 }
 
+// inject_particles! keys its random stream by (seed, step, cell, slot) with `step` an argument of the call.  A call captured into a
+// CUDA graph would replay the same `step` for ever; so every inject kernel adds a device word (stats[7], 0 outside graphs), and a
+// captured jp_inject / jp_inject_phase ends with k_step_advance: replay i of the graph injects with step + i, exactly what the
+// eager loop that passes step, step + 1, ... does.  JP_OPT_GRAPH_STEP_OFFSET reads / resets the word.
+__host__ __device__ inline unsigned int *jp_step_offset(long long *stats) { return reinterpret_cast<unsigned int *>(stats + 7); }
+__global__ void k_step_advance(long long *stats) { *jp_step_offset(stats) += 1u; }
+
 #ifndef JP_MINB_INJECT
 #define JP_MINB_INJECT 2
 #endif
 template <int N, bool PHASE>
-__global__ void __launch_bounds__(256, JP_MINB_INJECT) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ,
-                                                      uint8_t *inbox, const int *__restrict__ list, const unsigned int *__restrict__ count,
-                                                      int min_xcell, uint64_t seed, uint32_t step, long long *stats, InjPhase ph) {
+__device__ __forceinline__ void jp_inject_sweep_colour(const JpGrid &g, const Ptr3 &co, uint8_t *index, const JpArgs &args, uint64_t *occ,
+                                                       uint8_t *inbox, const int *__restrict__ list, const unsigned n,
+                                                       int min_xcell, uint64_t seed, uint32_t step, long long *stats, const InjPhase &ph) {
     const int lane = threadIdx.x & 31;
     const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    const unsigned n = *count;
     const int S = g.S, NQ = N == 2 ? 4 : 8;
     const int min_xq = (min_xcell + NQ - 1) / NQ;
     const uint64_t smask = S == 64 ? ~0ull : ((1ull << S) - 1);
@@ -701,6 +717,16 @@ __global__ void __launch_bounds__(256, JP_MINB_INJECT) k_inject_sweep(JpGrid g, 
     }
 }
 
+// One colour per launch (work lists built by k_inject_classify): a persistent grid of warps walks the list.  (All 2^N colours in one
+// cooperative launch with grid-wide barriers was measured and dropped: 0.097 -> 0.101 ms at 2-D 256^2, 1.54 -> 1.58 ms at 128^3.)
+template <int N, bool PHASE>
+__global__ void __launch_bounds__(256, JP_MINB_INJECT) k_inject_sweep(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, uint64_t *occ,
+                                                      uint8_t *inbox, const int *__restrict__ list, const unsigned int *__restrict__ count,
+                                                      int min_xcell, uint64_t seed, uint32_t step, long long *stats, InjPhase ph) {
+    step += *jp_step_offset(stats);                         // 0, or the number of replays of the CUDA graph this launch is part of
+    jp_inject_sweep_colour<N, PHASE>(g, co, index, args, occ, inbox, list, *count, min_xcell, seed, step, stats, ph);
+}
+
 // ---- max_xcell > JP_MAX_SLOTS ("wide" cells, e.g. the reference's tests with max_xcell = 80 / 150): move_particles! and
 // inject_particles!(_phase!) as literal per-cell kernels on the index bytes (thread = cell of the colour being swept).
 // Same results as the occupancy-word kernels (the GPU parity tests cover both); not tuned -- the word kernels
@@ -785,6 +811,7 @@ __device__ int jp_inject_phase_cell(const JpGrid &g, double *const *coords, uint
 template <int N, bool PHASE>
 __global__ void __launch_bounds__(128) k_inject_wide(JpGrid g, Ptr3 co, uint8_t *index, JpArgs args, int ox, int oy, int oz, int ncx, int ncy, int64_t ncol,
                                                      int min_xcell, uint64_t seed, uint32_t step, long long *stats, InjPhase ph) {
+    step += *jp_step_offset(stats);                         // 0, or the number of replays of the CUDA graph this launch is part of
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncol) return;
     int ci[3];
@@ -1222,12 +1249,25 @@ static int pack_args(double *const *args, int nargs, JpArgs &out, const char *wh
     for (int a = nargs; a < JP_MAX_ARGS; a++) out.a[a] = nullptr;
     return JP_OK;
 }
+// CUDA graphs: every entry point may be called on a stream that is being captured (cudaStreamBeginCapture / torch.cuda.graph).
+// Nothing on the hot path reads the device back; what cannot be captured -- growing a workspace -- is refused with a message that
+// says what to do (run the step once eagerly first), and jp_move skips its asynchronous staging-size feedback.
+static inline int jp_stream_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return cs == cudaStreamCaptureStatusActive;
+}
+#define JP_NO_ALLOC_IN_CAPTURE(what)                                                                                       \
+    if (ctx->capturing)                                                                                                    \
+        return jp_fail(JP_ERR_INVALID, "%s would have to be allocated while the stream is being captured into a CUDA graph: run the same calls once eagerly before capturing", what)
+
 #define PREP(who)                                                    \
     int rc__ = check_particles(ctx, p, who);                         \
     if (rc__) return rc__;                                           \
     JP_CUDA(cudaSetDevice(ctx->device));                             \
     const JpGrid &g = ctx->g;                                        \
     cudaStream_t st = (cudaStream_t)stream;                          \
+    ctx->capturing = jp_stream_capturing(st);                        \
     Ptr3 co = {{p->coords[0], p->coords[1], p->coords[2]}};          \
     CPtr3 cco = {{p->coords[0], p->coords[1], p->coords[2]}};        \
     const dim3 blk(JP_BX, JP_BY, 1);                                 \
@@ -1486,6 +1526,7 @@ static void move_plan_free(jp_ctx *ctx) {
 static int move_plan_alloc(jp_ctx *ctx) {
     const JpGrid &g = ctx->g;
     if (ctx->mp_ready) return JP_OK;
+    JP_NO_ALLOC_IN_CAPTURE("move_particles!: the plan workspace");
     cudaError_t e = cudaMalloc(&ctx->mp.code, sizeof(uint64_t) * (size_t)((g.S + 7) / 8) * g.C);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->mp.res, sizeof(uint64_t) * (size_t)((g.S + 7) / 8) * g.C);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->mp.occ0, sizeof(uint64_t) * g.C);
@@ -1513,6 +1554,7 @@ static int move_plan_alloc(jp_ctx *ctx) {
 
 static int stage_reserve(jp_ctx *ctx, size_t elems) {
     if (elems <= ctx->stage_elems) return JP_OK;
+    JP_NO_ALLOC_IN_CAPTURE("move_particles!: the staging buffer");
     if (ctx->stage) JP_CUDA(cudaFree(ctx->stage));
     ctx->stage = nullptr; ctx->stage_elems = 0;
     JP_CUDA(cudaMalloc(&ctx->stage, elems * sizeof(double)));
@@ -1522,7 +1564,10 @@ static int stage_reserve(jp_ctx *ctx, size_t elems) {
 
 static int p2g_ws_reserve(jp_ctx *ctx) {
     const int NQ = ctx->g.ndim == 2 ? 4 : 8;
-    if (!ctx->p2g_ws) JP_CUDA(cudaMalloc(&ctx->p2g_ws, sizeof(double) * 2 * NQ * ctx->g.C));
+    if (!ctx->p2g_ws) {
+        JP_NO_ALLOC_IN_CAPTURE("particle2grid!: the per-cell partial sums");
+        JP_CUDA(cudaMalloc(&ctx->p2g_ws, sizeof(double) * 2 * NQ * ctx->g.C));
+    }
     return JP_OK;
 }
 
@@ -1560,6 +1605,20 @@ static void launch_scatter_interp(const JpGrid &g, dim3 grd, dim3 blk, cudaStrea
 // direct sweeps instead (a particle on a cell face, a move of more than one cell, a staging buffer that turned out too
 // small) is decided ON THE DEVICE -- every kernel of this path returns at once when the flag is set, and the direct-sweep
 // kernels enqueued behind it (jp_move) run only then.
+// co-resident blocks of a cooperative kernel on this device (blocks of 256 threads, no dynamic shared memory)
+template <typename K>
+static int coop_max_blocks(jp_ctx *ctx, K kernel, int *cache) {
+    if (*cache > 0) return JP_OK;
+    int per_sm = 0, sms = 0, coop = 0;
+    JP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (!coop) return jp_fail(JP_ERR_UNSUPPORTED, "this device does not support cooperative launches");
+    JP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0));
+    JP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (per_sm < 1) return jp_fail(JP_ERR_CUDA, "cooperative kernel does not fit an SM");
+    *cache = per_sm * sms;
+    return JP_OK;
+}
+
 template <int N>
 static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cudaStream_t st) {
     const JpGrid &g = ctx->g;
@@ -1570,7 +1629,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     CPtr3 cco = {{p->coords[0], p->coords[1], p->coords[2]}};
     // JP_OPT_PROFILE: events between the stages (no synchronisation; jp_profile_read turns them into milliseconds later)
     cudaEvent_t *pev = nullptr;
-    if (ctx->prof_opt) {
+    if (ctx->prof_opt && !ctx->capturing) {
         if (!ctx->prof_ev) {
             ctx->prof_ev = (cudaEvent_t *)calloc(JP_PROF_RING * JP_PROF_MARKS, sizeof(cudaEvent_t));
             for (int i = 0; i < JP_PROF_RING * JP_PROF_MARKS; i++) JP_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
@@ -1607,7 +1666,9 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     const size_t AS = (size_t)((arrs.n + 3) & ~3);              // array-of-structs staging, stride padded to 4 doubles
     // staging capacity: the arrival count of the previous call comes back asynchronously (pinned word + event); grow when it is
     // known and calls for it.  Never blocks except to reallocate.
-    if (ctx->m_pending && cudaEventQuery(ctx->m_event) == cudaSuccess) {
+    // (While the stream is captured into a CUDA graph neither the query nor the read-back below happen: the replays run with the
+    // buffer the eager calls before the capture sized; one that turns out too small sends that replay to the direct sweeps.)
+    if (!ctx->capturing && ctx->m_pending && cudaEventQuery(ctx->m_event) == cudaSuccess) {
         ctx->m_pending = 0;
         const size_t lastM = ctx->h_pinned[1];
         if ((lastM + lastM / 4 + 2048) * AS > ctx->stage_elems) {           // keep >= 25 % + 2048 rows of head room over the last count ...
@@ -1620,14 +1681,25 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
     const unsigned nblk = (unsigned)((ncol + 255) / 256);
     const unsigned cblk = (unsigned)((g.C + 255) / 256);
     if (ctx->move_policy == JP_MOVE_POLICY_DENSE) k_move_prevacate<<<cblk, 256, 0, st>>>(g.C, ctx->mp, flag);
-    for (int ox = 0; ox < 3; ox++)
-        for (int oy = 0; oy < 3; oy++)
-            for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
-                k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy, flag);
+    rc = coop_max_blocks(ctx, k_move_plan_all<N>, &ctx->coop_plan_max);
+    if (rc) return rc;
+    if (nblk > (unsigned)ctx->coop_plan_max) {               // a colour does not fit the device at once: one launch per colour
+        for (int ox = 0; ox < 3; ox++)
+            for (int oy = 0; oy < 3; oy++)
+                for (int oz = 0; oz < (N == 3 ? 3 : 1); oz++)
+                    k_move_plan<N><<<nblk, 256, 0, st>>>(g, ctx->mp, ox, oy, oz, ncx, ncy, ncol, ctx->stats, ctx->move_policy, flag);
+    } else {                                                 // the 3^N ordered colours in one cooperative launch
+        JpGrid gk = g; MovePlanWs wk = ctx->mp; int kx = ncx, ky = ncy, pol = ctx->move_policy; int64_t kn = ncol; long long *ks = ctx->stats;
+        const unsigned int *kf = flag;
+        void *kargs[] = {&gk, &wk, &kx, &ky, &kn, &ks, &pol, &kf};
+        JP_CUDA(cudaLaunchCooperativeKernel((const void *)k_move_plan_all<N>, dim3(nblk), dim3(256), kargs, 0, st));
+    }
     mark();
     k_move_finalize<N><<<cblk, 256, 0, st>>>(g, ctx->mp, flag);
     JP_CHECK_LAUNCH();
     JP_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp, ctx->cub_tmp_bytes, ctx->mp.cnt, ctx->mp.off, (int)(g.C + 1), st));
+    if (!ctx->m_probed && ctx->capturing)
+        return jp_fail(JP_ERR_INVALID, "move_particles!: the first call on a context sizes the staging buffer with a read-back: run the step once eagerly before capturing it into a CUDA graph");
     if (!ctx->m_probed) {
         // very first planned call on this context: learn the arrival count now (the only blocking read-back there is)
         ctx->m_probed = 1;
@@ -1638,7 +1710,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
         if (rc) return rc;
     }
     k_move_after_scan<<<1, 1, 0, st>>>(ctx->stats, ctx->mp.off + g.C, (uint64_t)(ctx->stage_elems / AS), flag, flag + 1);
-    if (!ctx->m_pending) {
+    if (!ctx->m_pending && !ctx->capturing) {
         JP_CUDA(cudaMemcpyAsync(ctx->h_pinned + 1, flag + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         JP_CUDA(cudaEventRecord(ctx->m_event, st));
         ctx->m_pending = 1;
@@ -1662,6 +1734,7 @@ static int move_planned(jp_ctx *ctx, const jp_particles *p, const JpArgs &a, cud
             mi.K = ctx->mi_K;
             const size_t need = (size_t)mi.K * g.C;
             if (need > ctx->mi_rc_elems) {
+                JP_NO_ALLOC_IN_CAPTURE("move -> interpolation hand-off: the centre-ratio workspace");
                 if (ctx->mi_rc) JP_CUDA(cudaFree(ctx->mi_rc));
                 ctx->mi_rc = nullptr; ctx->mi_rc_elems = 0;
                 JP_CUDA(cudaMalloc(&ctx->mi_rc, need * sizeof(double)));
@@ -1744,14 +1817,17 @@ extern "C" int jp_move(jp_ctx *ctx, const jp_particles *p, double *const *args, 
     JP_CHECK_LAUNCH();
     const int ncx = (g.n[0] + 2) / 3, ncy = (g.n[1] + 2) / 3, ncz = g.ndim == 3 ? (g.n[2] + 2) / 3 : 1;
     const int64_t ncol = (int64_t)ncx * ncy * ncz;          // source cells per colour (upper bound)
-    const int64_t want_blk = (ncol + 7) / 8;                 // one warp per source cell, 8 warps per block, grid-stride beyond 148 x 16 blocks
-    const unsigned nblk = (unsigned)(want_blk < 148 * 16 ? want_blk : 148 * 16);
-    for (int ox = 0; ox < 3; ox++)
-        for (int oy = 0; oy < 3; oy++)
-            for (int oz = 0; oz < (g.ndim == 3 ? 3 : 1); oz++) {
-                if (g.ndim == 2) k_move_sweep<2><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, sweep_policy, run_flag);
-                else             k_move_sweep<3><<<nblk, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->leave, ox, oy, oz, ncx, ncy, ncol, ctx->stats, sweep_policy, run_flag);
-            }
+    const int64_t want_blk = (ncol + 7) / 8;                 // one warp per source cell, 8 warps per block, grid-stride beyond what is co-resident
+    {
+        JpGrid gk = g; Ptr3 kco = co; uint8_t *kidx = p->index; JpArgs ka = a; uint64_t *kocc = ctx->occ, *klv = ctx->leave;
+        int kx = ncx, ky = ncy, pol = sweep_policy; int64_t kn = ncol; long long *ks = ctx->stats; const unsigned int *kf = run_flag;
+        void *kargs[] = {&gk, &kco, &kidx, &ka, &kocc, &klv, &kx, &ky, &kn, &ks, &pol, &kf};
+        if (g.ndim == 2) rc = coop_max_blocks(ctx, k_move_sweep_all<2>, &ctx->coop_sweep_max);
+        else             rc = coop_max_blocks(ctx, k_move_sweep_all<3>, &ctx->coop_sweep_max);
+        if (rc) return rc;
+        const unsigned nblk = (unsigned)(want_blk < ctx->coop_sweep_max ? want_blk : ctx->coop_sweep_max);
+        JP_CUDA(cudaLaunchCooperativeKernel(g.ndim == 2 ? (const void *)k_move_sweep_all<2> : (const void *)k_move_sweep_all<3>, dim3(nblk), dim3(256), kargs, 0, st));
+    }
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1796,6 +1872,15 @@ static void launch_inject_wide(const JpGrid &g, cudaStream_t st, Ptr3 co, uint8_
             }
 }
 
+template <int N, bool PHASE>
+static int launch_inject_sweeps(jp_ctx *ctx, cudaStream_t st, Ptr3 co, uint8_t *index, const JpArgs &a, int min_xcell, uint64_t seed, uint32_t step,
+                                const InjPhase &ph) {
+    for (int col = 0; col < (N == 3 ? 8 : 4); col++)
+        k_inject_sweep<N, PHASE><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(ctx->g, co, index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap,
+                                                                          ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
+    return JP_OK;
+}
+
 extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args, int32_t nargs, int32_t min_xcell, uint64_t seed, uint32_t step, void *stream) {
     PREP("jp_inject");
     handoffs_invalidate(ctx);
@@ -1809,6 +1894,7 @@ extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args
     if ((int64_t)g.C >= (1ll << 31)) return jp_fail(JP_ERR_UNSUPPORTED, "jp_inject: more than 2^31 cells");
     if (g.S > JP_MAX_SLOTS) {
         launch_inject_wide<false>(g, st, co, p->index, a, min_xcell, seed, step, ctx->stats, InjPhase());
+        if (ctx->capturing) k_step_advance<<<1, 1, 0, st>>>(ctx->stats);
         JP_CHECK_LAUNCH();
         return JP_OK;
     }
@@ -1817,11 +1903,10 @@ extern "C" int jp_inject(jp_ctx *ctx, const jp_particles *p, double *const *args
     else             k_inject_classify<3, false><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
     JP_CHECK_LAUNCH();
     // colour order of the reference: offset_i outermost (src/Particles/injection.jl:30-49)
-    const int ncol = g.ndim == 3 ? 8 : 4;
-    for (int col = 0; col < ncol; col++) {
-        if (g.ndim == 2) k_inject_sweep<2, false><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, InjPhase());
-        else             k_inject_sweep<3, false><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, InjPhase());
-    }
+    rc = g.ndim == 2 ? launch_inject_sweeps<2, false>(ctx, st, co, p->index, a, min_xcell, seed, step, InjPhase())
+                     : launch_inject_sweeps<3, false>(ctx, st, co, p->index, a, min_xcell, seed, step, InjPhase());
+    if (rc) return rc;
+    if (ctx->capturing) k_step_advance<<<1, 1, 0, st>>>(ctx->stats);
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1849,6 +1934,7 @@ extern "C" int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phase
     JP_CUDA(cudaMemsetAsync(ctx->stats + 3, 0, sizeof(long long), st));
     if (g.S > JP_MAX_SLOTS) {
         launch_inject_wide<true>(g, st, co, p->index, a, min_xcell, seed, step, ctx->stats, ph);
+        if (ctx->capturing) k_step_advance<<<1, 1, 0, st>>>(ctx->stats);
         JP_CHECK_LAUNCH();
         return JP_OK;
     }
@@ -1856,11 +1942,10 @@ extern "C" int jp_inject_phase(jp_ctx *ctx, const jp_particles *p, double *phase
     if (g.ndim == 2) k_inject_classify<2, true><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
     else             k_inject_classify<3, true><<<grd, blk, 0, st>>>(g, cco, p->index, min_xq, ctx->occ, ctx->inbox, ctx->inj_list, ctx->inj_count, ctx->inj_cap);
     JP_CHECK_LAUNCH();
-    const int ncol = g.ndim == 3 ? 8 : 4;
-    for (int col = 0; col < ncol; col++) {
-        if (g.ndim == 2) k_inject_sweep<2, true><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
-        else             k_inject_sweep<3, true><<<148 * JP_MINB_INJECT * 2, 256, 0, st>>>(g, co, p->index, a, ctx->occ, ctx->inbox, ctx->inj_list + (int64_t)col * ctx->inj_cap, ctx->inj_count + col, min_xcell, seed, step, ctx->stats, ph);
-    }
+    rc = g.ndim == 2 ? launch_inject_sweeps<2, true>(ctx, st, co, p->index, a, min_xcell, seed, step, ph)
+                     : launch_inject_sweeps<3, true>(ctx, st, co, p->index, a, min_xcell, seed, step, ph);
+    if (rc) return rc;
+    if (ctx->capturing) k_step_advance<<<1, 1, 0, st>>>(ctx->stats);
     JP_CHECK_LAUNCH();
     return JP_OK;
 }
@@ -1993,6 +2078,12 @@ extern "C" int jp_set_option(jp_ctx *ctx, int32_t option, int32_t value) {
     if (option == JP_OPT_ADVECT_AFFINE && (value == 0 || value == 1)) { ctx->g.affine = value ? ctx->affine_detected : 0; return JP_OK; }
     if (option == JP_OPT_ADVECT_CLASSIFY && (value == 0 || value == 1)) { ctx->hint_opt = value; hint_invalidate(ctx); return JP_OK; }
     if (option == JP_OPT_MOVE_INTERP && (value == 0 || value == 1)) { ctx->mi_opt = value; mi_invalidate(ctx); return JP_OK; }
+    if (option == JP_OPT_GRAPH_STEP_OFFSET && value >= 0) {
+        const unsigned int v = (unsigned int)value;
+        JP_CUDA(cudaSetDevice(ctx->device));
+        JP_CUDA(cudaMemcpy(jp_step_offset(ctx->stats), &v, sizeof(v), cudaMemcpyHostToDevice));
+        return JP_OK;
+    }
     if (option == JP_OPT_PROFILE && (value == 0 || value == 1)) { ctx->prof_opt = value; ctx->prof_calls = 0; return JP_OK; }
     return jp_fail(JP_ERR_INVALID, "jp_set_option: unknown option/value");
 }
@@ -2020,6 +2111,13 @@ extern "C" int jp_get_option(const jp_ctx *ctx, int32_t option, int32_t *value) 
     if (option == JP_OPT_P2G_MODE) { *value = ctx->p2g_mode; return JP_OK; }
     if (option == JP_OPT_ADVECT_AFFINE) { *value = ctx->g.affine; return JP_OK; }
     if (option == JP_OPT_MOVE_POLICY) { *value = ctx->move_policy; return JP_OK; }
+    if (option == JP_OPT_GRAPH_STEP_OFFSET) {
+        unsigned int v = 0;
+        JP_CUDA(cudaSetDevice(ctx->device));
+        JP_CUDA(cudaMemcpy(&v, jp_step_offset(ctx->stats), sizeof(v), cudaMemcpyDeviceToHost));
+        *value = (int32_t)v;
+        return JP_OK;
+    }
     if (option == JP_OPT_ADVECT_CLASSIFY) { *value = ctx->hint_opt; return JP_OK; }
     if (option == JP_OPT_LAST_CLASSIFY) { *value = ctx->last_classify; return JP_OK; }
     if (option == JP_OPT_MOVE_INTERP) { *value = ctx->mi_opt; return JP_OK; }
@@ -2155,6 +2253,7 @@ static int update_phase_ratios_fused(jp_ctx *ctx, const jp_particles *p, const d
     const JpGrid &g = ctx->g;
     const size_t need = (size_t)P::NT * K * g.C;
     if (need > ctx->pr_ws_elems) {
+        JP_NO_ALLOC_IN_CAPTURE("update_phase_ratios!: the per-cell weight workspace");
         if (ctx->pr_ws) JP_CUDA(cudaFree(ctx->pr_ws));
         ctx->pr_ws = nullptr; ctx->pr_ws_elems = 0;
         JP_CUDA(cudaMalloc(&ctx->pr_ws, need * sizeof(double)));
