@@ -97,7 +97,10 @@ template <int N, bool UNIFORM, int H = 0> struct AdvSmem {
 // JP_ADV_STAGE1: the first interpolation of a particle (at its own position) skips the re-centring block when the library knows
 // that every particle lies strictly inside its storage cell (g.bucketed: the last call that touched the particles was
 // move_particles!, init, inject or clean -- not another advection!, a halo unpack or a foreign write); a particle that is not is
-// flagged and takes the literal routine (same result).  JP_ADV_NOVOTE: the later stages run the re-centring arithmetic unconditionally -- at CFL 0.5 nearly every warp holds
+// flagged and takes the literal routine (same result).  Read at run time the flag costs 0.29 ms at 256^3 (the re-centring code stays
+// in the loop: profiles/r02ad_ab_bucketed_flag.log), so the variants the time loops use -- trilinear, range grids -- exist twice:
+// BKT = true is launched when the flag is set and has the shortcut compiled in; all others test g.bucketed.
+// JP_ADV_NOVOTE: the later stages run the re-centring arithmetic unconditionally -- at CFL 0.5 nearly every warp holds
 // a lane whose stage position left its seed cell, so the vote only cost a divergent-branch frame.  Measured at 256^3 (r02l, all
 // bit-identical): 14.44 -> 13.44 (stage 1) -> 13.32 (no vote) -> 13.09 ms (2 CTAs / SM at <= 128 registers instead of 3 at 80).
 // Dropped: stencil loads as ld.shared.f64 on a 32-bit address held in one opaque register (the compiler re-derives the shared
@@ -118,7 +121,7 @@ template <int N, class T> struct AdvTileAcc {
         return tile[(i1 - 1 - c0x) + T::EX * ((j1 - 1 - c0y) + (N == 3 ? T::EY * (k1 - 1 - c0z) : 0))];
     }
 };
-template <int N, bool UNIFORM, int AFFINE, bool FIRST = false, int INTERP = 0>
+template <int N, bool UNIFORM, int AFFINE, bool FIRST = false, int INTERP = 0, bool BKT = false>
 __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *__restrict__ sm, const int *c0, const int *r0,
                                                 const double *gd0, const double *p, double *vout, unsigned amask) {
     using T = AdvTile<N, INTERP ? 1 : 0>;
@@ -143,9 +146,9 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
         else { a = xv[r]; b = xv[r + 1]; }
         const bool up = pd > b, dn = pd < a;
 #if JP_ADV_NOVOTE
-        if (!(JP_ADV_STAGE1 && FIRST && g.bucketed)) {   // later stages: nearly every warp holds a lane that left its seed cell -- no vote, no divergent branch
+        if (!(JP_ADV_STAGE1 && FIRST && (BKT || g.bucketed))) {   // later stages: nearly every warp holds a lane that left its seed cell -- no vote, no divergent branch
 #else
-        if (!(JP_ADV_STAGE1 && FIRST && g.bucketed) && __any_sync(amask, up || dn)) {          // warp-uniform: stage positions that left the seed cell
+        if (!(JP_ADV_STAGE1 && FIRST && (BKT || g.bucketed)) && __any_sync(amask, up || dn)) {          // warp-uniform: stage positions that left the seed cell
 #endif
             r += (up ? 1 : 0) - (dn ? 1 : 0);
             if (AFFINE) {
@@ -211,10 +214,10 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
     return !bad;
 }
 
-template <int N, bool UNIFORM, int AFFINE, bool FIRST = false, int INTERP = 0>
+template <int N, bool UNIFORM, int AFFINE, bool FIRST = false, int INTERP = 0, bool BKT = false>
 __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__restrict__ sm, const double *const *V, const int *c0,
                                            const int *r0, const double *gd0, const int *cell1, const double *p, double *vout, unsigned amask) {
-    if (adv_interp_tile<N, UNIFORM, AFFINE, FIRST, INTERP>(g, sm, c0, r0, gd0, p, vout, amask)) return;
+    if (adv_interp_tile<N, UNIFORM, AFFINE, FIRST, INTERP, BKT>(g, sm, c0, r0, gd0, p, vout, amask)) return;
     if (INTERP == 0) jp_interp_velocity_literal<N>(g, V, p, cell1, vout);
     else jp_interp_velocity_hi<N, INTERP>(g, V, p, cell1, vout);
 }
@@ -228,7 +231,7 @@ __device__ __forceinline__ void adv_interp(const JpGrid &g, const double *__rest
 // words of the move plan, in slot order, exactly as k_move_classify3 packs them; then the occupancy / leave words.
 // jp_move then starts at the plan kernels: no pass over the coordinates, no intermediate plane in HBM.
 #define ADV_HINT_ROW 72          // bytes per cell row: JP_MAX_SLOTS + 8 (18 words: 64-bit row loads of a half-warp hit 32 distinct banks)
-template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT, int INTERP = 0>
+template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT, int INTERP = 0, bool BKT = false>
 __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 768) / (AdvTile<N>::NW * 32)) k_advect_tile(JpGrid g, Ptr3 co, const uint8_t *__restrict__ index, CPtr3 V,
                                                                      double alpha, double dt,
                                                                      const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(AdvTile<N>::NW * 32, (UNIFORM ? JP_ADV_TPSM : 
                 double p0[3], k1[3], k2[3], qq[3], pn[3];
 #pragma unroll
                 for (int d = 0; d < N; d++) p0[d] = cur_p[d];
-                adv_interp<N, UNIFORM, AFFINE, true, INTERP>(g, sm, Vp, c0, r0, gd0, cell1, p0, k1, amask);
+                adv_interp<N, UNIFORM, AFFINE, true, INTERP, BKT>(g, sm, Vp, c0, r0, gd0, cell1, p0, k1, amask);
                 if (SCHEME == 0) {
                     const double cdt = 1.0 * dt;
 #pragma unroll

@@ -78,6 +78,7 @@ struct jp_ctx {
     int hint_ndirty; int hint_dirty[8][2];   // (dim, plane) rewritten since the hand-off
     int last_classify;       // 0: coordinates (k_move_classify3), 1: hand-off bytes (diagnostics)
     int adv_split;           // jp_advect_region: the shell part has run, the interior part is still to come
+    int adv_split_bucketed;  // ... and the bucketed state that call saw (a halo unpack between the two parts touches shell cells only)
     int coop_plan_max, coop_sweep_max;   // co-resident blocks of the two cooperative move kernels (lazy)
     int capturing;           // the stream of the current call is being captured into a CUDA graph (set by PREP): no allocation, no event query, no host read
     int bucketed;            // every live particle lies strictly inside its storage cell (set by move / init / inject / clean, cleared by advect, halo unpack, foreign writes)
@@ -1345,22 +1346,29 @@ static int build_advect_tma(const JpGrid &g, CPtr3 V, AdvTmaMaps &maps) {
 
 static int move_plan_alloc(jp_ctx *ctx);
 struct AdvHandoff { MovePlanWs ws; unsigned int *flag; };        // flag == nullptr: no hand-off
-template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT, int INTERP = 0>
-static cudaError_t launch_advect_tile_h(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, const AdvHandoff &ho) {
+template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT, int INTERP, bool BKT>
+static cudaError_t launch_advect_tile_k(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, const AdvHandoff &ho) {
     constexpr int H = INTERP ? 1 : 0;
     using T = AdvTile<N, H>;
     const size_t smem = AdvSmem<N, UNIFORM, H>::BYTES + (HINT ? (size_t)T::NW * 32 * ADV_HINT_ROW : 0);     // + the per-warp classification bytes
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT, INTERP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT, INTERP, BKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     AdvTmaMaps maps;
     const int tma_mask = build_advect_tma<N, H>(g, V, maps);
     const dim3 grd((g.n[0] + T::TX - 1) / T::TX, (g.n[1] + T::TY - 1) / T::TY, N == 3 ? (g.n[2] + T::TZ - 1) / T::TZ : 1);
-    k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT, INTERP><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask, ho.ws, ho.flag);
+    k_advect_tile<N, SCHEME, UNIFORM, AFFINE, HINT, INTERP, BKT><<<grd, T::NW * 32, smem, st>>>(g, co, index, V, alpha, dt, maps.m[0], maps.m[1], maps.m[2], tma_mask, ho.ws, ho.flag);
     return cudaSuccess;
+}
+template <int N, int SCHEME, bool UNIFORM, int AFFINE, bool HINT, int INTERP = 0>
+static cudaError_t launch_advect_tile_h(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, const AdvHandoff &ho) {
+    // the bucketed state compiled in for the variants of the time loops (trilinear, range grids); see jp_advect_tile.cuh
+    if constexpr (INTERP == 0 && UNIFORM)
+        if (g.bucketed) return launch_advect_tile_k<N, SCHEME, UNIFORM, AFFINE, HINT, INTERP, true>(g, st, co, index, V, alpha, dt, ho);
+    return launch_advect_tile_k<N, SCHEME, UNIFORM, AFFINE, HINT, INTERP, false>(g, st, co, index, V, alpha, dt, ho);
 }
 template <int N, int SCHEME, bool UNIFORM, int AFFINE>
 static cudaError_t launch_advect_tile(const JpGrid &g, cudaStream_t st, Ptr3 co, const uint8_t *index, CPtr3 V, double alpha, double dt, const AdvHandoff &ho) {
@@ -1428,7 +1436,7 @@ static int advect_impl(jp_ctx *ctx, const jp_particles *p, int32_t scheme, doubl
     for (int ch = 0; ch < jp_nchunks(g); ch++) {          // one launch unless max_xcell > 64
         SlotChunk k = jp_chunk(g, ch);
         k.g.region = tiled ? region : 0;
-        k.g.bucketed = ctx->bucketed;
+        k.g.bucketed = region == JP_REGION_INTERIOR ? ctx->adv_split_bucketed : ctx->bucketed;
         const Ptr3 kc = jp_shift(co, k.off);
         const uint8_t *ki = p->index + k.off;
         cudaError_t le;
@@ -1446,7 +1454,8 @@ static int advect_impl(jp_ctx *ctx, const jp_particles *p, int32_t scheme, doubl
     JP_CHECK_LAUNCH();
     const bool hint_void = ctx->adv_split == 2;
     ctx->adv_split = region == JP_REGION_SHELL;
-    if (region != JP_REGION_SHELL) ctx->bucketed = 0;             // (the interior launch of a split advection still sees the shell call's state)
+    if (region == JP_REGION_SHELL) ctx->adv_split_bucketed = ctx->bucketed;
+    else ctx->bucketed = 0;             // (the interior launch of a split advection still sees the shell call's state)
     if (hinted && region != JP_REGION_SHELL && !hint_void) {               // after a shell call the words are still incomplete
         ctx->hint_valid = 1;
         for (int d = 0; d < 3; d++) ctx->hint_key[d] = d < g.ndim ? (const void *)p->coords[d] : nullptr;
