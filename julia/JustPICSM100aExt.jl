@@ -77,8 +77,10 @@ jp(p::Particles{CUDABackend, N}) where {N} =
     Ref(JpParticles(pad3(map(cptr, p.coords), CuPtr{Float64}(0)), cptr(p.index)))
 stream() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
 argptrs(args) = CuPtr{Float64}[cptr(a) for a in args]
-# the reference's launch! synchronises after every kernel (src/launch.jl:60-69)
-done() = CUDA.synchronize()
+# the reference's launch! synchronises after every kernel (src/launch.jl:60-69); switch off for stream-ordered time loops and
+# while capturing a CUDA graph (every library call is asynchronous on the task's stream)
+const SYNC_EACH_CALL = Ref(true)
+done() = SYNC_EACH_CALL[] && CUDA.synchronize()
 
 scheme(::Euler) = (Int32(0), 0.0)
 scheme(m::RungeKutta2) = (Int32(1), Float64(m.α))
@@ -392,6 +394,16 @@ end
 # opt-in deviations keep the same particles in the same cells but pack them into lower slots (include/justpic_c.h); JUSTPIC_MOVE_POLICY=0|1|2
 set_move_policy!(p::Particles{CUDABackend}, policy::Integer = parse(Int32, get(ENV, "JUSTPIC_MOVE_POLICY", "0"))) =
     check(ccall((:jp_set_option, libjustpic), Cint, (Ptr{Cvoid}, Int32, Int32), context(p), Int32(4), Int32(policy)), "jp_set_option")
+
+# CUDA graphs (JP_OPT_GRAPH_STEP_OFFSET = 10): once a time step has run eagerly (workspaces sized), the same calls can be captured --
+#     graph = CUDA.capture() do; advection!(...); move_particles!(...); inject_particles!(...); particle2grid!(...); end
+#     exec = CUDA.instantiate(graph); CUDA.launch(exec)            # one launch per step
+# -- provided the shim's per-call synchronisation is off while capturing (SYNC_EACH_CALL[] = false).  The library notices the capture
+# (cudaStreamIsCapturing), skips move_particles!' asynchronous size feedback and refuses allocations with a message.  Arguments are
+# frozen; inject_particles!' step counter advances on the device: replay i injects with step + i.  Reset the offset before going back
+# to eager calls.
+graph_step_offset!(p::Particles{CUDABackend}, value::Integer = 0) =
+    check(ccall((:jp_set_option, libjustpic), Cint, (Ptr{Cvoid}, Int32, Int32), context(p), Int32(10), Int32(value)), "jp_set_option")
 
 # after a write to coords / index / a registered field that did not go through this extension
 invalidate_handoffs!(p::Particles{CUDABackend}) = check(ccall((:jp_invalidate_handoffs, libjustpic), Cint, (Ptr{Cvoid},), context(p)), "jp_invalidate_handoffs")
