@@ -290,14 +290,14 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
             for (int a = 0; a < JP_MV_A; a++) {
                 v[u][a] = NAN;
                 if (a < arrs.n) {
-                    if (ar) v[u][a] = sp[u][a];
-                    else if (keep && a < NG) v[u][a] = (a == 0 ? a0p : a == 1 ? a1p : a == 2 ? a2p : a3p)[e];
+                    if (ar) v[u][a] = JP_LDCS(sp[u] + a);
+                    else if (keep && a < NG) v[u][a] = JP_LDCS((a == 0 ? a0p : a == 1 ? a1p : a == 2 ? a2p : a3p) + e);
                 }
             }
             phv[u] = NAN;
             if (HAS_PH && N == 3) {
-                if (ar) phv[u] = sp[u][IP];
-                else if (keep) phv[u] = arrs.a[IP][e];
+                if (ar) phv[u] = JP_LDCS(sp[u] + IP);
+                else if (keep) phv[u] = JP_LDCS(arrs.a[IP] + e);
             }
         }
         // ---- stores of the changed slots
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
         for (int a0 = (HAS_PH && N == 3) ? JP_MV_A + 1 : JP_MV_A; a0 < arrs.n; a0++) {
             double o[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) o[u] = (((chb & arb) >> u) & 1u) ? sp[u][a0] : NAN;
+            for (int u = 0; u < U; u++) o[u] = (((chb & arb) >> u) & 1u) ? JP_LDCS(sp[u] + a0) : NAN;
 #pragma unroll
             for (int u = 0; u < U; u++) if ((chb >> u) & 1u) arrs.a[a0][c + (int64_t)(s0 + u) * g.C] = o[u];
         }
