@@ -94,13 +94,13 @@ template <int N, bool UNIFORM, int H = 0> struct AdvSmem {
 // bit -- instead of being loaded from shared memory:
 // the kernel is bound by LDS return bandwidth (128 B/clk/SM) and 30 of its 78 loads per particle
 // were grid-vector entries.
-// JP_ADV_STAGE1: the first interpolation of a particle (at its own position) skips the re-centring block when the library knows
+// Stage 1: the first interpolation of a particle (at its own position) skips the re-centring block when the library knows
 // that every particle lies strictly inside its storage cell (g.bucketed: the last call that touched the particles was
 // move_particles!, init, inject or clean -- not another advection!, a halo unpack or a foreign write); a particle that is not is
 // flagged and takes the literal routine (same result).  Read at run time the flag costs 0.29 ms at 256^3 (the re-centring code stays
 // in the loop: profiles/r02ad_ab_bucketed_flag.log), so the variants the time loops use -- trilinear, range grids -- exist twice:
 // BKT = true is launched when the flag is set and has the shortcut compiled in; all others test g.bucketed.
-// JP_ADV_NOVOTE: the later stages run the re-centring arithmetic unconditionally -- at CFL 0.5 nearly every warp holds
+// Later stages: they run the re-centring arithmetic unconditionally -- at CFL 0.5 nearly every warp holds
 // a lane whose stage position left its seed cell, so the vote only cost a divergent-branch frame.  Measured at 256^3 (r02l, all
 // bit-identical): 14.44 -> 13.44 (stage 1) -> 13.32 (no vote) -> 13.09 ms (2 CTAs / SM at <= 128 registers instead of 3 at 80).
 // Dropped: stencil loads as ld.shared.f64 on a 32-bit address held in one opaque register (the compiler re-derives the shared
@@ -108,12 +108,6 @@ template <int N, bool UNIFORM, int H = 0> struct AdvSmem {
 // (16 warps): 15.0 / 14.4 ms; 4 CTAs / SM at 64 registers: 17.5 ms; an extra stencil row per z-plane so that consecutive planes fall
 // into different banks (the plane pitch is 0 mod 32 banks): 13.08 -> 13.32 ms; a second, one-node-shifted copy of every tile so that
 // the two x-adjacent corners are one 16-byte LDS.128 (24 instead of 48 stencil loads per particle): 13.07 -> 13.67 ms.
-#ifndef JP_ADV_STAGE1
-#define JP_ADV_STAGE1 1
-#endif
-#ifndef JP_ADV_NOVOTE
-#define JP_ADV_NOVOTE 1
-#endif
 // stencil values of the LinP / MQS interpolants from the staged tile: A(i1, j1, k1) with 1-based GLOBAL node indices (jp_core.h)
 template <int N, class T> struct AdvTileAcc {
     const double *tile; int c0x, c0y, c0z;
@@ -145,11 +139,7 @@ __device__ __forceinline__ bool adv_interp_tile(const JpGrid &g, const double *_
         if (AFFINE) { a = fma(gd, g.aff_dv[d], g.aff_v0[d]); b = fma(gd + 1.0, g.aff_dv[d], g.aff_v0[d]); }
         else { a = xv[r]; b = xv[r + 1]; }
         const bool up = pd > b, dn = pd < a;
-#if JP_ADV_NOVOTE
-        if (!(JP_ADV_STAGE1 && FIRST && (BKT || g.bucketed))) {   // later stages: nearly every warp holds a lane that left its seed cell -- no vote, no divergent branch
-#else
-        if (!(JP_ADV_STAGE1 && FIRST && (BKT || g.bucketed)) && __any_sync(amask, up || dn)) {          // warp-uniform: stage positions that left the seed cell
-#endif
+        if (!(FIRST && (BKT || g.bucketed))) {    // first interpolation of a bucketed particle: nothing to re-centre; later stages: always (no vote)
             r += (up ? 1 : 0) - (dn ? 1 : 0);
             if (AFFINE) {
                 gd += (up ? 1.0 : 0.0) - (dn ? 1.0 : 0.0);

@@ -178,18 +178,9 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
 #ifndef JP_SCI_FAST_U
 #define JP_SCI_FAST_U 2
 #endif
-#ifndef JP_SCI_ACC_SMEM
-#define JP_SCI_ACC_SMEM 0
-#endif
-#ifndef JP_SCI_CONST_SMEM
-#define JP_SCI_CONST_SMEM 0
-#endif
 #ifndef JP_SCI_PREFETCH
 #define JP_SCI_PREFETCH 2        // batches ahead whose sectors are requested with prefetch.global.L1 (r02n: 14.9 -> 14.0 ms; 1: 14.0, 4: 14.4)
 #endif
-template <int N> constexpr size_t jp_sci_fast_smem() {
-    return sizeof(double) * 256 * ((JP_SCI_ACC_SMEM ? 2 * (N == 2 ? 4 : 8) : 0) + (JP_SCI_CONST_SMEM ? 12 : 0));
-}
 template <int N, int KMAX, bool FASTW, bool HAS_PH>
 __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_interp_fast(JpGrid g, MovePlanWs ws, MoveArrays arrs, uint8_t *index,
                                                                                           const double *__restrict__ stage, MoveInterp mi,
@@ -199,13 +190,6 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
     constexpr int IT = N;                                     // arrays: x, y[, z], Fp, phases, others...
     constexpr int IP = N + 1;
     constexpr int NG = HAS_PH ? N + 2 : N + 1;                // arrays the accumulation reads
-    extern __shared__ double sci_smem[];                      // dynamic: [2 * 2^N sums][256] (+ [12 cell constants][256])
-#if JP_SCI_ACC_SMEM
-    double (*acc_sm)[256] = reinterpret_cast<double (*)[256]>(sci_smem);
-#endif
-#if JP_SCI_CONST_SMEM
-    double (*cst_sm)[256] = reinterpret_cast<double (*)[256]>(sci_smem + (JP_SCI_ACC_SMEM ? 2 * NQ * 256 : 0));   // node / centre coordinates, reciprocal spacings
-#endif
     if (*skip_flag) return;
     int ci[3]; int64_t c;
     const bool ok = tile_cell<N>(g, ci, c);
@@ -215,15 +199,6 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
     const uint64_t changed = amask | lmask;
     const uint64_t visit = changed | occf;
     const unsigned base = ok ? ws.off[c] : 0;
-#if JP_SCI_CONST_SMEM
-    if (ok) {
-#pragma unroll
-        for (int d = 0; d < N; d++) {
-            cst_sm[2 * d][tid] = g.xv[d][ci[d]]; cst_sm[2 * d + 1][tid] = g.xv[d][ci[d] + 1];
-            if (HAS_PH) { cst_sm[6 + d][tid] = g.xc[d][ci[d]]; cst_sm[9 + d][tid] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
-        }
-    }
-#else
     double xn[3][2], xcn[3], idi[3];
     if (ok) {
 #pragma unroll
@@ -232,15 +207,9 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
             if (HAS_PH) { xcn[d] = g.xc[d][ci[d]]; idi[d] = 1.0 / jp_d_of(g.xv[d], g.uniform, ci[d]); }
         }
     }
-#endif
-#if JP_SCI_ACC_SMEM
-#pragma unroll
-    for (int q = 0; q < 2 * NQ; q++) acc_sm[q][tid] = 0.0;
-#else
     double aw[NQ], awf[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) { aw[q] = 0.0; awf[q] = 0.0; }
-#endif
     double w[KMAX];
 #pragma unroll
     for (int k = 0; k < KMAX; k++) w[k] = 0.0;
@@ -290,14 +259,14 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
             for (int a = 0; a < JP_MV_A; a++) {
                 v[u][a] = NAN;
                 if (a < arrs.n) {
-                    if (ar) v[u][a] = JP_LDCS(sp[u] + a);
-                    else if (keep && a < NG) v[u][a] = JP_LDCS((a == 0 ? a0p : a == 1 ? a1p : a == 2 ? a2p : a3p) + e);
+                    if (ar) v[u][a] = sp[u][a];
+                    else if (keep && a < NG) v[u][a] = (a == 0 ? a0p : a == 1 ? a1p : a == 2 ? a2p : a3p)[e];
                 }
             }
             phv[u] = NAN;
             if (HAS_PH && N == 3) {
-                if (ar) phv[u] = JP_LDCS(sp[u] + IP);
-                else if (keep) phv[u] = JP_LDCS(arrs.a[IP] + e);
+                if (ar) phv[u] = sp[u][IP];
+                else if (keep) phv[u] = arrs.a[IP][e];
             }
         }
         // ---- stores of the changed slots
@@ -313,7 +282,7 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
         for (int a0 = (HAS_PH && N == 3) ? JP_MV_A + 1 : JP_MV_A; a0 < arrs.n; a0++) {
             double o[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) o[u] = (((chb & arb) >> u) & 1u) ? JP_LDCS(sp[u] + a0) : NAN;
+            for (int u = 0; u < U; u++) o[u] = (((chb & arb) >> u) & 1u) ? sp[u][a0] : NAN;
 #pragma unroll
             for (int u = 0; u < U; u++) if ((chb >> u) & 1u) arrs.a[a0][c + (int64_t)(s0 + u) * g.C] = o[u];
         }
@@ -327,36 +296,7 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
             if ((fb >> u) & 1u) {                              // slot order = the reference's summation order
                 const double p[3] = {v[u][0], v[u][1], N == 3 ? v[u][2] : 0.0};
                 const double f = v[u][IT];
-#if JP_SCI_CONST_SMEM
-                double xn[3][2], xcn[3], idi[3];
-#pragma unroll
-                for (int d = 0; d < N; d++) {
-                    xn[d][0] = cst_sm[2 * d][tid]; xn[d][1] = cst_sm[2 * d + 1][tid];
-                    if (HAS_PH) { xcn[d] = cst_sm[6 + d][tid]; idi[d] = cst_sm[9 + d][tid]; }
-                }
-#endif
-#if JP_SCI_ACC_SMEM
-                {
-                    double d2[3][2];
-#pragma unroll
-                    for (int d = 0; d < N; d++) {
-                        const double b0 = xn[d][0] - p[d], b1 = xn[d][1] - p[d];
-                        d2[d][0] = b0 * b0; d2[d][1] = b1 * b1;
-                    }
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        double ss = d2[0][q & 1] + d2[1][(q >> 1) & 1];
-                        if (N == 3) ss = ss + d2[2][(q >> 2) & 1];
-                        double wi;
-                        if (FASTW) wi = jp_rcp_fast(ss);
-                        else { const double dist = sqrt(ss); wi = 1.0 / (dist * dist); }
-                        acc_sm[q][tid] += wi;
-                        acc_sm[NQ + q][tid] = fma(wi, f, acc_sm[NQ + q][tid]);
-                    }
-                }
-#else
                 jp_p2g_cell_accum<N, FASTW>(xn, p, f, aw, awf);
-#endif
                 if (HAS_PH) jp_phase_accum<N, KMAX>(xcn, idi, p, N == 3 ? phv[u] : v[u][IP], mi.K, w);
             }
         }
@@ -364,11 +304,7 @@ __global__ void __launch_bounds__(256, JP_MINB_SCATTER_INTERP) k_move_scatter_in
     if (ok) {
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
-#if JP_SCI_ACC_SMEM
-            mi.PW[(int64_t)q * g.C + c] = acc_sm[q][tid]; mi.PWF[(int64_t)q * g.C + c] = acc_sm[NQ + q][tid];
-#else
             mi.PW[(int64_t)q * g.C + c] = aw[q]; mi.PWF[(int64_t)q * g.C + c] = awf[q];
-#endif
         }
         if (HAS_PH) {
             double sum = w[0];

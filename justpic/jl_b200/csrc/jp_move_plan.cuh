@@ -139,12 +139,9 @@ __global__ void __launch_bounds__(256) k_move_prevacate(int64_t C, MovePlanWs ws
     ws.occ[c] = ws.occ0[c] & ~ws.leave[c];
 }
 
-// JP_PLAN_PREFETCH: request the neighbourhood's occupancy rows before the dependent chain starts.  Measured and left off: plan
+// (Tried: prefetch.global.L1 of the neighbourhood's occupancy rows before the dependent chain starts -- plan
 // 1.41 -> 1.72 ms at 256^3, 0.38 -> 0.43 ms at 128^3 (profiles/r02ag_ab_plan_prefetch.log) -- 18 more instructions per source cell,
-// wasted on the cells without leavers and the rows nobody asks for.
-#ifndef JP_PLAN_PREFETCH
-#define JP_PLAN_PREFETCH 0
-#endif
+// wasted on the cells without leavers and the rows nobody asks for.)
 // ---- B. one colour of the plan (thread = source cell; 8-byte words only).
 // Literal slot logic of move_kernel! (src/Particles/move_safe.jl:72-125) on the occupancy
 // words; the slot given to the k-th leaver goes to res (one byte: slot | placed << 6).
@@ -157,23 +154,6 @@ __device__ __forceinline__ void jp_move_plan_cell(const JpGrid &g, const MovePla
     ci[2] = N == 3 ? 3 * (int)(t / ((int64_t)ncx * ncy)) + oz : 0;
     if (ci[0] >= g.n[0] || ci[1] >= g.n[1] || (N == 3 && ci[2] >= g.n[2])) return;
     const int64_t c = jp_cell_lin<N>(g, ci);
-#if JP_PLAN_PREFETCH
-    // the occupancy words of the 3^N neighbourhood are read one after the other through the leavers' codes (a dependent chain):
-    // request their rows now
-    {
-        const int64_t sy = g.n[0], sz = (int64_t)g.n[0] * g.n[1];
-#pragma unroll
-        for (int dz = (N == 3 ? -1 : 0); dz <= (N == 3 ? 1 : 0); dz++)
-#pragma unroll
-            for (int dy = -1; dy <= 1; dy++) {
-                const int64_t r = c + dy * sy + dz * sz;
-                if (r - 1 >= 0 && r + 1 < g.C) {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ws.occ + r - 1));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ws.occ + r + 1));
-                }
-            }
-    }
-#endif
     uint64_t lv = ws.leave[c];
     if (lv == 0) return;
     const uint64_t smask = g.S == 64 ? ~0ull : ((1ull << g.S) - 1);
@@ -258,23 +238,10 @@ struct MoveArrays { double *a[JP_MAX_ARGS + 3]; int n; };
 #ifndef JP_MV_U
 #define JP_MV_U 4
 #endif
-// JP_STREAM_HINTS: single-use data (leaver payload, staging records, stayers read for the interpolation sums) marked evict-first
-// (ld.global.cs / st.global.cs) so that the partially written sectors of the arrays stay in the L2 longer.  Measured and left off:
-// gather 6.86 -> 7.44 ms, fused scatter 13.8 -> 17.2 ms at 256^3 (profiles/r02af_ab_stream_hints.log) -- the .cs loads lose the L1
-// lines the prefetches bring in.
-#ifndef JP_STREAM_HINTS
-#define JP_STREAM_HINTS 0
-#endif
-#if JP_STREAM_HINTS
-#define JP_LDCS(p) __ldcs(p)
-#define JP_STCS(p, v) __stcs(p, v)
-#else
-#define JP_LDCS(p) (*(p))
-#define JP_STCS(p, v) (*(p) = (v))
-#endif
-#ifndef JP_GATHER_PREFETCH
-#define JP_GATHER_PREFETCH 0
-#endif
+// (Tried on gather and fused scatter: single-use data -- leaver payload, staging records, stayers read for the interpolation sums --
+// marked evict-first (ld.global.cs / st.global.cs) so that the partially written sectors stay in the L2 longer: gather 6.86 -> 7.44 ms,
+// fused scatter 13.8 -> 17.2 ms at 256^3, profiles/r02af_ab_stream_hints.log; the .cs loads lose the L1 lines the prefetches bring in.
+// prefetch.global.L1 of the leavers' sectors a batch ahead in the gather: +0.5 ms, profiles/r02n_ab_gather_prefetch.log.)
 #define JP_MV_A 4      // arrays handled per register batch (coords + fields); more arrays loop again
 template <int N>
 __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, MovePlanWs ws, MoveArrays arrs, double *__restrict__ stage,
@@ -310,18 +277,6 @@ __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, M
                 }
             }
         }
-#if JP_GATHER_PREFETCH
-        {   // the leavers' sectors of the batch JP_GATHER_PREFETCH batches ahead: requested now, no register held
-            const int sn = s0 + JP_GATHER_PREFETCH * JP_MV_U;
-            const unsigned nb = sn < 64 ? (unsigned)(lv >> sn) & ((1u << JP_MV_U) - 1u) : 0u;
-#pragma unroll
-            for (int u = 0; u < JP_MV_U; u++)
-                if ((nb >> u) & 1u) {
-                    const int64_t en = c + (int64_t)(sn + u) * g.C;
-                    for (int a = 0; a < arrs.n; a++) asm volatile("prefetch.global.L1 [%0];" ::"l"(arrs.a[a] + en));
-                }
-        }
-#endif
         // staging is array-of-structs: one migrant = AS consecutive doubles (AS = n rounded up to 4,
         // padding written too), so every touched 32-byte sector is written completely (no fill read)
         const int AS = (arrs.n + 3) & ~3;
@@ -331,13 +286,13 @@ __global__ void __launch_bounds__(256, JP_MINB_GATHER) k_move_gather(JpGrid g, M
             for (int u = 0; u < JP_MV_U; u++)
 #pragma unroll
                 for (int a = 0; a < JP_MV_A; a++)
-                    v[u][a] = (act[u] && a0 + a < arrs.n) ? JP_LDCS(arrs.a[a0 + a] + e[u]) : 0.0;
+                    v[u][a] = (act[u] && a0 + a < arrs.n) ? arrs.a[a0 + a][e[u]] : 0.0;
 #pragma unroll
             for (int u = 0; u < JP_MV_U; u++)
                 if (act[u]) {
                     double2 *dst = reinterpret_cast<double2 *>(stage + pos[u] * AS + a0);
-                    JP_STCS(dst, make_double2(v[u][0], v[u][1]));
-                    JP_STCS(dst + 1, make_double2(v[u][2], v[u][3]));
+                    dst[0] = make_double2(v[u][0], v[u][1]);
+                    dst[1] = make_double2(v[u][2], v[u][3]);
                 }
         }
     }

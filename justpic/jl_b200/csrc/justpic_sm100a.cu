@@ -1586,15 +1586,7 @@ static void launch_scatter_interp(const JpGrid &g, dim3 grd, dim3 blk, cudaStrea
     // the usual argument order (Fp first, phases second): 4-slot batches, compile-time array indices (jp_move_interp.cuh)
     static const bool no_fast = getenv("JP_SCI_GENERIC") != nullptr;           // developer A/B switch
     if (!no_fast && mi.iT == N && (mi.iP == N + 1 || mi.iP < 0) && arrs.n >= (mi.iP >= 0 ? N + 2 : N + 1)) {
-#define JP_SCI_LAUNCH(KM, FW, PH)                                                                                                   \
-    do {                                                                                                                            \
-        static bool configured = false;                                                                                             \
-        if (!configured) {                                                                                                          \
-            cudaFuncSetAttribute(k_move_scatter_interp_fast<N, KM, FW, PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jp_sci_fast_smem<N>()); \
-            configured = true;                                                                                                      \
-        }                                                                                                                           \
-        k_move_scatter_interp_fast<N, KM, FW, PH><<<grd, blk, jp_sci_fast_smem<N>(), st>>>(g, ws, arrs, index, stage, mi, flag);    \
-    } while (0)
+#define JP_SCI_LAUNCH(KM, FW, PH) k_move_scatter_interp_fast<N, KM, FW, PH><<<grd, blk, 0, st>>>(g, ws, arrs, index, stage, mi, flag)
         if (mi.iP < 0) { if (fastw) JP_SCI_LAUNCH(2, true, false); else JP_SCI_LAUNCH(2, false, false); }
         else if (mi.K <= 2) { if (fastw) JP_SCI_LAUNCH(2, true, true); else JP_SCI_LAUNCH(2, false, true); }
         else { if (fastw) JP_SCI_LAUNCH(4, true, true); else JP_SCI_LAUNCH(4, false, true); }
