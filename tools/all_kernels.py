@@ -58,12 +58,15 @@ J.advection(p, rk2, V, 0.5 * dt, classify=True)
 J.move_particles(p, (strain, ph, pT))
 J.particle2grid(T, pT, p)
 J.move_interp_handoff(p, enable=False)
-# --- other integrators / interpolants
-J.advection(p, J.Euler(), V, 0.1 * dt, classify=False)
-J.advection(p, J.RungeKutta4(), V, 0.1 * dt)
-J.advection_LinP(p, rk2, V, 0.1 * dt)
+# --- the opt-in dense slot policy (k_move_prevacate + the plan without cursor)
+J.advection(p, rk2, V, 0.5 * dt, classify=False)
+J.move_particles(p, fields, policy="dense")
+# --- other integrators / interpolants (a move between them: each advection then starts from the bucketed state, as in a time loop)
+J.advection(p, J.Euler(), V, 0.1 * dt, classify=False); J.move_particles(p, fields)
+J.advection(p, J.RungeKutta4(), V, 0.1 * dt); J.move_particles(p, fields)
+J.advection_LinP(p, rk2, V, 0.1 * dt); J.move_particles(p, fields)
 J.advection_MQS(p, rk2, V, 0.1 * dt)
-J.move_particles(p, fields, mode="direct")            # literal sweeps
+J.move_particles(p, fields, mode="direct")            # literal sweeps (one cooperative launch)
 J.clean_particles(p, None, fields)
 # --- interpolations
 J.grid2particle(pT, T, p)
