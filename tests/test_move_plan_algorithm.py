@@ -16,8 +16,10 @@ from tests.problems import cfl_dt, make_grids, stream_velocity
 STAY, DELETE = 28, 27
 
 
-def planned_move(e, gr, S, coords, index, args):
-    """Returns (moved, dropped, deleted) or None when the planner hands over to the direct sweeps."""
+def planned_move(e, gr, S, coords, index, args, policy="reference"):
+    """Returns (moved, dropped, deleted) or None when the planner hands over to the direct sweeps.
+    policy: "reference" (carried-over cursor), "compact" (every search from slot 0), "dense" (k_move_prevacate first: all leavers give
+    up their slots before the first migrant is placed; the plan then neither clears bits nor carries a cursor)."""
     ndim = gr.ndim
     n = list(gr.n) + [1] * (3 - ndim)
     C = int(np.prod(n))
@@ -40,6 +42,8 @@ def planned_move(e, gr, S, coords, index, args):
             leave[c] |= 1 << s
             codes[c].append(code)
     occ0 = list(occ)
+    if policy == "dense":                                    # k_move_prevacate
+        occ = [occ0[c] & ~leave[c] for c in range(C)]
     # ---- B. k_move_plan x 3^N in the reference's colour order (offset_i outermost), words only
     res = [[None] * len(codes[c]) for c in range(C)]
     dropped = deleted = 0
@@ -56,7 +60,8 @@ def planned_move(e, gr, S, coords, index, args):
                                 if not (leave[c] >> ip) & 1:
                                     continue
                                 code = codes[c][kk]; kk += 1
-                                occ_c &= ~(1 << ip)
+                                if policy != "dense":
+                                    occ_c &= ~(1 << ip)
                                 if code == DELETE:
                                     deleted += 1
                                     continue
@@ -67,10 +72,12 @@ def planned_move(e, gr, S, coords, index, args):
                                     dropped += 1
                                     continue
                                 fs = (free & -free).bit_length() - 1
-                                cursor = fs                   # the reference's carried-over starting_point
+                                if policy == "reference":
+                                    cursor = fs               # the reference's carried-over starting_point
                                 occ[c2] |= 1 << fs
                                 res[c][kk - 1] = (c2, fs)
-                            occ[c] = occ_c
+                            if policy != "dense":
+                                occ[c] = occ_c
     # ---- C. k_move_finalize + exclusive scan
     arr = [occ[c] & (~occ0[c] | leave[c]) & smask for c in range(C)]
     off = np.concatenate([[0], np.cumsum([bin(a).count("1") for a in arr])]).astype(np.int64)
@@ -117,8 +124,10 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("policy", ["reference", "compact", "dense"])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}D-{c[1]}-{'range' if c[2] else 'vector'}-S{c[3]}")
-def test_plan_gather_scatter_equals_literal_sweeps(case):
+def test_plan_gather_scatter_equals_literal_sweeps(case, policy):
+    """(the oracle runs the same slot policy: its reference sweeps, or the twins of the library's two opt-in rules)"""
     ndim, n, uniform, S, nxcell, cfl = case
     gr = make_grids(n, ndim, uniform=uniform, stretch=0.4)
     o = Oracle(gr.xvi, gr.xci, gr.xi_vel, S, uniform)
@@ -130,8 +139,12 @@ def test_plan_gather_scatter_equals_literal_sweeps(case):
     for it in range(5):
         o.advect(co, idx, 1, 0.5, V, dt)
         A = [[c.copy() for c in co], idx.copy(), [f1.copy(), f2.copy()]]
-        st = planned_move(e, gr, S, A[0], A[1], A[2])
-        ref = o.move(co, idx, [f1, f2])
+        st = planned_move(e, gr, S, A[0], A[1], A[2], policy)
+        Oracle.set_move_policy(policy)
+        try:
+            ref = o.move(co, idx, [f1, f2])
+        finally:
+            Oracle.set_move_policy("reference")
         if st is None:
             handed_over += 1
             continue
@@ -143,4 +156,4 @@ def test_plan_gather_scatter_equals_literal_sweeps(case):
         assert np.array_equal(A[2][0], f1, equal_nan=True) and np.array_equal(A[2][1], f2, equal_nan=True), f"step {it}: fields"
     assert planned >= 4, (planned, handed_over)
     if S <= 12:
-        assert total_dropped > 0                         # the tight cases exercise the drop branch
+        assert total_dropped > 0                         # the tight cases exercise the drop branch (under every policy)
