@@ -55,3 +55,28 @@ def test_product_never_imports_oracle():
         if f.suffix in (".py", ".cu", ".h", ".cuh", ".cpp"):
             txt = f.read_text()
             assert "oracle" not in txt.replace("oracle twin", ""), f"{f} mentions the oracle"
+
+
+def header_enum_constants():
+    """every `NAME = value` inside the typedef enums of the header"""
+    txt = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    out = {}
+    for body in re.findall(r"typedef\s+enum\s*\{(.*?)\}", txt, flags=re.S):
+        for name, val in re.findall(r"\b(JP_[A-Z0-9_]+)\s*=\s*(-?\d+)", body):
+            out[name] = int(val)
+    return out
+
+
+def test_enum_constants_match_the_binding():
+    """the Python mirror passes plain integers to jp_set_option & co.: they must be the header's"""
+    consts = header_enum_constants()
+    assert len(consts) > 30
+    checked = 0
+    for name, val in consts.items():
+        if hasattr(_cabi, name):
+            assert getattr(_cabi, name) == val, f"{name}: header {val}, _cabi {getattr(_cabi, name)}"
+            checked += 1
+    for must in ("JP_OPT_MOVE_POLICY", "JP_MOVE_POLICY_DENSE", "JP_OPT_GRAPH_STEP_OFFSET", "JP_OPT_MOVE_INTERP", "JP_OPT_ADVECT_CLASSIFY",
+                 "JP_OPT_PROFILE", "JP_P2G_TWOPASS_FASTW", "JP_MOVE_DIRECT"):
+        assert must in consts and hasattr(_cabi, must), must
+    assert checked >= 20
