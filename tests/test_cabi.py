@@ -80,3 +80,9 @@ def test_enum_constants_match_the_binding():
                  "JP_OPT_PROFILE", "JP_P2G_TWOPASS_FASTW", "JP_MOVE_DIRECT"):
         assert must in consts and hasattr(_cabi, must), must
     assert checked >= 20
+
+
+def test_integration_doc_names_every_entry_point():
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    missing = [s for s in header_symbols() if s not in doc]
+    assert not missing, f"INTEGRATION.md does not mention {missing}"
